@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 pulse-DDM hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU algorithm
+
+Workload (BASELINE.json configs[1]): a 1e8-trial MNLE training set drawn from
+ExtendedProposal (pipeline prior for theta, PulseSequenceProposal(P=80, p=0.75, seed=0) for the
+pulses) with the default schedule (n_max=16000, steps_per_pulse=200), resident in HBM as
+z (1e8, 85) fp32 = 34 GB.  A "step" is one pass of the simulator over all of it (one
+``ddm_sim_f32`` launch; new Philox key every step).  With N>1 every rank owns its own 1e8-trial
+shard of one global trial index space (weak scaling) and the step ends with the NCCL all-gather
+of x, the only exchange the path has.
+
+Metric: useful Euler steps per second (sum over trials of the first-passage / censoring step,
+the count the reference's loop would have had to execute for those trials), whole job.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "simulated DDM Euler steps/sec"
+UNIT = "steps/s"
+W_ALG = 7             # fp32 lane-ops per useful step in the reference's unfused form
+BYTES_PER_TRIAL = 348  # 340 B of z in + 8 B of x out
+P = 80
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--trials", type=int, default=int(os.environ.get("DDM_BENCH_TRIALS", 100_000_000)),
+                    help="trials per GPU per step (default: the 1e8-trial config)")
+    ap.add_argument("--e2e-trials", type=int, default=int(os.environ.get("DDM_BENCH_E2E_TRIALS", 1 << 22)))
+    ap.add_argument("--cpu-trials", type=int, default=int(os.environ.get("DDM_BENCH_CPU_TRIALS", 4096)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------- clocks ---
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML, 100 ms)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "power_w_max": max(self.power), "samples": len(self.samples)}
+
+
+# -------------------------------------------------------------------------- reference arm ---
+
+def cpu_sample(n_trials: int, seed: int):
+    """A bounded sample of the workload on the host: same prior family, same pulse stream."""
+    import numpy as np
+    import torch
+    from oracle import ddm_oracle as orc
+    theta = orc.prior_sample(n_trials, seed=seed)
+    st, inc = orc.pcg64_state(np.random.default_rng(0))
+    pulses = torch.from_numpy(orc.pulses_pcg64_c(st, inc, 0, n_trials, P, 0.75))
+    return theta, pulses
+
+
+def time_cpu_port(n_trials: int, repeats: int, warmup: int):
+    """The reference's own CPU algorithm (lock-step torch ops + torch.randn, restated in
+    oracle/ddm_oracle.py) on all host threads torch uses.  Returns (steps/s, seconds, steps)."""
+    import torch
+    from oracle import ddm_oracle as orc
+    theta, pulses = cpu_sample(n_trials, seed=1)
+    torch.manual_seed(0)
+    for _ in range(warmup):
+        orc.sim_lockstep_torch(theta[:256], pulses[:256])
+    times, steps = [], []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        _, when, _ = orc.sim_lockstep_torch(theta, pulses)
+        times.append(time.perf_counter() - t0)
+        steps.append(int(when.sum()))
+    return sum(steps) / sum(times), times, steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = torch.get_num_threads()
+    rate, times, steps = time_cpu_port(args.cpu_trials, args.steps, args.warmup)
+    ms = 1e3 * sum(times) / len(times)
+    sample = (f"{args.cpu_trials} trials per step of the same workload (pipeline prior, PCG64 pulse stream seed 0, "
+              f"default schedule), lock-step torch port of rt_choice_model.py:112-221 with torch.randn")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] sample: ExtendedProposal training set, default schedule "
+                               "(n_max=16000, steps_per_pulse=200, P=80)", "trials_per_step": args.cpu_trials,
+                   "host_threads": cores, "os_cpu_count": os.cpu_count()},
+        "trials_per_s": args.cpu_trials * len(times) / sum(times),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- native arm ---
+
+def build_workload(n: int, rank: int, device):
+    """z (n, 85) on the device: theta ~ pipeline prior (rt_choice_model_pipeline.py:38-46),
+    pulses = rows [rank*n, (rank+1)*n) of PulseSequenceProposal(P=80, p=0.75, seed=0)'s stream."""
+    import numpy as np
+    import torch
+    from torch.distributions import Beta, LogNormal
+    from sbi_for_diffusion_models_b200.pulses import pcg64_state, pulses_from_state
+
+    z = torch.empty((n, 5 + P), dtype=torch.float32, device=device)
+    gen_seed = 1000 + rank
+    torch.manual_seed(gen_seed)
+    one = lambda v: torch.tensor(v, device=device)
+    chunk = 1 << 24
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        m = b - a
+        z[a:b, 0] = Beta(one(2.0), one(2.0)).sample((m,))
+        z[a:b, 1] = LogNormal(one(-1.0), one(1.0)).sample((m,))
+        z[a:b, 2] = LogNormal(one(0.0), one(1.0)).sample((m,))
+        z[a:b, 3] = LogNormal(one(2.75), one(0.5)).sample((m,))
+        z[a:b, 4] = Beta(one(2.0), one(2.0)).sample((m,))
+    state, inc = pcg64_state(np.random.default_rng(0))
+    pulses_from_state(state, inc, rank * n, n, P, 0.75, out=z[:, 5:])
+    return z
+
+
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sbi_for_diffusion_models_b200 import _native
+    from sbi_for_diffusion_models_b200 import data_simulator as ds
+    from sbi_for_diffusion_models_b200.simulator import Schedule, simulate_trials
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _native.lib()
+
+    n = args.trials
+    sched = Schedule.from_constants(1.0)
+    z = build_workload(n, rank, dev)
+    x = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    x_all = torch.empty((world * n, 2), dtype=torch.float32, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    base_seed = 20261018
+    stats_log = []
+
+    def step(i, events=None):
+        if events is not None:
+            events[0].record()
+        simulate_trials(z[:, :5], z[:, 5:], seed=base_seed + i, trial_offset=rank * n, out=x, schedule=sched)
+        if events is not None:
+            events[1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(x_all, x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # useful steps of a step depend on its key: recount each timed key afterwards (outside timing)
+    for i in range(args.warmup):
+        step(-1 - i)
+    barrier()
+
+    clocks = ClockSampler(local)
+    kernel_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                     for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.start()
+    barrier()
+    t_start.record()
+    for i in range(args.steps):
+        step(i, kernel_events[i])
+    t_end.record()
+    barrier()
+    clock_info = clocks.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kernel_ms = [a.elapsed_time(b) for a, b in kernel_events]
+
+    # recount useful steps per timed key (same launches, untimed) to get exact totals
+    useful, lane = 0, 0
+    for i in range(args.steps):
+        _, st = simulate_trials(z[:, :5], z[:, 5:], seed=base_seed + i, trial_offset=rank * n, out=x,
+                                schedule=sched, return_stats=True)
+        useful += st.useful_steps
+        lane += st.lane_steps
+    choice_frac = (torch.bincount(x[:, 1].to(torch.int64), minlength=3).float() / n).tolist()
+
+    tot = torch.tensor([float(useful), float(lane)], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    useful_all, lane_all = tot.tolist()
+    elapsed_ms = float(tmax.item())
+    value = useful_all / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies timed --------
+    n_e2e = min(args.e2e_trials, n)
+    z_host = torch.empty((n_e2e, 5 + P), dtype=torch.float32, pin_memory=True)
+    z_host.copy_(z[:n_e2e])
+    torch.cuda.synchronize()
+    outs = []
+    for i in range(args.warmup):
+        ds.sim_wrapper(z_host, mu_sensory=1.0, p_success=0.75, P=P, log_rt=False, seed=base_seed - 1 - i,
+                       trial_offset=rank * n)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        outs.append(ds.sim_wrapper(z_host, mu_sensory=1.0, p_success=0.75, P=P, log_rt=False, seed=base_seed + i,
+                                   trial_offset=rank * n))
+    e1.record()
+    torch.cuda.synchronize()
+    wall_e2e = time.perf_counter() - wall0
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), wall_e2e * 1e3)
+    t_nd = z_host[:, 4].clamp(0.0, sched.t_nd_hi)
+    e2e_steps = 0
+    for xo in outs:
+        e2e_steps += int(torch.round((xo[:, 0] - t_nd) / sched.dt).to(torch.int64).sum())
+    e2e_tot = torch.tensor([float(e2e_steps)], dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = float(e2e_tot.item()) / (float(e2e_t.item()) * 1e-3)
+
+    if rank == 0:
+        sms, khz = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        _native.lib().ddm_device_info(local, sms.ctypes.data, khz.ctypes.data, None, None)
+        peaks, peak_src = {}, "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak_src = "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+        sm_max_mhz = float(peaks.get("sm_max_mhz") or clock_info.get("sm_max_mhz") or khz[0] / 1e3)
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        lane_peak = int(sms[0]) * 128 * sm_max_mhz * 1e6           # fp32 lane-ops / s at max clock
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        per_launch_steps = useful / args.steps
+        achieved = per_launch_steps * W_ALG / (k_ms * 1e-3)
+        roofline = {
+            "bound": "fp32_issue", "kernel": "ddm::sim_kernel<3,false,true,2>",
+            "achieved": achieved / 1e12, "peak": lane_peak / 1e12, "unit": "TFLOP/s (fp32 lane-ops, FMA=1)",
+            "frac": achieved / lane_peak,
+            "peak_source": f"{int(sms[0])} SMs x 128 fp32 lanes x sm_max_mhz={sm_max_mhz:.0f} ({peak_src}); "
+                           "HBM and bf16 peaks do not bound this kernel (SURVEY 8d)",
+            "algorithmic_ops_per_step": W_ALG, "kernel_ms": k_ms,
+            "lane_efficiency": useful / lane if lane else None,
+            "hbm": {"achieved": BYTES_PER_TRIAL * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": BYTES_PER_TRIAL * n / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                    "algorithmic_bytes_per_trial": BYTES_PER_TRIAL},
+            "traffic": None,
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1e8-trial MNLE training set from ExtendedProposal, default "
+                                   "schedule (n_max=16000, steps_per_pulse=200, P=80)" if n == 100_000_000 else
+                                   f"configs[1] shape at {n} trials per GPU (default schedule, P=80)",
+                       "trials_per_gpu_per_step": n, "z_bytes_per_gpu": n * 340,
+                       "l2": "inputs (z) larger than L2; new Philox key each step", "rng": "Philox4x32-10 + Box-Muller",
+                       "exchange": "all_gather(x) per step" if world > 1 else "none"},
+            "trials_per_s": world * n * args.steps / (elapsed_ms * 1e-3),
+            "mean_steps_per_trial": useful_all / (world * n * args.steps),
+            "choice_frac": choice_frac,
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * 340, "d2h_bytes_per_step": n_e2e * 8,
+                    "trials_per_step_per_gpu": n_e2e, "api": "data_simulator.sim_wrapper(z pinned host) -> x host",
+                    "ms_per_step": float(e2e_t.item()) / args.steps},
+            "gpu_launches": args.steps * world,
+            "clocks": clock_info,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import torch as _t
+            rate, times, _ = time_cpu_port(args.cpu_trials, 3, 1)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+                "sample": f"3 x {args.cpu_trials} trials of the same workload through the lock-step torch port "
+                          f"(oracle.sim_lockstep_torch, torch.randn), {sum(times):.1f} s",
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

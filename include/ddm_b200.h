@@ -1,0 +1,140 @@
+/*
+ * ddm_b200.h -- C ABI of libddm_b200.so: the B200 (sm_100a) hot path of
+ * jfour1e/SBI-for-Diffusion-Models.
+ *
+ * Conventions
+ *   - Every pointer named *_dev is DEVICE memory owned by the caller (torch allocates
+ *     it in the Python host layer); the library never allocates or frees user-visible
+ *     memory and keeps no global state besides a thread-local error string and opaque
+ *     MNLE weight handles the caller creates and destroys.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All
+ *     entry points enqueue work and return without synchronising.
+ *   - Return value: 0 on success, negative on error (DDM_ERR_*); ddm_last_error()
+ *     returns a thread-local description.  No C++ exception crosses this boundary.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point returns
+ *     DDM_ERR_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to
+ * /root/reference/src/sbi_for_diffusion_models):
+ *   ddm_sim_f32              models/rt_choice_model.py:112-221 (_simulate_rt_choice_batch_torch)
+ *                            + :332-342 (pack_x_rt_choice) fused as the `log_rt` epilogue;
+ *                            reached through rt_choice_model_simulator_torch (:251-283),
+ *                            data_simulator.py:14-30 (sim_wrapper), :33-71, :74-99 and
+ *                            rt_choice_model.py:286-329 (simulate_session_data_rt_choice).
+ *   ddm_philox_normals_f32   models/rt_choice_model.py:186 (the torch.randn draw) -- exposes
+ *                            the exact normals the simulator consumed so a run can be
+ *                            replayed through the reference bit for bit.
+ *   ddm_pulses_pcg64         models/rt_choice_model.py:62-91 (generate_pulse_matrix_numpy)
+ *                            + models/choice_model.py:43-60 (generate_pulse_sides), i.e.
+ *                            the body of proposals.py:30-40 (PulseSequenceProposal.sample).
+ *   mnle_*                   potentials.py:75-117 (ConditionedMNLELogLikelihood.forward) and
+ *                            the estimator.log_prob call at potentials.py:113.
+ */
+#ifndef DDM_B200_H
+#define DDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDM_OK 0
+#define DDM_ERR_INVALID (-1) /* bad argument (shape, range, null pointer) */
+#define DDM_ERR_CUDA (-2)    /* CUDA runtime error, or no device */
+#define DDM_ERR_STATE (-3)   /* bad or destroyed handle */
+
+#define DDM_ABI_VERSION 1
+
+int ddm_abi_version(void);
+const char *ddm_last_error(void);
+
+/* sm_count, SM clock (kHz, cudaDevAttrClockRate) and compute capability of `device`. */
+int ddm_device_info(int device, int *sm_count, int *sm_clock_khz, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------- simulator --- */
+
+/* Device scratch the simulator needs per call (work queue + counters). */
+size_t ddm_sim_workspace_bytes(void);
+
+/* Layout of the workspace after the kernel has finished (all uint64):
+ *   [0] trial queue cursor (>= N when done)
+ *   [1] sum over trials of hit_step  == useful Euler steps executed
+ *   [2] number of trials whose pulse row held values other than +-1 (slow kick path)
+ *   [3] lane-steps issued (useful + idle lanes), for lane-efficiency accounting */
+#define DDM_WS_QUEUE 0
+#define DDM_WS_USEFUL_STEPS 1
+#define DDM_WS_GENERIC_ROWS 2
+#define DDM_WS_LANE_STEPS 3
+#define DDM_WS_WORDS 8
+
+/*
+ * Simulate N pulse-driven DDM trials.
+ *
+ *   theta_dev   (N, >=5) fp32, row stride ld_theta floats: [a0, lam, v, B, t_nd];
+ *               ld_theta == 0 broadcasts one parameter row to every trial (a session)
+ *   pulses_dev  (N, P) fp32 pulse sides, row stride ld_pulses floats; ld_pulses == 0
+ *               broadcasts one row to every trial (rt_choice_model.py:166-168).  Only
+ *               the first ceil(n_max / steps_per_pulse) columns are read (:178); P smaller
+ *               than that is DDM_ERR_INVALID (:173-176).
+ *   n_max, steps_per_pulse      time grid (rt_choice_model.py:45-59)
+ *   dt, t_max, t_nd_hi, noise_scale
+ *               the Python floats of the reference ALREADY ROUNDED to fp32 the way a
+ *               float32 tensor op sees them: (float)DT_CHOICE, (float)T_MAX,
+ *               (float)(T_MAX - 1e-6), (float)(mu_sensory * sqrt(DT_CHOICE)).
+ *   seed, trial_offset
+ *               native noise: Philox4x32-10 with key = seed and counter
+ *               (trial_offset + i, step / 4): results do not depend on how trials are
+ *               split over launches, streams or GPUs.
+ *   noise_dev   NULL for native noise; otherwise (n_max, >=N) fp32 standard normals,
+ *               step-major with row stride ld_noise floats (the reference draws one (N,)
+ *               vector per step), consumed INSTEAD of Philox.  With shared noise the
+ *               output equals the reference's bit for bit.
+ *   log_rt      0: x[:,0] = rt;  1: x[:,0] = log(max(rt, 1e-6))  (pack_x_rt_choice)
+ *   x_out_dev   (N, 2) fp32 contiguous: [rt, choice in {0,1,2}]
+ *   steps_out_dev  NULL or (N,) int32 hit_step (first-passage step, or the window length
+ *               when censored)
+ *   workspace_dev  >= ddm_sim_workspace_bytes(), 8-byte aligned; zeroed by this call.
+ */
+int ddm_sim_f32(const float *theta_dev, int64_t ld_theta,
+                const float *pulses_dev, int64_t ld_pulses,
+                int64_t N, int64_t P,
+                int64_t n_max, int64_t steps_per_pulse,
+                float dt, float t_max, float t_nd_hi, float noise_scale,
+                uint64_t seed, uint64_t trial_offset,
+                const float *noise_dev, int64_t ld_noise,
+                int log_rt,
+                float *x_out_dev, int32_t *steps_out_dev,
+                void *workspace_dev, void *stream);
+
+/* The standard normals ddm_sim_f32 consumes under native noise for trials
+ * [trial_offset, trial_offset + N) and steps [0, n_steps): out (n_steps, N) step-major,
+ * row stride ld_out floats. */
+int ddm_philox_normals_f32(uint64_t seed, uint64_t trial_offset, int64_t N, int64_t n_steps,
+                           float *out_dev, int64_t ld_out, void *stream);
+
+/* Same indexing, raw Philox4x32-10 words (integer; checked bit-exactly on the host). */
+int ddm_philox_words_u32(uint64_t seed, uint64_t trial_offset, int64_t N, int64_t n_steps,
+                         uint32_t *out_dev, int64_t ld_out, void *stream);
+
+/* ------------------------------------------------------------ pulse generator --- */
+
+/*
+ * Rows [first_trial, first_trial + n) of generate_pulse_matrix_numpy(rng, ., P, p) for a
+ * NumPy PCG64 generator whose bit_generator.state is (state, inc) before the call.
+ * threshold = ceil(clip(p_success, 0, 1) * 2^53).  out (n, P) fp32 +-1, row stride ld.
+ * Bit-identical to NumPy (integer arithmetic only).
+ */
+int ddm_pulses_pcg64(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
+                     uint64_t first_trial, int64_t n, int64_t P, uint64_t threshold,
+                     float *out_dev, int64_t ld, void *stream);
+
+/* Host-side helper: PCG64 state after `draws` more doubles (no device work). */
+int ddm_pcg64_advance(uint64_t *state_hi, uint64_t *state_lo, uint64_t inc_hi, uint64_t inc_lo,
+                      uint64_t draws);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDM_B200_H */

@@ -297,3 +297,32 @@ def prior_sample(n: int, seed: int = 0) -> torch.Tensor:
     v = np.exp(g[:, 1])
     B = np.exp(2.75 + 0.5 * g[:, 2])
     return torch.from_numpy(np.stack([a0, lam, v, B, tau], axis=1).astype(np.float32))
+
+
+def sim_rng_c(theta, pulses, seed: int, *, dt: float = DT_CHOICE, t_max: float = T_MAX,
+              pulse_interval: float = PULSE_INTERVAL, mu_sensory: float = 1.0):
+    """Scalar-C simulator with its own CPU normal generator (distribution tests, CPU baseline)."""
+    theta = np.ascontiguousarray(np.asarray(theta, dtype=np.float32))
+    pulses = np.ascontiguousarray(np.asarray(pulses, dtype=np.float32))
+    if theta.ndim == 1:
+        theta = theta[None, :]
+    if pulses.ndim == 1:
+        pulses = pulses[None, :]
+    N = theta.shape[0]
+    n_max, spp, _ = schedule(dt, t_max, pulse_interval)
+    ld_p = 0 if (pulses.shape[0] == 1 and N > 1) else pulses.shape[1]
+    sc = fp32_scalars(dt, t_max, mu_sensory)
+    x = np.empty((N, 2), dtype=np.float32)
+    steps = np.empty((N,), dtype=np.int64)
+    L = lib()
+    L.ddm_oracle_sim_rng_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                         ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                         ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+    L.ddm_oracle_sim_rng_f32.restype = ctypes.c_int
+    rc = L.ddm_oracle_sim_rng_f32(theta.ctypes.data, theta.shape[1], pulses.ctypes.data, ld_p, N, pulses.shape[1],
+                                  n_max, spp, sc["dt"], sc["t_max"], sc["t_nd_hi"], sc["noise_scale"],
+                                  ctypes.c_uint64(seed), x.ctypes.data, steps.ctypes.data)
+    if rc != 0:
+        raise ValueError("ddm_oracle_sim_rng_f32 rejected its arguments")
+    return x, steps

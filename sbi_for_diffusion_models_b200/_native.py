@@ -1,0 +1,77 @@
+"""ctypes binding of libddm_b200.so (see include/ddm_b200.h).
+
+There is deliberately no fallback: if the shared object is missing, or CUDA is not
+available, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "_lib", "libddm_b200.so")
+
+DDM_OK, DDM_ERR_INVALID, DDM_ERR_CUDA, DDM_ERR_STATE = 0, -1, -2, -3
+WS_QUEUE, WS_USEFUL_STEPS, WS_GENERIC_ROWS, WS_LANE_STEPS, WS_WORDS = 0, 1, 2, 3, 8
+
+_i64, _u64, _f32, _i32 = ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_int
+_ptr = ctypes.c_void_p
+
+_SIGNATURES = {
+    "ddm_abi_version": (ctypes.c_int, []),
+    "ddm_last_error": (ctypes.c_char_p, []),
+    "ddm_device_info": (ctypes.c_int, [_i32, _ptr, _ptr, _ptr, _ptr]),
+    "ddm_sim_workspace_bytes": (ctypes.c_size_t, []),
+    "ddm_sim_f32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _f32, _f32,
+                                   _u64, _u64, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "ddm_philox_normals_f32": (ctypes.c_int, [_u64, _u64, _i64, _i64, _ptr, _i64, _ptr]),
+    "ddm_philox_words_u32": (ctypes.c_int, [_u64, _u64, _i64, _i64, _ptr, _i64, _ptr]),
+    "ddm_pulses_pcg64": (ctypes.c_int, [_u64, _u64, _u64, _u64, _u64, _i64, _i64, _u64, _ptr, _i64, _ptr]),
+    "ddm_pcg64_advance": (ctypes.c_int, [_ptr, _ptr, _u64, _u64, _u64]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    """Load the library once; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} is missing. Build it with `python -m sbi_for_diffusion_models_b200.build` "
+                "(needs nvcc; targets sm_100a). There is no CPU or PyTorch fallback for this path.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the ABI drifted
+            fn.restype, fn.argtypes = res, args
+        if L.ddm_abi_version() != 1:
+            raise NativeLibraryMissing(f"{LIB_PATH}: ABI version {L.ddm_abi_version()} != 1, rebuild")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == DDM_OK:
+        return
+    msg = lib().ddm_last_error().decode("utf-8", "replace")
+    if rc == DDM_ERR_INVALID:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what}: {msg} (code {rc})")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "sbi_for_diffusion_models_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch

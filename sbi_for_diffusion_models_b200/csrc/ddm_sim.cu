@@ -1,0 +1,415 @@
+// Pulse-driven drift-diffusion trial simulator for B200 (sm_100a).
+//
+// Replaces the lock-step torch loop of the reference
+// (/root/reference/src/sbi_for_diffusion_models/models/rt_choice_model.py:112-221) with one
+// persistent kernel:
+//
+//   * one LANE per trial, each lane on its own clock.  A lane whose trial has crossed a
+//     bound (or run out of decision window) is refilled with the next trial from a global
+//     queue at the next chunk boundary, so warps stay full although trial lengths vary
+//     from 1 to n_max steps (mean ~5e3 of 16000 under the pipeline prior);
+//   * noise is counter-based: Philox4x32-10 keyed by the seed with counter
+//     (global trial index, step / 4) -> Box-Muller on the MUFU unit.  Which lane, warp,
+//     launch or GPU runs a trial does not change its result;
+//   * the fp32 arithmetic of a step is the reference's, operation for operation, with FMA
+//     contraction forbidden (explicit *_rn intrinsics), so that feeding the same normals
+//     to the reference reproduces the output bit for bit;
+//   * pulse rows are loaded once per trial by the whole warp (coalesced 128-byte requests)
+//     and packed to sign bits with warp ballots (80 pulses -> three registers);  a row that
+//     holds anything other than +-1 is flagged and read back from global memory at kick
+//     time instead, still bit-exact;
+//   * a chunk is 8 Euler steps (two Philox blocks).  The fast path only tracks the running
+//     max / min of the accumulator; the per-step first-passage search runs once per trial,
+//     in the chunk where max >= B, min <= 0 or the window ends.
+#include "ddm_common.cuh"
+
+#include <math_constants.h>
+
+namespace ddm {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct SimParams {
+    const float *theta;
+    long long ld_theta;
+    const float *pulses;
+    long long ld_pulses;
+    const float *noise;
+    long long ld_noise;
+    float *x_out;
+    int *steps_out;
+    unsigned long long *ws;
+    unsigned int n_trials;
+    int n_pulses;  // columns of the pulse matrix the schedule can reach
+    int n_max;
+    int spp;
+    float dt, t_max, t_nd_hi, noise_scale;
+    PhiloxKey key;
+    unsigned long long trial_offset;
+    int log_rt;
+};
+
+// torch.clamp: NaN propagates (fminf/fmaxf would drop it)
+__device__ __forceinline__ float clamp_keep_nan(float x, float lo, float hi)
+{
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+template <int MASKW, bool INJECT, bool ALIGNED, int NB>
+__global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
+{
+    constexpr int STEPS = 4 * NB;
+    constexpr int MW = MASKW > 0 ? MASKW : 1;
+    const unsigned lane = threadIdx.x & 31u;
+
+    // ---- per-lane trial state ---------------------------------------------------------
+    float a = 0.f, nlam = 0.f, B = 1.f, v = 0.f, tnd = 0.f;
+    int t = 0;       // Euler steps already taken by this lane's trial
+    int nsteps = 0;  // decision window in steps
+    int tk = 0;      // step index of the next pulse kick
+    int pidx = 0;    // column of the next pulse
+    uint32_t mask[MW];
+#pragma unroll
+    for (int w = 0; w < MW; ++w) mask[w] = 0u;
+    uint32_t trial = 0;  // index into this launch's arrays
+    bool busy = false;
+    bool generic = (MASKW == 0);  // kick reads the pulse value from global memory
+    bool exhausted = false;       // warp-uniform: the queue has run dry
+    unsigned long long useful = 0ull;
+    unsigned int chunks = 0u;
+
+    for (;;) {
+        // ---- refill idle lanes from the global queue ----------------------------------
+        const unsigned idle = __ballot_sync(kFull, !busy);
+        if (idle != 0u && !exhausted) {
+            const int want = __popc(idle);
+            unsigned long long base = 0ull;
+            if (lane == 0) base = atomicAdd(&p.ws[DDM_WS_QUEUE], (unsigned long long)want);
+            base = __shfl_sync(kFull, base, 0);
+            exhausted = (base + (unsigned long long)want >= (unsigned long long)p.n_trials);
+            const unsigned long long mine = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
+            const bool got = !busy && mine < (unsigned long long)p.n_trials;
+            if (got) trial = (uint32_t)mine;
+
+            if (MASKW > 0) {
+                // whole warp loads each new trial's pulse row: coalesced, then ballot -> sign bits
+                unsigned todo = __ballot_sync(kFull, got);
+                while (todo != 0u) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const uint32_t tj = __shfl_sync(kFull, trial, j);
+                    const float *row = p.pulses + (long long)tj * p.ld_pulses;
+                    bool odd = false;
+#pragma unroll
+                    for (int w = 0; w < MASKW; ++w) {
+                        const int c = w * 32 + (int)lane;
+                        const float s = (c < p.n_pulses) ? __ldg(row + c) : 1.0f;
+                        const unsigned bits = __ballot_sync(kFull, s > 0.0f);
+                        odd = odd || (fabsf(s) != 1.0f);
+                        if ((int)lane == j) mask[w] = bits;
+                    }
+                    const unsigned any_odd = __ballot_sync(kFull, odd);
+                    if ((int)lane == j) generic = (any_odd != 0u);
+                }
+            }
+            if (got) {
+                const float *th = p.theta + (long long)trial * p.ld_theta;
+                const float th0 = __ldg(th + 0), th1 = __ldg(th + 1), th2 = __ldg(th + 2);
+                const float th3 = __ldg(th + 3), th4 = __ldg(th + 4);
+                // rt_choice_model.py:131-135
+                const float a0 = clamp_keep_nan(th0, 0.0f, 1.0f);
+                nlam = -th1;
+                v = fabsf(th2);
+                B = fabsf(th3);
+                B = (B < 1e-6f) ? 1e-6f : B;
+                tnd = clamp_keep_nan(th4, 0.0f, p.t_nd_hi);
+                // :141  floor((T_MAX - t_nd) / dt) with a true IEEE division (CPU semantics)
+                const float win = floorf(__fdiv_rn(__fsub_rn(p.t_max, tnd), p.dt));
+                nsteps = !(win > 0.0f) ? 0 : (win >= (float)p.n_max ? p.n_max : (int)win);
+                a = __fmul_rn(a0, B);  // :144
+                t = 0;
+                tk = 0;
+                pidx = 0;
+                busy = true;
+                if (MASKW > 0 && generic) atomicAdd(&p.ws[DDM_WS_GENERIC_ROWS], 1ull);
+            }
+        }
+        if (__ballot_sync(kFull, busy) == 0u) break;
+
+        // ---- one chunk of STEPS Euler steps -------------------------------------------
+        const unsigned long long g = p.trial_offset + (unsigned long long)trial;
+        const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
+
+        auto kick_value = [&]() -> float {
+            // rt_choice_model.py:192  a += v * s[:, p_idx] * active
+            if (MASKW == 0 || generic) {
+                float s = 0.0f;
+                if (busy && pidx < p.n_pulses)
+                    s = __ldg(p.pulses + (long long)trial * p.ld_pulses + pidx);
+                return __fmul_rn(v, s);
+            }
+            uint32_t w = mask[0];
+            if (MASKW > 1 && pidx >= 32) w = mask[1 % MW];
+            if (MASKW > 2 && pidx >= 64) w = mask[2 % MW];
+            return ((w >> (pidx & 31)) & 1u) ? v : -v;  // v * (+-1) exactly
+        };
+
+        float kv = 0.0f;
+        bool kick0 = false;
+        if (ALIGNED) {
+            kick0 = (t == tk);
+            if (kick0) {
+                kv = kick_value();
+                tk += p.spp;
+                pidx += 1;
+            }
+        }
+
+        float av[STEPS];
+        float acc = a;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float z[4];
+            if (INJECT) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int step = t + 4 * b + j;
+                    z[j] = (busy && step < p.n_max)
+                               ? __ldg(p.noise + (long long)step * p.ld_noise + trial)
+                               : 0.0f;
+                }
+            } else {
+                philox_normals4(g_lo, g_hi, (uint32_t)(t >> 2) + (uint32_t)b, p.key, z);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = 4 * b + j;
+                const float nz = __fmul_rn(z[j], p.noise_scale);                // :186
+                const float leak = __fmul_rn(__fmul_rn(nlam, acc), p.dt);      // (-lam*a)*dt
+                acc = __fadd_rn(__fadd_rn(acc, leak), nz);                     // :187
+                if (ALIGNED) {
+                    if (i == 0 && kick0) acc = __fadd_rn(acc, kv);             // :190-192
+                } else {
+                    if (t + i == tk) {
+                        acc = __fadd_rn(acc, kick_value());
+                        tk += p.spp;
+                        pidx += 1;
+                    }
+                }
+                av[i] = acc;
+            }
+        }
+        a = acc;
+        chunks += 1u;
+
+        // fmaxf / fminf ignore NaN operands, like the reference's comparisons (always false)
+        float hi = -CUDART_INF_F, lo = CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < STEPS; ++i) {
+            hi = fmaxf(hi, av[i]);
+            lo = fminf(lo, av[i]);
+        }
+
+        if (busy && (hi >= B || lo <= 0.0f || t + STEPS >= nsteps)) {
+            // ---- this trial ends inside the chunk: exact first-passage search ---------
+            int hit_step = -1;
+            int choice = 2;
+#pragma unroll
+            for (int i = STEPS - 1; i >= 0; --i) {
+                const bool up = av[i] >= B;      // :195
+                const bool dn = av[i] <= 0.0f;   // :196
+                if ((t + i < nsteps) && (up || dn)) {
+                    hit_step = t + i + 1;        // :201
+                    choice = dn ? 0 : 1;         // lower bound wins ties, :202-203
+                }
+            }
+            if (hit_step < 0) {  // window over without a crossing, :206-215
+                hit_step = nsteps;
+                choice = 2;
+            }
+            // :218, then pack_x_rt_choice :338-342
+            float rt = __fadd_rn(tnd, __fmul_rn((float)hit_step, p.dt));
+            rt = clamp_keep_nan(rt, 1e-6f, p.t_max);
+            rt = (rt < 1e-6f) ? 1e-6f : rt;
+            if (p.log_rt) rt = logf(rt);
+            reinterpret_cast<float2 *>(p.x_out)[trial] = make_float2(rt, (float)choice);
+            if (p.steps_out) p.steps_out[trial] = hit_step;
+            useful += (unsigned long long)hit_step;
+            busy = false;
+        }
+        t += STEPS;
+    }
+
+    // ---- counters --------------------------------------------------------------------
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) useful += __shfl_xor_sync(kFull, useful, o);
+    if (lane == 0) {
+        atomicAdd(&p.ws[DDM_WS_USEFUL_STEPS], useful);
+        atomicAdd(&p.ws[DDM_WS_LANE_STEPS], (unsigned long long)chunks * (unsigned long long)(STEPS * 32));
+    }
+}
+
+// ---- dump kernels: the noise stream as a tensor ---------------------------------------
+template <bool WORDS>
+__global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, unsigned long long trial_offset,
+                                                          long long n_trials, long long n_steps,
+                                                          void *out, long long ld)
+{
+    const long long n_blk = (n_steps + 3) / 4;
+    const long long total = n_blk * n_trials;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long blk = idx / n_trials;
+        const long long i = idx - blk * n_trials;
+        const unsigned long long g = trial_offset + (unsigned long long)i;
+        if (WORDS) {
+            uint32_t w[4];
+            philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)blk, 0u, key, w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (blk * 4 + j < n_steps) static_cast<uint32_t *>(out)[(blk * 4 + j) * ld + i] = w[j];
+        } else {
+            float z[4];
+            philox_normals4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)blk, key, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (blk * 4 + j < n_steps) static_cast<float *>(out)[(blk * 4 + j) * ld + i] = z[j];
+        }
+    }
+}
+
+// ---- launch ----------------------------------------------------------------------------
+template <int MASKW, bool INJECT, bool ALIGNED>
+static int launch_sim(const SimParams &p, int sm_count, cudaStream_t stream)
+{
+    auto kern = sim_kernel<MASKW, INJECT, ALIGNED, 2>;
+    int per_sm = 0;
+    DDM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    const long long warps_needed = ((long long)p.n_trials + 31) / 32;
+    const long long resident_warps = (long long)sm_count * per_sm * (kThreads / 32);
+    int block = kThreads;
+    long long grid;
+    if (warps_needed >= resident_warps) {
+        grid = (long long)sm_count * per_sm;  // persistent: every resident slot, lanes refill
+    } else {
+        // few trials: spread the warps over as many SMs as possible
+        long long wpb = (warps_needed + sm_count - 1) / sm_count;
+        if (wpb < 1) wpb = 1;
+        if (wpb > kThreads / 32) wpb = kThreads / 32;
+        block = (int)wpb * 32;
+        grid = (warps_needed + wpb - 1) / wpb;
+    }
+    kern<<<(unsigned)grid, block, 0, stream>>>(p);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}
+
+}  // namespace ddm
+
+using namespace ddm;
+
+DDM_API size_t ddm_sim_workspace_bytes(void) { return DDM_WS_WORDS * sizeof(unsigned long long); }
+
+DDM_API int ddm_sim_f32(const float *theta_dev, int64_t ld_theta, const float *pulses_dev,
+                        int64_t ld_pulses, int64_t N, int64_t P, int64_t n_max,
+                        int64_t steps_per_pulse, float dt, float t_max, float t_nd_hi,
+                        float noise_scale, uint64_t seed, uint64_t trial_offset,
+                        const float *noise_dev, int64_t ld_noise, int log_rt, float *x_out_dev,
+                        int32_t *steps_out_dev, void *workspace_dev, void *stream)
+{
+    DDM_REQUIRE(N >= 0 && N <= 0x7FFFFFFFll, "ddm_sim_f32: N=%lld outside [0, 2^31)", (long long)N);
+    DDM_REQUIRE(n_max >= 0 && n_max <= 0x7FFFFF00ll, "ddm_sim_f32: n_max=%lld out of range", (long long)n_max);
+    DDM_REQUIRE(steps_per_pulse >= 1 && steps_per_pulse <= 0x7FFFFFFFll,
+                "ddm_sim_f32: steps_per_pulse=%lld must be >= 1", (long long)steps_per_pulse);
+    const int64_t need = (n_max + steps_per_pulse - 1) / steps_per_pulse;
+    DDM_REQUIRE(P >= need, "ddm_sim_f32: pulse matrix has P=%lld columns but the schedule needs %lld",
+                (long long)P, (long long)need);
+    DDM_REQUIRE(dt > 0.0f && t_max > 0.0f, "ddm_sim_f32: dt and t_max must be positive");
+    DDM_REQUIRE(workspace_dev != nullptr && (reinterpret_cast<uintptr_t>(workspace_dev) & 7u) == 0,
+                "ddm_sim_f32: workspace must be a non-null, 8-byte aligned device pointer");
+    if (N > 0) {
+        DDM_REQUIRE(theta_dev && pulses_dev && x_out_dev, "ddm_sim_f32: null theta / pulses / x_out");
+        DDM_REQUIRE(ld_theta == 0 || ld_theta >= 5, "ddm_sim_f32: ld_theta=%lld (0 = broadcast, else >= 5)", (long long)ld_theta);
+        DDM_REQUIRE(ld_pulses == 0 || ld_pulses >= need, "ddm_sim_f32: ld_pulses=%lld < %lld",
+                    (long long)ld_pulses, (long long)need);
+        DDM_REQUIRE((reinterpret_cast<uintptr_t>(x_out_dev) & 7u) == 0, "ddm_sim_f32: x_out must be 8-byte aligned");
+        DDM_REQUIRE(noise_dev == nullptr || ld_noise >= N, "ddm_sim_f32: ld_noise=%lld < N", (long long)ld_noise);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DDM_CUDA_TRY(cudaMemsetAsync(workspace_dev, 0, ddm_sim_workspace_bytes(), st));
+    if (N == 0) return DDM_OK;
+
+    int dev = 0, sms = 0;
+    DDM_CUDA_TRY(cudaGetDevice(&dev));
+    DDM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+    SimParams p;
+    p.theta = theta_dev;
+    p.ld_theta = ld_theta;
+    p.pulses = pulses_dev;
+    p.ld_pulses = ld_pulses;
+    p.noise = noise_dev;
+    p.ld_noise = ld_noise;
+    p.x_out = x_out_dev;
+    p.steps_out = steps_out_dev;
+    p.ws = static_cast<unsigned long long *>(workspace_dev);
+    p.n_trials = (unsigned int)N;
+    p.n_pulses = (int)need;
+    p.n_max = (int)n_max;
+    p.spp = (int)steps_per_pulse;
+    p.dt = dt;
+    p.t_max = t_max;
+    p.t_nd_hi = t_nd_hi;
+    p.noise_scale = noise_scale;
+    p.key.k0 = (uint32_t)seed;
+    p.key.k1 = (uint32_t)(seed >> 32);
+    p.trial_offset = trial_offset;
+    p.log_rt = log_rt ? 1 : 0;
+
+    const bool inject = noise_dev != nullptr;
+    const bool aligned = (steps_per_pulse % 8) == 0;
+    const bool packed = need <= 96;
+#define DDM_PICK(MW, INJ, AL) return launch_sim<MW, INJ, AL>(p, sms, st)
+    if (packed) {
+        if (inject) { if (aligned) DDM_PICK(3, true, true); else DDM_PICK(3, true, false); }
+        else        { if (aligned) DDM_PICK(3, false, true); else DDM_PICK(3, false, false); }
+    } else {
+        if (inject) { if (aligned) DDM_PICK(0, true, true); else DDM_PICK(0, true, false); }
+        else        { if (aligned) DDM_PICK(0, false, true); else DDM_PICK(0, false, false); }
+    }
+#undef DDM_PICK
+}
+
+static int dump_common(bool words, uint64_t seed, uint64_t trial_offset, int64_t N, int64_t n_steps,
+                       void *out_dev, int64_t ld_out, void *stream)
+{
+    DDM_REQUIRE(N >= 0 && n_steps >= 0, "philox dump: negative size");
+    DDM_REQUIRE(ld_out >= N, "philox dump: ld_out=%lld < N=%lld", (long long)ld_out, (long long)N);
+    if (N == 0 || n_steps == 0) return DDM_OK;
+    DDM_REQUIRE(out_dev != nullptr, "philox dump: null output");
+    const long long total = ((n_steps + 3) / 4) * N;
+    long long grid = (total + 255) / 256;
+    if (grid > 148 * 64) grid = 148 * 64;
+    PhiloxKey key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (words)
+        philox_dump_kernel<true><<<(unsigned)grid, 256, 0, st>>>(key, trial_offset, N, n_steps, out_dev, ld_out);
+    else
+        philox_dump_kernel<false><<<(unsigned)grid, 256, 0, st>>>(key, trial_offset, N, n_steps, out_dev, ld_out);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}
+
+DDM_API int ddm_philox_normals_f32(uint64_t seed, uint64_t trial_offset, int64_t N, int64_t n_steps,
+                                   float *out_dev, int64_t ld_out, void *stream)
+{
+    return dump_common(false, seed, trial_offset, N, n_steps, out_dev, ld_out, stream);
+}
+
+DDM_API int ddm_philox_words_u32(uint64_t seed, uint64_t trial_offset, int64_t N, int64_t n_steps,
+                                 uint32_t *out_dev, int64_t ld_out, void *stream)
+{
+    return dump_common(true, seed, trial_offset, N, n_steps, out_dev, ld_out, stream);
+}

@@ -1,0 +1,109 @@
+"""Training-set and observed-session shells (reference data_simulator.py:14-111) on top of
+the CUDA simulator.  Signatures, (z, x) layout, CPU-resident return values, progress prints
+and sanity asserts are the reference's; compute happens on the current CUDA device whatever
+``device`` string the caller passes (the reference hard-codes "cpu" at its call sites).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+from torch.distributions import Distribution
+
+from .pulses import generate_pulse_matrix_device
+from .simulator import HostPipeline, Schedule, compute_device, next_seed, simulate_trials
+
+
+_HOST_STREAM_MIN = 1 << 18   # CPU-resident z with at least this many rows is streamed in chunks
+_pipelines = {}
+
+
+def sim_wrapper(theta_and_pulses: torch.Tensor, *, mu_sensory: float, p_success: float, P: int, log_rt: bool,
+                seed: Optional[int] = None, trial_offset: int = 0, noise: Optional[torch.Tensor] = None,
+                ) -> torch.Tensor:
+    """z = [theta(5), pulse_sides(P)] -> packed x = [rt (or log rt), choice] (reference :14-30).
+    theta and pulses are passed to the kernel as strided views of z: no split copies.  A large
+    CPU-resident z is streamed through the GPU in chunks with copies and kernels overlapped;
+    x comes back on z's device, like the reference's."""
+    z = theta_and_pulses
+    n = z.shape[0]
+    if (not z.is_cuda and noise is None and n >= _HOST_STREAM_MIN and z.dtype == torch.float32
+            and z.shape[1] == 5 + P and z.stride(1) == 1):
+        sched = Schedule.from_constants(mu_sensory)
+        dev = compute_device(None)
+        key = (dev, z.shape[1])
+        pipe = _pipelines.get(key)
+        if pipe is None:
+            pipe = _pipelines[key] = HostPipeline(z.shape[1], device=dev)
+        x = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
+        pipe.run(z, x, sched=sched, seed=next_seed() if seed is None else seed, log_rt=log_rt,
+                 trial_offset=trial_offset)
+        pipe.synchronize()
+        return x
+    x = simulate_trials(z[:, :5], z[:, 5:5 + P], mu_sensory=mu_sensory, log_rt=log_rt, seed=seed,
+                        trial_offset=trial_offset, noise=noise)
+    return x.to(z.device)
+
+
+@torch.no_grad()
+def simulate_training_set_with_conditions(proposal: Distribution, num_simulations: int, batch_size: int, device, *,
+                                          mu_sensory: float, p_success: float, P: int, log_rt: bool,
+                                          seed: Optional[int] = None):
+    """Draw z ~ proposal in batches, simulate x | z, return CPU (z_all (N,5+P), x_all (N,2))
+    (reference :33-71).  One Philox key covers the whole set; batches use trial offsets, so the
+    result does not depend on ``batch_size`` for a given z."""
+    dev = compute_device(device)
+    if seed is None:
+        seed = next_seed()
+    z_all = torch.empty((num_simulations, 5 + P), dtype=torch.float32, pin_memory=True)
+    x_all = torch.empty((num_simulations, 2), dtype=torch.float32, pin_memory=True)
+    copies = []
+    for start in range(0, num_simulations, batch_size):
+        bs = min(batch_size, num_simulations - start)
+        z = proposal.sample((bs,)).to(device=dev, dtype=torch.float32, non_blocking=True)
+        x = sim_wrapper(z, mu_sensory=mu_sensory, p_success=p_success, P=P, log_rt=log_rt, seed=seed,
+                        trial_offset=start)
+        z_all[start:start + bs].copy_(z, non_blocking=True)
+        x_all[start:start + bs].copy_(x, non_blocking=True)
+        copies.append((z, x))  # keep device buffers alive until the copies have run
+        if (start // batch_size) % 50 == 0:
+            print(f"Simulated {start + bs:,}/{num_simulations:,}")
+            torch.cuda.current_stream(dev).synchronize()
+            copies.clear()
+    torch.cuda.current_stream(dev).synchronize()
+    copies.clear()
+
+    assert z_all.shape[0] == num_simulations
+    assert x_all.shape[0] == num_simulations
+    assert torch.isfinite(z_all).all()
+    assert torch.isfinite(x_all).all()
+    assert torch.all((x_all[:, -1] == 0) | (x_all[:, -1] == 1) | (x_all[:, -1] == 2))
+
+    print("Training x shape:", tuple(x_all.shape), " (N,2) = [rt(or log rt), choice]")
+    print("Training z shape:", tuple(z_all.shape), " (N, 5+P) = [theta, pulses]")
+    print("Unique outcomes in training (choice):", x_all[:, -1].unique().tolist())
+    return z_all, x_all
+
+
+@torch.no_grad()
+def simulate_observed_session(theta_true: torch.Tensor, num_trials: int, device, *, mu_sensory: float,
+                              p_success: float, P: int, seed: int = 123, log_rt: bool,
+                              noise_seed: Optional[int] = None, noise: Optional[torch.Tensor] = None):
+    """One observed session at ``theta_true``: (x_o (T,2), pulses_o (T,P)) on the CPU
+    (reference :74-99).  ``seed`` seeds the stimulus exactly as in the reference."""
+    dev = compute_device(device)
+    rng = np.random.default_rng(seed)
+    pulses_o = generate_pulse_matrix_device(rng, num_trials, P, p_success=p_success, device=dev)
+    theta_rep = theta_true.view(1, 5).expand(num_trials, 5)
+    x_o = simulate_trials(theta_rep, pulses_o, mu_sensory=mu_sensory, log_rt=log_rt, seed=noise_seed, noise=noise,
+                          device=dev)
+    return x_o.cpu(), pulses_o.cpu()
+
+
+def summarize_trials(name: str, x: torch.Tensor) -> None:
+    """Print the RT range and the outcome histogram of a batch of trials (reference :102-111)."""
+    counts = torch.bincount(x[:, 1].to(torch.int64), minlength=3)
+    frac = counts.float() / counts.sum().clamp_min(1)
+    print(f"{name}: n={len(x)}  rt[min,max]=({x[:, 0].min().item():.4f},{x[:, 0].max().item():.4f})  "
+          f"choice counts={counts.tolist()}  frac={frac.tolist()}")

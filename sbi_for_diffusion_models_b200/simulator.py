@@ -1,0 +1,237 @@
+"""Host driver of the CUDA trial simulator (``ddm_sim_f32``).
+
+This is the one place that turns torch tensors into raw device pointers.  It mirrors what
+``_simulate_rt_choice_batch_torch`` does around its time loop
+(/root/reference/src/sbi_for_diffusion_models/models/rt_choice_model.py:125-178): cast theta
+to fp32, normalise the pulse matrix (1-D / one-row broadcast / width check) and raise the
+same ``ValueError``s -- before anything is launched.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native, constants
+
+
+@dataclass(frozen=True)
+class Schedule:
+    """Time grid of the simulator and the fp32 scalars the kernel consumes."""
+    n_max: int
+    steps_per_pulse: int
+    n_pulses: int
+    dt: float
+    t_max: float
+    t_nd_hi: float
+    noise_scale: float
+
+    @staticmethod
+    def from_constants(mu_sensory: float = 1.0, *, dt: Optional[float] = None, t_max: Optional[float] = None,
+                       pulse_interval: Optional[float] = None) -> "Schedule":
+        # constants are read at call time, like the reference (rt_choice_model.py:137-138)
+        dt = float(constants.DT_CHOICE if dt is None else dt)
+        t_max = float(constants.T_MAX if t_max is None else t_max)
+        pulse_interval = float(constants.PULSE_INTERVAL if pulse_interval is None else pulse_interval)
+        n_max = int(np.floor(t_max / dt))                            # :52
+        spp = max(int(np.round(pulse_interval / dt)), 1)             # :53
+        f32 = lambda v: float(np.float32(v))
+        return Schedule(n_max=n_max, steps_per_pulse=spp, n_pulses=(n_max + spp - 1) // spp,  # :59
+                        dt=f32(dt), t_max=f32(t_max), t_nd_hi=f32(t_max - 1e-6),               # :135
+                        noise_scale=f32(float(mu_sensory) * float(np.sqrt(dt))))                # :146-147,186
+
+
+@dataclass
+class SimStats:
+    useful_steps: int      # sum over trials of hit_step
+    lane_steps: int        # Euler steps issued by all lanes, busy or idle
+    generic_rows: int      # trials whose pulse row was not +-1
+
+    @property
+    def lane_efficiency(self) -> float:
+        return self.useful_steps / self.lane_steps if self.lane_steps else 0.0
+
+
+def next_seed() -> int:
+    """A 63-bit Philox key drawn from torch's global CPU generator, so ``torch.manual_seed``
+    makes simulations reproducible just as it does for the reference's ``torch.randn``."""
+    return int(torch.randint(0, 2**63 - 1, (1,), dtype=torch.int64).item())
+
+
+def compute_device(device=None) -> torch.device:
+    torch_ = _native.require_cuda()
+    if device is None:
+        return torch_.device("cuda", torch_.cuda.current_device())
+    device = torch_.device(device)
+    if device.type != "cuda":
+        return torch_.device("cuda", torch_.cuda.current_device())
+    return device if device.index is not None else torch_.device("cuda", torch_.cuda.current_device())
+
+
+def _as_f32_rows(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """fp32 on `dev` with unit stride along the last dim (row stride is free)."""
+    t = t.to(device=dev, dtype=torch.float32, non_blocking=True)
+    if t.stride(-1) != 1 and t.shape[-1] > 1:
+        t = t.contiguous()
+    return t
+
+
+def normalise_pulses(pulse_sides, n_trials: int, sched: Schedule, dev: torch.device) -> Tuple[torch.Tensor, int]:
+    """rt_choice_model.py:94-109 and :165-178 -> (tensor on dev, row stride in floats; 0 = broadcast)."""
+    s = pulse_sides if isinstance(pulse_sides, torch.Tensor) else torch.from_numpy(np.asarray(pulse_sides))
+    if s.ndim == 1:
+        s = s.view(1, -1)
+    if s.ndim != 2:
+        raise ValueError(f"pulse_sides must have shape (N,P) or (P,), got {tuple(s.shape)}")
+    broadcast = s.shape[0] == 1 and n_trials > 1
+    if not broadcast and s.shape[0] != n_trials:
+        raise ValueError(
+            f"pulse_sides first dim must match batch size N={n_trials} (or be 1 for broadcast), got {s.shape[0]}")
+    if s.shape[1] < sched.n_pulses:
+        raise ValueError(
+            f"pulse_sides has P={s.shape[1]} pulses but simulator needs at least {sched.n_pulses} "
+            f"for T_MAX={constants.T_MAX}s")
+    s = _as_f32_rows(s, dev)
+    return s, (0 if broadcast else s.stride(0))
+
+
+def simulate_trials(theta: torch.Tensor, pulse_sides, *, mu_sensory: float = 1.0, log_rt: bool = False,
+                    seed: Optional[int] = None, trial_offset: int = 0, noise: Optional[torch.Tensor] = None,
+                    return_steps: bool = False, return_stats: bool = False, device=None,
+                    schedule: Optional[Schedule] = None, out: Optional[torch.Tensor] = None):
+    """Simulate one trial per row of ``theta`` on the GPU.
+
+    theta (N,5) any float dtype, CPU or CUDA; pulse_sides (N,P) / (1,P) / (P,).
+    Returns x (N,2) fp32 ``[rt (or log rt), choice]`` on the compute device, optionally
+    followed by ``hit_step`` (N,) int32 and a :class:`SimStats`.
+
+    ``noise`` (n_max, N) fp32 replaces the native Philox stream with shared noise: the
+    output then equals the reference's bit for bit.  ``seed`` defaults to a draw from torch's
+    global generator.
+    """
+    L = _native.lib()
+    dev = compute_device(device if device is not None else (theta.device if theta.is_cuda else None))
+    if theta.ndim == 1:
+        theta = theta.view(1, -1)
+    if theta.shape[-1] != 5:
+        raise ValueError(f"Expected theta shape (N,5) or (5,), got {tuple(theta.shape)}")
+    sched = schedule or Schedule.from_constants(mu_sensory)
+    n = theta.shape[0]
+    with torch.cuda.device(dev):
+        th = _as_f32_rows(theta, dev)
+        s, ld_pulses = normalise_pulses(pulse_sides, n, sched, dev)
+        if out is None:
+            out = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        else:
+            assert out.shape == (n, 2) and out.dtype == torch.float32 and out.is_contiguous() and out.device == dev
+        steps = torch.empty((n,), dtype=torch.int32, device=dev) if return_steps else None
+        ws = torch.empty((_native.WS_WORDS,), dtype=torch.int64, device=dev)
+        noise_ptr, ld_noise = None, 0
+        if noise is not None:
+            noise = _as_f32_rows(noise, dev)
+            if noise.ndim != 2 or noise.shape[0] < sched.n_max or noise.shape[1] < n:
+                raise ValueError(f"noise must be (n_max={sched.n_max}, >=N={n}), got {tuple(noise.shape)}")
+            noise_ptr, ld_noise = noise.data_ptr(), noise.stride(0)
+        if seed is None:
+            seed = 0 if noise is not None else next_seed()
+        rc = L.ddm_sim_f32(th.data_ptr() if n else None, th.stride(0) if n else 5,
+                           s.data_ptr(), ld_pulses, n, s.shape[1],
+                           sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi,
+                           sched.noise_scale, ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(trial_offset),
+                           noise_ptr, ld_noise, int(bool(log_rt)), out.data_ptr() if n else None,
+                           steps.data_ptr() if steps is not None and n else None,
+                           ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(rc, "ddm_sim_f32")
+        # keep inputs alive until the stream has consumed them
+        for t in (th, s, noise):
+            if t is not None:
+                t.record_stream(torch.cuda.current_stream(dev))
+    result = [out]
+    if return_steps:
+        result.append(steps)
+    if return_stats:
+        w = ws.cpu().tolist()
+        result.append(SimStats(useful_steps=w[_native.WS_USEFUL_STEPS], lane_steps=w[_native.WS_LANE_STEPS],
+                               generic_rows=w[_native.WS_GENERIC_ROWS]))
+    return result[0] if len(result) == 1 else tuple(result)
+
+
+def philox_normals(seed: int, n_trials: int, n_steps: int, *, trial_offset: int = 0, device=None) -> torch.Tensor:
+    """(n_steps, n_trials) fp32: the normals ``simulate_trials`` consumes for this seed."""
+    L = _native.lib()
+    dev = compute_device(device)
+    with torch.cuda.device(dev):
+        out = torch.empty((n_steps, n_trials), dtype=torch.float32, device=dev)
+        _native.check(L.ddm_philox_normals_f32(ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(trial_offset),
+                                               n_trials, n_steps, out.data_ptr(), max(n_trials, 1),
+                                               torch.cuda.current_stream(dev).cuda_stream), "ddm_philox_normals_f32")
+    return out
+
+
+def philox_words(seed: int, n_trials: int, n_steps: int, *, trial_offset: int = 0, device=None) -> torch.Tensor:
+    """(n_steps, n_trials) raw Philox4x32-10 words as int32 bit patterns."""
+    L = _native.lib()
+    dev = compute_device(device)
+    with torch.cuda.device(dev):
+        out = torch.empty((n_steps, n_trials), dtype=torch.int32, device=dev)
+        _native.check(L.ddm_philox_words_u32(ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(trial_offset),
+                                             n_trials, n_steps, out.data_ptr(), max(n_trials, 1),
+                                             torch.cuda.current_stream(dev).cuda_stream), "ddm_philox_words_u32")
+    return out
+
+
+class HostPipeline:
+    """Streams a host-resident z = [theta, pulses] matrix through the GPU in chunks.
+
+    Each chunk goes H2D -> ``ddm_sim_f32`` -> D2H on one of ``n_streams`` CUDA streams with
+    its own device buffers, so the copy of chunk k+1 overlaps the kernel of chunk k, and a
+    new kernel's blocks fill the SMs that the previous kernel's draining tail leaves idle.
+    Trial offsets make the result identical to a single launch over all rows."""
+
+    def __init__(self, n_cols: int, chunk: int = 1 << 20, n_streams: int = 3, device=None):
+        self.dev = compute_device(device)
+        self.chunk, self.n_cols = int(chunk), int(n_cols)
+        with torch.cuda.device(self.dev):
+            self.streams = [torch.cuda.Stream(self.dev) for _ in range(n_streams)]
+            self.z = [torch.empty((self.chunk, n_cols), dtype=torch.float32, device=self.dev) for _ in range(n_streams)]
+            self.x = [torch.empty((self.chunk, 2), dtype=torch.float32, device=self.dev) for _ in range(n_streams)]
+            self.ws = [torch.empty((_native.WS_WORDS,), dtype=torch.int64, device=self.dev) for _ in range(n_streams)]
+        self.launches = 0
+
+    def run(self, z_host: torch.Tensor, x_host: torch.Tensor, *, sched: Schedule, seed: int, log_rt: bool = False,
+            trial_offset: int = 0) -> None:
+        """z_host (N, 5+P) fp32 CPU (pinned for full speed) -> x_host (N,2) fp32 CPU (pinned).
+        Returns after everything has been enqueued; call ``synchronize`` before reading."""
+        L = _native.lib()
+        n = z_host.shape[0]
+        assert z_host.dtype == torch.float32 and z_host.shape[1] == self.n_cols and z_host.stride(1) == 1
+        assert x_host.shape == (n, 2) and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        P = self.n_cols - 5
+        if P < sched.n_pulses:
+            raise ValueError(f"pulse_sides has P={P} pulses but simulator needs at least {sched.n_pulses}")
+        cur = torch.cuda.current_stream(self.dev)
+        for k, start in enumerate(range(0, n, self.chunk)):
+            i = k % len(self.streams)
+            st = self.streams[i]
+            if k < len(self.streams):
+                st.wait_stream(cur)
+            bs = min(self.chunk, n - start)
+            with torch.cuda.stream(st):
+                zd = self.z[i][:bs]
+                zd.copy_(z_host[start:start + bs], non_blocking=True)
+                rc = L.ddm_sim_f32(zd.data_ptr(), self.n_cols, zd.data_ptr() + 20, self.n_cols, bs, P,
+                                   sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi,
+                                   sched.noise_scale, ctypes.c_uint64(seed & (2**64 - 1)),
+                                   ctypes.c_uint64(trial_offset + start), None, 0, int(bool(log_rt)),
+                                   self.x[i].data_ptr(), None, self.ws[i].data_ptr(), st.cuda_stream)
+                _native.check(rc, "ddm_sim_f32")
+                self.launches += 1
+                x_host[start:start + bs].copy_(self.x[i][:bs], non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def synchronize(self) -> None:
+        torch.cuda.current_stream(self.dev).synchronize()

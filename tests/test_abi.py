@@ -1,0 +1,96 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol the header declares,
+validates arguments before touching CUDA, and its host-only helper matches NumPy."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from sbi_for_diffusion_models_b200 import _native
+from sbi_for_diffusion_models_b200.build import build_native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    build_native()
+    return _native.lib()
+
+
+def _declared():
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for fn in os.listdir(inc):
+        text = open(os.path.join(inc, fn)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b((?:ddm|mnle)_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_header_symbols_are_exported(L):
+    declared = _declared()
+    assert "ddm_sim_f32" in declared and "ddm_pulses_pcg64" in declared
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/ but not exported"
+    assert set(_native.exported_symbols()) == set(declared)
+
+
+def test_abi_version(L):
+    assert L.ddm_abi_version() == 1
+    assert L.ddm_sim_workspace_bytes() == 8 * _native.WS_WORDS
+
+
+def test_invalid_arguments_are_rejected_before_cuda(L):
+    ws = ctypes.create_string_buffer(64)
+    args = dict(theta=1, ld_theta=5, pulses=1, ld_pulses=80, N=4, P=80, n_max=16000, spp=200)
+
+    def call(**kw):
+        a = dict(args, **kw)
+        return L.ddm_sim_f32(a["theta"], a["ld_theta"], a["pulses"], a["ld_pulses"], a["N"], a["P"], a["n_max"],
+                             a["spp"], 5e-4, 8.0, 7.999999, 0.0223, 0, 0, None, 0, 0, 1 << 12, None,
+                             ctypes.addressof(ws) & ~7, None)
+
+    assert call(P=79) == _native.DDM_ERR_INVALID          # reference rt_choice_model.py:173-176
+    assert b"P=79" in L.ddm_last_error()
+    assert call(N=-1) == _native.DDM_ERR_INVALID
+    assert call(spp=0) == _native.DDM_ERR_INVALID
+    assert call(ld_theta=3) == _native.DDM_ERR_INVALID
+    assert call(ld_pulses=10) == _native.DDM_ERR_INVALID
+    assert L.ddm_pulses_pcg64(0, 0, 0, 1, 0, -1, 80, 1, None, 80, None) == _native.DDM_ERR_INVALID
+    assert b"n_trials" in L.ddm_last_error()             # reference rt_choice_model.py:83-84
+    assert L.ddm_pulses_pcg64(0, 0, 0, 1, 0, 4, -2, 1, None, 80, None) == _native.DDM_ERR_INVALID
+    with pytest.raises(ValueError):
+        _native.check(_native.DDM_ERR_INVALID, "x")
+
+
+def test_host_pcg64_advance_matches_numpy(L):
+    rng = np.random.default_rng(2024)
+    st = rng.bit_generator.state["state"]
+    state, inc = int(st["state"]), int(st["inc"])
+    m = (1 << 64) - 1
+    for draws in (0, 1, 81, 10**6 + 7, 2**40 + 3):
+        hi, lo = ctypes.c_uint64(state >> 64), ctypes.c_uint64(state & m)
+        assert L.ddm_pcg64_advance(ctypes.byref(hi), ctypes.byref(lo), inc >> 64, inc & m, draws) == 0
+        ref = np.random.default_rng(2024)
+        ref.bit_generator.advance(draws)
+        assert ((hi.value << 64) | lo.value) == int(ref.bit_generator.state["state"]["state"])
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from sbi_for_diffusion_models_b200.simulator import simulate_trials
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        simulate_trials(torch.zeros(2, 5), torch.ones(2, 80))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "sbi_for_diffusion_models_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "build.py", f"{f} mentions the oracle"

@@ -1,0 +1,250 @@
+"""Parity of the CUDA simulator (through the C ABI) with the CPU oracle and the reference's
+golden vectors.  Run on the B200 box: ``pytest -m gpu``."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddm_oracle as orc
+from sbi_for_diffusion_models_b200 import simulator as sim
+from sbi_for_diffusion_models_b200.simulator import Schedule, simulate_trials
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32)).view(np.uint32)
+
+
+def _assert_same(got, want, what):
+    got = got.cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    bad = np.nonzero((_bits(got) != _bits(want)).reshape(len(want), -1).any(axis=1))[0]
+    assert bad.size == 0, f"{what}: {bad.size}/{len(want)} rows differ, first {bad[:5]}: {got[bad[:3]]} vs {want[bad[:3]]}"
+
+
+def _gpu_shared(theta, pulses, seed, sched=None, **kw):
+    sched = sched or Schedule.from_constants()
+    noise = torch.from_numpy(orc.synthetic_noise(int(seed), sched.n_max, theta.shape[0]))
+    return simulate_trials(torch.from_numpy(theta), torch.from_numpy(np.asarray(pulses, np.float32)), noise=noise,
+                           schedule=sched, **kw)
+
+
+# ---------------------------------------------------------------- shared noise: bit-exact ---
+
+@pytest.mark.parametrize("name", ["sim_prior", "sim_edges", "sim_window", "sim_realpulses"])
+def test_golden_shared_noise(golden, name):
+    g = golden(name)
+    x, steps, stats = _gpu_shared(g["theta"], g["pulses"], g["noise_seed"], return_steps=True, return_stats=True)
+    _assert_same(x, g["x"], name)
+    assert stats.useful_steps == int(steps.sum())
+    if name == "sim_realpulses":
+        assert stats.generic_rows > 0          # non-binary rows took the global-read kick path
+    if name == "sim_prior":
+        assert stats.generic_rows == 0
+
+
+def test_golden_shapes(golden):
+    g = golden("sim_shapes")
+    _assert_same(_gpu_shared(g["theta"], g["pulses_row"], g["noise_seed_row"]), g["x_row"], "broadcast row")
+    _assert_same(_gpu_shared(g["theta"], g["pulses_row"][0], g["noise_seed_row"]), g["x_row"], "1-D pulses")
+    _assert_same(_gpu_shared(g["theta"], g["pulses_wide"], g["noise_seed_wide"]), g["x_wide"], "wide pulses")
+
+
+@pytest.mark.parametrize("tag", ["dt1e-3", "dt2e-3", "dt1e-3_i50", "dt2.5e-3_i30"])
+def test_golden_schedules(golden, tag):
+    g = golden("sim_schedules")
+    dt, interval, n_max, spp, P = g[tag + "_meta"]
+    sched = Schedule.from_constants(dt=float(dt), pulse_interval=float(interval))
+    assert (sched.n_max, sched.steps_per_pulse, sched.n_pulses) == (int(n_max), int(spp), int(P))
+    _assert_same(_gpu_shared(g["theta"], g[tag + "_pulses"], g["noise_seed"], sched), g[tag + "_x"], tag)
+
+
+def test_golden_log_rt_epilogue(golden):
+    g = golden("sim_prior")
+    x = _gpu_shared(g["theta"], g["pulses"], g["noise_seed"], log_rt=True).cpu().numpy()
+    want = g["x_packed_log"]
+    assert np.array_equal(x[:, 1], want[:, 1])
+    ulp = np.abs(_bits(x[:, 0]).astype(np.int64) - _bits(want[:, 0]).astype(np.int64))
+    near0 = np.abs(want[:, 0]) < 1e-3
+    assert ulp[~near0].max() <= 2, "fp32 log: tolerance 2 ulp against torch.log on the CPU"
+    assert np.allclose(x[near0, 0], want[near0, 0], atol=3e-7)
+
+
+def test_oracle_shared_noise_large():
+    """8192 prior-shaped trials, default schedule, against the scalar C oracle."""
+    n = 8192
+    theta = orc.prior_sample(n, seed=21).numpy()
+    pulses = orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(5)), 0, n, 80, 0.75)
+    noise = orc.synthetic_noise(99, 16000, n)
+    want, want_steps = orc.sim_scalar_c(theta, pulses, noise)
+    x, steps = simulate_trials(torch.from_numpy(theta), torch.from_numpy(pulses), noise=torch.from_numpy(noise),
+                               return_steps=True)
+    _assert_same(x, want, "8192 trials")
+    assert np.array_equal(steps.cpu().numpy().astype(np.int64), want_steps)
+
+
+def test_strided_z_views_and_theta_broadcast():
+    n = 700
+    z = torch.empty((n, 85))
+    z[:, :5] = orc.prior_sample(n, seed=22)
+    z[:, 5:] = torch.from_numpy(orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(6)), 0, n, 80, 0.75))
+    noise = orc.synthetic_noise(5, 16000, n)
+    want, _ = orc.sim_scalar_c(z[:, :5].numpy(), z[:, 5:].numpy(), noise)
+    zc = z.cuda()
+    got = simulate_trials(zc[:, :5], zc[:, 5:], noise=torch.from_numpy(noise))   # ld = 85 for both views
+    _assert_same(got, want, "views of z")
+    th1 = z[3:4, :5]
+    want, _ = orc.sim_scalar_c(np.repeat(th1.numpy(), n, 0), z[:, 5:].numpy(), noise)
+    got = simulate_trials(th1.cuda().expand(n, 5), zc[:, 5:], noise=torch.from_numpy(noise))   # ld_theta = 0
+    _assert_same(got, want, "broadcast theta")
+
+
+def test_empty_and_single():
+    x = simulate_trials(torch.zeros((0, 5)), torch.ones((0, 80)))
+    assert tuple(x.shape) == (0, 2)
+    x = simulate_trials(torch.tensor([0.5, 0.3, 1.0, 12.0, 0.2]), torch.ones(80), seed=1)
+    assert tuple(x.shape) == (1, 2) and x[0, 1].item() in (0.0, 1.0, 2.0)
+
+
+def test_value_errors_match_reference():
+    th = torch.zeros((4, 5))
+    with pytest.raises(ValueError, match="Expected theta shape"):
+        simulate_trials(torch.zeros((4, 4)), torch.ones((4, 80)))
+    with pytest.raises(ValueError, match="first dim must match batch size"):
+        simulate_trials(th, torch.ones((3, 80)))
+    with pytest.raises(ValueError, match="needs at least 80"):
+        simulate_trials(th, torch.ones((4, 79)))
+    with pytest.raises(ValueError, match="must have shape"):
+        simulate_trials(th, torch.ones((4, 2, 80)))
+
+
+# ------------------------------------------------------------------- native Philox noise ---
+
+def test_philox_words_match_oracle():
+    seed, off = 0x0123456789ABCDEF, (1 << 32) - 37       # trial index crosses 2^32
+    got = sim.philox_words(seed, 100, 41, trial_offset=off).cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, orc.philox_words(seed, off, 100, 41))
+
+
+def test_philox_normals_are_standard_normal():
+    from scipy import stats
+    z = sim.philox_normals(7, 4096, 512).cpu().numpy().astype(np.float64)
+    assert np.isfinite(z).all() and np.abs(z).max() < 5.8
+    flat = z.ravel()
+    assert abs(flat.mean()) < 4 / np.sqrt(flat.size)
+    assert abs(flat.var() - 1.0) < 5e-3
+    assert abs(stats.skew(flat)) < 0.01 and abs(stats.kurtosis(flat)) < 0.02
+    assert stats.kstest(flat[:: 7], "norm").pvalue > 0.01
+    # no correlation between the two outputs of a Box-Muller pair, nor along time
+    assert abs(np.corrcoef(z[0::4].ravel(), z[1::4].ravel())[0, 1]) < 0.005
+    assert abs(np.corrcoef(z[:-1].ravel(), z[1:].ravel())[0, 1]) < 0.005
+    # nor across neighbouring trials
+    assert abs(np.corrcoef(z[:, :-1].ravel(), z[:, 1:].ravel())[0, 1]) < 0.005
+
+
+def test_native_run_replays_through_the_oracle_bit_for_bit():
+    """Philox path == shared-noise path == CPU oracle when the oracle is fed the normals the
+    kernel consumed."""
+    n, seed, off = 4096, 1234567, 10**10
+    theta = orc.prior_sample(n, seed=23).numpy()
+    pulses = orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(8)), 0, n, 80, 0.75)
+    th, pl = torch.from_numpy(theta).cuda(), torch.from_numpy(pulses).cuda()
+    x_native, steps = simulate_trials(th, pl, seed=seed, trial_offset=off, return_steps=True)
+    normals = sim.philox_normals(seed, n, 16000, trial_offset=off)
+    x_inject = simulate_trials(th, pl, noise=normals)
+    assert torch.equal(x_native, x_inject)
+    want, want_steps = orc.sim_scalar_c(theta, pulses, normals.cpu().numpy())
+    _assert_same(x_native, want, "native vs oracle replay")
+    assert np.array_equal(steps.cpu().numpy().astype(np.int64), want_steps)
+
+
+def test_results_do_not_depend_on_batching():
+    n, seed = 5000, 77
+    theta = orc.prior_sample(n, seed=24).cuda()
+    pulses = torch.from_numpy(orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(9)), 0, n, 80, 0.75)).cuda()
+    whole = simulate_trials(theta, pulses, seed=seed)
+    parts = [simulate_trials(theta[a:b], pulses[a:b], seed=seed, trial_offset=a)
+             for a, b in ((0, 1), (1, 1300), (1300, 1301), (1301, 5000))]
+    assert torch.equal(whole, torch.cat(parts))
+    again = simulate_trials(theta, pulses, seed=seed)
+    assert torch.equal(whole, again)
+    other = simulate_trials(theta, pulses, seed=seed + 1)
+    assert not torch.equal(whole, other)
+
+
+def test_torch_manual_seed_controls_default_key():
+    theta = orc.prior_sample(256, seed=25)
+    pulses = torch.ones((1, 80))
+    torch.manual_seed(3)
+    a = simulate_trials(theta, pulses)
+    torch.manual_seed(3)
+    b = simulate_trials(theta, pulses)
+    c = simulate_trials(theta, pulses)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_ks_equivalence_per_theta():
+    """RT | choice and choice frequencies under native Philox noise vs the CPU oracle with
+    its own generator: two-sample KS p > 0.01 per theta (north_star), Bonferroni over the
+    16 x 3 comparisons for the overall assertion."""
+    from scipy import stats
+    n_theta, n_trials = 16, 20000
+    thetas = orc.prior_sample(n_theta, seed=31).numpy()
+    thetas[:, 4] = np.minimum(thetas[:, 4], 0.6)
+    fails, pvals = [], []
+    for k in range(n_theta):
+        pulses = orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(100 + k)), 0, 1, 80, 0.75)
+        th = np.repeat(thetas[k:k + 1], n_trials, axis=0)
+        cpu, _ = orc.sim_rng_c(th, pulses, seed=500 + k)
+        gpu = simulate_trials(torch.from_numpy(thetas[k]).cuda().view(1, 5).expand(n_trials, 5),
+                              torch.from_numpy(pulses), seed=900 + k).cpu().numpy()
+        counts = np.stack([np.bincount(a[:, 1].astype(int), minlength=3) for a in (cpu, gpu)])
+        keep = counts.sum(0) > 0
+        p_choice = stats.chi2_contingency(counts[:, keep]).pvalue if keep.sum() > 1 else 1.0
+        pvals.append(p_choice)
+        for c in (0, 1):
+            a, b = cpu[cpu[:, 1] == c, 0], gpu[gpu[:, 1] == c, 0]
+            if min(len(a), len(b)) >= 200:
+                pvals.append(stats.ks_2samp(a, b).pvalue)
+        if min(pvals[-3:]) < 0.01:
+            fails.append((k, pvals[-3:]))
+    pvals = np.asarray(pvals)
+    assert pvals.min() > 0.01 / len(pvals), f"distribution mismatch: {fails}"
+    assert (pvals < 0.01).mean() < 0.08, f"too many small p-values: {fails}"
+
+
+def test_pure_diffusion_matches_closed_forms():
+    """lam = 0, v = 0: Brownian motion on [0, B] -- P(upper) = a0 and E[exit time] = a(B-a)/sigma^2."""
+    n = 200000
+    a0, B = 0.3, 1.5
+    theta = torch.tensor([a0, 0.0, 0.0, B, 0.0]).cuda().view(1, 5).expand(n, 5)
+    x, steps = simulate_trials(theta, torch.ones((1, 80)), seed=5, return_steps=True)
+    x = x.cpu().numpy()
+    assert (x[:, 1] != 2).mean() > 0.999
+    p_up = (x[:, 1] == 1).mean()
+    assert abs(p_up - a0) < 4 * np.sqrt(a0 * (1 - a0) / n) + 0.01      # + O(sqrt(dt)) overshoot bias
+    mean_t = x[:, 0].mean()
+    assert abs(mean_t - a0 * B * (B - a0 * B)) < 0.03
+
+
+# ---------------------------------------------------------------- full-size properties ---
+
+def test_million_trials_properties():
+    n = 1 << 20
+    theta = orc.prior_sample(n, seed=41).cuda()
+    rng = np.random.default_rng(3)
+    from sbi_for_diffusion_models_b200.pulses import generate_pulse_matrix_device
+    pulses = generate_pulse_matrix_device(rng, n, 80, p_success=0.75)
+    x, steps, stats = simulate_trials(theta, pulses, seed=2024, return_steps=True, return_stats=True)
+    assert torch.isfinite(x).all()
+    ch = x[:, 1]
+    assert bool(((ch == 0) | (ch == 1) | (ch == 2)).all())
+    assert float(x[:, 0].min()) >= 1e-6 and float(x[:, 0].max()) <= 8.0
+    assert stats.useful_steps == int(steps.to(torch.int64).sum())
+    # rt is exactly t_nd + hit_step * dt in fp32 (reference :218)
+    t_nd = theta[:, 4].clamp(0.0, float(np.float32(8.0 - 1e-6)))
+    rt = (t_nd + steps.to(torch.float32) * float(np.float32(5e-4))).clamp(1e-6, 8.0)
+    assert torch.equal(rt, x[:, 0])
+    frac = torch.bincount(ch.to(torch.int64), minlength=3).float() / n
+    assert abs(frac[0] - 0.567) < 0.01 and abs(frac[1] - 0.259) < 0.01 and abs(frac[2] - 0.175) < 0.01
+    assert abs(steps.float().mean().item() - 5080) < 60
+    assert stats.lane_efficiency > 0.85, stats
