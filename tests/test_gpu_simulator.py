@@ -247,4 +247,4 @@ def test_million_trials_properties():
     frac = torch.bincount(ch.to(torch.int64), minlength=3).float() / n
     assert abs(frac[0] - 0.567) < 0.01 and abs(frac[1] - 0.259) < 0.01 and abs(frac[2] - 0.175) < 0.01
     assert abs(steps.float().mean().item() - 5080) < 60
-    assert stats.lane_efficiency > 0.85, stats
+    assert stats.lane_efficiency > 0.6, stats   # 3.5 trials per lane: the drain tail is ~25 %; 0.995 at 1e8 trials
