@@ -187,6 +187,76 @@ def build_workload(n: int, rank: int, device):
     return z
 
 
+
+# ------------------------------------------------------------------- MNLE potential (cfg-4) ---
+
+def random_mnle_params(seed: int = 0):
+    """Seeded random MNLE parameters with the reference's architecture (no trained checkpoint
+    exists offline); same family as the test nets."""
+    import numpy as np
+    import torch
+    rs = np.random.RandomState(seed)
+
+    def lin(n_out, n_in, s=1.0):
+        b = s / np.sqrt(n_in)
+        return (torch.from_numpy(rs.uniform(-b, b, (n_out, n_in)).astype(np.float32)),
+                torch.from_numpy(rs.uniform(-b, b, (n_out,)).astype(np.float32)))
+
+    p = {"cond_mean": torch.cat([torch.tensor([0.5, 0.6, 1.6, 17.7, 0.5]), torch.zeros(80)]),
+         "cond_std": torch.cat([torch.tensor([0.22, 0.8, 2.1, 9.4, 0.22]), torch.ones(80)]),
+         "flow.mu_y": torch.tensor(0.35), "flow.sigma_y": torch.tensor(1.1)}
+    p["cat.W0"], p["cat.b0"] = lin(128, 85)
+    p["cat.W1"], p["cat.b1"] = lin(128, 128)
+    p["cat.W2"], p["cat.b2"] = lin(128, 128)
+    p["cat.Wo"], p["cat.bo"] = lin(3, 128)
+    for k in range(10):
+        p[f"flow.{k}.W1"], p[f"flow.{k}.b1"] = lin(128, 86)
+        p[f"flow.{k}.W2"], p[f"flow.{k}.b2"] = lin(128, 128)
+        p[f"flow.{k}.W3"], p[f"flow.{k}.b3"] = lin(71, 128, 4.0)
+    return p
+
+
+def mnle_bench(dev, with_cpu: bool):
+    """configs[3]: MNLE log-likelihood sum over T=50 trials x C=1024 chains, device-resident."""
+    import torch
+    from sbi_for_diffusion_models_b200.mnle_net import DeviceMNLE, PackedMNLE
+    from sbi_for_diffusion_models_b200.data_simulator import simulate_observed_session
+    T, C = 50, 1024
+    params = random_mnle_params(0)
+    est = DeviceMNLE(PackedMNLE.from_params(params))
+    x_o, pulses_o = simulate_observed_session(torch.tensor([0.45, 0.6, 1.3, 14.0, 0.25]), T, "cpu", mu_sensory=1.0,
+                                              p_success=0.75, P=P, seed=123, log_rt=False, noise_seed=1)
+    torch.manual_seed(0)
+    theta = torch.stack([torch.distributions.Beta(2.0, 2.0).sample((C,)), torch.distributions.LogNormal(-1.0, 1.0).sample((C,)),
+                         torch.distributions.LogNormal(0.0, 1.0).sample((C,)), torch.distributions.LogNormal(2.75, 0.5).sample((C,)),
+                         torch.distributions.Beta(2.0, 2.0).sample((C,))], dim=1)
+    th, xo, pl = theta.to(dev), x_o.to(dev), pulses_o.to(dev)
+    out = {"workload": f"configs[3]: MNLE log_prob sum over T={T} trials x C={C} chains, weights random-init (seed 0)",
+           "rows": T * C, "dense_mflop_per_row": 0.818}
+    for kernel in ("simt",):
+        for _ in range(3):
+            est.loglik_sum(th, xo, pl, kernel=kernel)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            ll = est.loglik_sum(th, xo, pl, kernel=kernel)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_call = e0.elapsed_time(e1) / reps
+        out[kernel] = {"ms_per_call": ms_call, "rows_per_s": T * C / (ms_call * 1e-3),
+                       "dense_tflops": 0.818e6 * T * C / (ms_call * 1e-3) / 1e12}
+    if with_cpu:
+        from oracle import mnle_spec
+        t0 = time.perf_counter()
+        ref = mnle_spec.loglik_sum(params, theta, x_o, pulses_o)
+        out["cpu_spec_fp32"] = {"ms_per_call": (time.perf_counter() - t0) * 1e3, "cores": torch.get_num_threads(),
+                                "kind": "port (oracle/mnle_spec.py; sbi itself is not installable offline)"}
+        out["max_rel_err_vs_cpu_spec"] = float(((ll.cpu() - ref).abs() / ref.abs()).max())
+    return out
+
+
 def run_native(args):
     import numpy as np
     import torch
@@ -356,6 +426,11 @@ def run_native(args):
                 "sample": f"3 x {args.cpu_trials} trials of the same workload through the lock-step torch port "
                           f"(oracle.sim_lockstep_torch, torch.randn), {sum(times):.1f} s",
             }
+        if world == 1:
+            try:
+                line["mnle_potential"] = mnle_bench(dev, with_cpu=not args.no_cpu_baseline)
+            except Exception as e:  # the headline metric must still print
+                line["mnle_potential"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -134,6 +134,47 @@ int ddm_pulses_pcg64(uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint
 int ddm_pcg64_advance(uint64_t *state_hi, uint64_t *state_lo, uint64_t inc_hi, uint64_t inc_lo,
                       uint64_t draws);
 
+/* ------------------------------------------------------- MNLE log-likelihood --- */
+
+/*
+ * Packed fp32 parameters of the MNLE density estimator the reference builds with
+ * likelihood_nn(model="mnle", hidden_features=128, num_transforms=10, num_bins=24,
+ * log_transform_x=True, z_score_theta="independent", z_score_x="independent")
+ * (mnle.py:31-39), in this order, z-scoring of the condition folded into the first layers
+ * by the host packer (sbi_for_diffusion_models_b200/mnle_net.py):
+ *   categorical net: W0[128][85] b0[128] W1[128][128] b1[128] W2[128][128] b2[128]
+ *                    Wo[K][128] bo[K]                      (K = n_choices, sigmoid)
+ *   flow k = 0..9:   W1[128][86] b1[128] W2[128][128] b2[128] W3[71][128] b3[71]   (ReLU)
+ *   mu_y, sigma_y    standardisation of log rt
+ * mnle_packed_floats(K) is the required length (0 if K is unsupported).
+ */
+size_t mnle_packed_floats(int n_choices);
+
+/* Copies the packed parameters to the current device; *handle_out is an opaque read-only
+ * handle owned by the caller (mnle_destroy).  One handle per (process, device). */
+int mnle_create(const float *packed_host, size_t n_floats, int n_choices, void **handle_out);
+int mnle_destroy(void *handle);
+
+/* estimator.log_prob(x (1,R,2), condition=(R,85)) -> (1,R)   (potentials.py:113):
+ * x_dev (R,2) = [rt seconds, choice], cond_dev (R,85) row stride ld_cond, out_dev (R,). */
+int mnle_log_prob_rows_f32(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond,
+                           int64_t R, float *out_dev, void *stream);
+
+/* Scratch floats mnle_loglik_sum_* needs for T trials x C chains. */
+size_t mnle_loglik_workspace_floats(int64_t T, int64_t C);
+
+/*
+ * ConditionedMNLELogLikelihood.forward (potentials.py:75-117) without materialising the
+ * (T*C, 85) condition matrix:  out[c] = sum_t log p(x[t] | [theta[c], pulses[t]]).
+ *   theta_dev (C,5) row stride ld_theta; x_dev (T,2) contiguous; pulses_dev (T,>=80) row
+ *   stride ld_pulses; out_dev (C,); workspace_dev >= mnle_loglik_workspace_floats(T,C) floats.
+ * The reduction order is fixed, so results are reproducible run to run.
+ * _simt: fp32 CUDA-core kernel (accuracy anchor).
+ */
+int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                             const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
+                             float *out_dev, float *workspace_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

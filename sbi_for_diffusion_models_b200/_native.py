@@ -29,6 +29,12 @@ _SIGNATURES = {
     "ddm_philox_words_u32": (ctypes.c_int, [_u64, _u64, _i64, _i64, _ptr, _i64, _ptr]),
     "ddm_pulses_pcg64": (ctypes.c_int, [_u64, _u64, _u64, _u64, _u64, _i64, _i64, _u64, _ptr, _i64, _ptr]),
     "ddm_pcg64_advance": (ctypes.c_int, [_ptr, _ptr, _u64, _u64, _u64]),
+    "mnle_packed_floats": (ctypes.c_size_t, [_i32]),
+    "mnle_create": (ctypes.c_int, [_ptr, ctypes.c_size_t, _i32, _ptr]),
+    "mnle_destroy": (ctypes.c_int, [_ptr]),
+    "mnle_log_prob_rows_f32": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
+    "mnle_loglik_workspace_floats": (ctypes.c_size_t, [_i64, _i64]),
+    "mnle_loglik_sum_simt_f32": (ctypes.c_int, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

@@ -1,0 +1,164 @@
+// MNLE (mixed neural likelihood estimator) pieces shared by the fp32 SIMT kernel and the
+// tcgen05 kernel: packed-weight layout, rational-quadratic spline, categorical head epilogue.
+//
+// Semantics: oracle/mnle_spec.py (restatement of sbi 0.25.0 MixedDensityEstimator.log_prob as
+// called at /root/reference/src/sbi_for_diffusion_models/potentials.py:113; hyper-parameters
+// from /root/reference/src/sbi_for_diffusion_models/mnle.py:31-39).
+#pragma once
+
+#include "ddm_common.cuh"
+
+namespace mnle {
+
+constexpr int kHidden = 128;
+constexpr int kBins = 24;
+constexpr int kTransforms = 10;
+constexpr int kCond = 85;           // theta(5) + pulses(80)
+constexpr int kCtx = 86;            // + choice
+constexpr int kSplineOut = 3 * kBins - 1;  // 71
+constexpr int kMaxChoices = 8;
+constexpr float kTail = 10.0f;
+constexpr float kMinBin = 1e-3f;
+constexpr float kMinDeriv = 1e-3f;
+
+// Packed fp32 parameter buffer (host packs with z-scoring folded into the first layers):
+//   cat: W0[128][85] b0[128] W1[128][128] b1[128] W2[128][128] b2[128] Wo[K][128] bo[K]
+//   flow k = 0..9: W1[128][86] b1[128] W2[128][128] b2[128] W3[71][128] b3[71]
+//   tail: mu_y, sigma_y
+struct Layout {
+    int n_choices;
+    size_t cat_W0, cat_b0, cat_W1, cat_b1, cat_W2, cat_b2, cat_Wo, cat_bo;
+    size_t fl_W1[kTransforms], fl_b1[kTransforms], fl_W2[kTransforms], fl_b2[kTransforms],
+        fl_W3[kTransforms], fl_b3[kTransforms];
+    size_t mu_y, sigma_y, total;
+};
+
+inline Layout make_layout(int n_choices)
+{
+    Layout L;
+    L.n_choices = n_choices;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t at = o; o += n; return at; };
+    L.cat_W0 = take((size_t)kHidden * kCond);
+    L.cat_b0 = take(kHidden);
+    L.cat_W1 = take((size_t)kHidden * kHidden);
+    L.cat_b1 = take(kHidden);
+    L.cat_W2 = take((size_t)kHidden * kHidden);
+    L.cat_b2 = take(kHidden);
+    L.cat_Wo = take((size_t)n_choices * kHidden);
+    L.cat_bo = take(n_choices);
+    for (int k = 0; k < kTransforms; ++k) {
+        L.fl_W1[k] = take((size_t)kHidden * kCtx);
+        L.fl_b1[k] = take(kHidden);
+        L.fl_W2[k] = take((size_t)kHidden * kHidden);
+        L.fl_b2[k] = take(kHidden);
+        L.fl_W3[k] = take((size_t)kSplineOut * kHidden);
+        L.fl_b3[k] = take(kSplineOut);
+    }
+    L.mu_y = take(1);
+    L.sigma_y = take(1);
+    L.total = o;
+    return L;
+}
+
+struct Handle {
+    uint32_t magic;
+    int device;
+    Layout layout;
+    float *params;   // device copy of the packed buffer
+    void *tc_pack;   // device copy of the tensor-core operand pack (bf16 hi/lo tiles), or null
+    float mu_y, sigma_y;
+};
+constexpr uint32_t kMagic = 0x4D4E4C45u;  // "MNLE"
+
+__device__ __forceinline__ float softplus_f(float x)
+{
+    return x > 20.0f ? x : log1pf(expf(x));  // torch.nn.functional.softplus, threshold 20
+}
+
+// One rational-quadratic spline transform with linear tails (Durkan et al. 2019) on a scalar.
+// q points at the 71 raw conditioner outputs of this row (stride qs floats between them).
+__device__ __forceinline__ void rqs_forward(float &u, float &logdet, const float *q, int qs)
+{
+    if (!(u >= -kTail && u <= kTail)) return;  // identity outside the tail bound
+    const float inv_sqrt_h = 0.08838834764831845f;  // 1/sqrt(128)
+    // ---- widths: softmax -> cumulative knots, locate the bin -------------------------
+    float m = -INFINITY;
+#pragma unroll 4
+    for (int j = 0; j < kBins; ++j) m = fmaxf(m, q[j * qs] * inv_sqrt_h);
+    float s = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < kBins; ++j) s += expf(q[j * qs] * inv_sqrt_h - m);
+    const float inv_s = 1.0f / s;
+    float cs = 0.f, prev = -kTail, left = -kTail, right = kTail;
+    int b = 0;
+#pragma unroll 4
+    for (int j = 0; j < kBins; ++j) {
+        const float w = kMinBin + (1.0f - kMinBin * kBins) * (expf(q[j * qs] * inv_sqrt_h - m) * inv_s);
+        cs += w;
+        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
+        if (u >= prev) {
+            b = j;
+            left = prev;
+            right = edge;
+        }
+        prev = edge;
+    }
+    // ---- heights: same construction, read knots b and b+1 -----------------------------
+    const float *qh = q + kBins * qs;
+    m = -INFINITY;
+#pragma unroll 4
+    for (int j = 0; j < kBins; ++j) m = fmaxf(m, qh[j * qs] * inv_sqrt_h);
+    s = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < kBins; ++j) s += expf(qh[j * qs] * inv_sqrt_h - m);
+    const float inv_sh = 1.0f / s;
+    cs = 0.f;
+    prev = -kTail;
+    float bottom = -kTail, top = kTail;
+#pragma unroll 4
+    for (int j = 0; j < kBins; ++j) {
+        const float h = kMinBin + (1.0f - kMinBin * kBins) * (expf(qh[j * qs] * inv_sqrt_h - m) * inv_sh);
+        cs += h;
+        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
+        if (j == b) {
+            bottom = prev;
+            top = edge;
+        }
+        prev = edge;
+    }
+    // ---- knot derivatives (boundary derivatives are exactly 1) ------------------------
+    const float *qd = q + 2 * kBins * qs;
+    const float edge_d = kMinDeriv + softplus_f(0.5403250582232235f);  // log(exp(1 - 1e-3) - 1)
+    const float d0 = (b == 0) ? edge_d : kMinDeriv + softplus_f(qd[(b - 1) * qs]);
+    const float d1 = (b == kBins - 1) ? edge_d : kMinDeriv + softplus_f(qd[b * qs]);
+
+    const float w = right - left, h = top - bottom;
+    const float delta = h / w;
+    const float th = (u - left) / w;
+    const float t1 = th * (1.0f - th);
+    const float den = delta + (d0 + d1 - 2.0f * delta) * t1;
+    const float out = bottom + h * (delta * th * th + d0 * t1) / den;
+    const float dnum = delta * delta * (d1 * th * th + 2.0f * delta * t1 + d0 * (1.0f - th) * (1.0f - th));
+    logdet += logf(dnum) - 2.0f * logf(den);
+    u = out;
+}
+
+// log Categorical(choice | softmax(logits)) with torch's probs clamp to [eps, 1 - eps].
+__device__ __forceinline__ float categorical_logp(const float *logits, int ls, int n_choices, int choice)
+{
+    float m = -INFINITY;
+    for (int j = 0; j < n_choices; ++j) m = fmaxf(m, logits[j * ls]);
+    float s = 0.f, pc = 0.f;
+    for (int j = 0; j < n_choices; ++j) {
+        const float e = expf(logits[j * ls] - m);
+        s += e;
+        if (j == choice) pc = e;
+    }
+    float p = pc / s;
+    const float eps = 1.1920928955078125e-07f;
+    p = fminf(fmaxf(p, eps), 1.0f - eps);
+    return logf(p);
+}
+
+}  // namespace mnle

@@ -1,0 +1,318 @@
+// MNLE log-likelihood on CUDA cores, fp32 throughout (sm_100a).
+//
+// One CTA pushes a tile of 64 rows through the categorical net and the ten spline
+// conditioners with activations resident in shared memory (never in HBM), applies the
+// categorical / spline epilogues row by row and, in potential mode, reduces the per-trial
+// log-probabilities of one chain with warp shuffles.  This is the accuracy anchor of the
+// tensor-core kernel (mnle_tc.cu) and the path used for shapes the latter does not cover.
+//
+// Replaces /root/reference/src/sbi_for_diffusion_models/potentials.py:96-115: the reference
+// materialises a (T*C, 85) condition matrix and a (1, T*C, 2) x tensor per call (17.8 MB at
+// T=50, C=1024) and runs estimator.log_prob over it; here row r = t*C + c is assembled on the
+// fly from theta[c], pulses[t], x[t].
+#include "mnle_common.cuh"
+
+namespace mnle {
+
+constexpr int kTM = 64;         // rows per CTA tile
+constexpr int kThreads = 256;
+constexpr int kLdIn = 89;       // padded leading dims (bank-conflict-free broadcast reads)
+constexpr int kLdH = 132;
+constexpr int kKC = 32;         // weight k-chunk staged in shared memory
+constexpr int kLdW = 129;
+
+struct SimtSmem {
+    float in[kTM * kLdIn];
+    float ha[kTM * kLdH];
+    float hb[kTM * kLdH];
+    float w[kKC * kLdW];
+    float red[8];
+};
+
+enum Act { kNone = 0, kRelu = 1, kSigmoid = 2 };
+
+// out[r][n] = act(sum_k in[r][k] * W[n][k] + b[n]) for r < 64, n < n_valid (<= 16 * NJ).
+template <int NJ, int ACT>
+__device__ __forceinline__ void dense(const float *__restrict__ W, const float *__restrict__ bias, int K,
+                                      int n_valid, const float *in_s, int ld_in, float *out_s, int ld_out,
+                                      float *w_s)
+{
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][NJ];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += kKC) {
+        __syncthreads();  // previous chunk consumed (and in_s / out_s hazards of the caller)
+        // stage W[:, k0:k0+32] transposed: w_s[kk][n]
+        {
+            const int kk = tid & 31;
+            for (int n = tid >> 5; n < 16 * NJ; n += kThreads / 32) {
+                float v = 0.f;
+                if (n < n_valid && k0 + kk < K) v = __ldg(W + (size_t)n * K + k0 + kk);
+                w_s[kk * kLdW + n] = v;
+            }
+        }
+        __syncthreads();
+        const int kend = min(kKC, K - k0);
+#pragma unroll 4
+        for (int kk = 0; kk < kend; ++kk) {
+            float a[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = in_s[(ty * 4 + i) * ld_in + k0 + kk];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const float wv = w_s[kk * kLdW + tx + 16 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(a[i], wv, acc[i][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int n = tx + 16 * j;
+        if (n < n_valid) {
+            const float bv = __ldg(bias + n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v = acc[i][j] + bv;
+                if (ACT == kRelu) v = fmaxf(v, 0.f);
+                if (ACT == kSigmoid) v = 1.0f / (1.0f + expf(-v));
+                out_s[(ty * 4 + i) * ld_out + n] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+struct RowSource {
+    // rows mode: x (R,2), cond (R,85).   potential mode: theta (C,5), x (T,2), pulses (T,P)
+    const float *x;
+    const float *cond;
+    const float *theta;
+    const float *pulses;
+    long long ld_cond, ld_theta, ld_pulses;
+    long long R;  // rows mode
+    int T, C;     // potential mode
+    int potential;
+};
+
+__global__ void __launch_bounds__(kThreads) mnle_simt_kernel(const float *__restrict__ params, Layout L, RowSource src,
+                                                             float mu_y, float sigma_y, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SimtSmem &S = *reinterpret_cast<SimtSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+
+    // ---- which rows does this tile hold? ----------------------------------------------
+    // potential mode: blockIdx.y = chain c, blockIdx.x = tile of 64 trials
+    // rows mode:      blockIdx.x = tile of 64 rows
+    const long long row0 = (long long)blockIdx.x * kTM;
+    const int c = blockIdx.y;
+    const long long n_rows = src.potential ? (long long)src.T : src.R;
+
+    // ---- assemble the 86-wide context [cond (85), choice] ------------------------------
+    for (int idx = tid; idx < kTM * kCtx; idx += kThreads) {
+        const int i = idx / kCtx, j = idx - i * kCtx;
+        const long long r = row0 + i;
+        float v = 0.f;
+        if (r < n_rows) {
+            if (j == kCond) v = __ldg(src.x + 2 * r + 1);
+            else if (!src.potential) v = __ldg(src.cond + r * src.ld_cond + j);
+            else if (j < 5) v = __ldg(src.theta + (long long)c * src.ld_theta + j);
+            else v = __ldg(src.pulses + r * src.ld_pulses + (j - 5));
+        }
+        S.in[i * kLdIn + j] = v;
+    }
+    __syncthreads();
+
+    // per-row running state lives in the registers of threads 0..63
+    const bool owner = tid < kTM;
+    const long long my_row = row0 + tid;
+    const bool live = owner && my_row < n_rows;
+    float lp = 0.f, u = 0.f, logdet = 0.f, y = 0.f;
+    int choice = 0;
+    if (live) {
+        const float rt = __ldg(src.x + 2 * my_row);
+        choice = (int)__ldg(src.x + 2 * my_row + 1);
+        y = logf(rt);
+        u = (y - mu_y) / sigma_y;
+        logdet = -logf(sigma_y);
+    }
+
+    // ---- categorical head: 85 -> 128 -> 128 -> 128 -> K, sigmoid ------------------------
+    dense<8, kSigmoid>(params + L.cat_W0, params + L.cat_b0, kCond, kHidden, S.in, kLdIn, S.ha, kLdH, S.w);
+    dense<8, kSigmoid>(params + L.cat_W1, params + L.cat_b1, kHidden, kHidden, S.ha, kLdH, S.hb, kLdH, S.w);
+    dense<8, kSigmoid>(params + L.cat_W2, params + L.cat_b2, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH, S.w);
+    dense<1, kNone>(params + L.cat_Wo, params + L.cat_bo, kHidden, L.n_choices, S.ha, kLdH, S.hb, kLdH, S.w);
+    if (live) lp = categorical_logp(S.hb + tid * kLdH, 1, L.n_choices, choice);
+
+    // ---- ten spline conditioners: 86 -> 128 -> 128 -> 71, relu --------------------------
+    for (int k = 0; k < kTransforms; ++k) {
+        dense<8, kRelu>(params + L.fl_W1[k], params + L.fl_b1[k], kCtx, kHidden, S.in, kLdIn, S.ha, kLdH, S.w);
+        dense<8, kRelu>(params + L.fl_W2[k], params + L.fl_b2[k], kHidden, kHidden, S.ha, kLdH, S.hb, kLdH, S.w);
+        dense<5, kNone>(params + L.fl_W3[k], params + L.fl_b3[k], kHidden, kSplineOut, S.hb, kLdH, S.ha, kLdH, S.w);
+        if (live) rqs_forward(u, logdet, S.ha + tid * kLdH, 1);
+    }
+
+    float total = 0.f;
+    if (live) total = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+
+    if (!src.potential) {
+        if (live) out[my_row] = total;
+        return;
+    }
+    // potential mode: deterministic reduction over the tile's trials (warps 0 and 1)
+    if (tid < kTM) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+        if ((tid & 31) == 0) S.red[tid >> 5] = total;
+    }
+    __syncthreads();
+    if (tid == 0) out[(long long)c * gridDim.x + blockIdx.x] = S.red[0] + S.red[1];
+}
+
+// out[c] = sum over tiles, fixed order
+__global__ void reduce_tiles_kernel(const float *__restrict__ partial, int n_tiles, int C, float *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int t = 0; t < n_tiles; ++t) s += partial[(long long)c * n_tiles + t];
+    out[c] = s;
+}
+
+static Handle *check_handle(void *h)
+{
+    Handle *H = static_cast<Handle *>(h);
+    if (H == nullptr || H->magic != kMagic) return nullptr;
+    return H;
+}
+
+static int launch(Handle *H, const RowSource &src, dim3 grid, float *out, cudaStream_t st)
+{
+    static_assert(sizeof(SimtSmem) < 227 * 1024, "tile does not fit shared memory");
+    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SimtSmem)));
+    mnle_simt_kernel<<<grid, kThreads, sizeof(SimtSmem), st>>>(H->params, H->layout, src, H->mu_y, H->sigma_y, out);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}
+
+}  // namespace mnle
+
+using namespace mnle;
+
+DDM_API size_t mnle_packed_floats(int n_choices)
+{
+    if (n_choices < 1 || n_choices > kMaxChoices) return 0;
+    return make_layout(n_choices).total;
+}
+
+DDM_API int mnle_create(const float *packed_host, size_t n_floats, int n_choices, void **handle_out)
+{
+    DDM_REQUIRE(handle_out != nullptr && packed_host != nullptr, "mnle_create: null argument");
+    DDM_REQUIRE(n_choices >= 1 && n_choices <= kMaxChoices, "mnle_create: n_choices=%d outside [1,%d]", n_choices,
+                kMaxChoices);
+    Layout L = make_layout(n_choices);
+    DDM_REQUIRE(n_floats == L.total, "mnle_create: packed buffer has %zu floats, layout needs %zu", n_floats, L.total);
+    const float sigma = packed_host[L.sigma_y];
+    DDM_REQUIRE(sigma > 0.0f, "mnle_create: sigma_y must be positive");
+    Handle *H = new Handle();
+    H->magic = kMagic;
+    H->layout = L;
+    H->tc_pack = nullptr;
+    H->mu_y = packed_host[L.mu_y];
+    H->sigma_y = sigma;
+    cudaError_t e = cudaGetDevice(&H->device);
+    if (e == cudaSuccess) e = cudaMalloc(&H->params, L.total * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(H->params, packed_host, L.total * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        delete H;
+        return ddm::cuda_fail(e, "mnle_create");
+    }
+    *handle_out = H;
+    return DDM_OK;
+}
+
+DDM_API int mnle_destroy(void *handle)
+{
+    Handle *H = check_handle(handle);
+    if (H == nullptr) {
+        ddm::set_error("mnle_destroy: bad handle");
+        return DDM_ERR_STATE;
+    }
+    H->magic = 0;
+    cudaFree(H->params);
+    if (H->tc_pack) cudaFree(H->tc_pack);
+    delete H;
+    return DDM_OK;
+}
+
+DDM_API int mnle_log_prob_rows_f32(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond, int64_t R,
+                                   float *out_dev, void *stream)
+{
+    Handle *H = check_handle(handle);
+    if (H == nullptr) {
+        ddm::set_error("mnle_log_prob_rows_f32: bad handle");
+        return DDM_ERR_STATE;
+    }
+    DDM_REQUIRE(R >= 0 && R <= 0x7FFFFFFFll * kTM, "mnle_log_prob_rows_f32: bad R");
+    if (R == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev && cond_dev && out_dev, "mnle_log_prob_rows_f32: null pointer");
+    DDM_REQUIRE(ld_cond >= kCond, "mnle_log_prob_rows_f32: ld_cond=%lld < 85", (long long)ld_cond);
+    RowSource src{};
+    src.x = x_dev;
+    src.cond = cond_dev;
+    src.ld_cond = ld_cond;
+    src.R = R;
+    src.potential = 0;
+    return launch(H, src, dim3((unsigned)((R + kTM - 1) / kTM), 1, 1), out_dev, static_cast<cudaStream_t>(stream));
+}
+
+DDM_API size_t mnle_loglik_workspace_floats(int64_t T, int64_t C)
+{
+    if (T <= 0 || C <= 0) return 0;
+    return (size_t)C * (size_t)((T + kTM - 1) / kTM);
+}
+
+DDM_API int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                     const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
+                                     float *out_dev, float *workspace_dev, void *stream)
+{
+    Handle *H = check_handle(handle);
+    if (H == nullptr) {
+        ddm::set_error("mnle_loglik_sum_simt_f32: bad handle");
+        return DDM_ERR_STATE;
+    }
+    DDM_REQUIRE(T >= 0 && C >= 0 && C <= 65535 && T <= 0x7FFFFFFFll, "mnle_loglik_sum: T=%lld C=%lld out of range",
+                (long long)T, (long long)C);
+    if (C == 0) return DDM_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DDM_REQUIRE(out_dev != nullptr, "mnle_loglik_sum: null output");
+    if (T == 0) {
+        DDM_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)C * sizeof(float), st));
+        return DDM_OK;
+    }
+    DDM_REQUIRE(theta_dev && x_dev && pulses_dev && workspace_dev, "mnle_loglik_sum: null pointer");
+    DDM_REQUIRE(ld_theta >= 5 && ld_pulses >= kCond - 5, "mnle_loglik_sum: ld_theta=%lld ld_pulses=%lld too small",
+                (long long)ld_theta, (long long)ld_pulses);
+    RowSource src{};
+    src.x = x_dev;
+    src.theta = theta_dev;
+    src.pulses = pulses_dev;
+    src.ld_theta = ld_theta;
+    src.ld_pulses = ld_pulses;
+    src.T = (int)T;
+    src.C = (int)C;
+    src.potential = 1;
+    const int n_tiles = (int)((T + kTM - 1) / kTM);
+    int rc = launch(H, src, dim3((unsigned)n_tiles, (unsigned)C, 1), workspace_dev, st);
+    if (rc != DDM_OK) return rc;
+    reduce_tiles_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(workspace_dev, n_tiles, (int)C, out_dev);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}

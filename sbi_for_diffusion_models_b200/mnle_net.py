@@ -1,0 +1,217 @@
+"""Packed MNLE parameters and the device-side estimator (``mnle_*`` entry points).
+
+The reference never touches MNLE weights itself: it asks sbi for an estimator
+(mnle.py:31-48) and calls ``estimator.log_prob(x, condition=...)`` (potentials.py:113).  To run
+that call on the GPU the weights are packed once into one fp32 buffer (layout documented in
+``include/ddm_b200.h``) with the per-dimension z-scoring of the condition folded into each
+first layer, copied to the device lazily per (process, device) -- the object pickles as the
+CPU buffer only, so it survives pyro's ``spawn`` chain workers (potentials.py:61).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _native
+from .simulator import compute_device
+
+HIDDEN, NUM_BINS, NUM_TRANSFORMS, COND_DIM = 128, 24, 10, 85
+CTX_DIM, SPLINE_OUT = COND_DIM + 1, 3 * NUM_BINS - 1
+
+
+class PackedMNLE:
+    """CPU-resident packed parameters + lazily created device handles."""
+
+    def __init__(self, packed: np.ndarray, n_choices: int):
+        packed = np.ascontiguousarray(packed, dtype=np.float32)
+        need = self.packed_floats(n_choices)
+        if packed.shape != (need,):
+            raise ValueError(f"packed MNLE buffer has shape {packed.shape}, expected ({need},)")
+        self.packed, self.n_choices = packed, int(n_choices)
+        self._handles: Dict[tuple, int] = {}
+
+    @staticmethod
+    def packed_floats(n_choices: int) -> int:
+        return (HIDDEN * COND_DIM + HIDDEN + 2 * (HIDDEN * HIDDEN + HIDDEN) + n_choices * HIDDEN + n_choices
+                + NUM_TRANSFORMS * (HIDDEN * CTX_DIM + HIDDEN + HIDDEN * HIDDEN + HIDDEN + SPLINE_OUT * HIDDEN + SPLINE_OUT)
+                + 2)
+
+    # ---- construction -----------------------------------------------------------------
+    @classmethod
+    def from_params(cls, p: Dict[str, torch.Tensor]) -> "PackedMNLE":
+        """From a dict with the names of ``oracle/mnle_spec.py`` (also what ``from_state_dict``
+        produces).  z-scoring is folded in float64: W' = W / std, b' = b - W (mean / std)."""
+        f64 = lambda t: np.asarray(t.detach().cpu().to(torch.float64).numpy())
+        mean, std = f64(p["cond_mean"]), np.maximum(f64(p["cond_std"]), 1e-7)
+        if mean.shape != (COND_DIM,) or std.shape != (COND_DIM,):
+            raise ValueError("condition mean/std must have 85 entries")
+
+        def fold(W, b):
+            W, b = f64(W), f64(b)
+            Wf = W.copy()
+            Wf[:, :COND_DIM] = W[:, :COND_DIM] / std[None, :]
+            return Wf, b - W[:, :COND_DIM] @ (mean / std)
+
+        def shape(t, s, what):
+            if tuple(t.shape) != s:
+                raise ValueError(f"{what}: shape {tuple(t.shape)}, expected {s}")
+            return t
+
+        n_choices = int(p["cat.Wo"].shape[0])
+        parts = []
+        W0, b0 = fold(shape(p["cat.W0"], (HIDDEN, COND_DIM), "cat.W0"), p["cat.b0"])
+        parts += [W0, b0, f64(shape(p["cat.W1"], (HIDDEN, HIDDEN), "cat.W1")), f64(p["cat.b1"]),
+                  f64(shape(p["cat.W2"], (HIDDEN, HIDDEN), "cat.W2")), f64(p["cat.b2"]),
+                  f64(shape(p["cat.Wo"], (n_choices, HIDDEN), "cat.Wo")), f64(p["cat.bo"])]
+        for k in range(NUM_TRANSFORMS):
+            W1, b1 = fold(shape(p[f"flow.{k}.W1"], (HIDDEN, CTX_DIM), f"flow.{k}.W1"), p[f"flow.{k}.b1"])
+            parts += [W1, b1, f64(shape(p[f"flow.{k}.W2"], (HIDDEN, HIDDEN), f"flow.{k}.W2")), f64(p[f"flow.{k}.b2"]),
+                      f64(shape(p[f"flow.{k}.W3"], (SPLINE_OUT, HIDDEN), f"flow.{k}.W3")), f64(p[f"flow.{k}.b3"])]
+        parts += [f64(p["flow.mu_y"]).reshape(1), f64(p["flow.sigma_y"]).reshape(1)]
+        packed = np.concatenate([a.reshape(-1) for a in parts]).astype(np.float32)
+        return cls(packed, n_choices)
+
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor]) -> "PackedMNLE":
+        """Shape-driven import of an sbi MNLE ``state_dict`` (the only way weights leave sbi,
+        reference mnle.py:247-259).  Key names are sbi/nflows internals, so layers are
+        recognised by their shapes in registration order and anything unexpected is refused.
+        UNVERIFIED against a real sbi checkpoint (sbi is not installable here)."""
+        layers, buffers = [], {}
+        items = list(sd.items())
+        i = 0
+        while i < len(items):
+            k, v = items[i]
+            if v.ndim == 2 and i + 1 < len(items) and items[i + 1][1].ndim == 1 \
+                    and items[i + 1][1].shape[0] == v.shape[0]:
+                layers.append((k, v, items[i + 1][1]))
+                i += 2
+                continue
+            if v.ndim == 1 and ("mean" in k or "std" in k):
+                buffers[k] = v
+            i += 1
+        shapes = [tuple(w.shape) for _, w, _ in layers]
+
+        def find_run(first, rest):
+            hits = [j for j, s in enumerate(shapes) if s == first and
+                    all(j + 1 + m < len(shapes) and (shapes[j + 1 + m] == r or (r is None and shapes[j + 1 + m][1] == HIDDEN))
+                        for m, r in enumerate(rest))]
+            return hits
+
+        cat = find_run((HIDDEN, COND_DIM), [(HIDDEN, HIDDEN), (HIDDEN, HIDDEN), None])
+        flows = find_run((HIDDEN, CTX_DIM), [(HIDDEN, HIDDEN), (SPLINE_OUT, HIDDEN)])
+        if len(cat) != 1 or len(flows) != NUM_TRANSFORMS:
+            raise ValueError(f"state_dict does not look like the reference's MNLE: found {len(cat)} categorical "
+                             f"nets and {len(flows)} spline conditioners (expected 1 and {NUM_TRANSFORMS}); "
+                             f"layer shapes {shapes}")
+        means = [v for k, v in buffers.items() if "mean" in k]
+        stds = [v for k, v in buffers.items() if "std" in k]
+        m85 = [v for v in means if v.shape[0] == COND_DIM]
+        s85 = [v for v in stds if v.shape[0] == COND_DIM]
+        m1 = [v for v in means if v.shape[0] == 1]
+        s1 = [v for v in stds if v.shape[0] == 1]
+        if not (m85 and s85 and len(m1) == 1 and len(s1) == 1):
+            raise ValueError("state_dict lacks the expected standardisation buffers (85-wide condition, 1-wide log rt); "
+                             "a flow that standardises all 86 context columns is not supported")
+        p: Dict[str, torch.Tensor] = {"cond_mean": m85[0], "cond_std": s85[0], "flow.mu_y": m1[0][0],
+                                      "flow.sigma_y": s1[0][0]}
+        j = cat[0]
+        for n, name in enumerate(("0", "1", "2", "o")):
+            p[f"cat.W{name}"], p[f"cat.b{name}"] = layers[j + n][1], layers[j + n][2]
+        for k, j in enumerate(flows):
+            for n in range(3):
+                p[f"flow.{k}.W{n + 1}"], p[f"flow.{k}.b{n + 1}"] = layers[j + n][1], layers[j + n][2]
+        return cls.from_params(p)
+
+    # ---- device handle ------------------------------------------------------------------
+    def handle(self, dev: torch.device) -> int:
+        key = (os.getpid(), dev.index)
+        h = self._handles.get(key)
+        if h is None:
+            out = ctypes.c_void_p()
+            with torch.cuda.device(dev):
+                rc = _native.lib().mnle_create(self.packed.ctypes.data, self.packed.size, self.n_choices,
+                                               ctypes.byref(out))
+            _native.check(rc, "mnle_create")
+            h = self._handles[key] = out.value
+        return h
+
+    def close(self) -> None:
+        for (pid, _), h in list(self._handles.items()):
+            if pid == os.getpid():
+                _native.lib().mnle_destroy(h)
+        self._handles.clear()
+
+    def __getstate__(self):
+        return {"packed": self.packed, "n_choices": self.n_choices}
+
+    def __setstate__(self, st):
+        self.packed, self.n_choices, self._handles = st["packed"], st["n_choices"], {}
+
+
+class DeviceMNLE(torch.nn.Module):
+    """Estimator object with the call shape the reference uses (potentials.py:113) plus the
+    fused potential.  Inputs may live on the CPU; results are returned on the input's device."""
+
+    def __init__(self, packed: PackedMNLE, device=None):
+        super().__init__()
+        self.packed = packed
+        self._device = device
+
+    def _dev(self, t: Optional[torch.Tensor] = None) -> torch.device:
+        return compute_device(self._device if self._device is not None else (t.device if t is not None and t.is_cuda else None))
+
+    def log_prob(self, x: torch.Tensor, condition: torch.Tensor) -> torch.Tensor:
+        """x (1,R,2) or (R,2) = [rt seconds, choice], condition (R,85) -> (1,R)."""
+        dev = self._dev(condition)
+        xr = x.reshape(-1, 2).to(device=dev, dtype=torch.float32).contiguous()
+        cond = condition.to(device=dev, dtype=torch.float32)
+        if cond.ndim != 2 or cond.shape[1] != COND_DIM or cond.shape[0] != xr.shape[0]:
+            raise ValueError(f"condition must be (R,{COND_DIM}) with R={xr.shape[0]}, got {tuple(cond.shape)}")
+        if cond.stride(1) != 1:
+            cond = cond.contiguous()
+        R = xr.shape[0]
+        with torch.cuda.device(dev):
+            out = torch.empty((R,), dtype=torch.float32, device=dev)
+            rc = _native.lib().mnle_log_prob_rows_f32(self.packed.handle(dev), xr.data_ptr(), cond.data_ptr(),
+                                                      cond.stride(0) if R > 1 else COND_DIM, R, out.data_ptr(),
+                                                      torch.cuda.current_stream(dev).cuda_stream)
+            _native.check(rc, "mnle_log_prob_rows_f32")
+        return out.to(condition.device).unsqueeze(0)
+
+    def loglik_sum(self, theta: torch.Tensor, x_o: torch.Tensor, pulses: torch.Tensor, *, kernel: str = "auto"
+                   ) -> torch.Tensor:
+        """out[c] = sum_t log p(x_o[t] | [theta[c], pulses[t]]): theta (C,5), x_o (T,2), pulses (T,>=80)."""
+        L = _native.lib()
+        dev = self._dev(theta)
+        th = theta.to(device=dev, dtype=torch.float32)
+        xo = x_o.reshape(-1, 2).to(device=dev, dtype=torch.float32).contiguous()
+        pl = pulses.to(device=dev, dtype=torch.float32)
+        if th.ndim != 2 or th.shape[1] != 5:
+            raise ValueError(f"theta must be (C,5), got {tuple(th.shape)}")
+        if pl.ndim != 2 or pl.shape[0] != xo.shape[0] or pl.shape[1] < COND_DIM - 5:
+            raise ValueError(f"pulses must be (T,>=80) with T={xo.shape[0]}, got {tuple(pl.shape)}")
+        if th.stride(1) != 1:
+            th = th.contiguous()
+        if pl.stride(1) != 1:
+            pl = pl.contiguous()
+        C, T = th.shape[0], xo.shape[0]
+        with torch.cuda.device(dev):
+            out = torch.empty((C,), dtype=torch.float32, device=dev)
+            ws = torch.empty((max(L.mnle_loglik_workspace_floats(T, C), 1),), dtype=torch.float32, device=dev)
+            fn = self._pick_kernel(kernel)
+            rc = fn(self.packed.handle(dev), th.data_ptr(), th.stride(0) if C > 1 else 5, xo.data_ptr(), pl.data_ptr(),
+                    pl.stride(0) if T > 1 else pl.shape[1], T, C, out.data_ptr(), ws.data_ptr(),
+                    torch.cuda.current_stream(dev).cuda_stream)
+            _native.check(rc, "mnle_loglik_sum")
+        return out.to(theta.device)
+
+    def _pick_kernel(self, kernel: str):
+        L = _native.lib()
+        if kernel in ("auto", "simt"):
+            return L.mnle_loglik_sum_simt_f32
+        raise ValueError(f"unknown kernel {kernel!r}")

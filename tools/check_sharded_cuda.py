@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Run under torchrun on >= 2 GPUs: the NCCL-sharded training set equals the single-GPU one.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29517 tools/check_sharded_cuda.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from sbi_for_diffusion_models_b200 import data_simulator as ds  # noqa: E402
+from sbi_for_diffusion_models_b200 import proposals  # noqa: E402
+from sbi_for_diffusion_models_b200.sharding import simulate_training_set_sharded  # noqa: E402
+
+
+class Prior:
+    def sample(self, shape):
+        return torch.rand((shape[0], 5)) * torch.tensor([1.0, 1.0, 2.0, 20.0, 1.0]) + torch.tensor([0.0, 0.0, 0.0, 5.0, 0.0])
+
+    def log_prob(self, th):
+        return torch.zeros(th.shape[:-1])
+
+
+def make():
+    torch.manual_seed(123)
+    return proposals.ExtendedProposal(Prior(), proposals.PulseSequenceProposal(P=80, p_success=0.75, seed=4))
+
+
+def main():
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, bs = 100003, 4096
+    z, x = simulate_training_set_sharded(make(), n, bs, torch.device("cuda", local), mu_sensory=1.0, p_success=0.75,
+                                         P=80, log_rt=False, seed=77)
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        z1, x1 = ds.simulate_training_set_with_conditions(make(), n, bs, "cpu", mu_sensory=1.0, p_success=0.75, P=80,
+                                                          log_rt=False, seed=77)
+        ok = torch.equal(z.cpu(), z1) and torch.equal(x.cpu(), x1)
+        print(f"sharded over {dist.get_world_size()} GPUs == single GPU: {ok}; outcomes "
+              f"{torch.bincount(x1[:, 1].long(), minlength=3).tolist()}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
