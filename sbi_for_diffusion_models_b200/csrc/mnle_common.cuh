@@ -129,7 +129,9 @@ __device__ __forceinline__ void rqs_forward(float &u, float &logdet, const float
     }
     // ---- knot derivatives (boundary derivatives are exactly 1) ------------------------
     const float *qd = q + 2 * kBins * qs;
-    const float edge_d = kMinDeriv + softplus_f(0.5403250582232235f);  // log(exp(1 - 1e-3) - 1)
+    // nflows pads the derivative logits with log(exp(1 - min_derivative) - 1), i.e.
+    // min_derivative + softplus(pad) == 1: the spline meets the linear tails with slope 1.
+    const float edge_d = 1.0f;
     const float d0 = (b == 0) ? edge_d : kMinDeriv + softplus_f(qd[(b - 1) * qs]);
     const float d1 = (b == kBins - 1) ? edge_d : kMinDeriv + softplus_f(qd[b * qs]);
 
