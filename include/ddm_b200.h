@@ -67,6 +67,7 @@ size_t ddm_sim_workspace_bytes(void);
 #define DDM_WS_USEFUL_STEPS 1
 #define DDM_WS_GENERIC_ROWS 2
 #define DDM_WS_LANE_STEPS 3
+#define DDM_WS_ERROR 4 /* non-zero: streaming launch timed out waiting for data */
 #define DDM_WS_WORDS 8
 
 /*
@@ -107,6 +108,25 @@ int ddm_sim_f32(const float *theta_dev, int64_t ld_theta,
                 int log_rt,
                 float *x_out_dev, int32_t *steps_out_dev,
                 void *workspace_dev, void *stream);
+
+/*
+ * Streaming variant for HOST-resident inputs: the caller enqueues the host->device copies of z
+ * in chunks on a copy stream, each followed by an 8-byte copy that raises *ready_dev to the
+ * number of trials delivered so far, and launches this ONE persistent kernel on another stream
+ * without waiting for them.  A warp that claims trials beyond *ready_dev sleeps until the copy
+ * engine has caught up, so ingest over PCIe and simulation overlap inside a single launch and
+ * there is only one drain phase per batch.  All copies must be enqueued BEFORE this call (the
+ * kernel never blocks them); if *ready_dev makes no progress for 20 s the kernel gives up and
+ * sets workspace[DDM_WS_ERROR].  Native Philox noise only; same results as ddm_sim_f32.
+ */
+int ddm_sim_stream_f32(const float *theta_dev, int64_t ld_theta,
+                       const float *pulses_dev, int64_t ld_pulses,
+                       int64_t N, int64_t P,
+                       int64_t n_max, int64_t steps_per_pulse,
+                       float dt, float t_max, float t_nd_hi, float noise_scale,
+                       uint64_t seed, uint64_t trial_offset, int log_rt,
+                       float *x_out_dev, void *workspace_dev,
+                       const uint64_t *ready_dev, void *stream);
 
 /* The standard normals ddm_sim_f32 consumes under native noise for trials
  * [trial_offset, trial_offset + N) and steps [0, n_steps): out (n_steps, N) step-major,

@@ -10,10 +10,11 @@ import os
 from typing import Optional
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "_lib", "libddm_b200.so")
+# DDM_B200_LIB overrides the location (kernel-variant sweeps); the default is the in-tree build
+LIB_PATH = os.environ.get("DDM_B200_LIB") or os.path.join(PKG, "_lib", "libddm_b200.so")
 
 DDM_OK, DDM_ERR_INVALID, DDM_ERR_CUDA, DDM_ERR_STATE = 0, -1, -2, -3
-WS_QUEUE, WS_USEFUL_STEPS, WS_GENERIC_ROWS, WS_LANE_STEPS, WS_WORDS = 0, 1, 2, 3, 8
+WS_QUEUE, WS_USEFUL_STEPS, WS_GENERIC_ROWS, WS_LANE_STEPS, WS_ERROR, WS_WORDS = 0, 1, 2, 3, 4, 8
 
 _i64, _u64, _f32, _i32 = ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_int
 _ptr = ctypes.c_void_p
@@ -25,6 +26,8 @@ _SIGNATURES = {
     "ddm_sim_workspace_bytes": (ctypes.c_size_t, []),
     "ddm_sim_f32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _f32, _f32,
                                    _u64, _u64, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "ddm_sim_stream_f32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _f32, _f32,
+                                          _u64, _u64, _i32, _ptr, _ptr, _ptr, _ptr]),
     "ddm_philox_normals_f32": (ctypes.c_int, [_u64, _u64, _i64, _i64, _ptr, _i64, _ptr]),
     "ddm_philox_words_u32": (ctypes.c_int, [_u64, _u64, _i64, _i64, _ptr, _i64, _ptr]),
     "ddm_pulses_pcg64": (ctypes.c_int, [_u64, _u64, _u64, _u64, _u64, _i64, _i64, _u64, _ptr, _i64, _ptr]),

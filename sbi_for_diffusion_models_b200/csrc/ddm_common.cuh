@@ -96,15 +96,25 @@ __device__ __forceinline__ float mufu_cos(float x)
     return y;
 }
 
+// (w & 0x007FFFFF) | one in ONE LOP3: `one` (= 0x3F800000) must sit in a register, because a
+// LOP3 can carry only one immediate; callers pass it from a kernel parameter so that the
+// compiler cannot fold it back into a second immediate (and a second instruction).
+__device__ __forceinline__ float mantissa_to_1_2(uint32_t w, uint32_t one)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(r) : "r"(w), "r"(one));
+    return __uint_as_float(r);
+}
+
 // Two 32-bit words -> two independent N(0,1) draws.
 //   radius word: low 23 bits -> f in [1,2) -> u = 2 - f in (0,1] -> r = sqrt(-2 ln u)
 //   angle  word: low 23 bits -> g in [1,2) -> phi = 2 pi (g - 1.5) in [-pi, pi)
-__device__ __forceinline__ void box_muller(uint32_t wr, uint32_t wa, float &z0, float &z1)
+__device__ __forceinline__ void box_muller(uint32_t wr, uint32_t wa, uint32_t one, float &z0, float &z1)
 {
-    const float f = __uint_as_float((wr & 0x007FFFFFu) | 0x3F800000u);
+    const float f = mantissa_to_1_2(wr, one);
     const float u = __fsub_rn(2.0f, f);
     const float r = mufu_sqrt(__fmul_rn(mufu_lg2(u), -1.3862943611198906f));  // -2 ln 2 * lg2 u
-    const float g = __uint_as_float((wa & 0x007FFFFFu) | 0x3F800000u);
+    const float g = mantissa_to_1_2(wa, one);
     const float phi = __fmaf_rn(g, 6.283185307179586f, -9.42477796076938f);
     z0 = __fmul_rn(r, mufu_cos(phi));
     z1 = __fmul_rn(r, mufu_sin(phi));
@@ -112,12 +122,79 @@ __device__ __forceinline__ void box_muller(uint32_t wr, uint32_t wa, float &z0, 
 
 // The four normals of steps 4*blk .. 4*blk+3 of global trial `trial`.
 __device__ __forceinline__ void philox_normals4(uint32_t trial_lo, uint32_t trial_hi, uint32_t blk,
-                                                PhiloxKey key, float (&z)[4])
+                                                PhiloxKey key, uint32_t one, float (&z)[4])
 {
     uint32_t w[4];
     philox4x32_10(trial_lo, trial_hi, blk, 0u, key, w);
-    box_muller(w[0], w[1], z[0], z[1]);
-    box_muller(w[2], w[3], z[2], z[3]);
+    box_muller(w[0], w[1], one, z[0], z[1]);
+    box_muller(w[2], w[3], one, z[2], z[3]);
+}
+
+// ---- Philox with the trial-constant part of rounds 1-2 hoisted -------------------------
+// With counter (g_lo, g_hi, blk, 0) only `blk` changes along a trial.  Round 1 multiplies
+// M0 * g_lo (constant per trial) and round 2 multiplies M1 * (hi(M0 g_lo) ^ k1) (also constant),
+// so four words per trial replace two IMAD.WIDE and one LOP3 in every block.  Same output bits
+// as philox4x32_10 (exact integer algebra).
+struct PhiloxTrial {
+    uint32_t a;  // g_hi ^ k0[0]
+    uint32_t d;  // hi(M1 * c2') ^ k0[1]          with c2' = hi(M0 g_lo) ^ k1[0]
+    uint32_t e;  // lo(M1 * c2')
+    uint32_t f;  // lo(M0 g_lo) ^ k1[1]
+};
+
+__device__ __forceinline__ PhiloxTrial philox_trial_setup(uint32_t g_lo, uint32_t g_hi, PhiloxKey key)
+{
+    const uint64_t p0 = (uint64_t)kPhiloxM0 * g_lo;
+    const uint32_t c2p = (uint32_t)(p0 >> 32) ^ key.k1;  // c3 = 0
+    const uint64_t p1 = (uint64_t)kPhiloxM1 * c2p;
+    PhiloxTrial t;
+    t.a = g_hi ^ key.k0;
+    t.d = (uint32_t)(p1 >> 32) ^ (key.k0 + kPhiloxW0);
+    t.e = (uint32_t)p1;
+    t.f = (uint32_t)p0 ^ (key.k1 + kPhiloxW1);
+    return t;
+}
+
+__device__ __forceinline__ void philox4x32_10_trial(const PhiloxTrial &t, uint32_t blk, PhiloxKey key,
+                                                    uint32_t (&out)[4])
+{
+    // round 1 (only M1 * blk varies)
+    const uint64_t q1 = (uint64_t)kPhiloxM1 * blk;
+    const uint32_t r1c0 = (uint32_t)(q1 >> 32) ^ t.a;
+    const uint32_t r1c1 = (uint32_t)q1;
+    // round 2 (only M0 * c0' varies)
+    const uint64_t q0 = (uint64_t)kPhiloxM0 * r1c0;
+    uint32_t c0 = t.d ^ r1c1;
+    uint32_t c1 = t.e;
+    uint32_t c2 = (uint32_t)(q0 >> 32) ^ t.f;
+    uint32_t c3 = (uint32_t)q0;
+    uint32_t k0 = key.k0 + 2u * kPhiloxW0, k1 = key.k1 + 2u * kPhiloxW1;
+#pragma unroll
+    for (int r = 2; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0;
+        c1 = (uint32_t)p1;
+        c2 = n2;
+        c3 = (uint32_t)p0;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+__device__ __forceinline__ void philox_normals4_trial(const PhiloxTrial &t, uint32_t blk, PhiloxKey key,
+                                                      uint32_t one, float (&z)[4])
+{
+    uint32_t w[4];
+    philox4x32_10_trial(t, blk, key, w);
+    box_muller(w[0], w[1], one, z[0], z[1]);
+    box_muller(w[2], w[3], one, z[2], z[3]);
 }
 
 }  // namespace ddm

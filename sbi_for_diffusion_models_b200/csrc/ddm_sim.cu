@@ -27,7 +27,10 @@
 
 namespace ddm {
 
-constexpr int kThreads = 256;
+#ifndef DDM_SIM_THREADS
+#define DDM_SIM_THREADS 256
+#endif
+constexpr int kThreads = DDM_SIM_THREADS;  // small CTAs retire sooner in the drain phase of a launch
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 struct SimParams {
@@ -48,7 +51,13 @@ struct SimParams {
     PhiloxKey key;
     unsigned long long trial_offset;
     int log_rt;
+    const unsigned long long *ready;  // streaming mode: trials [0, *ready) have arrived in HBM (else null)
+    uint32_t one_bits;  // 0x3F800000, kept in a register for the one-LOP3 mantissa insert
 };
+
+#ifndef DDM_SIM_NB
+#define DDM_SIM_NB 4  // Philox blocks (x4 Euler steps) per chunk: 16 steps (measured +4 % over 8)
+#endif
 
 // torch.clamp: NaN propagates (fminf/fmaxf would drop it)
 __device__ __forceinline__ float clamp_keep_nan(float x, float lo, float hi)
@@ -69,6 +78,8 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
     int nsteps = 0;  // decision window in steps
     int tk = 0;      // step index of the next pulse kick
     int pidx = 0;    // column of the next pulse
+    uint32_t cur = 0u;  // sign bits of pulses pidx.. (bit 0 = next pulse)
+    PhiloxTrial pt{0u, 0u, 0u, 0u};
     uint32_t mask[MW];
 #pragma unroll
     for (int w = 0; w < MW; ++w) mask[w] = 0u;
@@ -88,6 +99,33 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
             if (lane == 0) base = atomicAdd(&p.ws[DDM_WS_QUEUE], (unsigned long long)want);
             base = __shfl_sync(kFull, base, 0);
             exhausted = (base + (unsigned long long)want >= (unsigned long long)p.n_trials);
+            if (p.ready != nullptr && base < (unsigned long long)p.n_trials) {
+                // streaming mode: the copy engine is still delivering z; wait (bounded) until every
+                // trial this warp just claimed has landed.  Copies never wait on this kernel.
+                unsigned long long need = base + (unsigned long long)want;
+                if (need > (unsigned long long)p.n_trials) need = (unsigned long long)p.n_trials;
+                int failed = 0;
+                if (lane == 0) {
+                    const volatile unsigned long long *rdy = p.ready;
+                    unsigned long long t0 = 0ull, now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    while (*rdy < need) {
+                        __nanosleep(500);
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (now - t0 > 20000000000ull) {  // 20 s without progress: give up loudly
+                            atomicExch(&p.ws[DDM_WS_ERROR], 1ull);
+                            failed = 1;
+                            break;
+                        }
+                    }
+                    __threadfence();
+                }
+                failed = __shfl_sync(kFull, failed, 0);
+                if (failed) {
+                    exhausted = true;
+                    base = (unsigned long long)p.n_trials;  // nobody gets a trial
+                }
+            }
             const unsigned long long mine = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
             const bool got = !busy && mine < (unsigned long long)p.n_trials;
             if (got) trial = (uint32_t)mine;
@@ -104,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
 #pragma unroll
                     for (int w = 0; w < MASKW; ++w) {
                         const int c = w * 32 + (int)lane;
-                        const float s = (c < p.n_pulses) ? __ldg(row + c) : 1.0f;
+                        const float s = (c < p.n_pulses) ? __ldcg(row + c) : 1.0f;
                         const unsigned bits = __ballot_sync(kFull, s > 0.0f);
                         odd = odd || (fabsf(s) != 1.0f);
                         if ((int)lane == j) mask[w] = bits;
@@ -115,8 +153,8 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
             }
             if (got) {
                 const float *th = p.theta + (long long)trial * p.ld_theta;
-                const float th0 = __ldg(th + 0), th1 = __ldg(th + 1), th2 = __ldg(th + 2);
-                const float th3 = __ldg(th + 3), th4 = __ldg(th + 4);
+                const float th0 = __ldcg(th + 0), th1 = __ldcg(th + 1), th2 = __ldcg(th + 2);
+                const float th3 = __ldcg(th + 3), th4 = __ldcg(th + 4);
                 // rt_choice_model.py:131-135
                 const float a0 = clamp_keep_nan(th0, 0.0f, 1.0f);
                 nlam = -th1;
@@ -131,6 +169,11 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
                 t = 0;
                 tk = 0;
                 pidx = 0;
+                cur = mask[0];
+                if (!INJECT) {
+                    const unsigned long long g = p.trial_offset + (unsigned long long)trial;
+                    pt = philox_trial_setup((uint32_t)g, (uint32_t)(g >> 32), p.key);
+                }
                 busy = true;
                 if (MASKW > 0 && generic) atomicAdd(&p.ws[DDM_WS_GENERIC_ROWS], 1ull);
             }
@@ -138,33 +181,23 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
         if (__ballot_sync(kFull, busy) == 0u) break;
 
         // ---- one chunk of STEPS Euler steps -------------------------------------------
-        const unsigned long long g = p.trial_offset + (unsigned long long)trial;
-        const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)(g >> 32);
-
-        auto kick_value = [&]() -> float {
-            // rt_choice_model.py:192  a += v * s[:, p_idx] * active
+        auto kick = [&](float acc) -> float {
+            // rt_choice_model.py:192  a += v * s[:, p_idx] * active   (then advance to the next pulse)
+            float kv;
             if (MASKW == 0 || generic) {
                 float s = 0.0f;
                 if (busy && pidx < p.n_pulses)
-                    s = __ldg(p.pulses + (long long)trial * p.ld_pulses + pidx);
-                return __fmul_rn(v, s);
+                    s = __ldcg(p.pulses + (long long)trial * p.ld_pulses + pidx);
+                kv = __fmul_rn(v, s);
+            } else {
+                kv = (cur & 1u) ? v : -v;  // v * (+-1) exactly
             }
-            uint32_t w = mask[0];
-            if (MASKW > 1 && pidx >= 32) w = mask[1 % MW];
-            if (MASKW > 2 && pidx >= 64) w = mask[2 % MW];
-            return ((w >> (pidx & 31)) & 1u) ? v : -v;  // v * (+-1) exactly
+            cur >>= 1;
+            pidx += 1;
+            if (MASKW > 1 && (pidx & 31) == 0) cur = (pidx == 32) ? mask[1 % MW] : mask[2 % MW];
+            tk += p.spp;
+            return __fadd_rn(acc, kv);
         };
-
-        float kv = 0.0f;
-        bool kick0 = false;
-        if (ALIGNED) {
-            kick0 = (t == tk);
-            if (kick0) {
-                kv = kick_value();
-                tk += p.spp;
-                pidx += 1;
-            }
-        }
 
         float av[STEPS];
         float acc = a;
@@ -180,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
                                : 0.0f;
                 }
             } else {
-                philox_normals4(g_lo, g_hi, (uint32_t)(t >> 2) + (uint32_t)b, p.key, z);
+                philox_normals4_trial(pt, (uint32_t)(t >> 2) + (uint32_t)b, p.key, p.one_bits, z);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -188,14 +221,9 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
                 const float nz = __fmul_rn(z[j], p.noise_scale);                // :186
                 const float leak = __fmul_rn(__fmul_rn(nlam, acc), p.dt);      // (-lam*a)*dt
                 acc = __fadd_rn(__fadd_rn(acc, leak), nz);                     // :187
-                if (ALIGNED) {
-                    if (i == 0 && kick0) acc = __fadd_rn(acc, kv);             // :190-192
-                } else {
-                    if (t + i == tk) {
-                        acc = __fadd_rn(acc, kick_value());
-                        tk += p.spp;
-                        pidx += 1;
-                    }
+                // :190-192; with steps_per_pulse % 8 == 0 a kick can only fall on i % 8 == 0
+                if (!ALIGNED || (i & 7) == 0) {
+                    if (t + i == tk) acc = kick(acc);
                 }
                 av[i] = acc;
             }
@@ -252,7 +280,7 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
 
 // ---- dump kernels: the noise stream as a tensor ---------------------------------------
 template <bool WORDS>
-__global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, unsigned long long trial_offset,
+__global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, uint32_t one, unsigned long long trial_offset,
                                                           long long n_trials, long long n_steps,
                                                           void *out, long long ld)
 {
@@ -271,7 +299,7 @@ __global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, unsigne
                 if (blk * 4 + j < n_steps) static_cast<uint32_t *>(out)[(blk * 4 + j) * ld + i] = w[j];
         } else {
             float z[4];
-            philox_normals4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)blk, key, z);
+            philox_normals4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)blk, key, one, z);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (blk * 4 + j < n_steps) static_cast<float *>(out)[(blk * 4 + j) * ld + i] = z[j];
@@ -283,7 +311,7 @@ __global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, unsigne
 template <int MASKW, bool INJECT, bool ALIGNED>
 static int launch_sim(const SimParams &p, int sm_count, cudaStream_t stream)
 {
-    auto kern = sim_kernel<MASKW, INJECT, ALIGNED, 2>;
+    auto kern = sim_kernel<MASKW, INJECT, ALIGNED, DDM_SIM_NB>;
     int per_sm = 0;
     DDM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
@@ -312,12 +340,12 @@ using namespace ddm;
 
 DDM_API size_t ddm_sim_workspace_bytes(void) { return DDM_WS_WORDS * sizeof(unsigned long long); }
 
-DDM_API int ddm_sim_f32(const float *theta_dev, int64_t ld_theta, const float *pulses_dev,
-                        int64_t ld_pulses, int64_t N, int64_t P, int64_t n_max,
-                        int64_t steps_per_pulse, float dt, float t_max, float t_nd_hi,
-                        float noise_scale, uint64_t seed, uint64_t trial_offset,
-                        const float *noise_dev, int64_t ld_noise, int log_rt, float *x_out_dev,
-                        int32_t *steps_out_dev, void *workspace_dev, void *stream)
+static int sim_impl(const float *theta_dev, int64_t ld_theta, const float *pulses_dev,
+                    int64_t ld_pulses, int64_t N, int64_t P, int64_t n_max,
+                    int64_t steps_per_pulse, float dt, float t_max, float t_nd_hi,
+                    float noise_scale, uint64_t seed, uint64_t trial_offset,
+                    const float *noise_dev, int64_t ld_noise, int log_rt, float *x_out_dev,
+                    int32_t *steps_out_dev, void *workspace_dev, const uint64_t *ready_dev, void *stream)
 {
     DDM_REQUIRE(N >= 0 && N <= 0x7FFFFFFFll, "ddm_sim_f32: N=%lld outside [0, 2^31)", (long long)N);
     DDM_REQUIRE(n_max >= 0 && n_max <= 0x7FFFFF00ll, "ddm_sim_f32: n_max=%lld out of range", (long long)n_max);
@@ -367,6 +395,8 @@ DDM_API int ddm_sim_f32(const float *theta_dev, int64_t ld_theta, const float *p
     p.key.k1 = (uint32_t)(seed >> 32);
     p.trial_offset = trial_offset;
     p.log_rt = log_rt ? 1 : 0;
+    p.one_bits = 0x3F800000u;
+    p.ready = reinterpret_cast<const unsigned long long *>(ready_dev);
 
     const bool inject = noise_dev != nullptr;
     const bool aligned = (steps_per_pulse % 8) == 0;
@@ -382,6 +412,31 @@ DDM_API int ddm_sim_f32(const float *theta_dev, int64_t ld_theta, const float *p
 #undef DDM_PICK
 }
 
+DDM_API int ddm_sim_f32(const float *theta_dev, int64_t ld_theta, const float *pulses_dev,
+                        int64_t ld_pulses, int64_t N, int64_t P, int64_t n_max,
+                        int64_t steps_per_pulse, float dt, float t_max, float t_nd_hi,
+                        float noise_scale, uint64_t seed, uint64_t trial_offset,
+                        const float *noise_dev, int64_t ld_noise, int log_rt, float *x_out_dev,
+                        int32_t *steps_out_dev, void *workspace_dev, void *stream)
+{
+    return sim_impl(theta_dev, ld_theta, pulses_dev, ld_pulses, N, P, n_max, steps_per_pulse, dt, t_max, t_nd_hi,
+                    noise_scale, seed, trial_offset, noise_dev, ld_noise, log_rt, x_out_dev, steps_out_dev,
+                    workspace_dev, nullptr, stream);
+}
+
+DDM_API int ddm_sim_stream_f32(const float *theta_dev, int64_t ld_theta, const float *pulses_dev,
+                               int64_t ld_pulses, int64_t N, int64_t P, int64_t n_max,
+                               int64_t steps_per_pulse, float dt, float t_max, float t_nd_hi,
+                               float noise_scale, uint64_t seed, uint64_t trial_offset, int log_rt,
+                               float *x_out_dev, void *workspace_dev, const uint64_t *ready_dev, void *stream)
+{
+    DDM_REQUIRE(ready_dev != nullptr && (reinterpret_cast<uintptr_t>(ready_dev) & 7u) == 0,
+                "ddm_sim_stream_f32: ready_dev must be a non-null, 8-byte aligned device pointer");
+    return sim_impl(theta_dev, ld_theta, pulses_dev, ld_pulses, N, P, n_max, steps_per_pulse, dt, t_max, t_nd_hi,
+                    noise_scale, seed, trial_offset, nullptr, 0, log_rt, x_out_dev, nullptr, workspace_dev,
+                    ready_dev, stream);
+}
+
 static int dump_common(bool words, uint64_t seed, uint64_t trial_offset, int64_t N, int64_t n_steps,
                        void *out_dev, int64_t ld_out, void *stream)
 {
@@ -395,9 +450,9 @@ static int dump_common(bool words, uint64_t seed, uint64_t trial_offset, int64_t
     PhiloxKey key{(uint32_t)seed, (uint32_t)(seed >> 32)};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (words)
-        philox_dump_kernel<true><<<(unsigned)grid, 256, 0, st>>>(key, trial_offset, N, n_steps, out_dev, ld_out);
+        philox_dump_kernel<true><<<(unsigned)grid, 256, 0, st>>>(key, 0x3F800000u, trial_offset, N, n_steps, out_dev, ld_out);
     else
-        philox_dump_kernel<false><<<(unsigned)grid, 256, 0, st>>>(key, trial_offset, N, n_steps, out_dev, ld_out);
+        philox_dump_kernel<false><<<(unsigned)grid, 256, 0, st>>>(key, 0x3F800000u, trial_offset, N, n_steps, out_dev, ld_out);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }

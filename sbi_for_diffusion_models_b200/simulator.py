@@ -184,22 +184,37 @@ def philox_words(seed: int, n_trials: int, n_steps: int, *, trial_offset: int = 
 
 
 class HostPipeline:
-    """Streams a host-resident z = [theta, pulses] matrix through the GPU in chunks.
+    """Streams a host-resident z = [theta, pulses] matrix through the GPU.
 
-    Each chunk goes H2D -> ``ddm_sim_f32`` -> D2H on one of ``n_streams`` CUDA streams with
-    its own device buffers, so the copy of chunk k+1 overlaps the kernel of chunk k, and a
-    new kernel's blocks fill the SMs that the previous kernel's draining tail leaves idle.
-    Trial offsets make the result identical to a single launch over all rows."""
+    Per batch (up to ``max_batch`` rows) the copy stream carries z to the device in chunks, each
+    followed by an 8-byte copy that raises a device word ``ready`` to the number of rows delivered
+    so far, while ONE persistent ``ddm_sim_stream_f32`` launch on the kernel stream consumes
+    trials as they arrive (a warp that claims rows beyond ``ready`` sleeps until the copy engine
+    catches up).  PCIe ingest and simulation overlap inside a single launch, so a batch pays one
+    drain phase instead of one per chunk.  Two slots are double-buffered across batches.
+    Global trial offsets make the result identical to a single launch over all rows."""
 
-    def __init__(self, n_cols: int, chunk: int = 1 << 20, n_streams: int = 3, device=None):
+    def __init__(self, n_cols: int, max_batch: int = 1 << 22, chunk: int = 1 << 19, device=None):
         self.dev = compute_device(device)
-        self.chunk, self.n_cols = int(chunk), int(n_cols)
+        self.max_batch, self.chunk, self.n_cols = int(max_batch), int(chunk), int(n_cols)
+        n_marks = -(-self.max_batch // self.chunk)
         with torch.cuda.device(self.dev):
-            self.streams = [torch.cuda.Stream(self.dev) for _ in range(n_streams)]
-            self.z = [torch.empty((self.chunk, n_cols), dtype=torch.float32, device=self.dev) for _ in range(n_streams)]
-            self.x = [torch.empty((self.chunk, 2), dtype=torch.float32, device=self.dev) for _ in range(n_streams)]
-            self.ws = [torch.empty((_native.WS_WORDS,), dtype=torch.int64, device=self.dev) for _ in range(n_streams)]
+            self.copy_stream = torch.cuda.Stream(self.dev)
+            self.kernel_stream = torch.cuda.Stream(self.dev)
+            self.slots = []
+            for _ in range(2):
+                self.slots.append({
+                    "z": torch.empty((self.max_batch, n_cols), dtype=torch.float32, device=self.dev),
+                    "x": torch.empty((self.max_batch, 2), dtype=torch.float32, device=self.dev),
+                    "ws": torch.zeros((_native.WS_WORDS,), dtype=torch.int64, device=self.dev),
+                    "ready": torch.zeros((1,), dtype=torch.int64, device=self.dev),
+                    "done": None,
+                })
+            # constant pinned tables the flag copies read from (never rewritten: copies run later)
+            self.marks = (torch.arange(1, n_marks + 1, dtype=torch.int64) * self.chunk).pin_memory()
+            self.all_rows = torch.full((1,), 1 << 62, dtype=torch.int64).pin_memory()
         self.launches = 0
+        self._pending = []
 
     def run(self, z_host: torch.Tensor, x_host: torch.Tensor, *, sched: Schedule, seed: int, log_rt: bool = False,
             trial_offset: int = 0) -> None:
@@ -213,25 +228,45 @@ class HostPipeline:
         if P < sched.n_pulses:
             raise ValueError(f"pulse_sides has P={P} pulses but simulator needs at least {sched.n_pulses}")
         cur = torch.cuda.current_stream(self.dev)
-        for k, start in enumerate(range(0, n, self.chunk)):
-            i = k % len(self.streams)
-            st = self.streams[i]
-            if k < len(self.streams):
-                st.wait_stream(cur)
-            bs = min(self.chunk, n - start)
-            with torch.cuda.stream(st):
-                zd = self.z[i][:bs]
-                zd.copy_(z_host[start:start + bs], non_blocking=True)
-                rc = L.ddm_sim_f32(zd.data_ptr(), self.n_cols, zd.data_ptr() + 20, self.n_cols, bs, P,
-                                   sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi,
-                                   sched.noise_scale, ctypes.c_uint64(seed & (2**64 - 1)),
-                                   ctypes.c_uint64(trial_offset + start), None, 0, int(bool(log_rt)),
-                                   self.x[i].data_ptr(), None, self.ws[i].data_ptr(), st.cuda_stream)
-                _native.check(rc, "ddm_sim_f32")
+        cs, ks = self.copy_stream, self.kernel_stream
+        cs.wait_stream(cur)
+        ks.wait_stream(cur)
+        for b, start in enumerate(range(0, n, self.max_batch)):
+            slot = self.slots[b % 2]
+            bs = min(self.max_batch, n - start)
+            if slot["done"] is not None:
+                cs.wait_event(slot["done"])          # the previous kernel on this slot has finished
+            with torch.cuda.stream(cs):
+                slot["ready"].zero_()
+                reset = torch.cuda.Event()
+                reset.record(cs)
+                for k, a in enumerate(range(0, bs, self.chunk)):
+                    e = min(a + self.chunk, bs)
+                    slot["z"][a:e].copy_(z_host[start + a:start + e], non_blocking=True)
+                    src = self.all_rows if e == bs else self.marks[k:k + 1]
+                    slot["ready"].copy_(src, non_blocking=True)
+            # every copy of this batch is enqueued: the kernel may start as soon as `ready` was reset
+            ks.wait_event(reset)
+            with torch.cuda.stream(ks):
+                zd = slot["z"]
+                rc = L.ddm_sim_stream_f32(zd.data_ptr(), self.n_cols, zd.data_ptr() + 20, self.n_cols, bs, P,
+                                          sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi,
+                                          sched.noise_scale, ctypes.c_uint64(seed & (2**64 - 1)),
+                                          ctypes.c_uint64(trial_offset + start), int(bool(log_rt)),
+                                          slot["x"].data_ptr(), slot["ws"].data_ptr(), slot["ready"].data_ptr(),
+                                          ks.cuda_stream)
+                _native.check(rc, "ddm_sim_stream_f32")
                 self.launches += 1
-                x_host[start:start + bs].copy_(self.x[i][:bs], non_blocking=True)
-        for st in self.streams:
-            cur.wait_stream(st)
+                x_host[start:start + bs].copy_(slot["x"][:bs], non_blocking=True)
+                slot["done"] = torch.cuda.Event()
+                slot["done"].record(ks)
+                self._pending.append(slot)
+        cur.wait_stream(ks)
+        cur.wait_stream(cs)
 
     def synchronize(self) -> None:
         torch.cuda.current_stream(self.dev).synchronize()
+        failed = any(int(s["ws"][_native.WS_ERROR].item()) != 0 for s in self._pending)
+        self._pending.clear()
+        if failed:
+            raise RuntimeError("ddm_sim_stream_f32 timed out waiting for host->device copies")
