@@ -40,26 +40,35 @@ constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 
+// The key schedule (k + r * W) depends on the seed only: the host expands it once and the
+// kernels read the ten round keys straight from the constant bank (one LOP3 operand each).
 struct PhiloxKey {
-    uint32_t k0, k1;
+    uint32_t k0[10], k1[10];
 };
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              PhiloxKey key, uint32_t (&out)[4])
+inline PhiloxKey make_philox_key(uint64_t seed)
 {
-    uint32_t k0 = key.k0, k1 = key.k1;
+    PhiloxKey k;
+    for (int r = 0; r < 10; ++r) {
+        k.k0[r] = (uint32_t)seed + (uint32_t)r * kPhiloxW0;
+        k.k1[r] = (uint32_t)(seed >> 32) + (uint32_t)r * kPhiloxW1;
+    }
+    return k;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              const PhiloxKey &key, uint32_t (&out)[4])
+{
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;  // IMAD.WIDE.U32
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;  // one LOP3
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r];  // one LOP3
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k1[r];
         c0 = n0;
         c1 = (uint32_t)p1;
         c2 = n2;
         c3 = (uint32_t)p0;
-        k0 += kPhiloxW0;  // key schedule depends on the seed only: hoisted to uniform regs
-        k1 += kPhiloxW1;
     }
     out[0] = c0;
     out[1] = c1;
@@ -122,7 +131,7 @@ __device__ __forceinline__ void box_muller(uint32_t wr, uint32_t wa, uint32_t on
 
 // The four normals of steps 4*blk .. 4*blk+3 of global trial `trial`.
 __device__ __forceinline__ void philox_normals4(uint32_t trial_lo, uint32_t trial_hi, uint32_t blk,
-                                                PhiloxKey key, uint32_t one, float (&z)[4])
+                                                const PhiloxKey &key, uint32_t one, float (&z)[4])
 {
     uint32_t w[4];
     philox4x32_10(trial_lo, trial_hi, blk, 0u, key, w);
@@ -142,20 +151,20 @@ struct PhiloxTrial {
     uint32_t f;  // lo(M0 g_lo) ^ k1[1]
 };
 
-__device__ __forceinline__ PhiloxTrial philox_trial_setup(uint32_t g_lo, uint32_t g_hi, PhiloxKey key)
+__device__ __forceinline__ PhiloxTrial philox_trial_setup(uint32_t g_lo, uint32_t g_hi, const PhiloxKey &key)
 {
     const uint64_t p0 = (uint64_t)kPhiloxM0 * g_lo;
-    const uint32_t c2p = (uint32_t)(p0 >> 32) ^ key.k1;  // c3 = 0
+    const uint32_t c2p = (uint32_t)(p0 >> 32) ^ key.k1[0];  // c3 = 0
     const uint64_t p1 = (uint64_t)kPhiloxM1 * c2p;
     PhiloxTrial t;
-    t.a = g_hi ^ key.k0;
-    t.d = (uint32_t)(p1 >> 32) ^ (key.k0 + kPhiloxW0);
+    t.a = g_hi ^ key.k0[0];
+    t.d = (uint32_t)(p1 >> 32) ^ key.k0[1];
     t.e = (uint32_t)p1;
-    t.f = (uint32_t)p0 ^ (key.k1 + kPhiloxW1);
+    t.f = (uint32_t)p0 ^ key.k1[1];
     return t;
 }
 
-__device__ __forceinline__ void philox4x32_10_trial(const PhiloxTrial &t, uint32_t blk, PhiloxKey key,
+__device__ __forceinline__ void philox4x32_10_trial(const PhiloxTrial &t, uint32_t blk, const PhiloxKey &key,
                                                     uint32_t (&out)[4])
 {
     // round 1 (only M1 * blk varies)
@@ -168,19 +177,16 @@ __device__ __forceinline__ void philox4x32_10_trial(const PhiloxTrial &t, uint32
     uint32_t c1 = t.e;
     uint32_t c2 = (uint32_t)(q0 >> 32) ^ t.f;
     uint32_t c3 = (uint32_t)q0;
-    uint32_t k0 = key.k0 + 2u * kPhiloxW0, k1 = key.k1 + 2u * kPhiloxW1;
 #pragma unroll
     for (int r = 2; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k1[r];
         c0 = n0;
         c1 = (uint32_t)p1;
         c2 = n2;
         c3 = (uint32_t)p0;
-        k0 += kPhiloxW0;
-        k1 += kPhiloxW1;
     }
     out[0] = c0;
     out[1] = c1;
@@ -188,7 +194,7 @@ __device__ __forceinline__ void philox4x32_10_trial(const PhiloxTrial &t, uint32
     out[3] = c3;
 }
 
-__device__ __forceinline__ void philox_normals4_trial(const PhiloxTrial &t, uint32_t blk, PhiloxKey key,
+__device__ __forceinline__ void philox_normals4_trial(const PhiloxTrial &t, uint32_t blk, const PhiloxKey &key,
                                                       uint32_t one, float (&z)[4])
 {
     uint32_t w[4];

@@ -30,6 +30,9 @@ namespace ddm {
 #ifndef DDM_SIM_THREADS
 #define DDM_SIM_THREADS 256
 #endif
+#ifndef DDM_SIM_MIN_BLOCKS
+#define DDM_SIM_MIN_BLOCKS 4  // measured on B200: 4 blocks (<= 64 regs, no spills) 9.40e11 steps/s, 5: 9.23e11, 6: 9.12e11
+#endif
 constexpr int kThreads = DDM_SIM_THREADS;  // small CTAs retire sooner in the drain phase of a launch
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -65,8 +68,30 @@ __device__ __forceinline__ float clamp_keep_nan(float x, float lo, float hi)
     return x < lo ? lo : (x > hi ? hi : x);
 }
 
-template <int MASKW, bool INJECT, bool ALIGNED, int NB>
-__global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
+// Streaming mode: sleep until the copy engine has delivered `need` rows (bounded: 20 s without
+// progress sets the error word).  Only the STREAM instantiation of the kernel contains this spin
+// loop: its presence makes ptxas give up uniform-register round keys in the hot loop (+3
+// instructions per Euler step), which the resident-input kernel must not pay.
+__device__ __forceinline__ int wait_for_rows(const unsigned long long *ready, unsigned long long need,
+                                          unsigned long long *error_word)
+{
+    const volatile unsigned long long *rdy = ready;
+    unsigned long long t0 = 0ull, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*rdy < need) {
+        __nanosleep(500);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 20000000000ull) {
+            atomicExch(error_word, 1ull);
+            return 1;
+        }
+    }
+    __threadfence();
+    return 0;
+}
+
+template <int MASKW, bool INJECT, bool ALIGNED, int NB, bool STREAM>
+__global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim_kernel(const SimParams p)
 {
     constexpr int STEPS = 4 * NB;
     constexpr int MW = MASKW > 0 ? MASKW : 1;
@@ -99,27 +124,13 @@ __global__ void __launch_bounds__(kThreads) sim_kernel(const SimParams p)
             if (lane == 0) base = atomicAdd(&p.ws[DDM_WS_QUEUE], (unsigned long long)want);
             base = __shfl_sync(kFull, base, 0);
             exhausted = (base + (unsigned long long)want >= (unsigned long long)p.n_trials);
-            if (p.ready != nullptr && base < (unsigned long long)p.n_trials) {
+            if (STREAM && base < (unsigned long long)p.n_trials) {
                 // streaming mode: the copy engine is still delivering z; wait (bounded) until every
                 // trial this warp just claimed has landed.  Copies never wait on this kernel.
                 unsigned long long need = base + (unsigned long long)want;
                 if (need > (unsigned long long)p.n_trials) need = (unsigned long long)p.n_trials;
                 int failed = 0;
-                if (lane == 0) {
-                    const volatile unsigned long long *rdy = p.ready;
-                    unsigned long long t0 = 0ull, now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                    while (*rdy < need) {
-                        __nanosleep(500);
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                        if (now - t0 > 20000000000ull) {  // 20 s without progress: give up loudly
-                            atomicExch(&p.ws[DDM_WS_ERROR], 1ull);
-                            failed = 1;
-                            break;
-                        }
-                    }
-                    __threadfence();
-                }
+                if (lane == 0) failed = wait_for_rows(p.ready, need, &p.ws[DDM_WS_ERROR]);
                 failed = __shfl_sync(kFull, failed, 0);
                 if (failed) {
                     exhausted = true;
@@ -308,10 +319,10 @@ __global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, uint32_
 }
 
 // ---- launch ----------------------------------------------------------------------------
-template <int MASKW, bool INJECT, bool ALIGNED>
+template <int MASKW, bool INJECT, bool ALIGNED, bool STREAM>
 static int launch_sim(const SimParams &p, int sm_count, cudaStream_t stream)
 {
-    auto kern = sim_kernel<MASKW, INJECT, ALIGNED, DDM_SIM_NB>;
+    auto kern = sim_kernel<MASKW, INJECT, ALIGNED, DDM_SIM_NB, STREAM>;
     int per_sm = 0;
     DDM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
@@ -391,8 +402,7 @@ static int sim_impl(const float *theta_dev, int64_t ld_theta, const float *pulse
     p.t_max = t_max;
     p.t_nd_hi = t_nd_hi;
     p.noise_scale = noise_scale;
-    p.key.k0 = (uint32_t)seed;
-    p.key.k1 = (uint32_t)(seed >> 32);
+    p.key = make_philox_key(seed);
     p.trial_offset = trial_offset;
     p.log_rt = log_rt ? 1 : 0;
     p.one_bits = 0x3F800000u;
@@ -401,13 +411,17 @@ static int sim_impl(const float *theta_dev, int64_t ld_theta, const float *pulse
     const bool inject = noise_dev != nullptr;
     const bool aligned = (steps_per_pulse % 8) == 0;
     const bool packed = need <= 96;
-#define DDM_PICK(MW, INJ, AL) return launch_sim<MW, INJ, AL>(p, sms, st)
+#define DDM_PICK(MW, INJ, AL, ST) return launch_sim<MW, INJ, AL, ST>(p, sms, st)
+    if (ready_dev != nullptr) {  // streaming ingest: native noise only
+        if (packed) { if (aligned) DDM_PICK(3, false, true, true); else DDM_PICK(3, false, false, true); }
+        else        { if (aligned) DDM_PICK(0, false, true, true); else DDM_PICK(0, false, false, true); }
+    }
     if (packed) {
-        if (inject) { if (aligned) DDM_PICK(3, true, true); else DDM_PICK(3, true, false); }
-        else        { if (aligned) DDM_PICK(3, false, true); else DDM_PICK(3, false, false); }
+        if (inject) { if (aligned) DDM_PICK(3, true, true, false); else DDM_PICK(3, true, false, false); }
+        else        { if (aligned) DDM_PICK(3, false, true, false); else DDM_PICK(3, false, false, false); }
     } else {
-        if (inject) { if (aligned) DDM_PICK(0, true, true); else DDM_PICK(0, true, false); }
-        else        { if (aligned) DDM_PICK(0, false, true); else DDM_PICK(0, false, false); }
+        if (inject) { if (aligned) DDM_PICK(0, true, true, false); else DDM_PICK(0, true, false, false); }
+        else        { if (aligned) DDM_PICK(0, false, true, false); else DDM_PICK(0, false, false, false); }
     }
 #undef DDM_PICK
 }
@@ -447,7 +461,7 @@ static int dump_common(bool words, uint64_t seed, uint64_t trial_offset, int64_t
     const long long total = ((n_steps + 3) / 4) * N;
     long long grid = (total + 255) / 256;
     if (grid > 148 * 64) grid = 148 * 64;
-    PhiloxKey key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const PhiloxKey key = make_philox_key(seed);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (words)
         philox_dump_kernel<true><<<(unsigned)grid, 256, 0, st>>>(key, 0x3F800000u, trial_offset, N, n_steps, out_dev, ld_out);

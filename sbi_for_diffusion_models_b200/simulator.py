@@ -194,7 +194,7 @@ class HostPipeline:
     drain phase instead of one per chunk.  Two slots are double-buffered across batches.
     Global trial offsets make the result identical to a single launch over all rows."""
 
-    def __init__(self, n_cols: int, max_batch: int = 1 << 22, chunk: int = 1 << 19, device=None):
+    def __init__(self, n_cols: int, max_batch: int = 1 << 22, chunk: int = 1 << 18, device=None):
         self.dev = compute_device(device)
         self.max_batch, self.chunk, self.n_cols = int(max_batch), int(chunk), int(n_cols)
         n_marks = -(-self.max_batch // self.chunk)

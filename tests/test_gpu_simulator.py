@@ -248,3 +248,41 @@ def test_million_trials_properties():
     assert abs(frac[0] - 0.567) < 0.01 and abs(frac[1] - 0.259) < 0.01 and abs(frac[2] - 0.175) < 0.01
     assert abs(steps.float().mean().item() - 5080) < 60
     assert stats.lane_efficiency > 0.6, stats   # 3.5 trials per lane: the drain tail is ~25 %; 0.995 at 1e8 trials
+
+
+def test_long_schedule_dt_1e_4_shared_noise_and_native():
+    """configs[2]'s long pulse schedule: dt = 1e-4 -> n_max = 80000, steps_per_pulse = 1000, P = 80."""
+    sched = Schedule.from_constants(dt=1e-4)
+    assert (sched.n_max, sched.steps_per_pulse, sched.n_pulses) == (80000, 1000, 80)
+    n = 192
+    theta = orc.prior_sample(n, seed=51).numpy()
+    pulses = orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(12)), 0, n, 80, 0.75)
+    noise = orc.synthetic_noise(321, sched.n_max, n)
+    want, want_steps = orc.sim_scalar_c(theta, pulses, noise, dt=1e-4)
+    x, steps = simulate_trials(torch.from_numpy(theta), torch.from_numpy(pulses), noise=torch.from_numpy(noise),
+                               schedule=sched, return_steps=True)
+    _assert_same(x, want, "dt=1e-4 shared noise")
+    assert np.array_equal(steps.cpu().numpy().astype(np.int64), want_steps)
+    # native noise on the same schedule: replay through the oracle
+    xn = simulate_trials(torch.from_numpy(theta), torch.from_numpy(pulses), seed=9, schedule=sched)
+    normals = sim.philox_normals(9, n, sched.n_max)
+    want_n, _ = orc.sim_scalar_c(theta, pulses, normals.cpu().numpy(), dt=1e-4)
+    _assert_same(xn, want_n, "dt=1e-4 native replay")
+
+
+def test_streaming_host_pipeline_equals_resident_launch():
+    """ddm_sim_stream_f32 (copy engine feeds one persistent kernel) == ddm_sim_f32 on resident z."""
+    from sbi_for_diffusion_models_b200.simulator import HostPipeline
+    n = 300000 + 17
+    z = torch.empty((n, 85))
+    z[:, :5] = orc.prior_sample(n, seed=61)
+    z[:, 5:] = torch.from_numpy(orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(13)), 0, n, 80, 0.75))
+    zh = z.pin_memory()
+    xh = torch.empty((n, 2)).pin_memory()
+    sched = Schedule.from_constants()
+    pipe = HostPipeline(85, max_batch=1 << 17, chunk=1 << 14)      # 3 batches, 8 chunks each, ragged tail
+    pipe.run(zh, xh, sched=sched, seed=4242, trial_offset=1000)
+    pipe.synchronize()
+    want = simulate_trials(z[:, :5], z[:, 5:], seed=4242, trial_offset=1000)
+    assert torch.equal(xh, want.cpu())
+    assert pipe.launches == 3
