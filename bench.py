@@ -139,6 +139,11 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core it can
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
     rate, times, steps = time_cpu_port(args.cpu_trials, args.steps, args.warmup)
     ms = 1e3 * sum(times) / len(times)

@@ -195,6 +195,13 @@ int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_th
                              const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
                              float *out_dev, float *workspace_dev, void *stream);
 
+/* Tensor-core building-block check: D (128,N) = A (128,128) * B (N,128)^T through the smem
+ * operand layout, UMMA descriptors, tcgen05.mma and TMEM loads of the fused kernel.
+ * passes = 1: bf16(A) bf16(B); passes = 3: bf16 hi/lo split (near-fp32).  lbo_a / lbo_b / sbo = 0
+ * use the layout's own descriptor strides (non-zero values are for hardware probing only). */
+int mnle_tc_selftest(const float *a_dev, const float *b_dev, int N, int passes, uint32_t lbo_a,
+                     uint32_t lbo_b, uint32_t sbo, float *d_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
