@@ -238,7 +238,8 @@ def mnle_bench(dev, with_cpu: bool):
     th, xo, pl = theta.to(dev), x_o.to(dev), pulses_o.to(dev)
     out = {"workload": f"configs[3]: MNLE log_prob sum over T={T} trials x C={C} chains, weights random-init (seed 0)",
            "rows": T * C, "dense_mflop_per_row": 0.818}
-    for kernel in ("simt",):
+    lls = {}
+    for kernel in ("tc", "simt"):
         for _ in range(3):
             est.loglik_sum(th, xo, pl, kernel=kernel)
         torch.cuda.synchronize()
@@ -250,15 +251,21 @@ def mnle_bench(dev, with_cpu: bool):
         e1.record()
         torch.cuda.synchronize()
         ms_call = e0.elapsed_time(e1) / reps
+        lls[kernel] = ll
         out[kernel] = {"ms_per_call": ms_call, "rows_per_s": T * C / (ms_call * 1e-3),
                        "dense_tflops": 0.818e6 * T * C / (ms_call * 1e-3) / 1e12}
+    # tensor-core work actually issued: hi/lo split = 3 bf16 MMAs per product, N padded (71 -> 80, K -> 16)
+    tc_flop_row = 2.0 * (11 * 128 * 32 + 3 * (12 * 128 * 128 + 10 * 80 * 128 + 16 * 128))
+    out["tc"]["bf16_mma_tflops"] = tc_flop_row * T * C / (out["tc"]["ms_per_call"] * 1e-3) / 1e12
+    out["max_rel_diff_tc_vs_simt"] = float(((lls["tc"] - lls["simt"]).abs() / lls["simt"].abs()).max())
     if with_cpu:
         from oracle import mnle_spec
         t0 = time.perf_counter()
         ref = mnle_spec.loglik_sum(params, theta, x_o, pulses_o)
         out["cpu_spec_fp32"] = {"ms_per_call": (time.perf_counter() - t0) * 1e3, "cores": torch.get_num_threads(),
                                 "kind": "port (oracle/mnle_spec.py; sbi itself is not installable offline)"}
-        out["max_rel_err_vs_cpu_spec"] = float(((ll.cpu() - ref).abs() / ref.abs()).max())
+        for kernel, ll in lls.items():
+            out[kernel]["max_rel_err_vs_cpu_spec"] = float(((ll.cpu() - ref).abs() / ref.abs()).max())
     return out
 
 

@@ -195,6 +195,19 @@ int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_th
                              const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
                              float *out_dev, float *workspace_dev, void *stream);
 
+/*
+ * Same contract on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM): the
+ * 128x128 / 128x71 layers run as bf16 hi/lo split GEMMs (three MMAs per product, fp32
+ * accumulate), the five global parameters enter through a K = 32 six-term stage, and the
+ * pulse / choice part of every first layer is computed once per trial.  Sums agree with the
+ * _simt kernel to ~1e-6 relative.  workspace_dev >= mnle_loglik_tc_workspace_floats(T,C) floats,
+ * 16-byte aligned.  T <= 65535.
+ */
+size_t mnle_loglik_tc_workspace_floats(int64_t T, int64_t C);
+int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                           const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
+                           float *out_dev, float *workspace_dev, void *stream);
+
 /* Tensor-core building-block check: D (128,N) = A (128,128) * B (N,128)^T through the smem
  * operand layout, UMMA descriptors, tcgen05.mma and TMEM loads of the fused kernel.
  * passes = 1: bf16(A) bf16(B); passes = 3: bf16 hi/lo split (near-fp32).  lbo_a / lbo_b / sbo = 0

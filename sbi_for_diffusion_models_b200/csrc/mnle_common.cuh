@@ -61,14 +61,39 @@ inline Layout make_layout(int n_choices)
     return L;
 }
 
+// ---- tensor-core operand pack (mnle_tc.cu) ------------------------------------------------
+// One row tile goes through kTcStages GEMM stages: per net a "theta stage" (K = 32, the five
+// global parameters in a six-term bf16 expansion; the pulse / choice part of the first layer is
+// a per-trial bias computed once per call) followed by the K = 128 layers with bf16 hi/lo
+// operands.  Every stage is one contiguous blob (operand images in the shared-memory layout the
+// UMMA descriptors expect, then the fp32 bias) so a single bulk copy stages it.
+constexpr int kTcStages = 4 + 3 * kTransforms;  // cat: theta, W1, W2, Wo; flow: theta, W2, W3
+constexpr int kNets = 1 + kTransforms;
+constexpr int kSplineN = 80;                    // 71 spline parameters padded to a legal UMMA N
+enum TcEpilogue { kEpiRelu = 0, kEpiSigmoid = 1, kEpiSpline = 2, kEpiCategorical = 3 };
+struct TcStage {
+    uint32_t off, bytes;  // blob position in the pack (16-byte multiples)
+    uint32_t bias_off;    // where the N bias floats sit relative to the staged blob
+    uint16_t n;           // UMMA N (multiple of 16)
+    uint8_t k128;         // 1: K = 128 hi/lo stage, 0: theta stage
+    uint8_t epi;          // TcEpilogue
+    uint16_t net, pad;    // 0 = categorical net, 1 + k = spline conditioner k
+};
+struct TcPlan {
+    TcStage st[kTcStages];
+};
+
 struct Handle {
     uint32_t magic;
     int device;
     Layout layout;
     float *params;   // device copy of the packed buffer
     void *tc_pack;   // device copy of the tensor-core operand pack (bf16 hi/lo tiles), or null
+    size_t tc_pack_bytes;
+    TcPlan tc_plan;
     float mu_y, sigma_y;
 };
+int build_tc_pack(Handle *H, const float *packed_host);  // mnle_tc.cu
 constexpr uint32_t kMagic = 0x4D4E4C45u;  // "MNLE"
 
 __device__ __forceinline__ float softplus_f(float x)

@@ -7,6 +7,10 @@
 // TMEM): 16 mantissa bits per operand at 3/2 of the cost of a tf32 product.
 //
 // This file: the operand layout / descriptor self-test (mnle_tc_selftest) and the fused kernel.
+#include <string.h>
+
+#include <vector>
+
 #include "mnle_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -96,6 +100,432 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float *__restric
     if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+
+// ------------------------------------------------------------- operand pack (host side) ---
+// Round-to-nearest-even fp32 -> bf16, the same rounding as __float2bfloat16_rn.
+static inline uint16_t host_bf16(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);  // inf / nan
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float host_bf16_to_f(uint16_t h)
+{
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+// x = t[0] + t[1] + t[2] + O(2^-25 |x|)
+static inline void host_split3(float x, uint16_t (&t)[3])
+{
+    float r = x;
+    for (int i = 0; i < 3; ++i) {
+        t[i] = host_bf16(r);
+        r -= host_bf16_to_f(t[i]);
+    }
+}
+
+// K = 128 weight image of one bf16 term (0 = hi, 1 = lo) of W[n_valid][128], padded to N rows.
+static void pack_image_k128(std::vector<unsigned char> &blob, const float *W, int n_valid, int N, int term)
+{
+    const size_t base = blob.size();
+    blob.resize(base + (size_t)N * 256, 0);
+    for (int n = 0; n < n_valid; ++n)
+        for (int k = 0; k < kHidden; ++k) {
+            uint16_t t[3];
+            host_split3(W[(size_t)n * kHidden + k], t);
+            memcpy(&blob[base + tile_offset(N, n, k)], &t[term], 2);
+        }
+}
+static void pack_bias(std::vector<unsigned char> &blob, const float *b, int n_valid, int N)
+{
+    const size_t base = blob.size();
+    blob.resize(base + (size_t)N * 4, 0);
+    memcpy(&blob[base], b, (size_t)n_valid * 4);
+}
+// theta stage: image [128][32]; k = term * 5 + i pairs with the A image built by the kernel.
+//   A terms: t1 t1 t2 t1 t2 t3      B terms: w1 w2 w1 w3 w2 w1     (all products of order <= 4)
+static void pack_image_theta(std::vector<unsigned char> &blob, const float *W1, int ldw)
+{
+    static const int wterm[6] = {0, 1, 0, 2, 1, 0};
+    const size_t base = blob.size();
+    blob.resize(base + (size_t)kHidden * 64, 0);
+    for (int n = 0; n < kHidden; ++n)
+        for (int i = 0; i < 5; ++i) {
+            uint16_t t[3];
+            host_split3(W1[(size_t)n * ldw + i], t);
+            for (int term = 0; term < 6; ++term)
+                memcpy(&blob[base + tile_offset(kHidden, n, term * 5 + i)], &t[wterm[term]], 2);
+        }
+}
+
+int build_tc_pack(Handle *H, const float *packed_host)
+{
+    const Layout &L = H->layout;
+    std::vector<unsigned char> blob;
+    TcPlan &P = H->tc_plan;
+    int s = 0;
+    auto begin = [&](int n, int k128, int epi, int net) {
+        P.st[s].off = (uint32_t)blob.size();
+        P.st[s].n = (uint16_t)n;
+        P.st[s].k128 = (uint8_t)k128;
+        P.st[s].epi = (uint8_t)epi;
+        P.st[s].net = (uint16_t)net;
+    };
+    auto end = [&](bool bias_in_blob) {
+        P.st[s].bytes = (uint32_t)blob.size() - P.st[s].off;
+        P.st[s].bias_off = bias_in_blob ? P.st[s].bytes - (uint32_t)P.st[s].n * 4u : P.st[s].bytes;
+        ++s;
+    };
+    auto dense = [&](size_t W, size_t b, int n_valid, int N, int epi, int net) {
+        begin(N, 1, epi, net);
+        pack_image_k128(blob, packed_host + W, n_valid, N, 0);
+        pack_image_k128(blob, packed_host + W, n_valid, N, 1);
+        pack_bias(blob, packed_host + b, n_valid, N);
+        end(true);
+    };
+    // categorical net
+    begin(kHidden, 0, kEpiSigmoid, 0);
+    pack_image_theta(blob, packed_host + L.cat_W0, kCond);
+    end(false);
+    dense(L.cat_W1, L.cat_b1, kHidden, kHidden, kEpiSigmoid, 0);
+    dense(L.cat_W2, L.cat_b2, kHidden, kHidden, kEpiSigmoid, 0);
+    dense(L.cat_Wo, L.cat_bo, L.n_choices, 16, kEpiCategorical, 0);
+    for (int k = 0; k < kTransforms; ++k) {
+        begin(kHidden, 0, kEpiRelu, 1 + k);
+        pack_image_theta(blob, packed_host + L.fl_W1[k], kCtx);
+        end(false);
+        dense(L.fl_W2[k], L.fl_b2[k], kHidden, kHidden, kEpiRelu, 1 + k);
+        dense(L.fl_W3[k], L.fl_b3[k], kSplineOut, kSplineN, kEpiSpline, 1 + k);
+    }
+    if (s != kTcStages) {
+        ddm::set_error("build_tc_pack: %d stages, expected %d", s, kTcStages);
+        return DDM_ERR_STATE;
+    }
+    DDM_CUDA_TRY(cudaMalloc(&H->tc_pack, blob.size()));
+    DDM_CUDA_TRY(cudaMemcpy(H->tc_pack, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    H->tc_pack_bytes = blob.size();
+    return DDM_OK;
+}
+
+// ---------------------------------------------------------------- per-trial first layer ---
+// hoist[t][net][j] = b1[j] + sum_i W1[j][5 + i] * pulses[t][i] (+ W1[j][85] * choice[t] for the
+// spline conditioners): the part of every first layer that does not depend on the chain.
+__global__ void __launch_bounds__(kHidden) mnle_hoist_kernel(const float *__restrict__ params, Layout L,
+                                                            const float *__restrict__ x,
+                                                            const float *__restrict__ pulses, long long ld_pulses,
+                                                            float *__restrict__ hoist)
+{
+    __shared__ float in_s[kCtx - 5];
+    const int t = blockIdx.x, net = blockIdx.y, j = threadIdx.x;
+    if (j < kCond - 5) in_s[j] = __ldg(pulses + (long long)t * ld_pulses + j);
+    if (j == kCond - 5) in_s[j] = __ldg(x + 2 * t + 1);
+    __syncthreads();
+    const int K = net == 0 ? kCond : kCtx;
+    const float *W = params + (net == 0 ? L.cat_W0 : L.fl_W1[net - 1]) + (size_t)j * K + 5;
+    float acc = __ldg(params + (net == 0 ? L.cat_b0 : L.fl_b1[net - 1]) + j);
+    for (int i = 0; i < K - 5; ++i) acc = fmaf(__ldg(W + i), in_s[i], acc);
+    hoist[((size_t)t * kNets + net) * kHidden + j] = acc;
+}
+
+// ------------------------------------------------------------------------ fused kernel ---
+constexpr int kTcM = 128;                        // rows (chains) per CTA = UMMA M
+constexpr int kTcEpiThreads = 256;               // warps 0..7: epilogue; warp 8: issuer
+constexpr int kTcThreads = kTcEpiThreads + 32;
+constexpr uint32_t kImgBytes = kTcM * 256;       // one bf16 image of 128 rows x 128 k
+constexpr uint32_t kKGroupBytes = kTcM * 16;     // 8 k's of all 128 rows
+constexpr uint32_t kSmemAHi = 0, kSmemALo = kImgBytes, kSmemATh = 2 * kImgBytes;
+constexpr uint32_t kSmemSlot0 = kSmemATh + kTcM * 64;
+constexpr uint32_t kSlotBytes = 2 * kImgBytes + kHidden * 4;
+constexpr uint32_t kSmemBars = kSmemSlot0 + 2 * kSlotBytes;
+constexpr uint32_t kTcSmemBytes = kSmemBars + 64;
+static_assert(kTcSmemBytes <= 227 * 1024, "tile does not fit shared memory");
+
+// TMEM row of 32 fp32 accumulators + bias -> activation -> bf16 hi/lo images for the next GEMM
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue_act(uint32_t taddr, int col0, const float *bias, unsigned char *a_hi,
+                                                unsigned char *a_lo, int r)
+{
+#pragma unroll 1
+    for (int c0 = col0; c0 < col0 + 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 b0 = *reinterpret_cast<const float4 *>(bias + c0 + 8 * g);
+            const float4 b1 = *reinterpret_cast<const float4 *>(bias + c0 + 8 * g + 4);
+            float f[8] = {__uint_as_float(v[8 * g + 0]) + b0.x, __uint_as_float(v[8 * g + 1]) + b0.y,
+                          __uint_as_float(v[8 * g + 2]) + b0.z, __uint_as_float(v[8 * g + 3]) + b0.w,
+                          __uint_as_float(v[8 * g + 4]) + b1.x, __uint_as_float(v[8 * g + 5]) + b1.y,
+                          __uint_as_float(v[8 * g + 6]) + b1.z, __uint_as_float(v[8 * g + 7]) + b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                f[j] = (EPI == kEpiRelu) ? fmaxf(f[j], 0.f) : 1.0f / (1.0f + expf(-f[j]));
+            uint4 hi, lo;
+            split_bf16x2(f[0], f[1], hi.x, lo.x);
+            split_bf16x2(f[2], f[3], hi.y, lo.y);
+            split_bf16x2(f[4], f[5], hi.z, lo.z);
+            split_bf16x2(f[6], f[7], hi.w, lo.w);
+            const uint32_t at = (uint32_t)((c0 >> 3) + g) * kKGroupBytes + (uint32_t)r * 16u;
+            *reinterpret_cast<uint4 *>(a_hi + at) = hi;
+            *reinterpret_cast<uint4 *>(a_lo + at) = lo;
+        }
+    }
+}
+
+// The spline of mnle_common.cuh with its 71 parameters in registers (fully unrolled).
+__device__ __forceinline__ void rqs_forward_reg(float &u, float &logdet, const float (&q)[kSplineN])
+{
+    if (!(u >= -kTail && u <= kTail)) return;
+    const float inv_sqrt_h = 0.08838834764831845f;
+    float e[kBins];
+    float m = q[0] * inv_sqrt_h;
+#pragma unroll
+    for (int j = 1; j < kBins; ++j) m = fmaxf(m, q[j] * inv_sqrt_h);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) {
+        e[j] = __expf(q[j] * inv_sqrt_h - m);
+        s += e[j];
+    }
+    float sc = (1.0f - kMinBin * kBins) / s;
+    float cs = 0.f, prev = -kTail, left = -kTail, right = kTail;
+    int b = 0;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) {
+        cs += kMinBin + sc * e[j];
+        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
+        if (u >= prev) {
+            b = j;
+            left = prev;
+            right = edge;
+        }
+        prev = edge;
+    }
+    m = q[kBins] * inv_sqrt_h;
+#pragma unroll
+    for (int j = 1; j < kBins; ++j) m = fmaxf(m, q[kBins + j] * inv_sqrt_h);
+    s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) {
+        e[j] = __expf(q[kBins + j] * inv_sqrt_h - m);
+        s += e[j];
+    }
+    sc = (1.0f - kMinBin * kBins) / s;
+    cs = 0.f;
+    prev = -kTail;
+    float bottom = -kTail, top = kTail;
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) {
+        cs += kMinBin + sc * e[j];
+        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
+        if (j == b) {
+            bottom = prev;
+            top = edge;
+        }
+        prev = edge;
+    }
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kBins - 1; ++j) {
+        if (j == b - 1) r0 = q[2 * kBins + j];
+        if (j == b) r1 = q[2 * kBins + j];
+    }
+    const float d0 = (b == 0) ? 1.0f : kMinDeriv + softplus_f(r0);
+    const float d1 = (b == kBins - 1) ? 1.0f : kMinDeriv + softplus_f(r1);
+    const float w = right - left, h = top - bottom;
+    const float delta = h / w;
+    const float th = (u - left) / w;
+    const float t1 = th * (1.0f - th);
+    const float den = delta + (d0 + d1 - 2.0f * delta) * t1;
+    const float out = bottom + h * (delta * th * th + d0 * t1) / den;
+    const float dnum = delta * delta * (d1 * th * th + 2.0f * delta * t1 + d0 * (1.0f - th) * (1.0f - th));
+    logdet += logf(dnum) - 2.0f * logf(den);
+    u = out;
+}
+
+// grid = (ceil(C / 128), T): one CTA takes 128 chains of one trial through all 34 stages.
+__global__ void __launch_bounds__(kTcThreads, 1)
+    mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
+                   const float *__restrict__ theta, long long ld_theta, const float *__restrict__ x,
+                   const float *__restrict__ hoist, int C, float mu_y, float sigma_y, int n_choices,
+                   float *__restrict__ partial)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *a_hi = smem + kSmemAHi, *a_lo = smem + kSmemALo, *a_th = smem + kSmemATh;
+    uint64_t *wfull = reinterpret_cast<uint64_t *>(smem + kSmemBars);  // [2]
+    uint64_t *dfull = wfull + 2, *aready = wfull + 3;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBars + 32);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t = blockIdx.y, c_first = blockIdx.x * kTcM;
+
+    if (warp == 8) tmem_alloc<128>(tmem_slot);
+    if (tid == 0) {
+        mbar_init(&wfull[0], 1);
+        mbar_init(&wfull[1], 1);
+        mbar_init(dfull, 1);
+        mbar_init(aready, kTcEpiThreads);
+        fence_mbar_init();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ================= issuer: bulk copies of the stage blobs + every tcgen05.mma =========
+        if (lane == 0) {
+            auto load = [&](int s) {
+                const TcStage &st = plan.st[s];
+                unsigned char *slot = smem + kSmemSlot0 + (uint32_t)(s & 1) * kSlotBytes;
+                mbar_expect_tx(&wfull[s & 1], st.bytes + (st.k128 ? 0u : (uint32_t)kHidden * 4u));
+                bulk_g2s(slot, pack + st.off, st.bytes, &wfull[s & 1]);
+                if (!st.k128)
+                    bulk_g2s(slot + st.bytes, hoist + ((size_t)t * kNets + st.net) * kHidden, kHidden * 4,
+                             &wfull[s & 1]);
+            };
+            load(0);
+#pragma unroll 1
+            for (int s = 0; s < kTcStages; ++s) {
+                const TcStage &st = plan.st[s];
+                mbar_wait(aready, s & 1);  // A operand of this stage written, D drained
+                tc_fence_after_sync();
+                if (s + 1 < kTcStages) load(s + 1);
+                mbar_wait(&wfull[s & 1], (s >> 1) & 1);
+                const uint32_t slot = smem_u32(smem + kSmemSlot0 + (uint32_t)(s & 1) * kSlotBytes);
+                const uint32_t n = st.n, idesc = umma_idesc_bf16_f32(kTcM, (int)n);
+                if (!st.k128) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        umma_bf16(tmem, umma_desc_kmajor(smem_u32(a_th) + ks * 2 * kKGroupBytes, kKGroupBytes, 128),
+                                  umma_desc_kmajor(slot + ks * 2 * kKGroupBytes, kKGroupBytes, 128), idesc, ks);
+                } else {
+                    const uint32_t w_img = n * 256u, w_kg = n * 16u;
+#pragma unroll 1
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t a = smem_u32(pass == 2 ? a_lo : a_hi);
+                        const uint32_t w = slot + (pass == 1 ? w_img : 0u);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            umma_bf16(tmem, umma_desc_kmajor(a + ks * 2 * kKGroupBytes, kKGroupBytes, 128),
+                                      umma_desc_kmajor(w + ks * 2 * w_kg, w_kg, 128), idesc, (pass | ks) != 0);
+                    }
+                }
+                umma_commit(dfull);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue warps: lane quarter q, column half hf ======================
+        const int q = warp & 3, hf = warp >> 2, r = 32 * q + lane;
+        const int c = c_first + r;
+        const bool live = c < C;
+        const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
+        {   // A image of the theta stage: k = term * 5 + i, terms t1 t1 t2 t1 t2 t3 (pairs with pack_image_theta)
+            uint16_t tt[5][3];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) split3_bf16(live ? __ldg(theta + (long long)c * ld_theta + i) : 0.f, tt[i]);
+            const int aterm[6] = {0, 0, 1, 0, 1, 2};
+            uint16_t kv[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) kv[k] = (k < 30) ? tt[k % 5][aterm[k / 5]] : (uint16_t)0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if ((g >> 1) != hf) continue;
+                uint4 v;
+                v.x = kv[8 * g + 0] | ((uint32_t)kv[8 * g + 1] << 16);
+                v.y = kv[8 * g + 2] | ((uint32_t)kv[8 * g + 3] << 16);
+                v.z = kv[8 * g + 4] | ((uint32_t)kv[8 * g + 5] << 16);
+                v.w = kv[8 * g + 6] | ((uint32_t)kv[8 * g + 7] << 16);
+                *reinterpret_cast<uint4 *>(a_th + (uint32_t)g * kKGroupBytes + (uint32_t)r * 16u) = v;
+            }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(aready);
+
+        const float rt = __ldg(x + 2 * t);
+        const int choice = (int)__ldg(x + 2 * t + 1);
+        const float y = logf(rt);
+        float u = (y - mu_y) / sigma_y, logdet = -logf(sigma_y), lp = 0.f;
+
+#pragma unroll 1
+        for (int s = 0; s < kTcStages; ++s) {
+            const TcStage &st = plan.st[s];
+            mbar_wait(dfull, s & 1);
+            tc_fence_after_sync();
+            mbar_wait(&wfull[s & 1], (s >> 1) & 1);  // the bias travelled with the stage blob
+            const float *bias =
+                reinterpret_cast<const float *>(smem + kSmemSlot0 + (uint32_t)(s & 1) * kSlotBytes + st.bias_off);
+            if (st.epi == kEpiRelu) {
+                tc_epilogue_act<kEpiRelu>(taddr, 64 * hf, bias, a_hi, a_lo, r);
+            } else if (st.epi == kEpiSigmoid) {
+                tc_epilogue_act<kEpiSigmoid>(taddr, 64 * hf, bias, a_hi, a_lo, r);
+            } else if (hf == 0) {
+                if (st.epi == kEpiSpline) {
+                    uint32_t v0[32], v1[32], v2[16];
+                    tmem_ld32(taddr, v0);
+                    tmem_ld32(taddr + 32u, v1);
+                    tmem_ld16(taddr + 64u, v2);
+                    tmem_wait_ld();
+                    float qv[kSplineN];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        qv[j] = __uint_as_float(v0[j]) + bias[j];
+                        qv[32 + j] = __uint_as_float(v1[j]) + bias[32 + j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) qv[64 + j] = __uint_as_float(v2[j]) + bias[64 + j];
+                    rqs_forward_reg(u, logdet, qv);
+                } else {
+                    uint32_t v[16];
+                    tmem_ld16(taddr, v);
+                    tmem_wait_ld();
+                    float lg[kMaxChoices];
+#pragma unroll
+                    for (int j = 0; j < kMaxChoices; ++j) lg[j] = __uint_as_float(v[j]) + bias[j];
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < kMaxChoices; ++j)
+                        if (j < n_choices) m = fmaxf(m, lg[j]);
+                    float sum = 0.f, pc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kMaxChoices; ++j)
+                        if (j < n_choices) {
+                            const float ex = expf(lg[j] - m);
+                            sum += ex;
+                            if (j == choice) pc = ex;
+                        }
+                    const float eps = 1.1920928955078125e-07f;
+                    lp = logf(fminf(fmaxf(pc / sum, eps), 1.0f - eps));
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            mbar_arrive(aready);
+        }
+        if (hf == 0 && live)
+            partial[(size_t)t * C + c] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<128>(tmem);
+}
+
+// out[c] = sum_t partial[t][c], fixed order
+__global__ void tc_reduce_trials_kernel(const float *__restrict__ partial, int T, int C, float *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += partial[(size_t)t * C + c];
+    out[c] = s;
+}
+
 }  // namespace mnle
 
 using namespace mnle;
@@ -109,6 +539,48 @@ DDM_API int mnle_tc_selftest(const float *a_dev, const float *b_dev, int N, int 
     const int smem = 131072 + 64;
     DDM_CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     tc_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a_dev, b_dev, N, passes, lbo_a, lbo_b, sbo, d_dev);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}
+
+DDM_API size_t mnle_loglik_tc_workspace_floats(int64_t T, int64_t C)
+{
+    if (T <= 0 || C <= 0) return 0;
+    return (size_t)T * kNets * kHidden + (size_t)T * (size_t)C;
+}
+
+DDM_API int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                   const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C, float *out_dev,
+                                   float *workspace_dev, void *stream)
+{
+    Handle *H = static_cast<Handle *>(handle);
+    if (H == nullptr || H->magic != kMagic || H->tc_pack == nullptr) {
+        ddm::set_error("mnle_loglik_sum_tc_f32: bad handle");
+        return DDM_ERR_STATE;
+    }
+    DDM_REQUIRE(T >= 0 && C >= 0 && T <= 65535 && C <= 0x7FFFFFFFll - kTcM, "mnle_loglik_sum_tc: T=%lld C=%lld out of range",
+                (long long)T, (long long)C);
+    if (C == 0) return DDM_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DDM_REQUIRE(out_dev != nullptr, "mnle_loglik_sum_tc: null output");
+    if (T == 0) {
+        DDM_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)C * sizeof(float), st));
+        return DDM_OK;
+    }
+    DDM_REQUIRE(theta_dev && x_dev && pulses_dev && workspace_dev, "mnle_loglik_sum_tc: null pointer");
+    DDM_REQUIRE(ld_theta >= 5 && ld_pulses >= kCond - 5, "mnle_loglik_sum_tc: ld_theta=%lld ld_pulses=%lld too small",
+                (long long)ld_theta, (long long)ld_pulses);
+    DDM_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 15u) == 0, "mnle_loglik_sum_tc: workspace must be 16-byte aligned");
+    float *hoist = workspace_dev;
+    float *partial = workspace_dev + (size_t)T * kNets * kHidden;
+    mnle_hoist_kernel<<<dim3((unsigned)T, kNets), kHidden, 0, st>>>(H->params, H->layout, x_dev, pulses_dev, ld_pulses, hoist);
+    DDM_CUDA_TRY(cudaGetLastError());
+    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    mnle_tc_kernel<<<dim3((unsigned)((C + kTcM - 1) / kTcM), (unsigned)T), kTcThreads, kTcSmemBytes, st>>>(
+        static_cast<const unsigned char *>(H->tc_pack), H->tc_plan, theta_dev, ld_theta, x_dev, hoist, (int)C, H->mu_y,
+        H->sigma_y, H->layout.n_choices, partial);
+    DDM_CUDA_TRY(cudaGetLastError());
+    tc_reduce_trials_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(partial, (int)T, (int)C, out_dev);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }

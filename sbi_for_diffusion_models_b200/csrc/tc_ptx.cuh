@@ -26,6 +26,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
@@ -152,6 +156,26 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t &hi, uint16_t &lo)
     const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
     hi = __bfloat16_as_ushort(h);
     lo = __bfloat16_as_ushort(l);
+}
+
+// Two floats -> packed bf16 hi pair and packed bf16 lo pair (one cvt.rn.bf16x2 each).
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi, uint32_t &lo)
+{
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __low2float(h), x1 - __high2float(h));
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// x = t0 + t1 + t2 + O(2^-25 |x|)
+__device__ __forceinline__ void split3_bf16(float x, uint16_t (&t)[3])
+{
+    float r = x;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(r);
+        t[i] = __bfloat16_as_ushort(h);
+        r -= __bfloat162float(h);
+    }
 }
 
 }  // namespace tc

@@ -202,16 +202,23 @@ class DeviceMNLE(torch.nn.Module):
         C, T = th.shape[0], xo.shape[0]
         with torch.cuda.device(dev):
             out = torch.empty((C,), dtype=torch.float32, device=dev)
-            ws = torch.empty((max(L.mnle_loglik_workspace_floats(T, C), 1),), dtype=torch.float32, device=dev)
-            fn = self._pick_kernel(kernel)
+            fn, ws_floats = self._pick_kernel(kernel, T)
+            ws = torch.empty((max(ws_floats(T, C), 1),), dtype=torch.float32, device=dev)
             rc = fn(self.packed.handle(dev), th.data_ptr(), th.stride(0) if C > 1 else 5, xo.data_ptr(), pl.data_ptr(),
                     pl.stride(0) if T > 1 else pl.shape[1], T, C, out.data_ptr(), ws.data_ptr(),
                     torch.cuda.current_stream(dev).cuda_stream)
             _native.check(rc, "mnle_loglik_sum")
         return out.to(theta.device)
 
-    def _pick_kernel(self, kernel: str):
+    @staticmethod
+    def _pick_kernel(kernel: str, T: int):
+        """"tc": tcgen05 tensor-core kernel; "simt": fp32 CUDA-core kernel (accuracy anchor);
+        "auto": tensor cores whenever the shape is covered."""
         L = _native.lib()
-        if kernel in ("auto", "simt"):
-            return L.mnle_loglik_sum_simt_f32
+        if kernel == "auto":
+            kernel = "tc" if T <= 65535 else "simt"
+        if kernel == "tc":
+            return L.mnle_loglik_sum_tc_f32, L.mnle_loglik_tc_workspace_floats
+        if kernel == "simt":
+            return L.mnle_loglik_sum_simt_f32, L.mnle_loglik_workspace_floats
         raise ValueError(f"unknown kernel {kernel!r}")

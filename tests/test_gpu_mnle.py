@@ -49,27 +49,46 @@ def test_rows_api_matches_spec(net):
     assert est.log_prob(x.cuda(), condition=cond.cuda()).is_cuda
 
 
-@pytest.mark.parametrize("T,C", [(50, 1024), (1, 1), (64, 3), (65, 7), (200, 33), (50, 1)])
-def test_potential_sum_matches_spec(net, T, C):
+@pytest.mark.parametrize("kernel", ["tc", "simt"])
+@pytest.mark.parametrize("T,C", [(50, 1024), (1, 1), (64, 3), (65, 7), (200, 33), (50, 1), (3, 300)])
+def test_potential_sum_matches_spec(net, T, C, kernel):
     p32, p64, est, scale = net
     theta = orc.prior_sample(C, seed=3)
     x, pulses = _session(T)
-    got = est.loglik_sum(theta, x, pulses).double()
+    got = est.loglik_sum(theta, x, pulses, kernel=kernel).double()
     want = ms.loglik_sum(p64, theta, x, pulses)
     rel = ((got - want).abs() / want.abs()).max().item()
     assert rel < (1e-4 if scale == 1.0 else 1e-3), rel
     # same numbers through the rows API and the reference's row layout r = t*C + c
     xr, cond = ms.potential_rows(theta, x, pulses)
     rows = est.log_prob(xr.unsqueeze(0), condition=cond)[0].reshape(T, C).sum(0).double()
-    assert torch.allclose(rows, got, rtol=2e-6, atol=1e-3)
+    assert torch.allclose(rows, got, rtol=2e-6 if kernel == "simt" else 2e-5 * scale ** 3, atol=1e-3)
+
+
+def test_tensor_core_kernel_tracks_the_fp32_kernel(net):
+    """tcgen05 path (bf16 hi/lo split operands) vs the fp32 CUDA-core kernel, per (trial, chain)
+    row: T = 1 makes every output a single row's log-prob."""
+    _, p64, est, scale = net
+    theta = orc.prior_sample(700, seed=11)
+    x, pulses = _session(40)
+    worst = 0.0
+    for t in range(0, 40, 7):
+        a = est.loglik_sum(theta, x[t:t + 1], pulses[t:t + 1], kernel="tc").double()
+        b = est.loglik_sum(theta, x[t:t + 1], pulses[t:t + 1], kernel="simt").double()
+        want = ms.loglik_sum(p64, theta, x[t:t + 1], pulses[t:t + 1])
+        worst = max(worst, float((a - b).abs().max()))
+        # the tensor-core rows are as close to float64 as the fp32 rows are (within 2x + 1e-4)
+        assert float((a - want).abs().max()) < 2.0 * float((b - want).abs().max()) + 1e-4 * scale ** 3
+    assert worst < (5e-4 if scale == 1.0 else 5e-3), worst
 
 
 def test_potential_is_reproducible_and_handles_empty(net):
     _, _, est, _ = net
     theta = orc.prior_sample(100, seed=4)
     x, pulses = _session(50)
-    a, b = est.loglik_sum(theta, x, pulses), est.loglik_sum(theta, x, pulses)
-    assert torch.equal(a, b)
+    for kernel in ("tc", "simt"):
+        a, b = est.loglik_sum(theta, x, pulses, kernel=kernel), est.loglik_sum(theta, x, pulses, kernel=kernel)
+        assert torch.equal(a, b)
     assert est.loglik_sum(theta[:0], x, pulses).shape == (0,)
     assert torch.equal(est.loglik_sum(theta, x[:0], pulses[:0]), torch.zeros(100))
     with pytest.raises(ValueError, match="theta must be"):
