@@ -40,10 +40,28 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float *__restric
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 131072 + 16);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const bool a_in_tmem = (passes % 100) > 10 && passes < 100 || passes >= 200;
+    if (a_in_tmem && passes < 100) passes -= 10;
     if (warp == 0) tmem_alloc<256>(tmem_slot);
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (a_in_tmem) {
+        // A hi -> TMEM columns [128, 192), A lo -> [192, 256): lane = row, column j = k pair (2j, 2j+1)
+        const uint32_t tm = *tmem_slot + ((uint32_t)(warp * 32) << 16);
+        for (int j0 = 0; j0 < 64; j0 += 16) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                split_bf16x2(A[tid * 128 + 2 * (j0 + j)], A[tid * 128 + 2 * (j0 + j) + 1], hi[j], lo[j]);
+            tmem_st16(tm + 128u + (uint32_t)j0, hi);
+            tmem_st16(tm + 192u + (uint32_t)j0, lo);
+        }
+        tmem_wait_st();
     }
     // operands -> smem images (thread r owns row r of A and, if r < N, row r of B)
     for (int kg = 0; kg < 16; ++kg) {
@@ -69,17 +87,28 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float *__restric
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (tid == 0) {
+    // passes >= 100: throughput probe -- (passes % 100) rounds of the 24-MMA stage sequence back to
+    // back, D[0] = clock cycles from the first issue to the commit's arrival
+    const int reps = passes >= 100 ? passes % 100 : 0;
+    if (reps) passes = 3;
+    long long t_start = 0;
+    if (warp == 0 && elect_one_sync()) {
         const uint32_t idesc = umma_idesc_bf16_f32(128, N);
         const uint32_t la = lbo_a ? lbo_a : 128u * 16u, lb = lbo_b ? lbo_b : (uint32_t)N * 16u, sb = sbo ? sbo : 128u;
         uint32_t acc = 0;
+        t_start = clock64();
+        for (int rep = 0; rep < max(reps, 1); ++rep)
         for (int pass = 0; pass < passes; ++pass) {
             const unsigned char *pa = (pass == 2) ? a_lo : a_hi;
             const unsigned char *pb = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 const uint64_t da = umma_desc_kmajor(smem_u32(pa) + ks * 2 * 128 * 16, la, sb);
                 const uint64_t db = umma_desc_kmajor(smem_u32(pb) + ks * 2 * N * 16, lb, sb);
-                umma_bf16(tmem, da, db, idesc, acc);
+                if (a_in_tmem)
+                    umma_bf16_ts(tmem, tmem + (pass == 2 ? 192u : 128u) + (uint32_t)ks * 8u, db, idesc, acc);
+                else
+                    umma_bf16(tmem, da, db, idesc, acc);
                 acc = 1;
             }
         }
@@ -87,6 +116,15 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float *__restric
     }
     mbar_wait(bar, 0);
     tc_fence_after_sync();
+    const long long t_end = clock64();
+    if (reps) {
+        t_start = __shfl_sync(0xFFFFFFFFu, t_start, 0);  // (any lane may have been elected)
+        if (tid == 0) D[0] = (float)(t_end - t_start);
+        tc_fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc<256>(tmem);
+        return;
+    }
     // thread (warp w, lane l) reads TMEM lane 32 w + l = output row
     for (int c0 = 0; c0 < N; c0 += 16) {
         uint32_t r[16];
@@ -232,67 +270,93 @@ __global__ void __launch_bounds__(kHidden) mnle_hoist_kernel(const float *__rest
 }
 
 // ------------------------------------------------------------------------ fused kernel ---
-constexpr int kTcM = 128;                        // rows (chains) per CTA = UMMA M
-constexpr int kTcEpiThreads = 256;               // warps 0..7: epilogue; warp 8: issuer
-constexpr int kTcThreads = kTcEpiThreads + 32;
+// One CTA = two row tiles of 128 (trial, chain) rows in ping-pong: while the tensor core runs a
+// stage of one tile, the four epilogue warps of the other tile turn its accumulators into the
+// next A operand.  Activations never leave tensor memory: D (128 fp32 columns) -> registers ->
+// bias, activation, bf16 hi/lo split -> A_hi / A_lo (64 + 64 packed columns) of the same tile,
+// which the next stage's tcgen05.mma reads as its A operand.  2 x 256 columns = all of TMEM.
+// Shared memory holds only the streamed weight blobs (3 slots) and the theta-stage A images.
+constexpr int kTcM = 128;                        // rows per tile = UMMA M
+constexpr int kTcTiles = 2;                      // tiles per CTA
+constexpr int kTcEpiWarps = 16;                  // warp w: lane quarter w & 3, tile (w >> 2) & 1, column half w >> 3
+constexpr int kTcEpiThreads = kTcEpiWarps * 32;
+constexpr int kTcThreads = kTcEpiThreads + 32;   // + the issuer warp
+constexpr int kTcSlots = 3;
 constexpr uint32_t kImgBytes = kTcM * 256;       // one bf16 image of 128 rows x 128 k
 constexpr uint32_t kKGroupBytes = kTcM * 16;     // 8 k's of all 128 rows
-constexpr uint32_t kSmemAHi = 0, kSmemALo = kImgBytes, kSmemATh = 2 * kImgBytes;
-constexpr uint32_t kSmemSlot0 = kSmemATh + kTcM * 64;
-constexpr uint32_t kSlotBytes = 2 * kImgBytes + kHidden * 4;
-constexpr uint32_t kSmemBars = kSmemSlot0 + 2 * kSlotBytes;
-constexpr uint32_t kTcSmemBytes = kSmemBars + 64;
-static_assert(kTcSmemBytes <= 227 * 1024, "tile does not fit shared memory");
+constexpr uint32_t kAThBytes = kTcM * 64;        // theta-stage A image: 128 rows x 32 k
+constexpr uint32_t kSmemATh = 0;
+constexpr uint32_t kSmemSlot0 = kTcTiles * kAThBytes;
+constexpr uint32_t kSlotBytes = 2 * kImgBytes + kHidden * 4;   // largest blob; theta blobs are 8 KB + 2 biases
+constexpr uint32_t kSmemBars = kSmemSlot0 + kTcSlots * kSlotBytes;
+constexpr uint32_t kTcSmemBytes = kSmemBars + 128;
+static_assert(kTcSmemBytes <= 227 * 1024, "tiles do not fit shared memory");
+constexpr uint32_t kTmemD = 0, kTmemAHi = 128, kTmemALo = 192, kTmemTile = 256;  // columns
 
-// TMEM row of 32 fp32 accumulators + bias -> activation -> bf16 hi/lo images for the next GEMM
+// 64 accumulator columns + bias -> activation -> packed bf16 hi / lo columns of the A operand
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue_act(uint32_t taddr, int col0, const float *bias, unsigned char *a_hi,
-                                                unsigned char *a_lo, int r)
+__device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, const float *bias)
 {
 #pragma unroll 1
     for (int c0 = col0; c0 < col0 + 64; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
+        tmem_ld32(trow + kTmemD + (uint32_t)c0, v);
         tmem_wait_ld();
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const float4 b0 = *reinterpret_cast<const float4 *>(bias + c0 + 8 * g);
-            const float4 b1 = *reinterpret_cast<const float4 *>(bias + c0 + 8 * g + 4);
-            float f[8] = {__uint_as_float(v[8 * g + 0]) + b0.x, __uint_as_float(v[8 * g + 1]) + b0.y,
-                          __uint_as_float(v[8 * g + 2]) + b0.z, __uint_as_float(v[8 * g + 3]) + b0.w,
-                          __uint_as_float(v[8 * g + 4]) + b1.x, __uint_as_float(v[8 * g + 5]) + b1.y,
-                          __uint_as_float(v[8 * g + 6]) + b1.z, __uint_as_float(v[8 * g + 7]) + b1.w};
+        for (int g = 0; g < 8; ++g) {
+            const float4 b = *reinterpret_cast<const float4 *>(bias + c0 + 4 * g);
+            float f[4] = {__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                          __uint_as_float(v[4 * g + 3])};
+            add_f32x2(f[0], f[1], b.x, b.y);
+            add_f32x2(f[2], f[3], b.z, b.w);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 4; ++j)
                 f[j] = (EPI == kEpiRelu) ? fmaxf(f[j], 0.f) : 1.0f / (1.0f + expf(-f[j]));
-            uint4 hi, lo;
-            split_bf16x2(f[0], f[1], hi.x, lo.x);
-            split_bf16x2(f[2], f[3], hi.y, lo.y);
-            split_bf16x2(f[4], f[5], hi.z, lo.z);
-            split_bf16x2(f[6], f[7], hi.w, lo.w);
-            const uint32_t at = (uint32_t)((c0 >> 3) + g) * kKGroupBytes + (uint32_t)r * 16u;
-            *reinterpret_cast<uint4 *>(a_hi + at) = hi;
-            *reinterpret_cast<uint4 *>(a_lo + at) = lo;
+            split_bf16x2(f[0], f[1], hi[2 * g], lo[2 * g]);
+            split_bf16x2(f[2], f[3], hi[2 * g + 1], lo[2 * g + 1]);
         }
+        tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
+        tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
     }
+    tmem_wait_st();
 }
 
-// The spline of mnle_common.cuh with its 71 parameters in registers (fully unrolled).
-__device__ __forceinline__ void rqs_forward_reg(float &u, float &logdet, const float (&q)[kSplineN])
+// softmax -> bin widths (or heights) -> cumulative knots of one 24-bin block held in registers.
+// e[j] = exp((q[j] - max q) / sqrt(128)); returns the factor turning e[j] into its share of
+// (1 - 24 * min_bin).  Knot j+1 = 2 * tail * (sum_{i <= j} (min_bin + sc * e[i])) - tail.
+__device__ __forceinline__ float rqs_softmax(const uint32_t (&v)[kBins], const float *bias, float (&e)[kBins])
 {
-    if (!(u >= -kTail && u <= kTail)) return;
-    const float inv_sqrt_h = 0.08838834764831845f;
-    float e[kBins];
-    float m = q[0] * inv_sqrt_h;
+    const float c = 0.08838834764831845f * 1.4426950408889634f;  // log2(e) / sqrt(128)
+    float q[kBins];
 #pragma unroll
-    for (int j = 1; j < kBins; ++j) m = fmaxf(m, q[j] * inv_sqrt_h);
+    for (int j = 0; j < kBins; ++j) q[j] = __uint_as_float(v[j]) + bias[j];
+    float m = q[0];
+#pragma unroll
+    for (int j = 1; j < kBins; ++j) m = fmaxf(m, q[j]);
+    const float mc = m * c;
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
-        e[j] = __expf(q[j] * inv_sqrt_h - m);
+        e[j] = exp2f(fmaf(q[j], c, -mc));
         s += e[j];
     }
-    float sc = (1.0f - kMinBin * kBins) / s;
+    return (1.0f - kMinBin * kBins) / s;
+}
+
+// One spline transform of row `trow`: the 71 parameters are pulled from the accumulator columns in
+// three 24-column blocks (widths, derivatives, heights) so at most ~60 registers are live; the
+// tile's aready barrier is released as soon as the last block is in registers.
+__device__ __forceinline__ void tc_epilogue_spline(uint32_t trow, const float *bias, float &u, float &logdet,
+                                                   uint64_t *aready)
+{
+    uint32_t vw[kBins], vd[kBins];
+    tmem_ld_n<kBins>(trow + kTmemD, vw);
+    tmem_ld_n<kBins>(trow + kTmemD + 2 * kBins, vd);  // 23 derivatives + 1 padding column
+    tmem_wait_ld();
+    const bool inside = (u >= -kTail && u <= kTail);
+    float e[kBins];
+    float sc = rqs_softmax(vw, bias, e);
     float cs = 0.f, prev = -kTail, left = -kTail, right = kTail;
     int b = 0;
 #pragma unroll
@@ -306,16 +370,19 @@ __device__ __forceinline__ void rqs_forward_reg(float &u, float &logdet, const f
         }
         prev = edge;
     }
-    m = q[kBins] * inv_sqrt_h;
+    float r0 = 0.f, r1 = 0.f;
 #pragma unroll
-    for (int j = 1; j < kBins; ++j) m = fmaxf(m, q[kBins + j] * inv_sqrt_h);
-    s = 0.f;
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) {
-        e[j] = __expf(q[kBins + j] * inv_sqrt_h - m);
-        s += e[j];
+    for (int j = 0; j < kBins - 1; ++j) {
+        const float dj = __uint_as_float(vd[j]) + bias[2 * kBins + j];
+        if (j == b - 1) r0 = dj;
+        if (j == b) r1 = dj;
     }
-    sc = (1.0f - kMinBin * kBins) / s;
+    uint32_t vh[kBins];
+    tmem_ld_n<kBins>(trow + kTmemD + kBins, vh);
+    tmem_wait_ld();
+    tc_fence_before_sync();
+    mbar_arrive(aready);  // D is free: the next stage's MMA may start while the spline finishes
+    sc = rqs_softmax(vh, bias + kBins, e);
     cs = 0.f;
     prev = -kTail;
     float bottom = -kTail, top = kTail;
@@ -329,12 +396,7 @@ __device__ __forceinline__ void rqs_forward_reg(float &u, float &logdet, const f
         }
         prev = edge;
     }
-    float r0 = 0.f, r1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < kBins - 1; ++j) {
-        if (j == b - 1) r0 = q[2 * kBins + j];
-        if (j == b) r1 = q[2 * kBins + j];
-    }
+    if (!inside) return;  // identity outside the tail bound
     const float d0 = (b == 0) ? 1.0f : kMinDeriv + softplus_f(r0);
     const float d1 = (b == kBins - 1) ? 1.0f : kMinDeriv + softplus_f(r1);
     const float w = right - left, h = top - bottom;
@@ -348,28 +410,32 @@ __device__ __forceinline__ void rqs_forward_reg(float &u, float &logdet, const f
     u = out;
 }
 
-// grid = (ceil(C / 128), T): one CTA takes 128 chains of one trial through all 34 stages.
+// grid = ceil(T * ceil(C / 128) / 2): tile = t * CB + chain block (chain block fastest).
 __global__ void __launch_bounds__(kTcThreads, 1)
     mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
                    const float *__restrict__ theta, long long ld_theta, const float *__restrict__ x,
-                   const float *__restrict__ hoist, int C, float mu_y, float sigma_y, int n_choices,
+                   const float *__restrict__ hoist, int T, int C, float mu_y, float sigma_y, int n_choices,
                    float *__restrict__ partial)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *a_hi = smem + kSmemAHi, *a_lo = smem + kSmemALo, *a_th = smem + kSmemATh;
-    uint64_t *wfull = reinterpret_cast<uint64_t *>(smem + kSmemBars);  // [2]
-    uint64_t *dfull = wfull + 2, *aready = wfull + 3;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBars + 32);
+    uint64_t *wfull = reinterpret_cast<uint64_t *>(smem + kSmemBars);  // [kTcSlots]
+    uint64_t *dfull = wfull + kTcSlots;                                // [kTcTiles]
+    uint64_t *aready = dfull + kTcTiles;                               // [kTcTiles]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBars + 96);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t = blockIdx.y, c_first = blockIdx.x * kTcM;
+    const int CB = (C + kTcM - 1) / kTcM;
+    const int n_tiles = T * CB;
+    const int tile0 = blockIdx.x * kTcTiles;
+    const int n_active = min(kTcTiles, n_tiles - tile0);
 
-    if (warp == 8) tmem_alloc<128>(tmem_slot);
+    if (warp == kTcEpiWarps) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        mbar_init(&wfull[0], 1);
-        mbar_init(&wfull[1], 1);
-        mbar_init(dfull, 1);
-        mbar_init(aready, kTcEpiThreads);
+        for (int i = 0; i < kTcSlots; ++i) mbar_init(&wfull[i], 1);
+        for (int i = 0; i < kTcTiles; ++i) {
+            mbar_init(&dfull[i], 1);
+            mbar_init(&aready[i], kTcEpiThreads / kTcTiles);
+        }
         fence_mbar_init();
     }
     tc_fence_before_sync();
@@ -377,56 +443,70 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == kTcEpiWarps) {
         // ================= issuer: bulk copies of the stage blobs + every tcgen05.mma =========
-        if (lane == 0) {
-            auto load = [&](int s) {
-                const TcStage &st = plan.st[s];
-                unsigned char *slot = smem + kSmemSlot0 + (uint32_t)(s & 1) * kSlotBytes;
-                mbar_expect_tx(&wfull[s & 1], st.bytes + (st.k128 ? 0u : (uint32_t)kHidden * 4u));
-                bulk_g2s(slot, pack + st.off, st.bytes, &wfull[s & 1]);
+        // The whole warp walks the (uniform) stage loop; one elected lane issues.
+        const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
+        auto load = [&](int s) {
+            const TcStage &st = plan.st[s];
+            unsigned char *slot = smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes;
+            uint64_t *bar = &wfull[s % kTcSlots];
+            if (elect_one_sync()) {
+                mbar_expect_tx(bar, st.bytes + (st.k128 ? 0u : (uint32_t)n_active * kHidden * 4u));
+                bulk_g2s(slot, pack + st.off, st.bytes, bar);
                 if (!st.k128)
-                    bulk_g2s(slot + st.bytes, hoist + ((size_t)t * kNets + st.net) * kHidden, kHidden * 4,
-                             &wfull[s & 1]);
-            };
-            load(0);
+                    for (int X = 0; X < n_active; ++X)
+                        bulk_g2s(slot + st.bytes + X * kHidden * 4,
+                                 hoist + ((size_t)((tile0 + X) / CB) * kNets + st.net) * kHidden, kHidden * 4, bar);
+            }
+            __syncwarp();
+        };
+        load(0);
+        load(1);
 #pragma unroll 1
-            for (int s = 0; s < kTcStages; ++s) {
-                const TcStage &st = plan.st[s];
-                mbar_wait(aready, s & 1);  // A operand of this stage written, D drained
+        for (int s = 0; s < kTcStages; ++s) {
+            const TcStage &st = plan.st[s];
+            const uint32_t slot = smem_u32(smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes);
+            const uint32_t n = st.n, idesc = umma_idesc_bf16_f32(kTcM, (int)n);
+#pragma unroll 1
+            for (int X = 0; X < n_active; ++X) {
+                mbar_wait(&aready[X], s & 1);  // A operand of this stage written, D drained
                 tc_fence_after_sync();
-                if (s + 1 < kTcStages) load(s + 1);
-                mbar_wait(&wfull[s & 1], (s >> 1) & 1);
-                const uint32_t slot = smem_u32(smem + kSmemSlot0 + (uint32_t)(s & 1) * kSlotBytes);
-                const uint32_t n = st.n, idesc = umma_idesc_bf16_f32(kTcM, (int)n);
-                if (!st.k128) {
+                if (X == n_active - 1 && s + 2 < kTcStages) load(s + 2);  // slot of stage s-1 is free now
+                if (X == 0) mbar_wait(&wfull[s % kTcSlots], (s / kTcSlots) & 1);
+                const uint32_t tm = tmem_u + (uint32_t)X * kTmemTile;
+                if (elect_one_sync()) {
+                    if (!st.k128) {
+                        const uint32_t a = smem_u32(smem + kSmemATh + (uint32_t)X * kAThBytes);
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        umma_bf16(tmem, umma_desc_kmajor(smem_u32(a_th) + ks * 2 * kKGroupBytes, kKGroupBytes, 128),
-                                  umma_desc_kmajor(slot + ks * 2 * kKGroupBytes, kKGroupBytes, 128), idesc, ks);
-                } else {
-                    const uint32_t w_img = n * 256u, w_kg = n * 16u;
-#pragma unroll 1
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a = smem_u32(pass == 2 ? a_lo : a_hi);
-                        const uint32_t w = slot + (pass == 1 ? w_img : 0u);
+                        for (int ks = 0; ks < 2; ++ks)
+                            umma_bf16(tm + kTmemD, umma_desc_kmajor(a + ks * 2 * kKGroupBytes, kKGroupBytes, 128),
+                                      umma_desc_kmajor(slot + ks * 2 * kKGroupBytes, kKGroupBytes, 128), idesc, ks);
+                    } else {
+                        const uint32_t w_img = n * 256u, w_kg = n * 16u;
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            umma_bf16(tmem, umma_desc_kmajor(a + ks * 2 * kKGroupBytes, kKGroupBytes, 128),
-                                      umma_desc_kmajor(w + ks * 2 * w_kg, w_kg, 128), idesc, (pass | ks) != 0);
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t a = tm + (pass == 2 ? kTmemALo : kTmemAHi);
+                            const uint32_t w = slot + (pass == 1 ? w_img : 0u);
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks)
+                                umma_bf16_ts(tm + kTmemD, a + (uint32_t)ks * 8u,
+                                             umma_desc_kmajor(w + ks * 2 * w_kg, w_kg, 128), idesc, (pass | ks) != 0);
+                        }
                     }
+                    umma_commit(&dfull[X]);
                 }
-                umma_commit(dfull);
+                __syncwarp();
             }
         }
-        __syncwarp();
-    } else {
-        // ================= epilogue warps: lane quarter q, column half hf ======================
-        const int q = warp & 3, hf = warp >> 2, r = 32 * q + lane;
-        const int c = c_first + r;
+    } else if (((warp >> 2) & 1) < n_active) {
+        // ====== epilogue warps: tile X, lane quarter q (thread = row), column half hf ==========
+        const int X = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3, r = 32 * q + lane;
+        const int tile = tile0 + X, t = tile / CB, c = (tile - t * CB) * kTcM + r;
         const bool live = c < C;
-        const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16);
+        const uint32_t trow = tmem + (uint32_t)X * kTmemTile + ((uint32_t)(32 * q) << 16);
         {   // A image of the theta stage: k = term * 5 + i, terms t1 t1 t2 t1 t2 t3 (pairs with pack_image_theta)
+            unsigned char *a_th = smem + kSmemATh + (uint32_t)X * kAThBytes;
             uint16_t tt[5][3];
 #pragma unroll
             for (int i = 0; i < 5; ++i) split3_bf16(live ? __ldg(theta + (long long)c * ld_theta + i) : 0.f, tt[i]);
@@ -446,7 +526,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
         }
         fence_proxy_async_smem();
-        mbar_arrive(aready);
+        mbar_arrive(&aready[X]);
 
         const float rt = __ldg(x + 2 * t);
         const int choice = (int)__ldg(x + 2 * t + 1);
@@ -456,64 +536,53 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll 1
         for (int s = 0; s < kTcStages; ++s) {
             const TcStage &st = plan.st[s];
-            mbar_wait(dfull, s & 1);
-            tc_fence_after_sync();
-            mbar_wait(&wfull[s & 1], (s >> 1) & 1);  // the bias travelled with the stage blob
-            const float *bias =
-                reinterpret_cast<const float *>(smem + kSmemSlot0 + (uint32_t)(s & 1) * kSlotBytes + st.bias_off);
-            if (st.epi == kEpiRelu) {
-                tc_epilogue_act<kEpiRelu>(taddr, 64 * hf, bias, a_hi, a_lo, r);
-            } else if (st.epi == kEpiSigmoid) {
-                tc_epilogue_act<kEpiSigmoid>(taddr, 64 * hf, bias, a_hi, a_lo, r);
-            } else if (hf == 0) {
-                if (st.epi == kEpiSpline) {
-                    uint32_t v0[32], v1[32], v2[16];
-                    tmem_ld32(taddr, v0);
-                    tmem_ld32(taddr + 32u, v1);
-                    tmem_ld16(taddr + 64u, v2);
-                    tmem_wait_ld();
-                    float qv[kSplineN];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        qv[j] = __uint_as_float(v0[j]) + bias[j];
-                        qv[32 + j] = __uint_as_float(v1[j]) + bias[32 + j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) qv[64 + j] = __uint_as_float(v2[j]) + bias[64 + j];
-                    rqs_forward_reg(u, logdet, qv);
-                } else {
-                    uint32_t v[16];
-                    tmem_ld16(taddr, v);
-                    tmem_wait_ld();
-                    float lg[kMaxChoices];
-#pragma unroll
-                    for (int j = 0; j < kMaxChoices; ++j) lg[j] = __uint_as_float(v[j]) + bias[j];
-                    float m = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < kMaxChoices; ++j)
-                        if (j < n_choices) m = fmaxf(m, lg[j]);
-                    float sum = 0.f, pc = 0.f;
-#pragma unroll
-                    for (int j = 0; j < kMaxChoices; ++j)
-                        if (j < n_choices) {
-                            const float ex = expf(lg[j] - m);
-                            sum += ex;
-                            if (j == choice) pc = ex;
-                        }
-                    const float eps = 1.1920928955078125e-07f;
-                    lp = logf(fminf(fmaxf(pc / sum, eps), 1.0f - eps));
-                }
+            if (st.epi >= kEpiSpline && hf != 0) {  // row-wise epilogues are done by the hf = 0 thread of the row
+                mbar_wait(&dfull[X], s & 1);        // (never arrive twice within one phase of aready)
+                mbar_arrive(&aready[X]);
+                continue;
             }
-            fence_proxy_async_smem();
+            mbar_wait(&wfull[s % kTcSlots], (s / kTcSlots) & 1);  // the bias travelled with the stage blob
+            const float *bias = reinterpret_cast<const float *>(smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes +
+                                                                st.bias_off + (st.k128 ? 0u : (uint32_t)X * kHidden * 4u));
+            mbar_wait(&dfull[X], s & 1);
+            tc_fence_after_sync();
+            if (st.epi == kEpiRelu) {
+                tc_epilogue_act<kEpiRelu>(trow, 64 * hf, bias);
+            } else if (st.epi == kEpiSigmoid) {
+                tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, bias);
+            } else if (st.epi == kEpiSpline) {
+                tc_epilogue_spline(trow, bias, u, logdet, &aready[X]);
+                continue;
+            } else {
+                uint32_t v[16];
+                tmem_ld16(trow + kTmemD, v);
+                tmem_wait_ld();
+                float lg[kMaxChoices];
+#pragma unroll
+                for (int j = 0; j < kMaxChoices; ++j) lg[j] = __uint_as_float(v[j]) + bias[j];
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < kMaxChoices; ++j)
+                    if (j < n_choices) m = fmaxf(m, lg[j]);
+                float sum = 0.f, pc = 0.f;
+#pragma unroll
+                for (int j = 0; j < kMaxChoices; ++j)
+                    if (j < n_choices) {
+                        const float ex = expf(lg[j] - m);
+                        sum += ex;
+                        if (j == choice) pc = ex;
+                    }
+                const float eps = 1.1920928955078125e-07f;
+                lp = logf(fminf(fmaxf(pc / sum, eps), 1.0f - eps));
+            }
             tc_fence_before_sync();
-            mbar_arrive(aready);
+            mbar_arrive(&aready[X]);
         }
-        if (hf == 0 && live)
-            partial[(size_t)t * C + c] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+        if (hf == 0 && live) partial[(size_t)t * C + c] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<128>(tmem);
+    if (warp == kTcEpiWarps) tmem_dealloc<512>(tmem);
 }
 
 // out[c] = sum_t partial[t][c], fixed order
@@ -535,7 +604,8 @@ DDM_API int mnle_tc_selftest(const float *a_dev, const float *b_dev, int N, int 
 {
     DDM_REQUIRE(a_dev && b_dev && d_dev, "mnle_tc_selftest: null pointer");
     DDM_REQUIRE(N >= 16 && N <= 128 && N % 16 == 0, "mnle_tc_selftest: N=%d must be a multiple of 16 in [16,128]", N);
-    DDM_REQUIRE(passes == 1 || passes == 3, "mnle_tc_selftest: passes must be 1 or 3");
+    DDM_REQUIRE(passes == 1 || passes == 3 || passes == 11 || passes == 13 || (passes > 100 && passes < 300),
+                "mnle_tc_selftest: passes must be 1 or 3 (+10: A operand from TMEM; 100 + r / 200 + r: timing probe)");
     const int smem = 131072 + 64;
     DDM_CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     tc_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a_dev, b_dev, N, passes, lbo_a, lbo_b, sbo, d_dev);
@@ -576,9 +646,11 @@ DDM_API int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t
     mnle_hoist_kernel<<<dim3((unsigned)T, kNets), kHidden, 0, st>>>(H->params, H->layout, x_dev, pulses_dev, ld_pulses, hoist);
     DDM_CUDA_TRY(cudaGetLastError());
     DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    mnle_tc_kernel<<<dim3((unsigned)((C + kTcM - 1) / kTcM), (unsigned)T), kTcThreads, kTcSmemBytes, st>>>(
-        static_cast<const unsigned char *>(H->tc_pack), H->tc_plan, theta_dev, ld_theta, x_dev, hoist, (int)C, H->mu_y,
-        H->sigma_y, H->layout.n_choices, partial);
+    const long long n_tiles = (long long)T * ((C + kTcM - 1) / kTcM);
+    DDM_REQUIRE(n_tiles <= 0x7FFFFFFFll, "mnle_loglik_sum_tc: T * ceil(C / 128) = %lld tiles is too many", n_tiles);
+    mnle_tc_kernel<<<(unsigned)((n_tiles + kTcTiles - 1) / kTcTiles), kTcThreads, kTcSmemBytes, st>>>(
+        static_cast<const unsigned char *>(H->tc_pack), H->tc_plan, theta_dev, ld_theta, x_dev, hoist, (int)T, (int)C,
+        H->mu_y, H->sigma_y, H->layout.n_choices, partial);
     DDM_CUDA_TRY(cudaGetLastError());
     tc_reduce_trials_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(partial, (int)T, (int)C, out_dev);
     DDM_CUDA_TRY(cudaGetLastError());

@@ -13,6 +13,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp (the code around it stays warp-uniform, so descriptors live in
+// uniform registers and every tcgen05.mma / bulk copy is a single straight-line instruction).
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "@p mov.u32 %0, 1;\n\t"
+        "}\n"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -104,6 +119,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16])
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr)
+                 : "memory");
+}
+// N = 24 consecutive columns (x16 + x8)
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t addr, uint32_t (&r)[N])
+{
+    static_assert(N == 24, "only the 24-column form is used");
+    uint32_t a[16];
+    tmem_ld16(addr, a);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = a[j];
+    tmem_ld8(addr + 16u, r + 16);
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 consecutive 32-bit columns: thread l of the warp writes lane (base_lane + l)
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
 // ---- UMMA ----------------------------------------------------------------------------------
 // Shared-memory operand descriptor, K-major, no swizzle ("interleaved" canonical layout): in
 // 16-byte units the tile is ((8, n), 2) : ((1, SBO), LBO) -- 8 rows of one core matrix are
@@ -141,6 +186,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T : A = 128 lanes x (K/2) packed bf16x2 columns (row r in lane r,
+// k = 2j, 2j+1 in column j, low half first)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // mbarrier arrives when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
@@ -158,12 +217,27 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t &hi, uint16_t &lo)
     lo = __bfloat16_as_ushort(l);
 }
 
-// Two floats -> packed bf16 hi pair and packed bf16 lo pair (one cvt.rn.bf16x2 each).
+// Packed fp32 pair add (Blackwell FADD2): (a0, a1) += (b0, b1)
+__device__ __forceinline__ void add_f32x2(float &a0, float &a1, float b0, float b1)
+{
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%0, %1};\n\t"
+        "mov.b64 rb, {%2, %3};\n\t"
+        "add.rn.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t"
+        "}\n"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+// Two floats -> packed bf16 hi pair and packed bf16 lo pair: x = hi + lo + O(2^-18 |x|).
+// 2 F2FP + 2 unpack + 1 FADD2 per pair.
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi, uint32_t &lo)
 {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __low2float(h), x1 - __high2float(h));
     hi = *reinterpret_cast<const uint32_t *>(&h);
+    add_f32x2(x0, x1, -__uint_as_float(hi << 16), -__uint_as_float(hi & 0xFFFF0000u));
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0, x1);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 // x = t0 + t1 + t2 + O(2^-25 |x|)

@@ -14,6 +14,6 @@ def run(N, passes, lbo_a=0, lbo_b=0, sbo=0):
     refbf = A.bfloat16().double() @ B.bfloat16().double().T
     return rc, (D.double() - ref64).abs().max().item(), (D.double() - refbf).abs().max().item()
 for N in (128, 80, 16):
-    for passes in (1, 3):
+    for passes in (1, 3, 11, 13):
         print("N", N, "passes", passes, "rc, err_vs_fp64, err_vs_bf16prod:", run(N, passes))
 print("swapped lbo/sbo:", run(128, 1, lbo_a=128, lbo_b=128, sbo=2048))
