@@ -208,6 +208,11 @@ int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t ld_thet
                            const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
                            float *out_dev, float *workspace_dev, void *stream);
 
+/* Debug aid: when trace_dev != NULL, CTA 0 of every following mnle_loglik_sum_tc_f32 launch writes
+ * 34 stages x 2 tiles x 4 clock64() stamps there (issuer saw A operand / had the weights, epilogue
+ * saw the accumulators / finished).  NULL switches it off (the default). */
+int mnle_tc_set_trace(long long *trace_dev);
+
 /* Tensor-core building-block check: D (128,N) = A (128,128) * B (N,128)^T through the smem
  * operand layout, UMMA descriptors, tcgen05.mma and TMEM loads of the fused kernel.
  * passes = 1: bf16(A) bf16(B); passes = 3: bf16 hi/lo split (near-fp32).  lbo_a / lbo_b / sbo = 0

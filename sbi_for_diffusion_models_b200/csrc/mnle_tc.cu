@@ -252,21 +252,48 @@ int build_tc_pack(Handle *H, const float *packed_host)
 // ---------------------------------------------------------------- per-trial first layer ---
 // hoist[t][net][j] = b1[j] + sum_i W1[j][5 + i] * pulses[t][i] (+ W1[j][85] * choice[t] for the
 // spline conditioners): the part of every first layer that does not depend on the chain.
+// grid = (nets, ceil(T / 8)): the 128 x 81 weight block is staged in shared memory once per block
+// and reused for 8 trials.  Block (0, 0) also clears the per-chain-block arrival counters of the
+// fused kernel's final reduction.
+constexpr int kHoistTrials = 8;
+constexpr int kHoistK = kCtx - 5;  // 81
 __global__ void __launch_bounds__(kHidden) mnle_hoist_kernel(const float *__restrict__ params, Layout L,
                                                             const float *__restrict__ x,
-                                                            const float *__restrict__ pulses, long long ld_pulses,
-                                                            float *__restrict__ hoist)
+                                                            const float *__restrict__ pulses, long long ld_pulses, int T,
+                                                            float *__restrict__ hoist, unsigned int *__restrict__ counters,
+                                                            int n_counters)
 {
-    __shared__ float in_s[kCtx - 5];
-    const int t = blockIdx.x, net = blockIdx.y, j = threadIdx.x;
-    if (j < kCond - 5) in_s[j] = __ldg(pulses + (long long)t * ld_pulses + j);
-    if (j == kCond - 5) in_s[j] = __ldg(x + 2 * t + 1);
-    __syncthreads();
+    __shared__ float w_s[kHidden * kHoistK];
+    __shared__ float in_s[kHoistTrials][kHoistK + 3];
+    const int net = blockIdx.x, t0 = blockIdx.y * kHoistTrials, j = threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+        for (int i = j; i < n_counters; i += kHidden) counters[i] = 0u;
     const int K = net == 0 ? kCond : kCtx;
-    const float *W = params + (net == 0 ? L.cat_W0 : L.fl_W1[net - 1]) + (size_t)j * K + 5;
-    float acc = __ldg(params + (net == 0 ? L.cat_b0 : L.fl_b1[net - 1]) + j);
-    for (int i = 0; i < K - 5; ++i) acc = fmaf(__ldg(W + i), in_s[i], acc);
-    hoist[((size_t)t * kNets + net) * kHidden + j] = acc;
+    const float *W = params + (net == 0 ? L.cat_W0 : L.fl_W1[net - 1]);
+    for (int idx = j; idx < kHidden * kHoistK; idx += kHidden) {
+        const int row = idx / kHoistK, i = idx - row * kHoistK;
+        w_s[idx] = (5 + i < K) ? __ldg(W + (size_t)row * K + 5 + i) : 0.f;
+    }
+    for (int idx = j; idx < kHoistTrials * kHoistK; idx += kHidden) {
+        const int tr = idx / kHoistK, i = idx - tr * kHoistK, t = t0 + tr;
+        float v = 0.f;
+        if (t < T) v = (i < kCond - 5) ? __ldg(pulses + (long long)t * ld_pulses + i) : __ldg(x + 2 * t + 1);
+        in_s[tr][i] = v;
+    }
+    __syncthreads();
+    const float b = __ldg(params + (net == 0 ? L.cat_b0 : L.fl_b1[net - 1]) + j);
+    float acc[kHoistTrials];
+#pragma unroll
+    for (int tr = 0; tr < kHoistTrials; ++tr) acc[tr] = b;
+#pragma unroll 3
+    for (int i = 0; i < kHoistK; ++i) {
+        const float w = w_s[j * kHoistK + i];
+#pragma unroll
+        for (int tr = 0; tr < kHoistTrials; ++tr) acc[tr] = fmaf(w, in_s[tr][i], acc[tr]);
+    }
+#pragma unroll
+    for (int tr = 0; tr < kHoistTrials; ++tr)
+        if (t0 + tr < T) hoist[((size_t)(t0 + tr) * kNets + net) * kHidden + j] = acc[tr];
 }
 
 // ------------------------------------------------------------------------ fused kernel ---
@@ -293,7 +320,9 @@ constexpr uint32_t kTcSmemBytes = kSmemBars + 128;
 static_assert(kTcSmemBytes <= 227 * 1024, "tiles do not fit shared memory");
 constexpr uint32_t kTmemD = 0, kTmemAHi = 128, kTmemALo = 192, kTmemTile = 256;  // columns
 
-// 64 accumulator columns + bias -> activation -> packed bf16 hi / lo columns of the A operand
+// 64 accumulator columns + bias -> activation -> packed bf16 hi / lo columns of the A operand.
+// The CUDA-core side of this kernel is bound by the half-rate ALU pipe (min/max, selects,
+// conversions, logic), so the arithmetic is phrased for the FMA pipe wherever possible.
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, const float *bias)
 {
@@ -310,11 +339,12 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, const f
                           __uint_as_float(v[4 * g + 3])};
             add_f32x2(f[0], f[1], b.x, b.y);
             add_f32x2(f[2], f[3], b.z, b.w);
+            if (EPI == kEpiSigmoid) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                f[j] = (EPI == kEpiRelu) ? fmaxf(f[j], 0.f) : 1.0f / (1.0f + expf(-f[j]));
-            split_bf16x2(f[0], f[1], hi[2 * g], lo[2 * g]);
-            split_bf16x2(f[2], f[3], hi[2 * g + 1], lo[2 * g + 1]);
+                for (int j = 0; j < 4; ++j) f[j] = fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * f[j]));
+            }
+            split_relu_bf16x2(f[0], f[1], hi[2 * g], lo[2 * g]);
+            split_relu_bf16x2(f[2], f[3], hi[2 * g + 1], lo[2 * g + 1]);
         }
         tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
         tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
@@ -322,31 +352,35 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, const f
     tmem_wait_st();
 }
 
-// softmax -> bin widths (or heights) -> cumulative knots of one 24-bin block held in registers.
-// e[j] = exp((q[j] - max q) / sqrt(128)); returns the factor turning e[j] into its share of
-// (1 - 24 * min_bin).  Knot j+1 = 2 * tail * (sum_{i <= j} (min_bin + sc * e[i])) - tail.
+// softmax numerators of one 24-bin block held in registers: e[j] = exp((q[j] - max q) / sqrt(128));
+// returns 1 / sum e.
 __device__ __forceinline__ float rqs_softmax(const uint32_t (&v)[kBins], const float *bias, float (&e)[kBins])
 {
     const float c = 0.08838834764831845f * 1.4426950408889634f;  // log2(e) / sqrt(128)
     float q[kBins];
 #pragma unroll
     for (int j = 0; j < kBins; ++j) q[j] = __uint_as_float(v[j]) + bias[j];
-    float m = q[0];
+    float m = fmaxf(fmaxf(q[0], q[1]), q[2]);
 #pragma unroll
-    for (int j = 1; j < kBins; ++j) m = fmaxf(m, q[j]);
+    for (int j = 3; j < kBins; j += 3) m = fmaxf(fmaxf(m, q[j]), fmaxf(q[j + 1], q[j + 2]));
     const float mc = m * c;
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < kBins; ++j) {
-        e[j] = exp2f(fmaf(q[j], c, -mc));
-        s += e[j];
+    for (int j = 0; j < kBins; j += 2) {
+        e[j] = fast_ex2(fmaf(q[j], c, -mc));
+        e[j + 1] = fast_ex2(fmaf(q[j + 1], c, -mc));
+        s0 += e[j];
+        s1 += e[j + 1];
     }
-    return (1.0f - kMinBin * kBins) / s;
+    return fast_rcp(s0 + s1);
 }
 
-// One spline transform of row `trow`: the 71 parameters are pulled from the accumulator columns in
-// three 24-column blocks (widths, derivatives, heights) so at most ~60 registers are live; the
-// tile's aready barrier is released as soon as the last block is in registers.
+// One rational-quadratic spline transform (Durkan et al. 2019, linear tails) of row `trow`.
+// The 71 parameters are pulled from the accumulator columns in three 24-column blocks (widths,
+// derivatives, heights).  The bin is located without selects: p_j = [u >= knot_j] (one FSET per
+// knot) gives the one-hot ind_j = p_j - p_{j+1}, and every per-bin quantity is a dot product with
+// ind on the FMA pipe (exact: ind is 0 or 1).  The tile's aready barrier is released as soon as
+// the last block is in registers.
 __device__ __forceinline__ void tc_epilogue_spline(uint32_t trow, const float *bias, float &u, float &logdet,
                                                    uint64_t *aready)
 {
@@ -355,59 +389,61 @@ __device__ __forceinline__ void tc_epilogue_spline(uint32_t trow, const float *b
     tmem_ld_n<kBins>(trow + kTmemD + 2 * kBins, vd);  // 23 derivatives + 1 padding column
     tmem_wait_ld();
     const bool inside = (u >= -kTail && u <= kTail);
-    float e[kBins];
-    float sc = rqs_softmax(vw, bias, e);
-    float cs = 0.f, prev = -kTail, left = -kTail, right = kTail;
-    int b = 0;
+    const float uc = fminf(fmaxf(u, -kTail), kTail);  // (outside rows are computed and discarded)
+    float e[kBins], ind[kBins];
+    const float span = 2.0f * kTail * (1.0f - kMinBin * kBins), floor20 = 2.0f * kTail * kMinBin;
+    float sc = span * rqs_softmax(vw, bias, e);
+    float knot = -kTail, pprev = 1.0f, left = 0.f, wid = 0.f;
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
-        cs += kMinBin + sc * e[j];
-        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
-        if (u >= prev) {
-            b = j;
-            left = prev;
-            right = edge;
-        }
-        prev = edge;
+        const float w20 = (j == kBins - 1) ? kTail - knot : fmaf(sc, e[j], floor20);
+        const float next = (j == kBins - 1) ? kTail : knot + w20;
+        const float pnext = (j == kBins - 1) ? 0.0f : (uc >= next ? 1.0f : 0.0f);
+        ind[j] = pprev - pnext;
+        left = fmaf(ind[j], knot, left);
+        wid = fmaf(ind[j], w20, wid);
+        pprev = pnext;
+        knot = next;
     }
-    float r0 = 0.f, r1 = 0.f;
+    float r0 = 0.f, r1 = 0.f;  // derivative logits at the bin's two knots (interior knots only)
 #pragma unroll
     for (int j = 0; j < kBins - 1; ++j) {
         const float dj = __uint_as_float(vd[j]) + bias[2 * kBins + j];
-        if (j == b - 1) r0 = dj;
-        if (j == b) r1 = dj;
+        r0 = fmaf(ind[j + 1], dj, r0);
+        r1 = fmaf(ind[j], dj, r1);
     }
     uint32_t vh[kBins];
     tmem_ld_n<kBins>(trow + kTmemD + kBins, vh);
     tmem_wait_ld();
     tc_fence_before_sync();
     mbar_arrive(aready);  // D is free: the next stage's MMA may start while the spline finishes
-    sc = rqs_softmax(vh, bias + kBins, e);
-    cs = 0.f;
-    prev = -kTail;
-    float bottom = -kTail, top = kTail;
+    sc = span * rqs_softmax(vh, bias + kBins, e);
+    knot = -kTail;
+    float bottom = 0.f, hgt = 0.f;
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
-        cs += kMinBin + sc * e[j];
-        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
-        if (j == b) {
-            bottom = prev;
-            top = edge;
-        }
-        prev = edge;
+        const float h20 = (j == kBins - 1) ? kTail - knot : fmaf(sc, e[j], floor20);
+        bottom = fmaf(ind[j], knot, bottom);
+        hgt = fmaf(ind[j], h20, hgt);
+        knot += h20;
     }
     if (!inside) return;  // identity outside the tail bound
-    const float d0 = (b == 0) ? 1.0f : kMinDeriv + softplus_f(r0);
-    const float d1 = (b == kBins - 1) ? 1.0f : kMinDeriv + softplus_f(r1);
-    const float w = right - left, h = top - bottom;
-    const float delta = h / w;
-    const float th = (u - left) / w;
-    const float t1 = th * (1.0f - th);
-    const float den = delta + (d0 + d1 - 2.0f * delta) * t1;
-    const float out = bottom + h * (delta * th * th + d0 * t1) / den;
-    const float dnum = delta * delta * (d1 * th * th + 2.0f * delta * t1 + d0 * (1.0f - th) * (1.0f - th));
-    logdet += logf(dnum) - 2.0f * logf(den);
-    u = out;
+    // softplus(r) = log(1 + exp(r)); the boundary knots have derivative exactly 1
+    const float l2e = 1.4426950408889634f, ln2 = 0.6931471805599453f;
+    const float sp0 = r0 > 20.0f ? r0 : ln2 * fast_lg2(1.0f + fast_ex2(r0 * l2e));
+    const float sp1 = r1 > 20.0f ? r1 : ln2 * fast_lg2(1.0f + fast_ex2(r1 * l2e));
+    const float d0 = ind[0] > 0.5f ? 1.0f : kMinDeriv + sp0;
+    const float d1 = ind[kBins - 1] > 0.5f ? 1.0f : kMinDeriv + sp1;
+    const float rw = fast_rcp(wid);
+    const float delta = hgt * rw;
+    const float th = (uc - left) * rw;
+    const float om = 1.0f - th;
+    const float t1 = th * om;
+    const float den = fmaf(d0 + d1 - 2.0f * delta, t1, delta);
+    const float rden = fast_rcp(den);
+    const float dnum = delta * delta * (d1 * th * th + 2.0f * delta * t1 + d0 * om * om);
+    logdet = fmaf(ln2, fast_lg2(dnum * rden * rden), logdet);
+    u = fmaf(hgt * (delta * th * th + d0 * t1), rden, bottom);
 }
 
 // grid = ceil(T * ceil(C / 128) / 2): tile = t * CB + chain block (chain block fastest).
@@ -415,7 +451,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
                    const float *__restrict__ theta, long long ld_theta, const float *__restrict__ x,
                    const float *__restrict__ hoist, int T, int C, float mu_y, float sigma_y, int n_choices,
-                   float *__restrict__ partial)
+                   float *__restrict__ partial, unsigned int *__restrict__ counters, float *__restrict__ out,
+                   long long *__restrict__ trace)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *wfull = reinterpret_cast<uint64_t *>(smem + kSmemBars);  // [kTcSlots]
@@ -447,6 +484,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // ================= issuer: bulk copies of the stage blobs + every tcgen05.mma =========
         // The whole warp walks the (uniform) stage loop; one elected lane issues.
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
+        const int t_of[2] = {tile0 / CB, (tile0 + 1) / CB};
         auto load = [&](int s) {
             const TcStage &st = plan.st[s];
             unsigned char *slot = smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes;
@@ -454,10 +492,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (elect_one_sync()) {
                 mbar_expect_tx(bar, st.bytes + (st.k128 ? 0u : (uint32_t)n_active * kHidden * 4u));
                 bulk_g2s(slot, pack + st.off, st.bytes, bar);
-                if (!st.k128)
-                    for (int X = 0; X < n_active; ++X)
-                        bulk_g2s(slot + st.bytes + X * kHidden * 4,
-                                 hoist + ((size_t)((tile0 + X) / CB) * kNets + st.net) * kHidden, kHidden * 4, bar);
+                if (!st.k128) {
+                    bulk_g2s(slot + st.bytes, hoist + ((size_t)t_of[0] * kNets + st.net) * kHidden, kHidden * 4, bar);
+                    if (n_active > 1)
+                        bulk_g2s(slot + st.bytes + kHidden * 4, hoist + ((size_t)t_of[1] * kNets + st.net) * kHidden,
+                                 kHidden * 4, bar);
+                }
             }
             __syncwarp();
         };
@@ -472,8 +512,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int X = 0; X < n_active; ++X) {
                 mbar_wait(&aready[X], s & 1);  // A operand of this stage written, D drained
                 tc_fence_after_sync();
-                if (X == n_active - 1 && s + 2 < kTcStages) load(s + 2);  // slot of stage s-1 is free now
+                if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 4 + 0] = clock64();
                 if (X == 0) mbar_wait(&wfull[s % kTcSlots], (s / kTcSlots) & 1);
+                if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 4 + 1] = clock64();
                 const uint32_t tm = tmem_u + (uint32_t)X * kTmemTile;
                 if (elect_one_sync()) {
                     if (!st.k128) {
@@ -497,6 +538,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     umma_commit(&dfull[X]);
                 }
                 __syncwarp();
+                // every tile is past stage s-1, so its slot can take stage s+2 (issued after the
+                // MMAs: the copy has a whole stage of slack, the MMA issue is on the critical path)
+                if (X == n_active - 1 && s + 2 < kTcStages) load(s + 2);
             }
         }
     } else if (((warp >> 2) & 1) < n_active) {
@@ -546,12 +590,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                                                                 st.bias_off + (st.k128 ? 0u : (uint32_t)X * kHidden * 4u));
             mbar_wait(&dfull[X], s & 1);
             tc_fence_after_sync();
+            if (trace && blockIdx.x == 0 && q == 0 && hf == 0 && lane == 0) trace[(s * 2 + X) * 4 + 2] = clock64();
             if (st.epi == kEpiRelu) {
                 tc_epilogue_act<kEpiRelu>(trow, 64 * hf, bias);
             } else if (st.epi == kEpiSigmoid) {
                 tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, bias);
             } else if (st.epi == kEpiSpline) {
                 tc_epilogue_spline(trow, bias, u, logdet, &aready[X]);
+                if (trace && blockIdx.x == 0 && q == 0 && lane == 0) trace[(s * 2 + X) * 4 + 3] = clock64();
                 continue;
             } else {
                 uint32_t v[16];
@@ -577,22 +623,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             tc_fence_before_sync();
             mbar_arrive(&aready[X]);
+            if (trace && blockIdx.x == 0 && q == 0 && hf == 0 && lane == 0) trace[(s * 2 + X) * 4 + 3] = clock64();
         }
-        if (hf == 0 && live) partial[(size_t)t * C + c] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+        if (hf == 0) {
+            // ---- sum over trials, fixed order: the tile that arrives last at its chain block adds
+            // the T partial rows (every run gives the same bits whichever tile that is)
+            if (live) partial[(size_t)t * C + c] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+            uint32_t *last_s = tmem_slot + 1 + X;
+            __threadfence();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + X) : "memory");
+            if (q == 0 && lane == 0) *last_s = (atomicAdd(&counters[tile - t * CB], 1u) == (unsigned)(T - 1));
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + X) : "memory");
+            if (*last_s && live) {
+                __threadfence();
+                float sum = 0.f;
+#pragma unroll 10
+                for (int tt = 0; tt < T; ++tt) sum += __ldcg(partial + (size_t)tt * C + c);
+                out[c] = sum;
+            }
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kTcEpiWarps) tmem_dealloc<512>(tmem);
-}
-
-// out[c] = sum_t partial[t][c], fixed order
-__global__ void tc_reduce_trials_kernel(const float *__restrict__ partial, int T, int C, float *__restrict__ out)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float s = 0.f;
-    for (int t = 0; t < T; ++t) s += partial[(size_t)t * C + c];
-    out[c] = s;
 }
 
 }  // namespace mnle
@@ -613,10 +666,20 @@ DDM_API int mnle_tc_selftest(const float *a_dev, const float *b_dev, int N, int 
     return DDM_OK;
 }
 
+// Debug aid (tools/trace_mnle_tc.py): device buffer of kTcStages * 2 * 4 clock64 stamps written by
+// CTA 0 -- per (stage, tile): issuer saw the A operand, issuer had the weights, epilogue saw the
+// accumulators, epilogue finished.  nullptr (default) = off.
+static long long *g_tc_trace = nullptr;
+DDM_API int mnle_tc_set_trace(long long *trace_dev)
+{
+    g_tc_trace = trace_dev;
+    return DDM_OK;
+}
+
 DDM_API size_t mnle_loglik_tc_workspace_floats(int64_t T, int64_t C)
 {
     if (T <= 0 || C <= 0) return 0;
-    return (size_t)T * kNets * kHidden + (size_t)T * (size_t)C;
+    return (size_t)T * kNets * kHidden + (size_t)T * (size_t)C + (size_t)((C + kTcM - 1) / kTcM);
 }
 
 DDM_API int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
@@ -641,18 +704,19 @@ DDM_API int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t
     DDM_REQUIRE(ld_theta >= 5 && ld_pulses >= kCond - 5, "mnle_loglik_sum_tc: ld_theta=%lld ld_pulses=%lld too small",
                 (long long)ld_theta, (long long)ld_pulses);
     DDM_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 15u) == 0, "mnle_loglik_sum_tc: workspace must be 16-byte aligned");
+    const int CB = (int)((C + kTcM - 1) / kTcM);
     float *hoist = workspace_dev;
-    float *partial = workspace_dev + (size_t)T * kNets * kHidden;
-    mnle_hoist_kernel<<<dim3((unsigned)T, kNets), kHidden, 0, st>>>(H->params, H->layout, x_dev, pulses_dev, ld_pulses, hoist);
+    float *partial = hoist + (size_t)T * kNets * kHidden;
+    unsigned int *counters = reinterpret_cast<unsigned int *>(partial + (size_t)T * (size_t)C);
+    mnle_hoist_kernel<<<dim3(kNets, (unsigned)((T + kHoistTrials - 1) / kHoistTrials)), kHidden, 0, st>>>(
+        H->params, H->layout, x_dev, pulses_dev, ld_pulses, (int)T, hoist, counters, CB);
     DDM_CUDA_TRY(cudaGetLastError());
     DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    const long long n_tiles = (long long)T * ((C + kTcM - 1) / kTcM);
+    const long long n_tiles = (long long)T * CB;
     DDM_REQUIRE(n_tiles <= 0x7FFFFFFFll, "mnle_loglik_sum_tc: T * ceil(C / 128) = %lld tiles is too many", n_tiles);
     mnle_tc_kernel<<<(unsigned)((n_tiles + kTcTiles - 1) / kTcTiles), kTcThreads, kTcSmemBytes, st>>>(
         static_cast<const unsigned char *>(H->tc_pack), H->tc_plan, theta_dev, ld_theta, x_dev, hoist, (int)T, (int)C,
-        H->mu_y, H->sigma_y, H->layout.n_choices, partial);
-    DDM_CUDA_TRY(cudaGetLastError());
-    tc_reduce_trials_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(partial, (int)T, (int)C, out_dev);
+        H->mu_y, H->sigma_y, H->layout.n_choices, partial, counters, out_dev, g_tc_trace);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }

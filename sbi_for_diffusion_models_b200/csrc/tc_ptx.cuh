@@ -231,7 +231,6 @@ __device__ __forceinline__ void add_f32x2(float &a0, float &a1, float b0, float 
         : "f"(b0), "f"(b1));
 }
 // Two floats -> packed bf16 hi pair and packed bf16 lo pair: x = hi + lo + O(2^-18 |x|).
-// 2 F2FP + 2 unpack + 1 FADD2 per pair.
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi, uint32_t &lo)
 {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
@@ -239,6 +238,33 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi, u
     add_f32x2(x0, x1, -__uint_as_float(hi << 16), -__uint_as_float(hi & 0xFFFF0000u));
     const __nv_bfloat162 l = __floats2bfloat162_rn(x0, x1);
     lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// relu fused into the split: hi = bf16_rz(max(x, 0)), so x - hi >= 0 exactly when x >= 0 and the
+// .relu of the second conversion zeroes lo exactly when x < 0.  max(x, 0) = hi + lo + O(2^-17 x).
+// Two conversions, two unpack ops and one FADD2 per pair -- no FMNMX.
+__device__ __forceinline__ void split_relu_bf16x2(float x0, float x1, uint32_t &hi, uint32_t &lo)
+{
+    asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    add_f32x2(x0, x1, -__uint_as_float(hi * 65536u), -__uint_as_float(hi & 0xFFFF0000u));
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1), "f"(x0));
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 // x = t0 + t1 + t2 + O(2^-25 |x|)
 __device__ __forceinline__ void split3_bf16(float x, uint16_t (&t)[3])
