@@ -201,12 +201,23 @@ int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_th
  * accumulate), the five global parameters enter through a K = 32 six-term stage, and the
  * pulse / choice part of every first layer is computed once per trial.  Sums agree with the
  * _simt kernel to ~1e-6 relative.  workspace_dev >= mnle_loglik_tc_workspace_floats(T,C) floats,
- * 16-byte aligned.  T <= 65535.
+ * 16-byte aligned.
  */
 size_t mnle_loglik_tc_workspace_floats(int64_t T, int64_t C);
 int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
                            const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
                            float *out_dev, float *workspace_dev, void *stream);
+
+/*
+ * D independent datasets in one launch (the SBC loop, mnle.py:183-218, evaluates one potential per
+ * dataset): theta_dev (D*C,5), x_dev (D*T,2), pulses_dev (D*T,>=80), out_dev (D*C,);
+ * out[d*C + c] = sum_t log p(x[d*T + t] | [theta[d*C + c], pulses[d*T + t]]).
+ * D*T <= 524280 per call.
+ */
+size_t mnle_loglik_batched_tc_workspace_floats(int64_t D, int64_t T, int64_t C);
+int mnle_loglik_sum_batched_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                   const float *pulses_dev, int64_t ld_pulses, int64_t D, int64_t T, int64_t C,
+                                   float *out_dev, float *workspace_dev, void *stream);
 
 /* Debug aid: when trace_dev != NULL, CTA 0 of every following mnle_loglik_sum_tc_f32 launch writes
  * 34 stages x 2 tiles x 4 clock64() stamps there (issuer saw A operand / had the weights, epilogue

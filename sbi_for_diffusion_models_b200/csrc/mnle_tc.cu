@@ -446,11 +446,12 @@ __device__ __forceinline__ void tc_epilogue_spline(uint32_t trow, const float *b
     u = fmaf(hgt * (delta * th * th + d0 * t1), rden, bottom);
 }
 
-// grid = ceil(T * ceil(C / 128) / 2): tile = t * CB + chain block (chain block fastest).
+// grid = ceil(D * T * ceil(C / 128) / 2): tile = ((d * T + t) * CB + chain block), chain block fastest.
+// D independent datasets (own x, pulses and C chains each) share one launch.
 __global__ void __launch_bounds__(kTcThreads, 1)
     mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
                    const float *__restrict__ theta, long long ld_theta, const float *__restrict__ x,
-                   const float *__restrict__ hoist, int T, int C, float mu_y, float sigma_y, int n_choices,
+                   const float *__restrict__ hoist, int D, int T, int C, float mu_y, float sigma_y, int n_choices,
                    float *__restrict__ partial, unsigned int *__restrict__ counters, float *__restrict__ out,
                    long long *__restrict__ trace)
 {
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
-    const int n_tiles = T * CB;
+    const int n_tiles = D * T * CB;
     const int tile0 = blockIdx.x * kTcTiles;
     const int n_active = min(kTcTiles, n_tiles - tile0);
 
@@ -546,14 +547,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     } else if (((warp >> 2) & 1) < n_active) {
         // ====== epilogue warps: tile X, lane quarter q (thread = row), column half hf ==========
         const int X = (warp >> 2) & 1, q = warp & 3, hf = warp >> 3, r = 32 * q + lane;
-        const int tile = tile0 + X, t = tile / CB, c = (tile - t * CB) * kTcM + r;
+        // t = flattened (dataset, trial) index, c = chain within the dataset
+        const int tile = tile0 + X, t = tile / CB, cb = tile - t * CB, d = t / T, c = cb * kTcM + r;
         const bool live = c < C;
+        const long long c_glob = (long long)d * C + c;
         const uint32_t trow = tmem + (uint32_t)X * kTmemTile + ((uint32_t)(32 * q) << 16);
         {   // A image of the theta stage: k = term * 5 + i, terms t1 t1 t2 t1 t2 t3 (pairs with pack_image_theta)
             unsigned char *a_th = smem + kSmemATh + (uint32_t)X * kAThBytes;
             uint16_t tt[5][3];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) split3_bf16(live ? __ldg(theta + (long long)c * ld_theta + i) : 0.f, tt[i]);
+            for (int i = 0; i < 5; ++i) split3_bf16(live ? __ldg(theta + c_glob * ld_theta + i) : 0.f, tt[i]);
             const int aterm[6] = {0, 0, 1, 0, 1, 2};
             uint16_t kv[32];
 #pragma unroll
@@ -632,14 +635,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             uint32_t *last_s = tmem_slot + 1 + X;
             __threadfence();
             asm volatile("bar.sync %0, 128;" ::"r"(1 + X) : "memory");
-            if (q == 0 && lane == 0) *last_s = (atomicAdd(&counters[tile - t * CB], 1u) == (unsigned)(T - 1));
+            if (q == 0 && lane == 0) *last_s = (atomicAdd(&counters[d * CB + cb], 1u) == (unsigned)(T - 1));
             asm volatile("bar.sync %0, 128;" ::"r"(1 + X) : "memory");
             if (*last_s && live) {
                 __threadfence();
+                const float *col = partial + (size_t)d * T * C + c;
                 float sum = 0.f;
 #pragma unroll 10
-                for (int tt = 0; tt < T; ++tt) sum += __ldcg(partial + (size_t)tt * C + c);
-                out[c] = sum;
+                for (int tt = 0; tt < T; ++tt) sum += __ldcg(col + (size_t)tt * C);
+                out[c_glob] = sum;
             }
         }
     }
@@ -676,47 +680,63 @@ DDM_API int mnle_tc_set_trace(long long *trace_dev)
     return DDM_OK;
 }
 
-DDM_API size_t mnle_loglik_tc_workspace_floats(int64_t T, int64_t C)
+DDM_API size_t mnle_loglik_batched_tc_workspace_floats(int64_t D, int64_t T, int64_t C)
 {
-    if (T <= 0 || C <= 0) return 0;
-    return (size_t)T * kNets * kHidden + (size_t)T * (size_t)C + (size_t)((C + kTcM - 1) / kTcM);
+    if (D <= 0 || T <= 0 || C <= 0) return 0;
+    return (size_t)D * T * kNets * kHidden + (size_t)D * T * (size_t)C + (size_t)D * (size_t)((C + kTcM - 1) / kTcM);
 }
 
-DDM_API int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
-                                   const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C, float *out_dev,
-                                   float *workspace_dev, void *stream)
+DDM_API size_t mnle_loglik_tc_workspace_floats(int64_t T, int64_t C)
+{
+    return mnle_loglik_batched_tc_workspace_floats(1, T, C);
+}
+
+DDM_API int mnle_loglik_sum_batched_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                           const float *pulses_dev, int64_t ld_pulses, int64_t D, int64_t T, int64_t C,
+                                           float *out_dev, float *workspace_dev, void *stream)
 {
     Handle *H = static_cast<Handle *>(handle);
     if (H == nullptr || H->magic != kMagic || H->tc_pack == nullptr) {
-        ddm::set_error("mnle_loglik_sum_tc_f32: bad handle");
+        ddm::set_error("mnle_loglik_sum_tc: bad handle");
         return DDM_ERR_STATE;
     }
-    DDM_REQUIRE(T >= 0 && C >= 0 && T <= 65535 && C <= 0x7FFFFFFFll - kTcM, "mnle_loglik_sum_tc: T=%lld C=%lld out of range",
-                (long long)T, (long long)C);
-    if (C == 0) return DDM_OK;
+    DDM_REQUIRE(D >= 0 && T >= 0 && C >= 0 && D <= 0x7FFFFFFFll && T <= 0x7FFFFFFFll && C <= 0x7FFFFFFFll - kTcM,
+                "mnle_loglik_sum_tc: D=%lld T=%lld C=%lld out of range", (long long)D, (long long)T, (long long)C);
+    if (C == 0 || D == 0) return DDM_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DDM_REQUIRE(out_dev != nullptr, "mnle_loglik_sum_tc: null output");
     if (T == 0) {
-        DDM_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)C * sizeof(float), st));
+        DDM_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)D * (size_t)C * sizeof(float), st));
         return DDM_OK;
     }
     DDM_REQUIRE(theta_dev && x_dev && pulses_dev && workspace_dev, "mnle_loglik_sum_tc: null pointer");
     DDM_REQUIRE(ld_theta >= 5 && ld_pulses >= kCond - 5, "mnle_loglik_sum_tc: ld_theta=%lld ld_pulses=%lld too small",
                 (long long)ld_theta, (long long)ld_pulses);
     DDM_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 15u) == 0, "mnle_loglik_sum_tc: workspace must be 16-byte aligned");
-    const int CB = (int)((C + kTcM - 1) / kTcM);
+    const long long CB = (C + kTcM - 1) / kTcM;
+    const long long n_tiles = D * T * CB;
+    DDM_REQUIRE(D * T <= 0x7FFFFFFFll / kHoistTrials && n_tiles <= 0x7FFFFFFFll && D * CB <= 0x7FFFFFFFll,
+                "mnle_loglik_sum_tc: D * T * ceil(C / 128) = %lld tiles is too many", n_tiles);
     float *hoist = workspace_dev;
-    float *partial = hoist + (size_t)T * kNets * kHidden;
-    unsigned int *counters = reinterpret_cast<unsigned int *>(partial + (size_t)T * (size_t)C);
-    mnle_hoist_kernel<<<dim3(kNets, (unsigned)((T + kHoistTrials - 1) / kHoistTrials)), kHidden, 0, st>>>(
-        H->params, H->layout, x_dev, pulses_dev, ld_pulses, (int)T, hoist, counters, CB);
+    float *partial = hoist + (size_t)D * T * kNets * kHidden;
+    unsigned int *counters = reinterpret_cast<unsigned int *>(partial + (size_t)D * T * (size_t)C);
+    const long long hoist_blocks = (D * T + kHoistTrials - 1) / kHoistTrials;
+    DDM_REQUIRE(hoist_blocks <= 65535, "mnle_loglik_sum_tc: D * T = %lld trials is too many for one call", (long long)(D * T));
+    mnle_hoist_kernel<<<dim3(kNets, (unsigned)hoist_blocks), kHidden, 0, st>>>(H->params, H->layout, x_dev, pulses_dev, ld_pulses,
+                                                                            (int)(D * T), hoist, counters, (int)(D * CB));
     DDM_CUDA_TRY(cudaGetLastError());
     DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    const long long n_tiles = (long long)T * CB;
-    DDM_REQUIRE(n_tiles <= 0x7FFFFFFFll, "mnle_loglik_sum_tc: T * ceil(C / 128) = %lld tiles is too many", n_tiles);
     mnle_tc_kernel<<<(unsigned)((n_tiles + kTcTiles - 1) / kTcTiles), kTcThreads, kTcSmemBytes, st>>>(
-        static_cast<const unsigned char *>(H->tc_pack), H->tc_plan, theta_dev, ld_theta, x_dev, hoist, (int)T, (int)C,
+        static_cast<const unsigned char *>(H->tc_pack), H->tc_plan, theta_dev, ld_theta, x_dev, hoist, (int)D, (int)T, (int)C,
         H->mu_y, H->sigma_y, H->layout.n_choices, partial, counters, out_dev, g_tc_trace);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
+}
+
+DDM_API int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                   const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C, float *out_dev,
+                                   float *workspace_dev, void *stream)
+{
+    return mnle_loglik_sum_batched_tc_f32(handle, theta_dev, ld_theta, x_dev, pulses_dev, ld_pulses, 1, T, C, out_dev,
+                                          workspace_dev, stream);
 }

@@ -1,0 +1,151 @@
+"""Inference and calibration drivers around the fused MNLE potential (reference mnle.py:52-237).
+
+``run_inference_mcmc`` and ``run_sbc`` keep the reference's arguments and return values.  What
+changes is where the work happens: the potential is the tcgen05 kernel, and the sampler is the
+device-resident many-chain slice sampler of ``samplers.py`` instead of sbi's ``MCMCPosterior`` /
+pyro NUTS (third-party, CPU, one process per chain).  ``run_sbc`` pre-draws every dataset in the
+reference's order, simulates all sessions of a rank in one launch, samples all
+(dataset, chain) pairs in lock-step through the batched potential, and shards datasets over the
+GPUs of the box (all-gather of the ranks at the end).
+
+Training the estimator (reference mnle.py:16-50, ``sbi.inference.MNLE``) is not part of the hot
+path; estimators arrive here as ``DeviceMNLE`` / ``PackedMNLE`` or anything exposing an
+MNLE-shaped ``state_dict()``.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .potentials import (ConditionedMNLELogLikelihood, ThetaOnlyPosteriorPotential, as_device_estimator,
+                         prior_log_prob)
+from .samplers import VectorizedSliceSampler
+from .sbc import compute_ranks, draw_sbc_datasets, simulate_sbc_sessions
+from .sharding import _world, gather_sbc, shard_bounds
+from .simulator import compute_device
+
+MIN_VECTOR_CHAINS = 128   # one row tile of the potential kernel
+
+
+def _init_from_prior(prior_theta, log_prob_fn, n: int, device, max_tries: int = 20) -> torch.Tensor:
+    """``init_strategy="proposal"`` (reference mnle.py:85): prior draws, redrawn where the
+    posterior potential is not finite."""
+    x = prior_theta.sample((n,)).to(device=device, dtype=torch.float32)
+    for _ in range(max_tries):
+        bad = ~torch.isfinite(log_prob_fn(x))
+        if not bool(bad.any()):
+            return x
+        x[bad] = prior_theta.sample((int(bad.sum()),)).to(device=device, dtype=torch.float32)
+    raise RuntimeError("could not find starting points with finite posterior potential")
+
+
+@torch.no_grad()
+def run_inference_mcmc(cfg, prior_theta, density_estimator, x_o, pulses_o, *, num_chains: Optional[int] = None,
+                       device=None, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Posterior samples over theta (dim 5) given one observed session (reference mnle.py:52-95).
+
+    Returns (cfg.POSTERIOR_SAMPLES, 5) on the CPU.  ``num_chains`` defaults to
+    max(cfg.NUM_CHAINS, 128): the sampler advances all chains with one potential call per step, so
+    fewer chains than one row tile would leave the kernel idle.  Each chain contributes
+    ceil(POSTERIOR_SAMPLES / num_chains) draws after cfg.WARMUP_STEPS tuning sweeps."""
+    dev = compute_device(device)
+    chains = int(num_chains) if num_chains is not None else max(int(cfg.NUM_CHAINS), MIN_VECTOR_CHAINS)
+    cll = ConditionedMNLELogLikelihood(as_device_estimator(density_estimator), pulses_o.to(dev), device=dev)
+    potential = ThetaOnlyPosteriorPotential(conditioned_loglike=cll, prior_theta=prior_theta, x_o=x_o.to(dev), device=dev,
+                                            temperature=float(cfg.TEMPERATURE))
+    fn = lambda th: potential(th, track_gradients=False)
+    init = _init_from_prior(prior_theta, fn, chains, dev)
+    sampler = VectorizedSliceSampler(fn, init, generator=generator)
+    want = int(cfg.POSTERIOR_SAMPLES)
+    per_chain = -(-want // chains)
+    draws = sampler.run(per_chain, warmup=int(cfg.WARMUP_STEPS), thin=1)          # (per_chain, chains, 5)
+    return draws.reshape(-1, draws.shape[-1])[:want].detach().cpu()
+
+
+class _BatchedPotential:
+    """log prior + loglik / temperature for D datasets x C chains as one flat (D*C, 5) batch."""
+
+    def __init__(self, estimator, prior_theta, x, pulses, temperature: float):
+        self.est, self.prior, self.x, self.pulses = estimator, prior_theta, x, pulses
+        self.D, self.temperature = x.shape[0], float(temperature)
+
+    def __call__(self, theta_flat: torch.Tensor) -> torch.Tensor:
+        lp = prior_log_prob(self.prior, theta_flat)
+        ll = self.est.loglik_sum_batched(theta_flat.view(self.D, -1, theta_flat.shape[-1]), self.x, self.pulses).reshape(-1)
+        return torch.where(torch.isfinite(lp), lp + ll / self.temperature, lp)
+
+
+@torch.no_grad()
+def run_sbc(cfg, *, prior_theta, density_estimator, device: str = "cpu", num_datasets: int = 25,
+            posterior_samples_per_dataset: Optional[int] = None, seed: int = 0,
+            param_names: Sequence[str] = ("a0", "lam", "v", "B", "tau"), outdir: str = "sbc_outputs", plot_bins: int = 30,
+            chains_per_dataset: int = MIN_VECTOR_CHAINS, group=None, save: bool = True) -> dict:
+    """Simulation-based calibration (reference mnle.py:128-237): for every dataset draw
+    theta_true ~ prior, simulate a session, sample the posterior, rank theta_true among the draws.
+
+    Returns {"thetas_true": (N,5) float32 ndarray, "ranks": (N,5) int64 ndarray,
+    "all_samples": list of N CPU tensors (S,5)} on every rank.  ``device`` is accepted for
+    signature compatibility; the work runs on this rank's GPU."""
+    dev = compute_device(None)
+    rank, world = _world(group)
+    S = int(posterior_samples_per_dataset) if posterior_samples_per_dataset is not None else int(cfg.POSTERIOR_SAMPLES)
+    T = int(cfg.NUM_TRIALS_OBS)
+    thetas_true, ds_seeds = draw_sbc_datasets(prior_theta, int(num_datasets), seed)       # reference order
+    lo, hi = shard_bounds(int(num_datasets), rank, world)
+    est = as_device_estimator(density_estimator)
+    ranks_local = torch.empty((hi - lo, 5), dtype=torch.int64)
+    samples_local = torch.empty((hi - lo, S, 5), dtype=torch.float32)
+    if hi > lo:
+        x, pulses = simulate_sbc_sessions(thetas_true[lo:hi], ds_seeds[lo:hi], T, mu_sensory=float(cfg.MU_SENSORY),
+                                          p_success=float(cfg.P_SUCCESS), noise_seed=seed, first_dataset=lo, device=dev)
+        if bool(cfg.LOG_RT_MANUALLY):
+            x = x.clone()
+            x[..., 0] = torch.log(x[..., 0].clamp_min(1e-6))
+        D, C = hi - lo, int(chains_per_dataset)
+        potential = _BatchedPotential(est, prior_theta, x, pulses, float(cfg.TEMPERATURE))
+        g = torch.Generator(device=dev).manual_seed(int(seed) * 1_000_003 + lo)
+        init = _init_from_prior(prior_theta, potential, D * C, dev)
+        sampler = VectorizedSliceSampler(potential, init, generator=g)
+        per_chain = -(-S // C)
+        draws = sampler.run(per_chain, warmup=int(cfg.WARMUP_STEPS), thin=1)              # (per_chain, D*C, 5)
+        draws = draws.view(per_chain, D, C, 5).permute(1, 0, 2, 3).reshape(D, per_chain * C, 5)[:, :S]
+        samples_local = draws.cpu()
+        for i in range(D):
+            ranks_local[i] = compute_ranks(thetas_true[lo + i], samples_local[i])
+    thetas_all, ranks_all = gather_sbc(thetas_true[lo:hi].to(dev), ranks_local.to(dev), int(num_datasets), group)
+    from .sharding import all_gather_rows
+    samples_all = all_gather_rows(samples_local.to(dev), int(num_datasets), group).cpu()
+    out = {"thetas_true": thetas_all.cpu().numpy(), "ranks": ranks_all.cpu().numpy(),
+           "all_samples": [samples_all[i] for i in range(int(num_datasets))]}
+    if save and rank == 0:
+        os.makedirs(outdir, exist_ok=True)
+        np.save(os.path.join(outdir, "sbc_thetas_true.npy"), out["thetas_true"])
+        np.save(os.path.join(outdir, "sbc_ranks.npy"), out["ranks"])
+        _plot_sbc_rank_histograms(out["ranks"], param_names=param_names,
+                                  outpath=os.path.join(outdir, "sbc_rank_histograms.png"), bins=plot_bins)
+    return out
+
+
+def _plot_sbc_rank_histograms(ranks: np.ndarray, *, param_names: Sequence[str], outpath: Optional[str] = None, bins: int = 30):
+    """Rank histograms (reference mnle.py:107-126); skipped when matplotlib is not installed."""
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except Exception:
+        return None
+    D = ranks.shape[1]
+    fig, axes = plt.subplots(D, 1, figsize=(8, 2.5 * D), constrained_layout=True)
+    axes = [axes] if D == 1 else axes
+    for d, ax in enumerate(axes):
+        ax.hist(ranks[:, d], bins=bins)
+        ax.set_title(f"SBC ranks: {param_names[d]}")
+        ax.set_xlabel("rank")
+        ax.set_ylabel("count")
+    if outpath is not None:
+        os.makedirs(os.path.dirname(outpath) or ".", exist_ok=True)
+        fig.savefig(outpath, dpi=150, bbox_inches="tight")
+    return fig

@@ -210,13 +210,39 @@ class DeviceMNLE(torch.nn.Module):
             _native.check(rc, "mnle_loglik_sum")
         return out.to(theta.device)
 
+    def loglik_sum_batched(self, theta: torch.Tensor, x_o: torch.Tensor, pulses: torch.Tensor) -> torch.Tensor:
+        """D independent datasets in one launch (the SBC loop evaluates one potential per dataset,
+        reference mnle.py:183-218): theta (D,C,5), x_o (D,T,2), pulses (D,T,>=80) -> (D,C) with
+        out[d,c] = sum_t log p(x_o[d,t] | [theta[d,c], pulses[d,t]]).  Tensor-core kernel only."""
+        L = _native.lib()
+        dev = self._dev(theta)
+        if theta.ndim != 3 or theta.shape[2] != 5:
+            raise ValueError(f"theta must be (D,C,5), got {tuple(theta.shape)}")
+        D, C = theta.shape[0], theta.shape[1]
+        if x_o.ndim != 3 or x_o.shape[0] != D or x_o.shape[2] != 2:
+            raise ValueError(f"x_o must be (D,T,2) with D={D}, got {tuple(x_o.shape)}")
+        T = x_o.shape[1]
+        if pulses.ndim != 3 or pulses.shape[0] != D or pulses.shape[1] != T or pulses.shape[2] < COND_DIM - 5:
+            raise ValueError(f"pulses must be (D,T,>=80) with D={D}, T={T}, got {tuple(pulses.shape)}")
+        th = theta.to(device=dev, dtype=torch.float32).contiguous()
+        xo = x_o.to(device=dev, dtype=torch.float32).contiguous()
+        pl = pulses.to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            out = torch.empty((D, C), dtype=torch.float32, device=dev)
+            ws = torch.empty((max(L.mnle_loglik_batched_tc_workspace_floats(D, T, C), 1),), dtype=torch.float32, device=dev)
+            rc = L.mnle_loglik_sum_batched_tc_f32(self.packed.handle(dev), th.data_ptr(), 5, xo.data_ptr(), pl.data_ptr(),
+                                                  pl.shape[2], D, T, C, out.data_ptr(), ws.data_ptr(),
+                                                  torch.cuda.current_stream(dev).cuda_stream)
+            _native.check(rc, "mnle_loglik_sum_batched_tc_f32")
+        return out.to(theta.device)
+
     @staticmethod
     def _pick_kernel(kernel: str, T: int):
         """"tc": tcgen05 tensor-core kernel; "simt": fp32 CUDA-core kernel (accuracy anchor);
         "auto": tensor cores whenever the shape is covered."""
         L = _native.lib()
         if kernel == "auto":
-            kernel = "tc" if T <= 65535 else "simt"
+            kernel = "tc" if T <= 524280 else "simt"
         if kernel == "tc":
             return L.mnle_loglik_sum_tc_f32, L.mnle_loglik_tc_workspace_floats
         if kernel == "simt":

@@ -32,6 +32,18 @@ def as_device_estimator(estimator) -> DeviceMNLE:
                     "whose state_dict() holds the reference's MNLE architecture")
 
 
+def prior_log_prob(prior, theta: torch.Tensor) -> torch.Tensor:
+    """``prior.log_prob(theta)`` on theta's device; priors whose parameters live on the CPU (the
+    reference builds its prior there, rt_choice_model_pipeline.py:38-46) are evaluated on the CPU
+    and the result is moved back."""
+    try:
+        return prior.log_prob(theta)
+    except RuntimeError:
+        if theta.device.type == "cpu":
+            raise
+        return prior.log_prob(theta.cpu()).to(theta.device)
+
+
 class ConditionedMNLELogLikelihood(torch.nn.Module):
     """sum_t log p(x_t | global_theta, local_theta_t) for every row of ``global_theta``.
     Pickles as CPU data only (packed weights + the pulse buffer)."""
@@ -87,7 +99,7 @@ class ThetaOnlyPosteriorPotential:
         if theta.ndim == 1:
             theta = theta.view(1, -1)
         theta = theta.to(self.device, dtype=torch.float32)
-        log_prior = self.prior_theta.log_prob(theta)
+        log_prior = prior_log_prob(self.prior_theta, theta)
         inside = torch.isfinite(log_prior)
         if not bool(inside.any()):
             return log_prior
