@@ -196,6 +196,18 @@ int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_th
                              float *out_dev, float *workspace_dev, void *stream);
 
 /*
+ * Value and gradient with respect to theta of the same sum (what autograd gives the reference's
+ * NUTS sampler through potentials.py:112 with track_gradients=True): out_dev (C,),
+ * grad_dev (C,5) row-major, grad[c][i] = d out[c] / d theta[c][i].  Forward-mode (five tangents
+ * per row) on the fp32 CUDA-core path; C <= 65535.  workspace_dev >=
+ * mnle_loglik_grad_workspace_floats(T,C) floats.
+ */
+size_t mnle_loglik_grad_workspace_floats(int64_t T, int64_t C);
+int mnle_loglik_sum_grad_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                             const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
+                             float *out_dev, float *grad_dev, float *workspace_dev, void *stream);
+
+/*
  * Same contract on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM): the
  * 128x128 / 128x71 layers run as bf16 hi/lo split GEMMs (three MMAs per product, fp32
  * accumulate), the five global parameters enter through a K = 32 six-term stage, and the

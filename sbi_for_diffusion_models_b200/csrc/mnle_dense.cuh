@@ -1,0 +1,87 @@
+// fp32 CUDA-core dense layer over a 64-row tile held in shared memory: shared by the forward
+// kernel (mnle_simt.cu) and the forward-mode gradient kernel (mnle_grad.cu).
+#pragma once
+
+#include "mnle_common.cuh"
+
+namespace mnle {
+
+constexpr int kTM = 64;         // rows per CTA tile
+constexpr int kThreads = 256;
+constexpr int kLdIn = 89;       // padded leading dims (bank-conflict-free broadcast reads)
+constexpr int kLdH = 132;
+constexpr int kKC = 32;         // weight k-chunk staged in shared memory
+constexpr int kLdW = 129;
+
+struct SimtSmem {
+    float in[kTM * kLdIn];
+    float ha[kTM * kLdH];
+    float hb[kTM * kLdH];
+    float w[kKC * kLdW];
+    float red[8];
+};
+
+enum Act { kNone = 0, kRelu = 1, kSigmoid = 2 };
+
+// out[r][n] = act(sum_k in[r][k] * W[n][k] + b[n]) for r < 64, n < n_valid (<= 16 * NJ).
+// DUAL: rows come in groups of kDualRows = 6 (one primal row followed by its five tangent rows
+// d/d theta_i); the layer is linear in the tangents, so they get no bias (and ACT must be kNone:
+// the caller applies the activation and its derivative afterwards).
+constexpr int kDualRows = 6;
+template <int NJ, int ACT, bool DUAL = false>
+__device__ __forceinline__ void dense(const float *__restrict__ W, const float *__restrict__ bias, int K,
+                                      int n_valid, const float *in_s, int ld_in, float *out_s, int ld_out,
+                                      float *w_s)
+{
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][NJ];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += kKC) {
+        __syncthreads();  // previous chunk consumed (and in_s / out_s hazards of the caller)
+        // stage W[:, k0:k0+32] transposed: w_s[kk][n]
+        {
+            const int kk = tid & 31;
+            for (int n = tid >> 5; n < 16 * NJ; n += kThreads / 32) {
+                float v = 0.f;
+                if (n < n_valid && k0 + kk < K) v = __ldg(W + (size_t)n * K + k0 + kk);
+                w_s[kk * kLdW + n] = v;
+            }
+        }
+        __syncthreads();
+        const int kend = min(kKC, K - k0);
+#pragma unroll 4
+        for (int kk = 0; kk < kend; ++kk) {
+            float a[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = in_s[(ty * 4 + i) * ld_in + k0 + kk];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const float wv = w_s[kk * kLdW + tx + 16 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(a[i], wv, acc[i][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int n = tx + 16 * j;
+        if (n < n_valid) {
+            const float bv = __ldg(bias + n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v = acc[i][j] + ((!DUAL || (ty * 4 + i) % kDualRows == 0) ? bv : 0.f);
+                if (ACT == kRelu) v = fmaxf(v, 0.f);
+                if (ACT == kSigmoid) v = 1.0f / (1.0f + expf(-v));
+                out_s[(ty * 4 + i) * ld_out + n] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace mnle

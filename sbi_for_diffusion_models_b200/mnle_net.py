@@ -210,6 +210,28 @@ class DeviceMNLE(torch.nn.Module):
             _native.check(rc, "mnle_loglik_sum")
         return out.to(theta.device)
 
+    def loglik_sum_and_grad(self, theta: torch.Tensor, x_o: torch.Tensor, pulses: torch.Tensor):
+        """(out (C,), grad (C,5)) with grad[c] = d out[c] / d theta[c]: forward-mode kernel."""
+        L = _native.lib()
+        dev = self._dev(theta)
+        th = theta.detach().to(device=dev, dtype=torch.float32).contiguous()
+        xo = x_o.reshape(-1, 2).to(device=dev, dtype=torch.float32).contiguous()
+        pl = pulses.to(device=dev, dtype=torch.float32).contiguous()
+        if th.ndim != 2 or th.shape[1] != 5:
+            raise ValueError(f"theta must be (C,5), got {tuple(th.shape)}")
+        if pl.ndim != 2 or pl.shape[0] != xo.shape[0] or pl.shape[1] < COND_DIM - 5:
+            raise ValueError(f"pulses must be (T,>=80) with T={xo.shape[0]}, got {tuple(pl.shape)}")
+        C, T = th.shape[0], xo.shape[0]
+        with torch.cuda.device(dev):
+            out = torch.empty((C,), dtype=torch.float32, device=dev)
+            grad = torch.empty((C, 5), dtype=torch.float32, device=dev)
+            ws = torch.empty((max(L.mnle_loglik_grad_workspace_floats(T, C), 1),), dtype=torch.float32, device=dev)
+            rc = L.mnle_loglik_sum_grad_f32(self.packed.handle(dev), th.data_ptr(), 5, xo.data_ptr(), pl.data_ptr(),
+                                            pl.shape[1], T, C, out.data_ptr(), grad.data_ptr(), ws.data_ptr(),
+                                            torch.cuda.current_stream(dev).cuda_stream)
+            _native.check(rc, "mnle_loglik_sum_grad_f32")
+        return out.to(theta.device), grad.to(theta.device)
+
     def loglik_sum_batched(self, theta: torch.Tensor, x_o: torch.Tensor, pulses: torch.Tensor) -> torch.Tensor:
         """D independent datasets in one launch (the SBC loop evaluates one potential per dataset,
         reference mnle.py:183-218): theta (D,C,5), x_o (D,T,2), pulses (D,T,>=80) -> (D,C) with

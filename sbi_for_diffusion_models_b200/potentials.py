@@ -9,8 +9,10 @@ expands (C thetas) x (T trials) into T*C rows of 85 numbers and calls ``estimato
 (potentials.py:100-113); here nothing is materialised: the kernel assembles row r = t*C + c
 from ``theta[c]``, ``local_theta[t]`` and ``x_o[t]`` and returns the sum over t.
 
-Gradients: the forward kernel has no backward yet, so a call that needs
-``d loglik / d theta`` (NUTS) raises instead of silently returning a constant.
+Gradients: a call that needs d loglik / d theta (NUTS: ``track_gradients=True`` with a theta that
+requires grad, reference potentials.py:33, 112) runs the forward-mode CUDA kernel
+(``mnle_loglik_sum_grad_f32``: value and the five partials in one pass) behind a
+``torch.autograd.Function``; everything else runs the tensor-core forward kernel.
 """
 from __future__ import annotations
 
@@ -44,6 +46,24 @@ def prior_log_prob(prior, theta: torch.Tensor) -> torch.Tensor:
         return prior.log_prob(theta.cpu()).to(theta.device)
 
 
+class _LoglikSumWithGrad(torch.autograd.Function):
+    """sum_t log p(x_t | theta_c, pulses_t) with its Jacobian-vector product taken from the
+    forward-mode kernel: each output depends on its own theta row only, so
+    d L / d theta[c] = grad_output[c] * d out[c] / d theta[c]."""
+
+    @staticmethod
+    def forward(ctx, theta, estimator, x, pulses):
+        out, grad = estimator.loglik_sum_and_grad(theta.to(dtype=torch.float32), x, pulses)
+        ctx.save_for_backward(grad)
+        ctx.theta_dtype = theta.dtype
+        return out.to(theta.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (grad,) = ctx.saved_tensors
+        return (grad_output.to(grad.dtype).unsqueeze(1) * grad).to(ctx.theta_dtype), None, None, None
+
+
 class ConditionedMNLELogLikelihood(torch.nn.Module):
     """sum_t log p(x_t | global_theta, local_theta_t) for every row of ``global_theta``.
     Pickles as CPU data only (packed weights + the pulse buffer)."""
@@ -55,10 +75,6 @@ class ConditionedMNLELogLikelihood(torch.nn.Module):
         self.register_buffer("local_theta", local_theta.to(device=device, dtype=torch.float32))
 
     def forward(self, global_theta: torch.Tensor, x_o: torch.Tensor, track_gradients: bool = True) -> torch.Tensor:
-        if track_gradients and torch.is_grad_enabled() and global_theta.requires_grad:
-            raise NotImplementedError(
-                "the CUDA MNLE potential is forward-only in this release: gradient-based samplers (nuts_pyro, hmc) "
-                "are not supported yet; use a gradient-free sampler (slice_np_vectorized) or detach theta")
         x = x_o.to(dtype=torch.float32)
         if x.dim() == 3:
             assert x.shape[1] == 1, "This implementation supports a single observed x batch (num_xs=1)."
@@ -66,6 +82,8 @@ class ConditionedMNLELogLikelihood(torch.nn.Module):
         num_trials = x.shape[0]
         assert self.local_theta.shape[0] == num_trials, (
             f"local_theta must have shape (num_trials, P). Got {tuple(self.local_theta.shape)}")
+        if track_gradients and torch.is_grad_enabled() and global_theta.requires_grad:
+            return _LoglikSumWithGrad.apply(global_theta, self.estimator, x, self.local_theta).to(self.device)
         theta = global_theta.detach().to(dtype=torch.float32)
         ll = self.estimator.loglik_sum(theta, x, self.local_theta)
         return ll.to(self.device)

@@ -138,11 +138,44 @@ def test_reference_shaped_potential_objects(net):
     assert torch.allclose(cll(theta[:3], x.unsqueeze(1), track_gradients=False), cll(theta[:3], x, track_gradients=False))
     with pytest.raises(AssertionError, match="local_theta must have shape"):
         cll(theta[:3], x[:10], track_gradients=False)
-    # survives pickling (pyro chain workers) and refuses gradient requests loudly
+    # survives pickling (pyro chain workers)
     clone = pickle.loads(pickle.dumps(cll))
     assert torch.equal(clone(theta[:3], x, track_gradients=False), cll(theta[:3], x, track_gradients=False))
-    with pytest.raises(NotImplementedError, match="forward-only"):
-        cll(theta[:3].clone().requires_grad_(True), x, track_gradients=True)
+
+
+@pytest.mark.parametrize("T,C", [(50, 4), (7, 1), (23, 11)])
+def test_potential_gradient_matches_autograd_of_the_spec(net, T, C):
+    """track_gradients=True (reference potentials.py:33, 112; NUTS): value and d/d theta from the
+    forward-mode kernel against torch autograd through the float64 spec."""
+    p32, p64, est, scale = net
+    theta = orc.prior_sample(C, seed=21)
+    x, pulses = _session(T)
+    th64 = theta.double().requires_grad_(True)
+    want = ms.loglik_sum(p64, th64, x, pulses)
+    (want_grad,) = torch.autograd.grad(want.sum(), th64)
+    cll = ConditionedMNLELogLikelihood(est, pulses, "cpu")
+    th = theta.clone().requires_grad_(True)
+    got = cll(th, x, track_gradients=True)
+    assert got.requires_grad and tuple(got.shape) == (C,)
+    weights = torch.arange(1, C + 1, dtype=torch.float32)            # a non-trivial grad_output
+    (got_grad,) = torch.autograd.grad((got * weights).sum(), th)
+    assert float(((got.detach().double() - want.detach()).abs() / want.detach().abs()).max()) < (1e-4 if scale == 1.0 else 1e-3)
+    ref = want_grad * weights.double()[:, None]
+    err = (got_grad.double() - ref).abs() / (ref.abs() + 1e-2 * ref.abs().max())
+    assert float(err.max()) < (2e-3 if scale == 1.0 else 2e-2), float(err.max())
+    # value of the gradient path = the fp32 forward kernel's, and no graph without the flag
+    assert torch.allclose(got.detach(), est.loglik_sum(theta, x, pulses, kernel="simt"), rtol=1e-5, atol=1e-3)
+    assert not cll(th, x, track_gradients=False).requires_grad
+    # through the full potential: d/d theta of (log prior + loglik / temperature)
+    from sbi_for_diffusion_models_b200.priors import build_prior_theta
+    prior = build_prior_theta()
+    pot = ThetaOnlyPosteriorPotential(conditioned_loglike=cll, prior_theta=prior, x_o=x, device="cpu", temperature=2.0)
+    th2 = theta.clone().requires_grad_(True)
+    (g2,) = torch.autograd.grad(pot(th2, track_gradients=True).sum(), th2)
+    th3 = theta.double().requires_grad_(True)
+    (g3,) = torch.autograd.grad((prior.log_prob(th3) + ms.loglik_sum(p64, th3, x, pulses) / 2.0).sum(), th3)
+    err2 = (g2.double() - g3).abs() / (g3.abs() + 1e-2 * g3.abs().max())
+    assert float(err2.max()) < (2e-3 if scale == 1.0 else 2e-2), float(err2.max())
 
 
 def test_sbc_sessions_one_launch_matches_per_dataset_calls():
