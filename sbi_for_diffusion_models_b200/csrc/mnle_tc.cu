@@ -270,7 +270,10 @@ __global__ void __launch_bounds__(kHidden) mnle_hoist_kernel(const float *__rest
         for (int i = j; i < n_counters; i += kHidden) counters[i] = 0u;
     const int K = net == 0 ? kCond : kCtx;
     const float *W = params + (net == 0 ? L.cat_W0 : L.fl_W1[net - 1]);
-    for (int idx = j; idx < kHidden * kHoistK; idx += kHidden) {
+    // 81 independent loads per thread in flight (fully unrolled): the block is latency-bound
+#pragma unroll
+    for (int it = 0; it < kHoistK; ++it) {
+        const int idx = it * kHidden + j;
         const int row = idx / kHoistK, i = idx - row * kHoistK;
         w_s[idx] = (5 + i < K) ? __ldg(W + (size_t)row * K + 5 + i) : 0.f;
     }
