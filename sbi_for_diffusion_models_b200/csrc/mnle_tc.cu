@@ -323,14 +323,14 @@ constexpr uint32_t kTcSmemBytes = kSmemBars + 128;
 static_assert(kTcSmemBytes <= 227 * 1024, "tiles do not fit shared memory");
 constexpr uint32_t kTmemD = 0, kTmemAHi = 128, kTmemALo = 192, kTmemTile = 256;  // columns
 
-// 64 accumulator columns + bias -> activation -> packed bf16 hi / lo columns of the A operand.
+// ncols accumulator columns + bias -> activation -> packed bf16 hi / lo columns of the A operand.
 // The CUDA-core side of this kernel is bound by the half-rate ALU pipe (min/max, selects,
 // conversions, logic), so the arithmetic is phrased for the FMA pipe wherever possible.
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, const float *bias)
+__device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int ncols, const float *bias)
 {
 #pragma unroll 1
-    for (int c0 = col0; c0 < col0 + 64; c0 += 32) {
+    for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(trow + kTmemD + (uint32_t)c0, v);
         tmem_wait_ld();
@@ -357,12 +357,9 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, const f
 
 // softmax numerators of one 24-bin block held in registers: e[j] = exp((q[j] - max q) / sqrt(128));
 // returns 1 / sum e.
-__device__ __forceinline__ float rqs_softmax(const uint32_t (&v)[kBins], const float *bias, float (&e)[kBins])
+__device__ __forceinline__ float rqs_softmax(const float (&q)[kBins], float (&e)[kBins])
 {
     const float c = 0.08838834764831845f * 1.4426950408889634f;  // log2(e) / sqrt(128)
-    float q[kBins];
-#pragma unroll
-    for (int j = 0; j < kBins; ++j) q[j] = __uint_as_float(v[j]) + bias[j];
     float m = fmaxf(fmaxf(q[0], q[1]), q[2]);
 #pragma unroll
     for (int j = 3; j < kBins; j += 3) m = fmaxf(fmaxf(m, q[j]), fmaxf(q[j + 1], q[j + 2]));
@@ -393,9 +390,11 @@ __device__ __forceinline__ void tc_epilogue_spline(uint32_t trow, const float *b
     tmem_wait_ld();
     const bool inside = (u >= -kTail && u <= kTail);
     const float uc = fminf(fmaxf(u, -kTail), kTail);  // (outside rows are computed and discarded)
-    float e[kBins], ind[kBins];
+    float q[kBins], e[kBins], ind[kBins];
     const float span = 2.0f * kTail * (1.0f - kMinBin * kBins), floor20 = 2.0f * kTail * kMinBin;
-    float sc = span * rqs_softmax(vw, bias, e);
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) q[j] = __uint_as_float(vw[j]) + bias[j];
+    float sc = span * rqs_softmax(q, e);
     float knot = -kTail, pprev = 1.0f, left = 0.f, wid = 0.f;
 #pragma unroll
     for (int j = 0; j < kBins; ++j) {
@@ -418,9 +417,12 @@ __device__ __forceinline__ void tc_epilogue_spline(uint32_t trow, const float *b
     uint32_t vh[kBins];
     tmem_ld_n<kBins>(trow + kTmemD + kBins, vh);
     tmem_wait_ld();
+    // bias is part of the weight slot, which may be refilled once this tile has arrived: read it first
+#pragma unroll
+    for (int j = 0; j < kBins; ++j) q[j] = __uint_as_float(vh[j]) + bias[kBins + j];
     tc_fence_before_sync();
-    mbar_arrive(aready);  // D is free: the next stage's MMA may start while the spline finishes
-    sc = span * rqs_softmax(vh, bias + kBins, e);
+    mbar_arrive(aready);  // D and the slot are free: the next stage's MMA runs while the spline finishes
+    sc = span * rqs_softmax(q, e);
     knot = -kTail;
     float bottom = 0.f, hgt = 0.f;
 #pragma unroll
@@ -591,19 +593,34 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 mbar_arrive(&aready[X]);
                 continue;
             }
+            if (!st.k128 && hf == 0) {
+                // theta stages belong to the hf = 1 warps (all 128 columns, arriving for both halves):
+                // the stage follows a spline, whose tail the hf = 0 warps are still computing
+                mbar_wait(&dfull[X], s & 1);        // keep in step with the barrier's phases
+                continue;
+            }
             mbar_wait(&wfull[s % kTcSlots], (s / kTcSlots) & 1);  // the bias travelled with the stage blob
             const float *bias = reinterpret_cast<const float *>(smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes +
                                                                 st.bias_off + (st.k128 ? 0u : (uint32_t)X * kHidden * 4u));
             mbar_wait(&dfull[X], s & 1);
             tc_fence_after_sync();
-            if (trace && blockIdx.x == 0 && q == 0 && hf == 0 && lane == 0) trace[(s * 2 + X) * 4 + 2] = clock64();
+            const bool tracer = trace && blockIdx.x == 0 && q == 0 && lane == 0 && hf == (st.k128 ? 0 : 1);
+            if (tracer) trace[(s * 2 + X) * 4 + 2] = clock64();
+            if (!st.k128) {
+                if (st.epi == kEpiRelu) tc_epilogue_act<kEpiRelu>(trow, 0, kHidden, bias);
+                else tc_epilogue_act<kEpiSigmoid>(trow, 0, kHidden, bias);
+                tc_fence_before_sync();
+                mbar_arrive_n(&aready[X], 2);
+                if (tracer) trace[(s * 2 + X) * 4 + 3] = clock64();
+                continue;
+            }
             if (st.epi == kEpiRelu) {
-                tc_epilogue_act<kEpiRelu>(trow, 64 * hf, bias);
+                tc_epilogue_act<kEpiRelu>(trow, 64 * hf, 64, bias);
             } else if (st.epi == kEpiSigmoid) {
-                tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, bias);
+                tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, 64, bias);
             } else if (st.epi == kEpiSpline) {
                 tc_epilogue_spline(trow, bias, u, logdet, &aready[X]);
-                if (trace && blockIdx.x == 0 && q == 0 && lane == 0) trace[(s * 2 + X) * 4 + 3] = clock64();
+                if (tracer) trace[(s * 2 + X) * 4 + 3] = clock64();
                 continue;
             } else {
                 uint32_t v[16];
@@ -629,7 +646,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             tc_fence_before_sync();
             mbar_arrive(&aready[X]);
-            if (trace && blockIdx.x == 0 && q == 0 && hf == 0 && lane == 0) trace[(s * 2 + X) * 4 + 3] = clock64();
+            if (tracer) trace[(s * 2 + X) * 4 + 3] = clock64();
         }
         if (hf == 0) {
             // ---- sum over trials, fixed order: the tile that arrives last at its chain block adds
