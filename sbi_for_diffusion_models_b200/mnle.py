@@ -20,11 +20,10 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
-from .potentials import (ConditionedMNLELogLikelihood, ThetaOnlyPosteriorPotential, as_device_estimator,
-                         prior_log_prob)
-from .samplers import VectorizedSliceSampler
+from .potentials import as_device_estimator, prior_log_prob
+from .samplers import GraphedLogProb, PhiloxUniforms, VectorizedSliceSampler
 from .sbc import compute_ranks, draw_sbc_datasets, simulate_sbc_sessions
-from .sharding import _world, gather_sbc, shard_bounds
+from .sharding import _world, all_gather_rows, gather_sbc, shard_bounds
 from .simulator import compute_device
 
 MIN_VECTOR_CHAINS = 128   # one row tile of the potential kernel
@@ -53,12 +52,18 @@ def run_inference_mcmc(cfg, prior_theta, density_estimator, x_o, pulses_o, *, nu
     ceil(POSTERIOR_SAMPLES / num_chains) draws after cfg.WARMUP_STEPS tuning sweeps."""
     dev = compute_device(device)
     chains = int(num_chains) if num_chains is not None else max(int(cfg.NUM_CHAINS), MIN_VECTOR_CHAINS)
-    cll = ConditionedMNLELogLikelihood(as_device_estimator(density_estimator), pulses_o.to(dev), device=dev)
-    potential = ThetaOnlyPosteriorPotential(conditioned_loglike=cll, prior_theta=prior_theta, x_o=x_o.to(dev), device=dev,
-                                            temperature=float(cfg.TEMPERATURE))
-    fn = lambda th: potential(th, track_gradients=False)
+    # the same potential as ThetaOnlyPosteriorPotential(ConditionedMNLELogLikelihood(...)) (reference
+    # mnle.py:61-73), in the sync-free form a CUDA graph can record: every row is evaluated and rows
+    # outside the prior's support keep their -inf
+    x = x_o.to(device=dev, dtype=torch.float32)
+    if x.dim() == 3:
+        assert x.shape[1] == 1, "This implementation supports a single observed x batch (num_xs=1)."
+        x = x[:, 0, :]
+    pulses = pulses_o.to(device=dev, dtype=torch.float32)
+    assert pulses.shape[0] == x.shape[0], f"local_theta must have shape (num_trials, P). Got {tuple(pulses.shape)}"
+    fn = _BatchedPotential(as_device_estimator(density_estimator), prior_theta, x[None], pulses[None], float(cfg.TEMPERATURE))
     init = _init_from_prior(prior_theta, fn, chains, dev)
-    sampler = VectorizedSliceSampler(fn, init, generator=generator)
+    sampler = VectorizedSliceSampler(GraphedLogProb(fn, init), init, generator=generator)
     want = int(cfg.POSTERIOR_SAMPLES)
     per_chain = -(-want // chains)
     draws = sampler.run(per_chain, warmup=int(cfg.WARMUP_STEPS), thin=1)          # (per_chain, chains, 5)
@@ -79,6 +84,40 @@ class _BatchedPotential:
 
 
 @torch.no_grad()
+def sbc_shard(cfg, prior_theta, estimator, thetas_true: torch.Tensor, ds_seeds, init_all: torch.Tensor, lo: int, hi: int,
+              num_samples: int, seed: int, device=None):
+    """Datasets [lo, hi) of an SBC run: simulate their sessions (one launch), sample all their chains
+    in lock-step through the batched potential, rank.  -> (ranks (hi-lo,5) int64 CPU, samples
+    (hi-lo,S,5) float32 CPU).  Everything random is indexed by the GLOBAL dataset / chain number
+    (Philox trial offsets in the simulator, starting points ``init_all`` drawn for all datasets,
+    counter-based uniforms, per-dataset slice widths), so the result for a dataset does not depend on
+    which other datasets share its launch -- any split into shards reproduces the unsplit run."""
+    dev = compute_device(device)
+    D, S, T = hi - lo, int(num_samples), int(cfg.NUM_TRIALS_OBS)
+    C = init_all.shape[0] // thetas_true.shape[0]
+    ranks = torch.empty((D, 5), dtype=torch.int64)
+    if D == 0:
+        return ranks, torch.empty((0, S, 5), dtype=torch.float32)
+    x, pulses = simulate_sbc_sessions(thetas_true[lo:hi], ds_seeds[lo:hi], T, mu_sensory=float(cfg.MU_SENSORY),
+                                      p_success=float(cfg.P_SUCCESS), noise_seed=seed, first_dataset=lo, device=dev)
+    if bool(cfg.LOG_RT_MANUALLY):
+        x = x.clone()
+        x[..., 0] = torch.log(x[..., 0].clamp_min(1e-6))
+    potential = _BatchedPotential(estimator, prior_theta, x, pulses, float(cfg.TEMPERATURE))
+    init = init_all[lo * C:hi * C].to(device=dev, dtype=torch.float32)
+    if not bool(torch.isfinite(potential(init)).all()):
+        raise RuntimeError("a prior draw has a non-finite posterior potential")
+    sampler = VectorizedSliceSampler(GraphedLogProb(potential, init), init, chain_groups=D,
+                                     uniforms=PhiloxUniforms(int(seed) * 1_000_003 + 17, lo * C, D * C, dev))
+    per_chain = -(-S // C)
+    draws = sampler.run(per_chain, warmup=int(cfg.WARMUP_STEPS), thin=1)                  # (per_chain, D*C, 5)
+    samples = draws.view(per_chain, D, C, 5).permute(1, 0, 2, 3).reshape(D, per_chain * C, 5)[:, :S].cpu()
+    for i in range(D):
+        ranks[i] = compute_ranks(thetas_true[lo + i], samples[i])
+    return ranks, samples
+
+
+@torch.no_grad()
 def run_sbc(cfg, *, prior_theta, density_estimator, device: str = "cpu", num_datasets: int = 25,
             posterior_samples_per_dataset: Optional[int] = None, seed: int = 0,
             param_names: Sequence[str] = ("a0", "lam", "v", "B", "tau"), outdir: str = "sbc_outputs", plot_bins: int = 30,
@@ -87,39 +126,21 @@ def run_sbc(cfg, *, prior_theta, density_estimator, device: str = "cpu", num_dat
     theta_true ~ prior, simulate a session, sample the posterior, rank theta_true among the draws.
 
     Returns {"thetas_true": (N,5) float32 ndarray, "ranks": (N,5) int64 ndarray,
-    "all_samples": list of N CPU tensors (S,5)} on every rank.  ``device`` is accepted for
-    signature compatibility; the work runs on this rank's GPU."""
+    "all_samples": list of N CPU tensors (S,5)} on every rank, identical for any number of ranks.
+    ``device`` is accepted for signature compatibility; the work runs on this rank's GPU."""
     dev = compute_device(None)
     rank, world = _world(group)
+    N = int(num_datasets)
     S = int(posterior_samples_per_dataset) if posterior_samples_per_dataset is not None else int(cfg.POSTERIOR_SAMPLES)
-    T = int(cfg.NUM_TRIALS_OBS)
-    thetas_true, ds_seeds = draw_sbc_datasets(prior_theta, int(num_datasets), seed)       # reference order
-    lo, hi = shard_bounds(int(num_datasets), rank, world)
-    est = as_device_estimator(density_estimator)
-    ranks_local = torch.empty((hi - lo, 5), dtype=torch.int64)
-    samples_local = torch.empty((hi - lo, S, 5), dtype=torch.float32)
-    if hi > lo:
-        x, pulses = simulate_sbc_sessions(thetas_true[lo:hi], ds_seeds[lo:hi], T, mu_sensory=float(cfg.MU_SENSORY),
-                                          p_success=float(cfg.P_SUCCESS), noise_seed=seed, first_dataset=lo, device=dev)
-        if bool(cfg.LOG_RT_MANUALLY):
-            x = x.clone()
-            x[..., 0] = torch.log(x[..., 0].clamp_min(1e-6))
-        D, C = hi - lo, int(chains_per_dataset)
-        potential = _BatchedPotential(est, prior_theta, x, pulses, float(cfg.TEMPERATURE))
-        g = torch.Generator(device=dev).manual_seed(int(seed) * 1_000_003 + lo)
-        init = _init_from_prior(prior_theta, potential, D * C, dev)
-        sampler = VectorizedSliceSampler(potential, init, generator=g)
-        per_chain = -(-S // C)
-        draws = sampler.run(per_chain, warmup=int(cfg.WARMUP_STEPS), thin=1)              # (per_chain, D*C, 5)
-        draws = draws.view(per_chain, D, C, 5).permute(1, 0, 2, 3).reshape(D, per_chain * C, 5)[:, :S]
-        samples_local = draws.cpu()
-        for i in range(D):
-            ranks_local[i] = compute_ranks(thetas_true[lo + i], samples_local[i])
-    thetas_all, ranks_all = gather_sbc(thetas_true[lo:hi].to(dev), ranks_local.to(dev), int(num_datasets), group)
-    from .sharding import all_gather_rows
-    samples_all = all_gather_rows(samples_local.to(dev), int(num_datasets), group).cpu()
+    thetas_true, ds_seeds = draw_sbc_datasets(prior_theta, N, seed)                       # reference order
+    init_all = prior_theta.sample((N * int(chains_per_dataset),)).to(torch.float32)       # same on every rank
+    lo, hi = shard_bounds(N, rank, world)
+    ranks_local, samples_local = sbc_shard(cfg, prior_theta, as_device_estimator(density_estimator), thetas_true, ds_seeds,
+                                           init_all, lo, hi, S, seed, dev)
+    thetas_all, ranks_all = gather_sbc(thetas_true[lo:hi].to(dev), ranks_local.to(dev), N, group)
+    samples_all = all_gather_rows(samples_local.to(dev), N, group).cpu()
     out = {"thetas_true": thetas_all.cpu().numpy(), "ranks": ranks_all.cpu().numpy(),
-           "all_samples": [samples_all[i] for i in range(int(num_datasets))]}
+           "all_samples": [samples_all[i] for i in range(N)]}
     if save and rank == 0:
         os.makedirs(outdir, exist_ok=True)
         np.save(os.path.join(outdir, "sbc_thetas_true.npy"), out["thetas_true"])

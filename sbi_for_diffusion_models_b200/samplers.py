@@ -16,26 +16,92 @@ from typing import Callable, Optional
 import torch
 
 
+class GraphedLogProb:
+    """``fn``: (N, D) -> (N,) captured once into a CUDA graph and replayed on static buffers.
+
+    A slice-sampler step is one potential evaluation followed by a handful of tiny elementwise
+    ops; at the sizes of one observed session the Python / launch path of the potential (prior,
+    workspace allocation, two kernel launches) costs several times the kernels themselves, so the
+    whole evaluation is recorded once and replayed.  Falls back to calling ``fn`` for inputs that
+    are not CUDA tensors of the captured shape."""
+
+    def __init__(self, fn: Callable[[torch.Tensor], torch.Tensor], example: torch.Tensor, warmup: int = 2):
+        self.fn = fn
+        self.graph = None
+        if not example.is_cuda:
+            return
+        self.x = example.clone()
+        side = torch.cuda.Stream(example.device)
+        side.wait_stream(torch.cuda.current_stream(example.device))
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    fn(self.x)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    self.y = fn(self.x)
+            self.graph = graph
+        except Exception:       # fn synchronises or leaves the device (e.g. a CPU-only prior): call it directly
+            self.graph = None
+            torch.cuda.synchronize(example.device)
+        torch.cuda.current_stream(example.device).wait_stream(side)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if self.graph is None or x.shape != self.x.shape or x.device != self.x.device or x.dtype != self.x.dtype:
+            return self.fn(x)
+        self.x.copy_(x)
+        self.graph.replay()
+        return self.y.clone()
+
+
+class PhiloxUniforms:
+    """Counter-based uniforms for chains [first_row, first_row + n_rows): draw k of global chain g is
+    Philox4x32-10(key = seed + k // block, counter = (g, k % block)), whichever process owns the chain
+    and whatever other chains run beside it -- so a sampler run sharded over GPUs reproduces the
+    single-GPU run bit for bit.  Uses the simulator's device generator (``ddm_philox_words_u32``)."""
+
+    def __init__(self, seed: int, first_row: int, n_rows: int, device, block: int = 256):
+        self.seed, self.first, self.n, self.device, self.block = int(seed), int(first_row), int(n_rows), device, int(block)
+        self._buf, self._blk = None, -1
+
+    def __call__(self, k: int) -> torch.Tensor:
+        """Draw number ``k`` of every chain: (n_rows,) fp32 in (0, 1)."""
+        from .simulator import philox_words
+        blk, j = divmod(int(k), self.block)
+        if blk != self._blk:
+            words = philox_words(self.seed + blk, self.n, self.block, trial_offset=self.first, device=self.device)
+            # top 24 bits -> (0, 1): ((w >> 8) + 0.5) * 2^-24, exact in fp32
+            self._buf = ((words >> 8) & 0xFFFFFF).to(torch.float32).add_(0.5).mul_(2.0 ** -24)
+            self._blk = blk
+        return self._buf[j]
+
+
 class VectorizedSliceSampler:
     """``log_prob_fn``: (N, D) -> (N,), ``-inf`` outside the support.  ``init``: (N, D) starting
     points with finite log-probability."""
 
     def __init__(self, log_prob_fn: Callable[[torch.Tensor], torch.Tensor], init: torch.Tensor, *,
                  init_width: float = 0.1, max_step_out: int = 16, max_shrink: int = 64,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, uniforms: Optional[Callable[[int], torch.Tensor]] = None,
+                 chain_groups: int = 1):
         if init.ndim != 2:
             raise ValueError(f"init must be (num_chains, dim), got {tuple(init.shape)}")
         self.f = log_prob_fn
         self.x = init.clone()
-        self.gen = generator
+        self.gen, self.uniforms = generator, uniforms
+        # chains come in ``chain_groups`` equal consecutive groups (SBC: one group per dataset), each
+        # with its own slice widths, so that a group's trajectory does not depend on its neighbours
+        self.groups = int(chain_groups)
+        if init.shape[0] % self.groups:
+            raise ValueError("the number of chains must be a multiple of chain_groups")
         self.N, self.D = init.shape
         self.lp = self._eval(self.x)
         if not bool(torch.isfinite(self.lp).all()):
             raise ValueError("every chain must start at a point of finite log-probability")
-        self.width = torch.full((self.D,), float(init_width), dtype=init.dtype, device=init.device) * \
-            init.abs().mean(dim=0).clamp_min(1e-3)
+        per = self.N // self.groups
+        self.width = float(init_width) * init.abs().view(self.groups, per, self.D).mean(dim=1).clamp_min(1e-3)   # (G, D)
         self.max_step_out, self.max_shrink = int(max_step_out), int(max_shrink)
-        self.n_evals = 0
+        self.n_evals, self._updates = 0, 0
 
     # ------------------------------------------------------------------------------------
     def _eval(self, x: torch.Tensor) -> torch.Tensor:
@@ -43,7 +109,12 @@ class VectorizedSliceSampler:
         self.n_evals = getattr(self, "n_evals", 0) + 1
         return torch.nan_to_num(lp, nan=-float("inf"), posinf=float("inf"), neginf=-float("inf"))
 
-    def _rand(self) -> torch.Tensor:
+    def _rand(self, k: int) -> torch.Tensor:
+        """Uniform number ``k`` of every chain.  With a counter-based source the index is explicit
+        (update number, draw within the update), so chains that need more shrinkage steps than others
+        do not shift anybody's later draws."""
+        if self.uniforms is not None:
+            return self.uniforms(k).to(self.x.dtype)
         return torch.rand((self.N,), dtype=self.x.dtype, device=self.x.device, generator=self.gen)
 
     def _with(self, d: int, v: torch.Tensor) -> torch.Tensor:
@@ -54,9 +125,11 @@ class VectorizedSliceSampler:
     def _update_dim(self, d: int) -> torch.Tensor:
         """One slice update of coordinate ``d`` for all chains; returns the bracket sizes."""
         x0 = self.x[:, d]
-        w = self.width[d]
-        log_y = self.lp + torch.log(self._rand().clamp_min(1e-37))
-        lo = x0 - w * self._rand()
+        w = self.width[:, d].repeat_interleave(self.N // self.groups)        # per-chain width of its group
+        base = self._updates * (2 + self.max_shrink)
+        self._updates += 1
+        log_y = self.lp + torch.log(self._rand(base).clamp_min(1e-37))
+        lo = x0 - w * self._rand(base + 1)
         hi = lo + w
         # stepping out: only chains whose bracket end is still inside the slice move
         grow = torch.ones_like(x0, dtype=torch.bool)
@@ -75,8 +148,8 @@ class VectorizedSliceSampler:
         # shrinkage
         todo = torch.ones_like(x0, dtype=torch.bool)
         new_x, new_lp = x0.clone(), self.lp.clone()
-        for _ in range(self.max_shrink):
-            prop = lo + (hi - lo) * self._rand()
+        for it in range(self.max_shrink):
+            prop = lo + (hi - lo) * self._rand(base + 2 + it)
             lp = self._eval(self._with(d, torch.where(todo, prop, new_x)))
             ok = todo & (lp > log_y)
             new_x = torch.where(ok, prop, new_x)
@@ -96,7 +169,7 @@ class VectorizedSliceSampler:
         for d in range(self.D):
             size = self._update_dim(d)
             if tune:   # running estimate of the typical slice width, as sbi's slice samplers do
-                self.width[d] = 0.5 * self.width[d] + 0.5 * size.mean().clamp_min(1e-6)
+                self.width[:, d] = 0.5 * self.width[:, d] + 0.5 * size.view(self.groups, -1).mean(dim=1).clamp_min(1e-6)
 
     @torch.no_grad()
     def run(self, num_samples_per_chain: int, *, warmup: int = 100, thin: int = 1) -> torch.Tensor:

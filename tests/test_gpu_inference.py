@@ -6,7 +6,7 @@ import torch
 
 from oracle import ddm_oracle as orc
 from oracle import mnle_spec as ms
-from sbi_for_diffusion_models_b200.mnle import run_inference_mcmc, run_sbc
+from sbi_for_diffusion_models_b200.mnle import run_inference_mcmc, run_sbc, sbc_shard
 from sbi_for_diffusion_models_b200.mnle_net import DeviceMNLE, PackedMNLE
 from sbi_for_diffusion_models_b200.priors import build_prior_theta
 from sbi_for_diffusion_models_b200.run_config import RunConfig
@@ -72,3 +72,19 @@ def test_run_sbc_reference_outputs(est, tmp_path):
     for i in range(4):
         assert np.array_equal(out["ranks"][i], (out["all_samples"][i] < want_thetas[i][None, :]).sum(0).numpy())
     assert (tmp_path / "sbc" / "sbc_ranks.npy").exists() and (tmp_path / "sbc" / "sbc_thetas_true.npy").exists()
+
+
+def test_sbc_result_does_not_depend_on_the_sharding(est):
+    """Any split of the datasets into shards (GPUs) reproduces the unsplit run bit for bit: Philox trial
+    offsets in the simulator, starting points drawn for all datasets, counter-based sampler uniforms,
+    per-dataset slice widths, and a potential kernel whose rows do not depend on their neighbours."""
+    cfg = RunConfig(WARMUP_STEPS=4, NUM_TRIALS_OBS=12)
+    prior = build_prior_theta()
+    N, C, S = 5, 128, 200
+    thetas, seeds = draw_sbc_datasets(prior, N, seed=3)
+    init_all = prior.sample((N * C,)).to(torch.float32)
+    whole_r, whole_s = sbc_shard(cfg, prior, est, thetas, seeds, init_all, 0, N, S, 3)
+    for lo, hi in ((0, 2), (2, 5), (4, 5), (3, 3)):
+        r, s = sbc_shard(cfg, prior, est, thetas, seeds, init_all, lo, hi, S, 3)
+        assert torch.equal(r, whole_r[lo:hi]) and torch.equal(s, whole_s[lo:hi]), (lo, hi)
+    assert tuple(whole_s.shape) == (N, S, 5) and bool((whole_r >= 0).all()) and bool((whole_r <= S).all())

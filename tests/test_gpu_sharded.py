@@ -17,4 +17,5 @@ def test_two_gpu_sharding_matches_single_gpu():
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "check_sharded_cuda.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "== single GPU: True" in r.stdout
+    assert "sharded over 2 GPUs == single GPU: True" in r.stdout
+    assert "SBC sharded over 2 GPUs == single GPU: True" in r.stdout

@@ -45,6 +45,23 @@ def main():
         ok = torch.equal(z.cpu(), z1) and torch.equal(x.cpu(), x1)
         print(f"sharded over {dist.get_world_size()} GPUs == single GPU: {ok}; outcomes "
               f"{torch.bincount(x1[:, 1].long(), minlength=3).tolist()}", flush=True)
+    # SBC: datasets sharded over the ranks == the same run on one rank
+    from sbi_for_diffusion_models_b200.mnle import run_sbc
+    from sbi_for_diffusion_models_b200.mnle_net import DeviceMNLE, PackedMNLE
+    from sbi_for_diffusion_models_b200.priors import build_prior_theta
+    from sbi_for_diffusion_models_b200.run_config import RunConfig
+    import bench
+    est = DeviceMNLE(PackedMNLE.from_params(bench.random_mnle_params(0)))
+    cfg = RunConfig(WARMUP_STEPS=3, NUM_TRIALS_OBS=10)
+    solo = dist.new_group([0])
+    out = run_sbc(cfg, prior_theta=build_prior_theta(), density_estimator=est, num_datasets=7,
+                  posterior_samples_per_dataset=130, seed=5, save=False)
+    if rank == 0:
+        one = run_sbc(cfg, prior_theta=build_prior_theta(), density_estimator=est, num_datasets=7,
+                      posterior_samples_per_dataset=130, seed=5, save=False, group=solo)
+        same = (out["ranks"] == one["ranks"]).all() and all(torch.equal(a, b) for a, b in zip(out["all_samples"], one["all_samples"]))
+        print(f"SBC sharded over {dist.get_world_size()} GPUs == single GPU: {bool(same)}", flush=True)
+        ok = ok and bool(same)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
