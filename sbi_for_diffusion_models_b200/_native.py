@@ -36,6 +36,7 @@ _SIGNATURES = {
     "mnle_create": (ctypes.c_int, [_ptr, ctypes.c_size_t, _i32, _ptr]),
     "mnle_destroy": (ctypes.c_int, [_ptr]),
     "mnle_log_prob_rows_f32": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
+    "mnle_log_prob_rows_tc_f32": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
     "mnle_loglik_workspace_floats": (ctypes.c_size_t, [_i64, _i64]),
     "mnle_loglik_tc_workspace_floats": (ctypes.c_size_t, [_i64, _i64]),
     "mnle_loglik_sum_tc_f32": (ctypes.c_int, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),

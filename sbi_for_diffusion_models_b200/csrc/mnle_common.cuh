@@ -71,11 +71,14 @@ constexpr int kTcStages = 4 + 3 * kTransforms;  // cat: theta, W1, W2, Wo; flow:
 constexpr int kNets = 1 + kTransforms;
 constexpr int kSplineN = 80;                    // 71 spline parameters padded to a legal UMMA N
 enum TcEpilogue { kEpiRelu = 0, kEpiSigmoid = 1, kEpiSpline = 2, kEpiCategorical = 3 };
+// theta stage (K = 32, potential mode) | K = 128 hi/lo layer | whole first layer (K = 96, rows mode)
+enum TcStageKind { kStageTheta = 0, kStageK128 = 1, kStageInput = 2 };
+constexpr int kInputK = 96;                     // 86 context columns padded to a multiple of 16
 struct TcStage {
     uint32_t off, bytes;  // blob position in the pack (16-byte multiples)
     uint32_t bias_off;    // where the N bias floats sit relative to the staged blob
     uint16_t n;           // UMMA N (multiple of 16)
-    uint8_t k128;         // 1: K = 128 hi/lo stage, 0: theta stage
+    uint8_t kind;         // TcStageKind
     uint8_t epi;          // TcEpilogue
     uint16_t net, pad;    // 0 = categorical net, 1 + k = spline conditioner k
 };
@@ -90,7 +93,8 @@ struct Handle {
     float *params;   // device copy of the packed buffer
     void *tc_pack;   // device copy of the tensor-core operand pack (bf16 hi/lo tiles), or null
     size_t tc_pack_bytes;
-    TcPlan tc_plan;
+    TcPlan tc_plan;       // potential mode: rows = (trial, chain), first layers hoisted per trial
+    TcPlan tc_rows_plan;  // rows mode: arbitrary (R, 85) conditions, first layers on the tensor cores
     float mu_y, sigma_y;
 };
 int build_tc_pack(Handle *H, const float *packed_host);  // mnle_tc.cu

@@ -206,10 +206,10 @@ int build_tc_pack(Handle *H, const float *packed_host)
     std::vector<unsigned char> blob;
     TcPlan &P = H->tc_plan;
     int s = 0;
-    auto begin = [&](int n, int k128, int epi, int net) {
+    auto begin = [&](int n, int kind, int epi, int net) {
         P.st[s].off = (uint32_t)blob.size();
         P.st[s].n = (uint16_t)n;
-        P.st[s].k128 = (uint8_t)k128;
+        P.st[s].kind = (uint8_t)kind;
         P.st[s].epi = (uint8_t)epi;
         P.st[s].net = (uint16_t)net;
     };
@@ -219,21 +219,21 @@ int build_tc_pack(Handle *H, const float *packed_host)
         ++s;
     };
     auto dense = [&](size_t W, size_t b, int n_valid, int N, int epi, int net) {
-        begin(N, 1, epi, net);
+        begin(N, kStageK128, epi, net);
         pack_image_k128(blob, packed_host + W, n_valid, N, 0);
         pack_image_k128(blob, packed_host + W, n_valid, N, 1);
         pack_bias(blob, packed_host + b, n_valid, N);
         end(true);
     };
     // categorical net
-    begin(kHidden, 0, kEpiSigmoid, 0);
+    begin(kHidden, kStageTheta, kEpiSigmoid, 0);
     pack_image_theta(blob, packed_host + L.cat_W0, kCond);
     end(false);
     dense(L.cat_W1, L.cat_b1, kHidden, kHidden, kEpiSigmoid, 0);
     dense(L.cat_W2, L.cat_b2, kHidden, kHidden, kEpiSigmoid, 0);
     dense(L.cat_Wo, L.cat_bo, L.n_choices, 16, kEpiCategorical, 0);
     for (int k = 0; k < kTransforms; ++k) {
-        begin(kHidden, 0, kEpiRelu, 1 + k);
+        begin(kHidden, kStageTheta, kEpiRelu, 1 + k);
         pack_image_theta(blob, packed_host + L.fl_W1[k], kCtx);
         end(false);
         dense(L.fl_W2[k], L.fl_b2[k], kHidden, kHidden, kEpiRelu, 1 + k);
@@ -242,6 +242,32 @@ int build_tc_pack(Handle *H, const float *packed_host)
     if (s != kTcStages) {
         ddm::set_error("build_tc_pack: %d stages, expected %d", s, kTcStages);
         return DDM_ERR_STATE;
+    }
+    // rows mode: the same plan with every theta stage replaced by the whole first layer (K = 96)
+    TcPlan &R = H->tc_rows_plan;
+    R = P;
+    for (int i = 0; i < kTcStages; ++i) {
+        if (P.st[i].kind != kStageTheta) continue;
+        const int net = P.st[i].net;
+        const float *W = packed_host + (net == 0 ? L.cat_W0 : L.fl_W1[net - 1]);
+        const float *b = packed_host + (net == 0 ? L.cat_b0 : L.fl_b1[net - 1]);
+        const int K = net == 0 ? kCond : kCtx;
+        TcStage &st = R.st[i];
+        st.off = (uint32_t)blob.size();
+        st.kind = kStageInput;
+        for (int term = 0; term < 2; ++term) {
+            const size_t base = blob.size();
+            blob.resize(base + (size_t)kHidden * kInputK * 2, 0);
+            for (int n = 0; n < kHidden; ++n)
+                for (int k = 0; k < K; ++k) {
+                    uint16_t t[3];
+                    host_split3(W[(size_t)n * K + k], t);
+                    memcpy(&blob[base + tile_offset(kHidden, n, k)], &t[term], 2);
+                }
+        }
+        pack_bias(blob, b, kHidden, kHidden);
+        st.bytes = (uint32_t)blob.size() - st.off;
+        st.bias_off = st.bytes - (uint32_t)kHidden * 4u;
     }
     DDM_CUDA_TRY(cudaMalloc(&H->tc_pack, blob.size()));
     DDM_CUDA_TRY(cudaMemcpy(H->tc_pack, blob.data(), blob.size(), cudaMemcpyHostToDevice));
@@ -453,6 +479,11 @@ __device__ __forceinline__ void tc_epilogue_spline(uint32_t trow, const float *b
 
 // grid = ceil(D * T * ceil(C / 128) / 2): tile = ((d * T + t) * CB + chain block), chain block fastest.
 // D independent datasets (own x, pulses and C chains each) share one launch.
+// ROWS: estimator.log_prob over arbitrary rows -- `theta` is the (R, 85) condition matrix (row stride
+// ld_theta), x is (R, 2), C = R, one tile per CTA; the 86-wide context goes into TMEM columns
+// [256, 352) as bf16 hi / lo and every net's first layer is a K = 96 stage; out[row] = log-prob.
+constexpr uint32_t kTmemInHi = 256, kTmemInLo = 256 + kInputK / 2;
+template <bool ROWS>
 __global__ void __launch_bounds__(kTcThreads, 1)
     mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
                    const float *__restrict__ theta, long long ld_theta, const float *__restrict__ x,
@@ -469,8 +500,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
     const int n_tiles = D * T * CB;
-    const int tile0 = blockIdx.x * kTcTiles;
-    const int n_active = min(kTcTiles, n_tiles - tile0);
+    const int tile0 = ROWS ? blockIdx.x : blockIdx.x * kTcTiles;
+    const int n_active = ROWS ? 1 : min(kTcTiles, n_tiles - tile0);
 
     if (warp == kTcEpiWarps) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
@@ -496,9 +527,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             unsigned char *slot = smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes;
             uint64_t *bar = &wfull[s % kTcSlots];
             if (elect_one_sync()) {
-                mbar_expect_tx(bar, st.bytes + (st.k128 ? 0u : (uint32_t)n_active * kHidden * 4u));
+                mbar_expect_tx(bar, st.bytes + (st.kind != kStageTheta ? 0u : (uint32_t)n_active * kHidden * 4u));
                 bulk_g2s(slot, pack + st.off, st.bytes, bar);
-                if (!st.k128) {
+                if (st.kind == kStageTheta) {
                     bulk_g2s(slot + st.bytes, hoist + ((size_t)t_of[0] * kNets + st.net) * kHidden, kHidden * 4, bar);
                     if (n_active > 1)
                         bulk_g2s(slot + st.bytes + kHidden * 4, hoist + ((size_t)t_of[1] * kNets + st.net) * kHidden,
@@ -523,7 +554,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 4 + 1] = clock64();
                 const uint32_t tm = tmem_u + (uint32_t)X * kTmemTile;
                 if (elect_one_sync()) {
-                    if (!st.k128) {
+                    if (st.kind == kStageInput) {
+                        const uint32_t w_img = kHidden * kInputK * 2u;
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t a = tmem_u + (pass == 2 ? kTmemInLo : kTmemInHi);
+                            const uint32_t w = slot + (pass == 1 ? w_img : 0u);
+#pragma unroll
+                            for (int ks = 0; ks < kInputK / 16; ++ks)
+                                umma_bf16_ts(tm + kTmemD, a + (uint32_t)ks * 8u,
+                                             umma_desc_kmajor(w + ks * 2 * kKGroupBytes, kKGroupBytes, 128), idesc,
+                                             (pass | ks) != 0);
+                        }
+                    } else if (st.kind == kStageTheta) {
                         const uint32_t a = smem_u32(smem + kSmemATh + (uint32_t)X * kAThBytes);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks)
@@ -557,7 +600,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const bool live = c < C;
         const long long c_glob = (long long)d * C + c;
         const uint32_t trow = tmem + (uint32_t)X * kTmemTile + ((uint32_t)(32 * q) << 16);
-        {   // A image of the theta stage: k = term * 5 + i, terms t1 t1 t2 t1 t2 t3 (pairs with pack_image_theta)
+        if (ROWS) {
+            // context row [cond (85), choice, 0...] -> bf16 hi / lo in TMEM; this thread: k in [48 hf, 48 hf + 48)
+            const float *crow = theta + c_glob * ld_theta;
+            const float ch = live ? __ldg(x + 2 * c_glob + 1) : 0.f;
+#pragma unroll 1
+            for (int k0 = 48 * hf; k0 < 48 * hf + 48; k0 += 16) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float v[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = k0 + 2 * j + e;
+                        v[e] = !live ? 0.f : (k < kCond ? __ldg(crow + k) : (k == kCond ? ch : 0.f));
+                    }
+                    split_bf16x2(v[0], v[1], hi[j], lo[j]);
+                }
+                tmem_st8(trow - (uint32_t)X * kTmemTile + kTmemInHi + (uint32_t)(k0 >> 1), hi);
+                tmem_st8(trow - (uint32_t)X * kTmemTile + kTmemInLo + (uint32_t)(k0 >> 1), lo);
+            }
+            tmem_wait_st();
+            tc_fence_before_sync();
+        } else {   // A image of the theta stage: k = term * 5 + i, terms t1 t1 t2 t1 t2 t3 (pairs with pack_image_theta)
             unsigned char *a_th = smem + kSmemATh + (uint32_t)X * kAThBytes;
             uint16_t tt[5][3];
 #pragma unroll
@@ -580,8 +645,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         fence_proxy_async_smem();
         mbar_arrive(&aready[X]);
 
-        const float rt = __ldg(x + 2 * t);
-        const int choice = (int)__ldg(x + 2 * t + 1);
+        const long long xi = ROWS ? (live ? c_glob : 0) : t;
+        const float rt = __ldg(x + 2 * xi);
+        const int choice = (int)__ldg(x + 2 * xi + 1);
         const float y = logf(rt);
         float u = (y - mu_y) / sigma_y, logdet = -logf(sigma_y), lp = 0.f;
 
@@ -593,7 +659,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 mbar_arrive(&aready[X]);
                 continue;
             }
-            if (!st.k128 && hf == 0) {
+            if (st.kind == kStageTheta && hf == 0) {
                 // theta stages belong to the hf = 1 warps (all 128 columns, arriving for both halves):
                 // the stage follows a spline, whose tail the hf = 0 warps are still computing
                 mbar_wait(&dfull[X], s & 1);        // keep in step with the barrier's phases
@@ -601,12 +667,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             mbar_wait(&wfull[s % kTcSlots], (s / kTcSlots) & 1);  // the bias travelled with the stage blob
             const float *bias = reinterpret_cast<const float *>(smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes +
-                                                                st.bias_off + (st.k128 ? 0u : (uint32_t)X * kHidden * 4u));
+                                                                st.bias_off + (st.kind != kStageTheta ? 0u : (uint32_t)X * kHidden * 4u));
             mbar_wait(&dfull[X], s & 1);
             tc_fence_after_sync();
-            const bool tracer = trace && blockIdx.x == 0 && q == 0 && lane == 0 && hf == (st.k128 ? 0 : 1);
+            const bool tracer = trace && blockIdx.x == 0 && q == 0 && lane == 0 && hf == (st.kind != kStageTheta ? 0 : 1);
             if (tracer) trace[(s * 2 + X) * 4 + 2] = clock64();
-            if (!st.k128) {
+            if (st.kind == kStageTheta) {
                 if (st.epi == kEpiRelu) tc_epilogue_act<kEpiRelu>(trow, 0, kHidden, bias);
                 else tc_epilogue_act<kEpiSigmoid>(trow, 0, kHidden, bias);
                 tc_fence_before_sync();
@@ -648,7 +714,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_arrive(&aready[X]);
             if (tracer) trace[(s * 2 + X) * 4 + 3] = clock64();
         }
-        if (hf == 0) {
+        if (ROWS) {
+            if (hf == 0 && live) out[c_glob] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+        } else if (hf == 0) {
             // ---- sum over trials, fixed order: the tile that arrives last at its chain block adds
             // the T partial rows (every run gives the same bits whichever tile that is)
             if (live) partial[(size_t)t * C + c] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
@@ -745,8 +813,8 @@ DDM_API int mnle_loglik_sum_batched_tc_f32(void *handle, const float *theta_dev,
     mnle_hoist_kernel<<<dim3(kNets, (unsigned)hoist_blocks), kHidden, 0, st>>>(H->params, H->layout, x_dev, pulses_dev, ld_pulses,
                                                                             (int)(D * T), hoist, counters, (int)(D * CB));
     DDM_CUDA_TRY(cudaGetLastError());
-    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    mnle_tc_kernel<<<(unsigned)((n_tiles + kTcTiles - 1) / kTcTiles), kTcThreads, kTcSmemBytes, st>>>(
+    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    mnle_tc_kernel<false><<<(unsigned)((n_tiles + kTcTiles - 1) / kTcTiles), kTcThreads, kTcSmemBytes, st>>>(
         static_cast<const unsigned char *>(H->tc_pack), H->tc_plan, theta_dev, ld_theta, x_dev, hoist, (int)D, (int)T, (int)C,
         H->mu_y, H->sigma_y, H->layout.n_choices, partial, counters, out_dev, g_tc_trace);
     DDM_CUDA_TRY(cudaGetLastError());
@@ -759,4 +827,25 @@ DDM_API int mnle_loglik_sum_tc_f32(void *handle, const float *theta_dev, int64_t
 {
     return mnle_loglik_sum_batched_tc_f32(handle, theta_dev, ld_theta, x_dev, pulses_dev, ld_pulses, 1, T, C, out_dev,
                                           workspace_dev, stream);
+}
+
+DDM_API int mnle_log_prob_rows_tc_f32(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond, int64_t R,
+                                      float *out_dev, void *stream)
+{
+    Handle *H = static_cast<Handle *>(handle);
+    if (H == nullptr || H->magic != kMagic || H->tc_pack == nullptr) {
+        ddm::set_error("mnle_log_prob_rows_tc_f32: bad handle");
+        return DDM_ERR_STATE;
+    }
+    DDM_REQUIRE(R >= 0 && R <= 0x7FFFFFFFll - kTcM, "mnle_log_prob_rows_tc_f32: bad R");
+    if (R == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev && cond_dev && out_dev, "mnle_log_prob_rows_tc_f32: null pointer");
+    DDM_REQUIRE(ld_cond >= kCond, "mnle_log_prob_rows_tc_f32: ld_cond=%lld < 85", (long long)ld_cond);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    mnle_tc_kernel<true><<<(unsigned)((R + kTcM - 1) / kTcM), kTcThreads, kTcSmemBytes, st>>>(
+        static_cast<const unsigned char *>(H->tc_pack), H->tc_rows_plan, cond_dev, ld_cond, x_dev, nullptr, 1, 1, (int)R,
+        H->mu_y, H->sigma_y, H->layout.n_choices, nullptr, nullptr, out_dev, nullptr);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
 }

@@ -153,6 +153,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&r)[16]
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 // ---- UMMA ----------------------------------------------------------------------------------
 // Shared-memory operand descriptor, K-major, no swizzle ("interleaved" canonical layout): in
 // 16-byte units the tile is ((8, n), 2) : ((1, SBO), LBO) -- 8 rows of one core matrix are

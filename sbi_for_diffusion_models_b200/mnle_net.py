@@ -165,8 +165,11 @@ class DeviceMNLE(torch.nn.Module):
     def _dev(self, t: Optional[torch.Tensor] = None) -> torch.device:
         return compute_device(self._device if self._device is not None else (t.device if t is not None and t.is_cuda else None))
 
-    def log_prob(self, x: torch.Tensor, condition: torch.Tensor) -> torch.Tensor:
-        """x (1,R,2) or (R,2) = [rt seconds, choice], condition (R,85) -> (1,R)."""
+    def log_prob(self, x: torch.Tensor, condition: torch.Tensor, *, kernel: str = "auto") -> torch.Tensor:
+        """x (1,R,2) or (R,2) = [rt seconds, choice], condition (R,85) -> (1,R).
+        ``kernel``: "tc" / "auto" tensor cores (tcgen05), "simt" fp32 CUDA cores."""
+        if kernel not in ("auto", "tc", "simt"):
+            raise ValueError(f"unknown kernel {kernel!r}")
         dev = self._dev(condition)
         xr = x.reshape(-1, 2).to(device=dev, dtype=torch.float32).contiguous()
         cond = condition.to(device=dev, dtype=torch.float32)
@@ -177,10 +180,11 @@ class DeviceMNLE(torch.nn.Module):
         R = xr.shape[0]
         with torch.cuda.device(dev):
             out = torch.empty((R,), dtype=torch.float32, device=dev)
-            rc = _native.lib().mnle_log_prob_rows_f32(self.packed.handle(dev), xr.data_ptr(), cond.data_ptr(),
-                                                      cond.stride(0) if R > 1 else COND_DIM, R, out.data_ptr(),
-                                                      torch.cuda.current_stream(dev).cuda_stream)
-            _native.check(rc, "mnle_log_prob_rows_f32")
+            L = _native.lib()
+            fn = L.mnle_log_prob_rows_f32 if kernel == "simt" else L.mnle_log_prob_rows_tc_f32
+            rc = fn(self.packed.handle(dev), xr.data_ptr(), cond.data_ptr(), cond.stride(0) if R > 1 else COND_DIM, R,
+                    out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _native.check(rc, "mnle_log_prob_rows")
         return out.to(condition.device).unsqueeze(0)
 
     def loglik_sum(self, theta: torch.Tensor, x_o: torch.Tensor, pulses: torch.Tensor, *, kernel: str = "auto"

@@ -30,7 +30,8 @@ def net(request):
     return p, ms.cast_params(p, torch.float64), DeviceMNLE(PackedMNLE.from_params(p)), scale
 
 
-def test_rows_api_matches_spec(net):
+@pytest.mark.parametrize("kernel", ["tc", "simt"])
+def test_rows_api_matches_spec(net, kernel):
     p32, p64, est, scale = net
     R = 3000
     theta = orc.prior_sample(R, seed=2)
@@ -39,14 +40,22 @@ def test_rows_api_matches_spec(net):
     rs = np.random.RandomState(0)
     x = torch.from_numpy(np.stack([np.exp(rs.uniform(-3, 2.1, R)), rs.randint(0, 3, R)], 1).astype(np.float32))
     x[:5, 0] = torch.tensor([1e-6, 8.0, 7.999999, 1e-3, 3e-5])      # tails of the spline / log transform
-    got = est.log_prob(x.unsqueeze(0), condition=cond)
+    got = est.log_prob(x.unsqueeze(0), condition=cond, kernel=kernel)
     assert tuple(got.shape) == (1, R) and got.device.type == "cpu"
     want = ms.log_prob(p64, x, cond)
     err = (got[0].double() - want).abs()
-    assert float(err.max()) < (2e-3 if scale == 1.0 else 2e-2), float(err.max())
-    assert float(err.mean()) < 2e-4 * scale ** 3
-    # CUDA inputs come back on CUDA
-    assert est.log_prob(x.cuda(), condition=cond.cuda()).is_cuda
+    if kernel == "simt":
+        assert float(err.max()) < (2e-3 if scale == 1.0 else 2e-2), float(err.max())
+        assert float(err.mean()) < 2e-4 * scale ** 3
+    else:   # bf16 hi/lo operands (~17 bits), the sharpened net amplifies it (see the potential tests)
+        assert float(err.max()) < (4e-3 if scale == 1.0 else 1.0), float(err.max())
+        assert float(err.mean()) < (3e-4 if scale == 1.0 else 4e-3), float(err.mean())
+    # CUDA inputs come back on CUDA; strided condition views (z[:, :85] of a wider matrix) are read in place
+    assert est.log_prob(x.cuda(), condition=cond.cuda(), kernel=kernel).is_cuda
+    wide = torch.cat([cond, torch.zeros(R, 7)], dim=1).cuda()
+    assert torch.equal(est.log_prob(x.cuda(), condition=wide[:, :85], kernel=kernel).cpu(), got)
+    for r in (1, 127, 129):                                             # ragged last tile
+        assert torch.equal(est.log_prob(x[:r], condition=cond[:r], kernel=kernel)[0], got[0, :r])
 
 
 @pytest.mark.parametrize("kernel", ["tc", "simt"])
@@ -64,7 +73,7 @@ def test_potential_sum_matches_spec(net, T, C, kernel):
     assert rel < (1e-4 if scale == 1.0 else (1e-3 if kernel == "simt" else 6e-3)), rel
     # same numbers through the rows API and the reference's row layout r = t*C + c
     xr, cond = ms.potential_rows(theta, x, pulses)
-    rows = est.log_prob(xr.unsqueeze(0), condition=cond)[0].reshape(T, C).sum(0).double()
+    rows = est.log_prob(xr.unsqueeze(0), condition=cond, kernel=kernel)[0].reshape(T, C).sum(0).double()
     if kernel == "simt":
         assert torch.allclose(rows, got, rtol=2e-6, atol=1e-3)
     else:   # bf16 hi/lo operands carry ~17 bits: per-row noise ~1e-4 (2e-3 on the sharpened net), random in sign
