@@ -238,6 +238,34 @@ int mnle_loglik_sum_batched_tc_f32(void *handle, const float *theta_dev, int64_t
                                    const float *pulses_dev, int64_t ld_pulses, int64_t D, int64_t T, int64_t C,
                                    float *out_dev, float *workspace_dev, void *stream);
 
+/* ------------------------------------------------------------ MNLE training --- */
+
+/*
+ * One optimisation step of what sbi's MNLE.train does for the reference (mnle.py:41-48; Adam on
+ * -mean log p over minibatches of TRAIN_BATCH_SIZE rows, run_config.py:12), on device buffers the
+ * caller owns.  params_dev / grad_dev / m_dev / v_dev hold mnle_packed_floats(K) floats in the
+ * packed layout above (during training the condition is standardised by the caller, so the first
+ * layers are the raw ones; mu_y / sigma_y at the tail are read, never updated).
+ *
+ * mnle_train_nll_grad_f32: minibatch row r is dataset row row_index_dev[r] (int64; NULL = rows
+ * 0..R-1) of x_dev (N,2) = [rt seconds, choice] and cond_dev (N,85) with row stride ld_cond.
+ *   stats_dev[0] = -mean_r log p(x_r | cond_r),  stats_dev[1] = |grad|^2
+ *   grad_dev[i]  = d stats[0] / d params[i]   (NULL: loss only, e.g. the validation pass)
+ * All reductions run in a fixed order: results are bit-reproducible.  workspace_dev >=
+ * mnle_train_workspace_floats(K, R) floats.
+ *
+ * mnle_train_adam_f32: torch.optim.Adam update (no weight decay) for step = 1, 2, ... after
+ * scaling the gradient like torch.nn.utils.clip_grad_norm_(max_grad_norm) using stats_dev[1]
+ * (max_grad_norm <= 0: no clipping).
+ */
+size_t mnle_train_workspace_floats(int n_choices, int64_t R);
+int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, const float *x_dev, const float *cond_dev,
+                            int64_t ld_cond, const int64_t *row_index_dev, int64_t R, float *stats_dev,
+                            float *grad_dev, float *workspace_dev, void *stream);
+int mnle_train_adam_f32(float *params_dev, const float *grad_dev, float *m_dev, float *v_dev, int n_choices,
+                        const float *stats_dev, float lr, float beta1, float beta2, float eps, int64_t step,
+                        float max_grad_norm, void *stream);
+
 /* Debug aid: when trace_dev != NULL, CTA 0 of every following mnle_loglik_sum_tc_f32 launch writes
  * 34 stages x 2 tiles x 4 clock64() stamps there (issuer saw A operand / had the weights, epilogue
  * saw the accumulators / finished).  NULL switches it off (the default). */

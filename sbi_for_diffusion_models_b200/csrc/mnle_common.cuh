@@ -107,7 +107,8 @@ __device__ __forceinline__ float softplus_f(float x)
 
 // One rational-quadratic spline transform with linear tails (Durkan et al. 2019) on a scalar.
 // q points at the 71 raw conditioner outputs of this row (stride qs floats between them).
-__device__ __forceinline__ void rqs_forward(float &u, float &logdet, const float *q, int qs)
+template <typename Stride>
+__device__ __forceinline__ void rqs_forward(float &u, float &logdet, const float *q, Stride qs)
 {
     if (!(u >= -kTail && u <= kTail)) return;  // identity outside the tail bound
     const float inv_sqrt_h = 0.08838834764831845f;  // 1/sqrt(128)

@@ -21,17 +21,22 @@ struct SimtSmem {
     float red[8];
 };
 
-enum Act { kNone = 0, kRelu = 1, kSigmoid = 2 };
+// kMaskRelu / kMaskSigmoid (backward passes): the product is multiplied by the derivative of the
+// activation whose OUTPUT currently sits in out_s, and replaces it there.
+enum Act { kNone = 0, kRelu = 1, kSigmoid = 2, kMaskRelu = 3, kMaskSigmoid = 4 };
 
 // out[r][n] = act(sum_k in[r][k] * W[n][k] + b[n]) for r < 64, n < n_valid (<= 16 * NJ).
 // DUAL: rows come in groups of kDualRows = 6 (one primal row followed by its five tangent rows
 // d/d theta_i); the layer is linear in the tangents, so they get no bias (and ACT must be kNone:
 // the caller applies the activation and its derivative afterwards).
 constexpr int kDualRows = 6;
-template <int NJ, int ACT, bool DUAL = false>
+// TRANS: W is read transposed, out[r][n] = sum_k in[r][k] * W[k][n] with row stride ldw (the
+// backward-data product of a layer whose forward weights are W[k][n]); bias may then be null.
+// out_s must not alias in_s.
+template <int NJ, int ACT, bool DUAL = false, bool TRANS = false>
 __device__ __forceinline__ void dense(const float *__restrict__ W, const float *__restrict__ bias, int K,
                                       int n_valid, const float *in_s, int ld_in, float *out_s, int ld_out,
-                                      float *w_s)
+                                      float *w_s, int ldw = 0)
 {
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
@@ -44,12 +49,19 @@ __device__ __forceinline__ void dense(const float *__restrict__ W, const float *
     for (int k0 = 0; k0 < K; k0 += kKC) {
         __syncthreads();  // previous chunk consumed (and in_s / out_s hazards of the caller)
         // stage W[:, k0:k0+32] transposed: w_s[kk][n]
-        {
+        if (!TRANS) {
             const int kk = tid & 31;
             for (int n = tid >> 5; n < 16 * NJ; n += kThreads / 32) {
                 float v = 0.f;
                 if (n < n_valid && k0 + kk < K) v = __ldg(W + (size_t)n * K + k0 + kk);
                 w_s[kk * kLdW + n] = v;
+            }
+        } else {
+            const int n = tid & 127;
+            for (int kk = tid >> 7; kk < kKC; kk += kThreads / 128) {
+                float v = 0.f;
+                if (n < n_valid && n < 16 * NJ && k0 + kk < K) v = W[(size_t)(k0 + kk) * ldw + n];
+                if (n < 16 * NJ) w_s[kk * kLdW + n] = v;
             }
         }
         __syncthreads();
@@ -71,12 +83,17 @@ __device__ __forceinline__ void dense(const float *__restrict__ W, const float *
     for (int j = 0; j < NJ; ++j) {
         const int n = tx + 16 * j;
         if (n < n_valid) {
-            const float bv = __ldg(bias + n);
+            const float bv = (TRANS && bias == nullptr) ? 0.f : __ldg(bias + n);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float v = acc[i][j] + ((!DUAL || (ty * 4 + i) % kDualRows == 0) ? bv : 0.f);
                 if (ACT == kRelu) v = fmaxf(v, 0.f);
                 if (ACT == kSigmoid) v = 1.0f / (1.0f + expf(-v));
+                if (ACT == kMaskRelu) v = out_s[(ty * 4 + i) * ld_out + n] > 0.f ? v : 0.f;
+                if (ACT == kMaskSigmoid) {
+                    const float h = out_s[(ty * 4 + i) * ld_out + n];
+                    v *= h * (1.0f - h);
+                }
                 out_s[(ty * 4 + i) * ld_out + n] = v;
             }
         }

@@ -1,0 +1,577 @@
+// MNLE training step on the device, fp32 CUDA cores (sm_100a).
+//
+// The reference trains the estimator with sbi's MNLE.train (mnle.py:41-48): Adam on
+// loss = -mean log p(x | z) over minibatches of TRAIN_BATCH_SIZE = 4096 rows (run_config.py:12),
+// autograd through the categorical net and the ten spline conditioners.  Here one call gives the
+// loss and its gradient with respect to every packed parameter (layout: mnle_common.cuh):
+//
+//   1. train_forward_kernel    one CTA per (64-row tile, net): the eleven nets depend only on the
+//                              context, so they run side by side (activations in shared memory);
+//                              keeps the 71 raw spline parameters per (row, transform), the choice
+//                              logits and the hidden activations.
+//   2. train_rows_kernel       one thread per row: choice log-probability, the ten splines forward
+//                              (log p of the row), then backwards (reverse mode written out by
+//                              hand), turning the stored spline parameters and logits into
+//                              d loss / d (spline parameters, logits) in place.
+//   3. train_backward_kernel   one CTA per (row tile, net): back-propagates through its net
+//                              (transposed dense products with the activation derivative fused into
+//                              the epilogue) and forms the weight gradients as 64-row outer-product
+//                              sums in registers.  Each CTA owns a slice of the partial-gradient
+//                              buffer: no atomics.
+//   4. train_reduce_kernel     sums the partials in a fixed order (bit-reproducible gradients) and
+//                              the squared gradient norm; train_stats_kernel: loss and norm.
+//   5. adam_kernel             torch.optim.Adam update with clip_grad_norm_ folded in.
+#include "mnle_dense.cuh"
+
+namespace mnle {
+
+constexpr int kQRows = 72;         // 71 spline parameters per transform, padded
+constexpr int kMaxGroups = 128;    // partial-gradient slices (row tiles beyond that share slices)
+constexpr int kReduceThreads = 256;
+
+struct TrainBufs {
+    float *Q;    // [kTransforms][kQRows][Rp]  spline parameters -> their gradients
+    float *LG;   // [kMaxChoices][Rp]          choice logits -> their gradients
+    float *LP;   // [Rp]                       log p per row
+    float *H;    // [kNets][3][Rp][128]        hidden activations kept for the backward pass
+    float *P;    // [groups][total]            partial gradients
+    float *SS;   // [reduce blocks]            partial sums of grad^2
+};
+
+struct TrainDims {
+    long long R, Rp;
+    int tiles, groups, reduce_blocks;
+};
+
+static TrainDims train_dims(const Layout &L, long long R)
+{
+    TrainDims d;
+    d.R = R;
+    d.tiles = (int)((R + kTM - 1) / kTM);
+    d.Rp = (long long)d.tiles * kTM;
+    d.groups = d.tiles < kMaxGroups ? d.tiles : kMaxGroups;
+    d.reduce_blocks = (int)((L.total + kReduceThreads - 1) / kReduceThreads);
+    return d;
+}
+
+static size_t train_floats(const Layout &L, const TrainDims &d)
+{
+    return (size_t)d.Rp * (kTransforms * kQRows + kMaxChoices + 1 + kNets * 3 * kHidden) + (size_t)d.groups * L.total +
+           (size_t)d.reduce_blocks;
+}
+
+static TrainBufs carve(float *ws, const Layout &L, const TrainDims &d)
+{
+    TrainBufs b;
+    b.Q = ws;
+    b.LG = b.Q + (size_t)kTransforms * kQRows * d.Rp;
+    b.LP = b.LG + (size_t)kMaxChoices * d.Rp;
+    b.H = b.LP + d.Rp;
+    b.P = b.H + (size_t)kNets * 3 * kHidden * d.Rp;
+    b.SS = b.P + (size_t)d.groups * L.total;
+    return b;
+}
+
+struct TrainRows {
+    const float *x;        // (N,2) [rt seconds, choice]
+    const float *cond;     // (N,85), row stride ld_cond
+    const long long *idx;  // minibatch row r is dataset row idx[r]; null = identity
+    long long ld_cond, R;
+};
+
+__device__ __forceinline__ long long data_row(const TrainRows &rows, long long r)
+{
+    return rows.idx ? rows.idx[r] : r;
+}
+
+// 86-wide context [condition, choice] of the tile's rows; rows past R are zero
+__device__ __forceinline__ void load_context(const TrainRows &rows, long long row0, float *in_s)
+{
+    for (int idx = threadIdx.x; idx < kTM * kCtx; idx += kThreads) {
+        const int i = idx / kCtx, j = idx - i * kCtx;
+        const long long r = row0 + i;
+        float v = 0.f;
+        if (r < rows.R) {
+            const long long dr = data_row(rows, r);
+            v = (j == kCond) ? __ldg(rows.x + 2 * dr + 1) : __ldg(rows.cond + dr * rows.ld_cond + j);
+        }
+        in_s[i * kLdIn + j] = v;
+    }
+}
+
+// ---- 1. forward through the nets ------------------------------------------------------------
+// hidden activations of one net for the backward pass: [net][slot][row][128]
+__device__ __forceinline__ void save_hidden(const float *h_s, float *H, long long Rp, int net, int slot, long long row0)
+{
+    float *dst = H + (((size_t)net * 3 + slot) * Rp + row0) * kHidden;
+    for (int idx = threadIdx.x; idx < kTM * kHidden; idx += kThreads)
+        dst[idx] = h_s[(idx >> 7) * kLdH + (idx & (kHidden - 1))];
+}
+
+__device__ __forceinline__ void load_hidden(float *h_s, const float *H, long long Rp, int net, int slot, long long row0)
+{
+    const float *src = H + (((size_t)net * 3 + slot) * Rp + row0) * kHidden;
+    for (int idx = threadIdx.x; idx < kTM * kHidden; idx += kThreads)
+        h_s[(idx >> 7) * kLdH + (idx & (kHidden - 1))] = src[idx];
+}
+
+// rows of a tile from a shared-memory tile [i][j] to [j][row] storage (coalesced over rows) and back
+__device__ __forceinline__ void store_rows(const float *src_s, int ld, float *dst, long long Rp, long long row0, int n)
+{
+    for (int idx = threadIdx.x; idx < kTM * n; idx += kThreads) {
+        const int i = idx & (kTM - 1), j = idx >> 6;
+        dst[(size_t)j * Rp + row0 + i] = src_s[i * ld + j];
+    }
+}
+
+__device__ __forceinline__ void load_rows(const float *src, long long Rp, long long row0, int n, float *dst_s)
+{
+    for (int idx = threadIdx.x; idx < kTM * n; idx += kThreads) {
+        const int i = idx & (kTM - 1), j = idx >> 6;
+        dst_s[i * kLdIn + j] = src[(size_t)j * Rp + row0 + i];
+    }
+}
+
+// grid (row tiles, nets): the eleven nets depend only on the context, so they run side by side
+__global__ void __launch_bounds__(kThreads) train_forward_kernel(const float *__restrict__ params, Layout L,
+                                                                 TrainRows rows, long long Rp, TrainBufs B, int keep)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SimtSmem &S = *reinterpret_cast<SimtSmem *>(smem_raw);
+    const long long row0 = (long long)blockIdx.x * kTM;
+    const int net = blockIdx.y;
+    load_context(rows, row0, S.in);
+    if (net == 0) {
+        dense<8, kSigmoid>(params + L.cat_W0, params + L.cat_b0, kCond, kHidden, S.in, kLdIn, S.ha, kLdH, S.w);
+        if (keep) save_hidden(S.ha, B.H, Rp, 0, 0, row0);
+        dense<8, kSigmoid>(params + L.cat_W1, params + L.cat_b1, kHidden, kHidden, S.ha, kLdH, S.hb, kLdH, S.w);
+        if (keep) save_hidden(S.hb, B.H, Rp, 0, 1, row0);
+        dense<8, kSigmoid>(params + L.cat_W2, params + L.cat_b2, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH, S.w);
+        if (keep) save_hidden(S.ha, B.H, Rp, 0, 2, row0);
+        dense<1, kNone>(params + L.cat_Wo, params + L.cat_bo, kHidden, L.n_choices, S.ha, kLdH, S.hb, kLdH, S.w);
+        store_rows(S.hb, kLdH, B.LG, Rp, row0, L.n_choices);
+    } else {
+        const int k = net - 1;
+        dense<8, kRelu>(params + L.fl_W1[k], params + L.fl_b1[k], kCtx, kHidden, S.in, kLdIn, S.ha, kLdH, S.w);
+        if (keep) save_hidden(S.ha, B.H, Rp, net, 0, row0);
+        dense<8, kRelu>(params + L.fl_W2[k], params + L.fl_b2[k], kHidden, kHidden, S.ha, kLdH, S.hb, kLdH, S.w);
+        if (keep) save_hidden(S.hb, B.H, Rp, net, 1, row0);
+        dense<5, kNone>(params + L.fl_W3[k], params + L.fl_b3[k], kHidden, kSplineOut, S.hb, kLdH, S.ha, kLdH, S.w);
+        store_rows(S.ha, kLdH, B.Q + (size_t)k * kQRows * Rp, Rp, row0, kSplineOut);
+    }
+}
+
+// ---- 2. reverse sweep over the splines -----------------------------------------------------
+// One rational-quadratic spline, reverse mode.  In: u (input of the transform), q (its 71 raw
+// parameters, stride qs), g = d l / d u_out with l = log p of the row (d l / d logdet = 1).
+// Out: q[j] <- scale * d l / d q[j], g <- d l / d u.  Same bin search and arithmetic as rqs_forward.
+__device__ __forceinline__ void rqs_backward(float u, float *q, size_t qs, float &g, float scale)
+{
+    if (!(u >= -kTail && u <= kTail)) {  // identity: no parameter dependence
+        for (int j = 0; j < kSplineOut; ++j) q[j * qs] = 0.f;
+        return;
+    }
+    const float inv_sqrt_h = 0.08838834764831845f;
+    const float c = 1.0f - kMinBin * kBins;
+    // widths
+    float mw = -INFINITY;
+    for (int j = 0; j < kBins; ++j) mw = fmaxf(mw, q[j * qs] * inv_sqrt_h);
+    float s = 0.f;
+    for (int j = 0; j < kBins; ++j) s += expf(q[j * qs] * inv_sqrt_h - mw);
+    const float inv_sw = 1.0f / s;
+    float cs = 0.f, prev = -kTail, left = -kTail, right = kTail, cume = 0.f, Sw = 0.f, ew = 0.f;
+    int b = 0;
+    for (int j = 0; j < kBins; ++j) {
+        const float e = expf(q[j * qs] * inv_sqrt_h - mw) * inv_sw;
+        cs += kMinBin + c * e;
+        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
+        if (u >= prev) {
+            b = j;
+            left = prev;
+            right = edge;
+            Sw = cume;
+            ew = e;
+        }
+        prev = edge;
+        cume += e;
+    }
+    // heights
+    float *qh = q + kBins * qs;
+    float mh = -INFINITY;
+    for (int j = 0; j < kBins; ++j) mh = fmaxf(mh, qh[j * qs] * inv_sqrt_h);
+    s = 0.f;
+    for (int j = 0; j < kBins; ++j) s += expf(qh[j * qs] * inv_sqrt_h - mh);
+    const float inv_sh = 1.0f / s;
+    cs = 0.f;
+    prev = -kTail;
+    cume = 0.f;
+    float bottom = -kTail, top = kTail, Sh = 0.f, eh = 0.f;
+    for (int j = 0; j < kBins; ++j) {
+        const float e = expf(qh[j * qs] * inv_sqrt_h - mh) * inv_sh;
+        cs += kMinBin + c * e;
+        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
+        if (j == b) {
+            bottom = prev;
+            top = edge;
+            Sh = cume;
+            eh = e;
+        }
+        prev = edge;
+        cume += e;
+    }
+    float *qd = q + 2 * kBins * qs;
+    const float qd0 = (b == 0) ? 0.f : qd[(b - 1) * qs];
+    const float qd1 = (b == kBins - 1) ? 0.f : qd[b * qs];
+    const float d0 = (b == 0) ? 1.0f : kMinDeriv + softplus_f(qd0);
+    const float d1 = (b == kBins - 1) ? 1.0f : kMinDeriv + softplus_f(qd1);
+
+    // forward values
+    const float w = right - left, h = top - bottom;
+    const float delta = h / w;
+    const float th = (u - left) / w;
+    const float omt = 1.0f - th;
+    const float t1 = th * omt;
+    const float dd = d0 + d1 - 2.0f * delta;
+    const float den = delta + dd * t1;
+    const float s1 = delta * th * th + d0 * t1;
+    const float num = h * s1;
+    const float s2 = d1 * th * th + 2.0f * delta * t1 + d0 * omt * omt;
+    const float dnum = delta * delta * s2;
+    // reverse
+    const float inv_den = 1.0f / den;
+    const float g_num = g * inv_den;
+    const float g_den = -g * num * inv_den * inv_den - 2.0f * inv_den;
+    const float g_s2 = delta * delta / dnum;           // d log(dnum) / d s2
+    const float g_s1 = g_num * h;
+    float g_h = g_num * s1;
+    float g_delta = g_s1 * th * th + g_den * (1.0f - 2.0f * t1) + (2.0f * delta * s2) / dnum + g_s2 * 2.0f * t1;
+    float g_th = g_s1 * 2.0f * delta * th + g_s2 * (2.0f * d1 * th - 2.0f * d0 * omt);
+    const float g_t1 = g_s1 * d0 + g_den * dd + g_s2 * 2.0f * delta;
+    const float g_d0 = g_s1 * t1 + g_den * t1 + g_s2 * omt * omt;
+    const float g_d1 = g_den * t1 + g_s2 * th * th;
+    g_th += g_t1 * (1.0f - 2.0f * th);
+    const float inv_w = 1.0f / w;
+    const float g_u = g_th * inv_w;
+    g_h += g_delta * inv_w;
+    const float g_w = -g_th * th * inv_w - g_delta * delta * inv_w;
+    const float g_left = -g_u - g_w, g_right = g_w;
+    const float g_bottom = g - g_h, g_top = g_h;
+    // knots -> softmax logits: cw_j = 20 * sum_{i<j} (m + c e_i) - 10 for 1 <= j <= K-1, ends fixed
+    const float gl = (b >= 1) ? g_left : 0.f, gr = (b <= kBins - 2) ? g_right : 0.f;
+    const float gb = (b >= 1) ? g_bottom : 0.f, gt = (b <= kBins - 2) ? g_top : 0.f;
+    const float k20 = 2.0f * kTail * c;
+    const float dot_w = k20 * (gl * Sw + gr * (Sw + ew));
+    const float dot_h = k20 * (gb * Sh + gt * (Sh + eh));
+    const float out_scale = scale * inv_sqrt_h;
+    for (int j = 0; j < kBins; ++j) {
+        const float e = expf(q[j * qs] * inv_sqrt_h - mw) * inv_sw;
+        const float ge = k20 * ((j < b ? gl : 0.f) + (j <= b ? gr : 0.f));
+        q[j * qs] = out_scale * e * (ge - dot_w);
+    }
+    for (int j = 0; j < kBins; ++j) {
+        const float e = expf(qh[j * qs] * inv_sqrt_h - mh) * inv_sh;
+        const float ge = k20 * ((j < b ? gb : 0.f) + (j <= b ? gt : 0.f));
+        qh[j * qs] = out_scale * e * (ge - dot_h);
+    }
+    for (int j = 0; j < kBins - 1; ++j) {
+        float v = 0.f;
+        if (j == b - 1) v = g_d0 / (1.0f + expf(-qd0));  // softplus' = sigmoid
+        if (j == b) v = g_d1 / (1.0f + expf(-qd1));
+        qd[j * qs] = scale * v;
+    }
+    g = g_u;
+}
+
+// One thread per row: log p (choice head + ten splines forward), then, when the gradient is wanted,
+// the reverse sweep that leaves d loss / d (spline parameters, logits) where the values were.
+__global__ void __launch_bounds__(kTM) train_rows_kernel(const float *__restrict__ params, Layout L, TrainRows rows,
+                                                         long long Rp, float scale, int backward, TrainBufs B)
+{
+    const long long row = (long long)blockIdx.x * kTM + threadIdx.x;
+    if (row >= Rp) return;
+    const int n_choices = L.n_choices;
+    if (row >= rows.R) {  // padding rows of the last tile contribute nothing
+        if (backward) {
+            for (int k = 0; k < kTransforms; ++k)
+                for (int j = 0; j < kSplineOut; ++j) B.Q[((size_t)k * kQRows + j) * Rp + row] = 0.f;
+            for (int j = 0; j < n_choices; ++j) B.LG[(size_t)j * Rp + row] = 0.f;
+        }
+        return;
+    }
+    const long long dr = data_row(rows, row);
+    // categorical head: l = log clamp(softmax(logits)[choice], eps, 1 - eps)
+    float lp;
+    {
+        const int choice = (int)__ldg(rows.x + 2 * dr + 1);
+        float m = -INFINITY;
+        for (int j = 0; j < n_choices; ++j) m = fmaxf(m, B.LG[(size_t)j * Rp + row]);
+        float s = 0.f, pc = 0.f;
+        for (int j = 0; j < n_choices; ++j) {
+            const float e = expf(B.LG[(size_t)j * Rp + row] - m);
+            s += e;
+            if (j == choice) pc = e;
+        }
+        const float eps = 1.1920928955078125e-07f;
+        const float p = pc / s;  // same arithmetic as categorical_logp()
+        lp = logf(fminf(fmaxf(p, eps), 1.0f - eps));
+        if (backward) {
+            const float inv_s = 1.0f / s;
+            const bool clamped = p < eps || p > 1.0f - eps;  // torch.clamp passes no gradient outside
+            for (int j = 0; j < n_choices; ++j) {
+                const float pj = expf(B.LG[(size_t)j * Rp + row] - m) * inv_s;
+                B.LG[(size_t)j * Rp + row] = clamped ? 0.f : scale * ((j == choice ? 1.0f : 0.f) - pj);
+            }
+        }
+    }
+    const float mu_y = params[L.mu_y], sigma_y = params[L.sigma_y];
+    const float y = logf(__ldg(rows.x + 2 * dr));
+    float u = (y - mu_y) / sigma_y;
+    float logdet = -logf(sigma_y);
+    float u_in[kTransforms];
+#pragma unroll
+    for (int k = 0; k < kTransforms; ++k) {
+        u_in[k] = u;
+        rqs_forward(u, logdet, B.Q + (size_t)k * kQRows * Rp + row, (size_t)Rp);
+    }
+    B.LP[row] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+    if (!backward) return;
+    float g = -u;  // d/du of the standard-normal base log-density
+#pragma unroll
+    for (int k = kTransforms - 1; k >= 0; --k)
+        rqs_backward(u_in[k], B.Q + (size_t)k * kQRows * Rp + row, (size_t)Rp, g, scale);
+}
+
+// ---- 3. backward through the nets ------------------------------------------------------------
+// out[n][k] (+)= sum_{r < 64} dy[r][n] * x[r][k]  (n < n_valid <= 16 NI, k < K <= 16 NJ), row-major
+// with row stride K, and bias_out[n] (+)= sum_r dy[r][n].  8 x 8 accumulators per thread.
+template <int NI, int NJ>
+__device__ __forceinline__ void wgrad(const float *dy_s, int ld_dy, int n_valid, const float *x_s, int ld_x, int K,
+                                      float *__restrict__ out, float *__restrict__ bias_out, bool accumulate)
+{
+    const int tid = threadIdx.x;
+    const int tk = tid & 15, tn = tid >> 4;
+    float acc[NI][NJ];
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+    for (int r = 0; r < kTM; ++r) {
+        float a[NI], bb[NJ];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) a[i] = dy_s[r * ld_dy + tn + 16 * i];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) bb[j] = x_s[r * ld_x + tk + 16 * j];
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int n = tn + 16 * i;
+        if (n < n_valid) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int k = tk + 16 * j;
+                if (k < K) {
+                    float *p = out + (size_t)n * K + k;
+                    *p = accumulate ? *p + acc[i][j] : acc[i][j];
+                }
+            }
+        }
+    }
+    if (tid < n_valid) {
+        float sb = 0.f;
+        for (int r = 0; r < kTM; ++r) sb += dy_s[r * ld_dy + tid];
+        bias_out[tid] = accumulate ? bias_out[tid] + sb : sb;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) train_backward_kernel(const float *__restrict__ params, Layout L,
+                                                                  TrainRows rows, long long Rp, int tiles, TrainBufs B)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SimtSmem &S = *reinterpret_cast<SimtSmem *>(smem_raw);
+    const int net = blockIdx.y;  // 0 = categorical head, 1 + k = conditioner of transform k
+    float *P = B.P + (size_t)blockIdx.x * L.total;
+    bool acc = false;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, acc = true) {
+        const long long row0 = (long long)tile * kTM;
+        __syncthreads();
+        if (net > 0) {
+            const int k = net - 1;
+            load_rows(B.Q + (size_t)k * kQRows * Rp, Rp, row0, kSplineOut, S.in);
+            load_hidden(S.hb, B.H, Rp, net, 1, row0);
+            __syncthreads();
+            wgrad<5, 8>(S.in, kLdIn, kSplineOut, S.hb, kLdH, kHidden, P + L.fl_W3[k], P + L.fl_b3[k], acc);
+            dense<8, kMaskRelu, false, true>(params + L.fl_W3[k], nullptr, kSplineOut, kHidden, S.in, kLdIn, S.hb, kLdH,
+                                             S.w, kHidden);
+            load_hidden(S.ha, B.H, Rp, net, 0, row0);
+            __syncthreads();
+            wgrad<8, 8>(S.hb, kLdH, kHidden, S.ha, kLdH, kHidden, P + L.fl_W2[k], P + L.fl_b2[k], acc);
+            dense<8, kMaskRelu, false, true>(params + L.fl_W2[k], nullptr, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH,
+                                             S.w, kHidden);
+            load_context(rows, row0, S.in);
+            __syncthreads();
+            wgrad<8, 6>(S.ha, kLdH, kHidden, S.in, kLdIn, kCtx, P + L.fl_W1[k], P + L.fl_b1[k], acc);
+        } else {
+            load_rows(B.LG, Rp, row0, L.n_choices, S.in);
+            load_hidden(S.ha, B.H, Rp, 0, 2, row0);
+            __syncthreads();
+            wgrad<1, 8>(S.in, kLdIn, L.n_choices, S.ha, kLdH, kHidden, P + L.cat_Wo, P + L.cat_bo, acc);
+            dense<8, kMaskSigmoid, false, true>(params + L.cat_Wo, nullptr, L.n_choices, kHidden, S.in, kLdIn, S.ha,
+                                                kLdH, S.w, kHidden);
+            load_hidden(S.hb, B.H, Rp, 0, 1, row0);
+            __syncthreads();
+            wgrad<8, 8>(S.ha, kLdH, kHidden, S.hb, kLdH, kHidden, P + L.cat_W2, P + L.cat_b2, acc);
+            dense<8, kMaskSigmoid, false, true>(params + L.cat_W2, nullptr, kHidden, kHidden, S.ha, kLdH, S.hb, kLdH,
+                                                S.w, kHidden);
+            load_hidden(S.ha, B.H, Rp, 0, 0, row0);
+            __syncthreads();
+            wgrad<8, 8>(S.hb, kLdH, kHidden, S.ha, kLdH, kHidden, P + L.cat_W1, P + L.cat_b1, acc);
+            dense<8, kMaskSigmoid, false, true>(params + L.cat_W1, nullptr, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH,
+                                                S.w, kHidden);
+            load_context(rows, row0, S.in);
+            __syncthreads();
+            wgrad<8, 6>(S.ha, kLdH, kHidden, S.in, kLdIn, kCond, P + L.cat_W0, P + L.cat_b0, acc);
+        }
+    }
+}
+
+// ---- 4. fixed-order reductions ---------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float *red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(kReduceThreads) train_reduce_kernel(const float *__restrict__ P, int groups,
+                                                                      size_t total, size_t n_trainable,
+                                                                      float *__restrict__ grad, float *__restrict__ SS)
+{
+    __shared__ float red[kReduceThreads / 32];
+    const size_t i = (size_t)blockIdx.x * kReduceThreads + threadIdx.x;
+    float g = 0.f;
+    if (i < n_trainable)
+        for (int s = 0; s < groups; ++s) g += P[(size_t)s * total + i];
+    if (i < total) grad[i] = g;  // the log rt standardisation (tail of the buffer) is not trained
+    const float t = block_sum(g * g, red);
+    if (threadIdx.x == 0) SS[blockIdx.x] = t;
+}
+
+// stats[0] = loss = -mean log p, stats[1] = |grad|^2 (0 when no gradient was asked for)
+__global__ void __launch_bounds__(1024) train_stats_kernel(const float *__restrict__ LP, long long R,
+                                                           const float *__restrict__ SS, int n_ss,
+                                                           float *__restrict__ stats)
+{
+    __shared__ float red[32];
+    float v = 0.f;
+    for (long long r = threadIdx.x; r < R; r += blockDim.x) v += LP[r];
+    const float sum_lp = block_sum(v, red);
+    v = 0.f;
+    for (int b = threadIdx.x; b < n_ss; b += blockDim.x) v += SS[b];
+    const float ss = block_sum(v, red);
+    if (threadIdx.x == 0) {
+        stats[0] = -sum_lp / (float)R;
+        stats[1] = ss;
+    }
+}
+
+// ---- 5. Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) with clip_grad_norm_ ------
+__global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ params, const float *__restrict__ grad,
+                                                   float *__restrict__ m, float *__restrict__ v, size_t n,
+                                                   const float *__restrict__ stats, float lr, float beta1, float beta2,
+                                                   float eps, float bc1, float bc2_sqrt, float max_norm)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float clip = 1.0f;
+    if (max_norm > 0.f) {
+        const float norm = sqrtf(stats[1]);
+        clip = fminf(max_norm / (norm + 1e-6f), 1.0f);  // torch.nn.utils.clip_grad_norm_
+    }
+    const float g = grad[i] * clip;
+    const float mi = beta1 * m[i] + (1.0f - beta1) * g;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    params[i] -= (lr / bc1) * (mi / denom);
+}
+
+}  // namespace mnle
+
+using namespace mnle;
+
+DDM_API size_t mnle_train_workspace_floats(int n_choices, int64_t R)
+{
+    if (n_choices < 1 || n_choices > kMaxChoices || R <= 0) return 0;
+    const Layout L = make_layout(n_choices);
+    return train_floats(L, train_dims(L, R));
+}
+
+DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, const float *x_dev, const float *cond_dev,
+                                    int64_t ld_cond, const int64_t *row_index_dev, int64_t R, float *stats_dev,
+                                    float *grad_dev, float *workspace_dev, void *stream)
+{
+    DDM_REQUIRE(n_choices >= 1 && n_choices <= kMaxChoices, "mnle_train_nll_grad_f32: n_choices=%d outside [1,%d]",
+                n_choices, kMaxChoices);
+    DDM_REQUIRE(R >= 1 && R <= 0x7FFFFFFFll * kTM / 2, "mnle_train_nll_grad_f32: R=%lld out of range", (long long)R);
+    DDM_REQUIRE(params_dev && x_dev && cond_dev && stats_dev && workspace_dev,
+                "mnle_train_nll_grad_f32: null pointer");
+    DDM_REQUIRE(ld_cond >= kCond, "mnle_train_nll_grad_f32: ld_cond=%lld < 85", (long long)ld_cond);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Layout L = make_layout(n_choices);
+    const TrainDims d = train_dims(L, R);
+    const TrainBufs B = carve(workspace_dev, L, d);
+    TrainRows rows{x_dev, cond_dev, reinterpret_cast<const long long *>(row_index_dev), (long long)ld_cond, (long long)R};
+
+    static_assert(sizeof(SimtSmem) < 113 * 1024, "two CTAs per SM");
+    DDM_CUDA_TRY(cudaFuncSetAttribute(train_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SimtSmem)));
+    const int want_grad = grad_dev != nullptr;
+    train_forward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, rows, d.Rp, B, want_grad);
+    DDM_CUDA_TRY(cudaGetLastError());
+    train_rows_kernel<<<d.tiles, kTM, 0, st>>>(params_dev, L, rows, d.Rp, -1.0f / (float)R, want_grad, B);
+    DDM_CUDA_TRY(cudaGetLastError());
+    int n_ss = 0;
+    if (want_grad) {
+        DDM_CUDA_TRY(cudaFuncSetAttribute(train_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SimtSmem)));
+        train_backward_kernel<<<dim3(d.groups, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, rows, d.Rp,
+                                                                                         d.tiles, B);
+        DDM_CUDA_TRY(cudaGetLastError());
+        train_reduce_kernel<<<d.reduce_blocks, kReduceThreads, 0, st>>>(B.P, d.groups, L.total, L.mu_y, grad_dev, B.SS);
+        DDM_CUDA_TRY(cudaGetLastError());
+        n_ss = d.reduce_blocks;
+    }
+    train_stats_kernel<<<1, 1024, 0, st>>>(B.LP, (long long)R, B.SS, n_ss, stats_dev);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}
+
+DDM_API int mnle_train_adam_f32(float *params_dev, const float *grad_dev, float *m_dev, float *v_dev, int n_choices,
+                                const float *stats_dev, float lr, float beta1, float beta2, float eps, int64_t step,
+                                float max_grad_norm, void *stream)
+{
+    DDM_REQUIRE(n_choices >= 1 && n_choices <= kMaxChoices, "mnle_train_adam_f32: n_choices=%d outside [1,%d]",
+                n_choices, kMaxChoices);
+    DDM_REQUIRE(params_dev && grad_dev && m_dev && v_dev, "mnle_train_adam_f32: null pointer");
+    DDM_REQUIRE(step >= 1, "mnle_train_adam_f32: step counts from 1, got %lld", (long long)step);
+    DDM_REQUIRE(max_grad_norm <= 0.f || stats_dev != nullptr, "mnle_train_adam_f32: clipping needs stats_dev");
+    const Layout L = make_layout(n_choices);
+    const size_t n = L.mu_y;  // everything before the (fixed) log rt standardisation
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        params_dev, grad_dev, m_dev, v_dev, n, stats_dev, lr, beta1, beta2, eps, bc1, bc2_sqrt, max_grad_norm);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}

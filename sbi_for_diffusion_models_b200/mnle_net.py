@@ -23,6 +23,30 @@ HIDDEN, NUM_BINS, NUM_TRANSFORMS, COND_DIM = 128, 24, 10, 85
 CTX_DIM, SPLINE_OUT = COND_DIM + 1, 3 * NUM_BINS - 1
 
 
+def packed_sections(n_choices: int):
+    """(name, shape) of every tensor in the packed buffer, in order (names of ``oracle/mnle_spec.py``)."""
+    out = [("cat.W0", (HIDDEN, COND_DIM)), ("cat.b0", (HIDDEN,)), ("cat.W1", (HIDDEN, HIDDEN)), ("cat.b1", (HIDDEN,)),
+           ("cat.W2", (HIDDEN, HIDDEN)), ("cat.b2", (HIDDEN,)), ("cat.Wo", (n_choices, HIDDEN)), ("cat.bo", (n_choices,))]
+    for k in range(NUM_TRANSFORMS):
+        out += [(f"flow.{k}.W1", (HIDDEN, CTX_DIM)), (f"flow.{k}.b1", (HIDDEN,)), (f"flow.{k}.W2", (HIDDEN, HIDDEN)),
+                (f"flow.{k}.b2", (HIDDEN,)), (f"flow.{k}.W3", (SPLINE_OUT, HIDDEN)), (f"flow.{k}.b3", (SPLINE_OUT,))]
+    out += [("flow.mu_y", ()), ("flow.sigma_y", ())]
+    return out
+
+
+def unpack_params(packed: torch.Tensor, n_choices: int) -> Dict[str, torch.Tensor]:
+    """Views of a packed buffer (any device) by name.  No un-folding: first layers come out as
+    stored (the trainer keeps them raw, its condition is standardised beforehand)."""
+    out, o = {}, 0
+    for name, shape in packed_sections(n_choices):
+        n = int(np.prod(shape)) if shape else 1
+        out[name] = packed[o:o + n].reshape(shape)
+        o += n
+    if o != packed.numel():
+        raise ValueError(f"packed MNLE buffer has {packed.numel()} floats, layout needs {o}")
+    return out
+
+
 class PackedMNLE:
     """CPU-resident packed parameters + lazily created device handles."""
 
