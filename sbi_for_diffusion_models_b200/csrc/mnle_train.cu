@@ -30,8 +30,8 @@ constexpr int kMaxGroups = 128;    // partial-gradient slices (row tiles beyond 
 constexpr int kReduceThreads = 256;
 
 struct TrainBufs {
-    float *Q;    // [kTransforms][kQRows][Rp]  spline parameters -> their gradients
-    float *LG;   // [kMaxChoices][Rp]          choice logits -> their gradients
+    float *Q;    // [kTransforms][Rp][kQRows]  spline parameters -> their gradients
+    float *LG;   // [Rp][kMaxChoices]          choice logits -> their gradients
     float *LP;   // [Rp]                       log p per row
     float *H;    // [kNets][3][Rp][128]        hidden activations kept for the backward pass
     float *P;    // [groups][total]            partial gradients
@@ -115,20 +115,20 @@ __device__ __forceinline__ void load_hidden(float *h_s, const float *H, long lon
         h_s[(idx >> 7) * kLdH + (idx & (kHidden - 1))] = src[idx];
 }
 
-// rows of a tile from a shared-memory tile [i][j] to [j][row] storage (coalesced over rows) and back
-__device__ __forceinline__ void store_rows(const float *src_s, int ld, float *dst, long long Rp, long long row0, int n)
+// n leading columns of a tile between shared memory [i][ld] and row-major global storage [row][ldg]
+__device__ __forceinline__ void store_rows(const float *src_s, int ld, float *dst, int ldg, long long row0, int n)
 {
     for (int idx = threadIdx.x; idx < kTM * n; idx += kThreads) {
-        const int i = idx & (kTM - 1), j = idx >> 6;
-        dst[(size_t)j * Rp + row0 + i] = src_s[i * ld + j];
+        const int i = idx / n, j = idx - i * n;
+        dst[(size_t)(row0 + i) * ldg + j] = src_s[i * ld + j];
     }
 }
 
-__device__ __forceinline__ void load_rows(const float *src, long long Rp, long long row0, int n, float *dst_s)
+__device__ __forceinline__ void load_rows(const float *src, int ldg, long long row0, int n, float *dst_s)
 {
     for (int idx = threadIdx.x; idx < kTM * n; idx += kThreads) {
-        const int i = idx & (kTM - 1), j = idx >> 6;
-        dst_s[i * kLdIn + j] = src[(size_t)j * Rp + row0 + i];
+        const int i = idx / n, j = idx - i * n;
+        dst_s[i * kLdIn + j] = src[(size_t)(row0 + i) * ldg + j];
     }
 }
 
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) train_forward_kernel(const float *__
         dense<8, kSigmoid>(params + L.cat_W2, params + L.cat_b2, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH, S.w);
         if (keep) save_hidden(S.ha, B.H, Rp, 0, 2, row0);
         dense<1, kNone>(params + L.cat_Wo, params + L.cat_bo, kHidden, L.n_choices, S.ha, kLdH, S.hb, kLdH, S.w);
-        store_rows(S.hb, kLdH, B.LG, Rp, row0, L.n_choices);
+        store_rows(S.hb, kLdH, B.LG, kMaxChoices, row0, L.n_choices);
     } else {
         const int k = net - 1;
         dense<8, kRelu>(params + L.fl_W1[k], params + L.fl_b1[k], kCtx, kHidden, S.in, kLdIn, S.ha, kLdH, S.w);
@@ -157,75 +157,85 @@ __global__ void __launch_bounds__(kThreads) train_forward_kernel(const float *__
         dense<8, kRelu>(params + L.fl_W2[k], params + L.fl_b2[k], kHidden, kHidden, S.ha, kLdH, S.hb, kLdH, S.w);
         if (keep) save_hidden(S.hb, B.H, Rp, net, 1, row0);
         dense<5, kNone>(params + L.fl_W3[k], params + L.fl_b3[k], kHidden, kSplineOut, S.hb, kLdH, S.ha, kLdH, S.w);
-        store_rows(S.ha, kLdH, B.Q + (size_t)k * kQRows * Rp, Rp, row0, kSplineOut);
+        store_rows(S.ha, kLdH, B.Q + (size_t)k * kQRows * Rp, kQRows, row0, kSplineOut);
     }
 }
 
-// ---- 2. reverse sweep over the splines -----------------------------------------------------
-// One rational-quadratic spline, reverse mode.  In: u (input of the transform), q (its 71 raw
-// parameters, stride qs), g = d l / d u_out with l = log p of the row (d l / d logdet = 1).
-// Out: q[j] <- scale * d l / d q[j], g <- d l / d u.  Same bin search and arithmetic as rqs_forward.
-__device__ __forceinline__ void rqs_backward(float u, float *q, size_t qs, float &g, float scale)
+// ---- 2. per-row work: one warp per row, lane j owns bin j ------------------------------------
+constexpr int kRowWarps = 8;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ float warp_max(float v)
 {
-    if (!(u >= -kTail && u <= kTail)) {  // identity: no parameter dependence
-        for (int j = 0; j < kSplineOut; ++j) q[j * qs] = 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float warp_scan(float v, int lane)  // inclusive prefix sum over lanes
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// softmax over the 24 logits held by lanes 0..23 (one per lane) and the knot positions built from it:
+// e = softmax probability of the lane's bin, cum = sum of e over bins before it, lo / hi = the bin's
+// edges 20 * cumsum(m + c e) - 10 with both ends pinned to -+10.
+struct Knots {
+    float e, cum, lo, hi;
+};
+__device__ __forceinline__ Knots knots(float logit, int lane)
+{
+    const float inv_sqrt_h = 0.08838834764831845f;  // 1/sqrt(128)
+    const float c = 1.0f - kMinBin * kBins;
+    const bool on = lane < kBins;
+    const float a = on ? logit * inv_sqrt_h : -INFINITY;
+    const float m = warp_max(a);
+    const float ex = on ? expf(a - m) : 0.f;
+    const float sc = warp_scan(ex, lane);
+    const float inv_s = 1.0f / __shfl_sync(kFull, sc, kBins - 1);
+    Knots k;
+    k.e = ex * inv_s;
+    const float inc = sc * inv_s;  // inclusive cumulative probability
+    k.cum = inc - k.e;
+    k.hi = (lane >= kBins - 1) ? kTail : 2.0f * kTail * (kMinBin * (float)(lane + 1) + c * inc) - kTail;
+    const float up = __shfl_up_sync(kFull, k.hi, 1);
+    k.lo = (lane == 0) ? -kTail : up;
+    return k;
+}
+
+// One rational-quadratic spline for the warp's row (Durkan et al. 2019, linear tails).  q points at the
+// row's 71 raw parameters of this transform.  Forward: u <- spline(u), logdet += log |du_out / du|.
+// BACKWARD (reverse mode written out by hand): u is the transform's INPUT, g = d l / d u_out on entry
+// (l = log p of the row, d l / d logdet = 1) and d l / d u on exit; q[j] <- scale * d l / d q[j].
+template <bool BACKWARD>
+__device__ __forceinline__ void rqs_warp(float &u, float &logdet, float *q, int lane, float &g, float scale)
+{
+    if (!(u >= -kTail && u <= kTail)) {  // identity outside the tail bound: no parameter dependence
+        if (BACKWARD) {
+            q[lane] = 0.f;
+            q[32 + lane] = 0.f;
+            if (lane < kSplineOut - 64) q[64 + lane] = 0.f;
+        }
         return;
     }
-    const float inv_sqrt_h = 0.08838834764831845f;
-    const float c = 1.0f - kMinBin * kBins;
-    // widths
-    float mw = -INFINITY;
-    for (int j = 0; j < kBins; ++j) mw = fmaxf(mw, q[j * qs] * inv_sqrt_h);
-    float s = 0.f;
-    for (int j = 0; j < kBins; ++j) s += expf(q[j * qs] * inv_sqrt_h - mw);
-    const float inv_sw = 1.0f / s;
-    float cs = 0.f, prev = -kTail, left = -kTail, right = kTail, cume = 0.f, Sw = 0.f, ew = 0.f;
-    int b = 0;
-    for (int j = 0; j < kBins; ++j) {
-        const float e = expf(q[j * qs] * inv_sqrt_h - mw) * inv_sw;
-        cs += kMinBin + c * e;
-        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
-        if (u >= prev) {
-            b = j;
-            left = prev;
-            right = edge;
-            Sw = cume;
-            ew = e;
-        }
-        prev = edge;
-        cume += e;
-    }
-    // heights
-    float *qh = q + kBins * qs;
-    float mh = -INFINITY;
-    for (int j = 0; j < kBins; ++j) mh = fmaxf(mh, qh[j * qs] * inv_sqrt_h);
-    s = 0.f;
-    for (int j = 0; j < kBins; ++j) s += expf(qh[j * qs] * inv_sqrt_h - mh);
-    const float inv_sh = 1.0f / s;
-    cs = 0.f;
-    prev = -kTail;
-    cume = 0.f;
-    float bottom = -kTail, top = kTail, Sh = 0.f, eh = 0.f;
-    for (int j = 0; j < kBins; ++j) {
-        const float e = expf(qh[j * qs] * inv_sqrt_h - mh) * inv_sh;
-        cs += kMinBin + c * e;
-        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
-        if (j == b) {
-            bottom = prev;
-            top = edge;
-            Sh = cume;
-            eh = e;
-        }
-        prev = edge;
-        cume += e;
-    }
-    float *qd = q + 2 * kBins * qs;
-    const float qd0 = (b == 0) ? 0.f : qd[(b - 1) * qs];
-    const float qd1 = (b == kBins - 1) ? 0.f : qd[b * qs];
+    const float qw = lane < kBins ? q[lane] : 0.f;
+    const float qh = lane < kBins ? q[kBins + lane] : 0.f;
+    const float qd = lane < kBins - 1 ? q[2 * kBins + lane] : 0.f;
+    const Knots W = knots(qw, lane), H = knots(qh, lane);
+    // bin: the last one whose left edge is <= u (left edges are increasing, the first is -10)
+    const int b = __popc(__ballot_sync(kFull, lane < kBins && u >= W.lo)) - 1;
+    const float left = __shfl_sync(kFull, W.lo, b), right = __shfl_sync(kFull, W.hi, b);
+    const float bottom = __shfl_sync(kFull, H.lo, b), top = __shfl_sync(kFull, H.hi, b);
+    const float qd0 = __shfl_sync(kFull, qd, b > 0 ? b - 1 : 0), qd1 = __shfl_sync(kFull, qd, b);
+    // knot derivatives; the boundary ones are exactly 1 (min_derivative + softplus(pad) == 1)
     const float d0 = (b == 0) ? 1.0f : kMinDeriv + softplus_f(qd0);
     const float d1 = (b == kBins - 1) ? 1.0f : kMinDeriv + softplus_f(qd1);
 
-    // forward values
     const float w = right - left, h = top - bottom;
     const float delta = h / w;
     const float th = (u - left) / w;
@@ -237,14 +247,18 @@ __device__ __forceinline__ void rqs_backward(float u, float *q, size_t qs, float
     const float num = h * s1;
     const float s2 = d1 * th * th + 2.0f * delta * t1 + d0 * omt * omt;
     const float dnum = delta * delta * s2;
-    // reverse
+    if (!BACKWARD) {
+        logdet += logf(dnum) - 2.0f * logf(den);
+        u = bottom + num / den;
+        return;
+    }
     const float inv_den = 1.0f / den;
     const float g_num = g * inv_den;
     const float g_den = -g * num * inv_den * inv_den - 2.0f * inv_den;
-    const float g_s2 = delta * delta / dnum;           // d log(dnum) / d s2
+    const float g_s2 = 1.0f / s2;  // d log(dnum) / d s2
     const float g_s1 = g_num * h;
     float g_h = g_num * s1;
-    float g_delta = g_s1 * th * th + g_den * (1.0f - 2.0f * t1) + (2.0f * delta * s2) / dnum + g_s2 * 2.0f * t1;
+    const float g_delta = g_s1 * th * th + g_den * (1.0f - 2.0f * t1) + 2.0f / delta + g_s2 * 2.0f * t1;
     float g_th = g_s1 * 2.0f * delta * th + g_s2 * (2.0f * d1 * th - 2.0f * d0 * omt);
     const float g_t1 = g_s1 * d0 + g_den * dd + g_s2 * 2.0f * delta;
     const float g_d0 = g_s1 * t1 + g_den * t1 + g_s2 * omt * omt;
@@ -254,47 +268,47 @@ __device__ __forceinline__ void rqs_backward(float u, float *q, size_t qs, float
     const float g_u = g_th * inv_w;
     g_h += g_delta * inv_w;
     const float g_w = -g_th * th * inv_w - g_delta * delta * inv_w;
-    const float g_left = -g_u - g_w, g_right = g_w;
-    const float g_bottom = g - g_h, g_top = g_h;
-    // knots -> softmax logits: cw_j = 20 * sum_{i<j} (m + c e_i) - 10 for 1 <= j <= K-1, ends fixed
-    const float gl = (b >= 1) ? g_left : 0.f, gr = (b <= kBins - 2) ? g_right : 0.f;
-    const float gb = (b >= 1) ? g_bottom : 0.f, gt = (b <= kBins - 2) ? g_top : 0.f;
-    const float k20 = 2.0f * kTail * c;
+    // knots -> softmax logits: edge_j = 20 * sum_{i<j} (m + c e_i) - 10 for 1 <= j <= K-1, ends pinned
+    const float gl = (b >= 1) ? -g_u - g_w : 0.f, gr = (b <= kBins - 2) ? g_w : 0.f;
+    const float gb = (b >= 1) ? g - g_h : 0.f, gt = (b <= kBins - 2) ? g_h : 0.f;
+    const float k20 = 2.0f * kTail * (1.0f - kMinBin * kBins);
+    const float Sw = __shfl_sync(kFull, W.cum, b), ew = __shfl_sync(kFull, W.e, b);
+    const float Sh = __shfl_sync(kFull, H.cum, b), eh = __shfl_sync(kFull, H.e, b);
     const float dot_w = k20 * (gl * Sw + gr * (Sw + ew));
     const float dot_h = k20 * (gb * Sh + gt * (Sh + eh));
-    const float out_scale = scale * inv_sqrt_h;
-    for (int j = 0; j < kBins; ++j) {
-        const float e = expf(q[j * qs] * inv_sqrt_h - mw) * inv_sw;
-        const float ge = k20 * ((j < b ? gl : 0.f) + (j <= b ? gr : 0.f));
-        q[j * qs] = out_scale * e * (ge - dot_w);
+    const float out_scale = scale * 0.08838834764831845f;
+    if (lane < kBins) {
+        const float sel_w = k20 * ((lane < b ? gl : 0.f) + (lane <= b ? gr : 0.f));
+        const float sel_h = k20 * ((lane < b ? gb : 0.f) + (lane <= b ? gt : 0.f));
+        q[lane] = out_scale * W.e * (sel_w - dot_w);
+        q[kBins + lane] = out_scale * H.e * (sel_h - dot_h);
     }
-    for (int j = 0; j < kBins; ++j) {
-        const float e = expf(qh[j * qs] * inv_sqrt_h - mh) * inv_sh;
-        const float ge = k20 * ((j < b ? gb : 0.f) + (j <= b ? gt : 0.f));
-        qh[j * qs] = out_scale * e * (ge - dot_h);
-    }
-    for (int j = 0; j < kBins - 1; ++j) {
+    if (lane < kBins - 1) {
         float v = 0.f;
-        if (j == b - 1) v = g_d0 / (1.0f + expf(-qd0));  // softplus' = sigmoid
-        if (j == b) v = g_d1 / (1.0f + expf(-qd1));
-        qd[j * qs] = scale * v;
+        if (lane == b - 1) v = g_d0 / (1.0f + expf(-qd0));  // softplus' = sigmoid
+        if (lane == b) v = g_d1 / (1.0f + expf(-qd1));
+        q[2 * kBins + lane] = scale * v;
     }
     g = g_u;
 }
 
-// One thread per row: log p (choice head + ten splines forward), then, when the gradient is wanted,
-// the reverse sweep that leaves d loss / d (spline parameters, logits) where the values were.
-__global__ void __launch_bounds__(kTM) train_rows_kernel(const float *__restrict__ params, Layout L, TrainRows rows,
-                                                         long long Rp, float scale, int backward, TrainBufs B)
+// log p of every row (choice head + ten splines forward) and, when the gradient is wanted, the
+// reverse sweep that leaves d loss / d (spline parameters, logits) where the values were.
+__global__ void __launch_bounds__(kRowWarps * 32) train_rows_kernel(const float *__restrict__ params, Layout L,
+                                                                    TrainRows rows, long long Rp, float scale,
+                                                                    int backward, TrainBufs B)
 {
-    const long long row = (long long)blockIdx.x * kTM + threadIdx.x;
+    __shared__ float u_in[kRowWarps][kTransforms];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long row = (long long)blockIdx.x * kRowWarps + wib;
     if (row >= Rp) return;
     const int n_choices = L.n_choices;
+    float *lg = B.LG + (size_t)row * kMaxChoices;
     if (row >= rows.R) {  // padding rows of the last tile contribute nothing
         if (backward) {
             for (int k = 0; k < kTransforms; ++k)
-                for (int j = 0; j < kSplineOut; ++j) B.Q[((size_t)k * kQRows + j) * Rp + row] = 0.f;
-            for (int j = 0; j < n_choices; ++j) B.LG[(size_t)j * Rp + row] = 0.f;
+                for (int j = lane; j < kSplineOut; j += 32) B.Q[((size_t)k * Rp + row) * kQRows + j] = 0.f;
+            if (lane < n_choices) lg[lane] = 0.f;
         }
         return;
     }
@@ -303,42 +317,37 @@ __global__ void __launch_bounds__(kTM) train_rows_kernel(const float *__restrict
     float lp;
     {
         const int choice = (int)__ldg(rows.x + 2 * dr + 1);
-        float m = -INFINITY;
-        for (int j = 0; j < n_choices; ++j) m = fmaxf(m, B.LG[(size_t)j * Rp + row]);
-        float s = 0.f, pc = 0.f;
-        for (int j = 0; j < n_choices; ++j) {
-            const float e = expf(B.LG[(size_t)j * Rp + row] - m);
-            s += e;
-            if (j == choice) pc = e;
-        }
+        const float logit = lane < n_choices ? lg[lane] : -INFINITY;
+        const float m = warp_max(logit);
+        const float e = lane < n_choices ? expf(logit - m) : 0.f;
+        const float s = __shfl_sync(kFull, warp_scan(e, lane), 31);
+        const float p = __shfl_sync(kFull, e, choice) / s;
         const float eps = 1.1920928955078125e-07f;
-        const float p = pc / s;  // same arithmetic as categorical_logp()
         lp = logf(fminf(fmaxf(p, eps), 1.0f - eps));
-        if (backward) {
-            const float inv_s = 1.0f / s;
+        if (backward && lane < n_choices) {
             const bool clamped = p < eps || p > 1.0f - eps;  // torch.clamp passes no gradient outside
-            for (int j = 0; j < n_choices; ++j) {
-                const float pj = expf(B.LG[(size_t)j * Rp + row] - m) * inv_s;
-                B.LG[(size_t)j * Rp + row] = clamped ? 0.f : scale * ((j == choice ? 1.0f : 0.f) - pj);
-            }
+            lg[lane] = clamped ? 0.f : scale * ((lane == choice ? 1.0f : 0.f) - e / s);
         }
     }
     const float mu_y = params[L.mu_y], sigma_y = params[L.sigma_y];
     const float y = logf(__ldg(rows.x + 2 * dr));
     float u = (y - mu_y) / sigma_y;
     float logdet = -logf(sigma_y);
-    float u_in[kTransforms];
-#pragma unroll
+    float g = 0.f;
+#pragma unroll 1
     for (int k = 0; k < kTransforms; ++k) {
-        u_in[k] = u;
-        rqs_forward(u, logdet, B.Q + (size_t)k * kQRows * Rp + row, (size_t)Rp);
+        if (lane == 0) u_in[wib][k] = u;
+        rqs_warp<false>(u, logdet, B.Q + ((size_t)k * Rp + row) * kQRows, lane, g, scale);
     }
-    B.LP[row] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+    if (lane == 0) B.LP[row] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
     if (!backward) return;
-    float g = -u;  // d/du of the standard-normal base log-density
-#pragma unroll
-    for (int k = kTransforms - 1; k >= 0; --k)
-        rqs_backward(u_in[k], B.Q + (size_t)k * kQRows * Rp + row, (size_t)Rp, g, scale);
+    __syncwarp();
+    g = -u;  // d/du of the standard-normal base log-density
+#pragma unroll 1
+    for (int k = kTransforms - 1; k >= 0; --k) {
+        float uk = u_in[wib][k];
+        rqs_warp<true>(uk, logdet, B.Q + ((size_t)k * Rp + row) * kQRows, lane, g, scale);
+    }
 }
 
 // ---- 3. backward through the nets ------------------------------------------------------------
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(kThreads) train_backward_kernel(const float *_
         __syncthreads();
         if (net > 0) {
             const int k = net - 1;
-            load_rows(B.Q + (size_t)k * kQRows * Rp, Rp, row0, kSplineOut, S.in);
+            load_rows(B.Q + (size_t)k * kQRows * Rp, kQRows, row0, kSplineOut, S.in);
             load_hidden(S.hb, B.H, Rp, net, 1, row0);
             __syncthreads();
             wgrad<5, 8>(S.in, kLdIn, kSplineOut, S.hb, kLdH, kHidden, P + L.fl_W3[k], P + L.fl_b3[k], acc);
@@ -416,7 +425,7 @@ __global__ void __launch_bounds__(kThreads) train_backward_kernel(const float *_
             __syncthreads();
             wgrad<8, 6>(S.ha, kLdH, kHidden, S.in, kLdIn, kCtx, P + L.fl_W1[k], P + L.fl_b1[k], acc);
         } else {
-            load_rows(B.LG, Rp, row0, L.n_choices, S.in);
+            load_rows(B.LG, kMaxChoices, row0, L.n_choices, S.in);
             load_hidden(S.ha, B.H, Rp, 0, 2, row0);
             __syncthreads();
             wgrad<1, 8>(S.in, kLdIn, L.n_choices, S.ha, kLdH, kHidden, P + L.cat_Wo, P + L.cat_bo, acc);
@@ -539,7 +548,8 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
     const int want_grad = grad_dev != nullptr;
     train_forward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, rows, d.Rp, B, want_grad);
     DDM_CUDA_TRY(cudaGetLastError());
-    train_rows_kernel<<<d.tiles, kTM, 0, st>>>(params_dev, L, rows, d.Rp, -1.0f / (float)R, want_grad, B);
+    train_rows_kernel<<<(unsigned)((d.Rp + kRowWarps - 1) / kRowWarps), kRowWarps * 32, 0, st>>>(
+        params_dev, L, rows, d.Rp, -1.0f / (float)R, want_grad, B);
     DDM_CUDA_TRY(cudaGetLastError());
     int n_ss = 0;
     if (want_grad) {
