@@ -301,6 +301,66 @@ def mnle_bench(dev, with_cpu: bool):
     return out
 
 
+def mnle_train_bench(dev, with_cpu: bool, rows: int = 4096):
+    """Row f4: one MNLE training step (TRAIN_BATCH_SIZE = 4096 rows, run_config.py:12) = loss + gradient +
+    Adam on the device; the same step through the CPU spec under torch autograd beside it."""
+    import numpy as np
+    import torch
+    from sbi_for_diffusion_models_b200.mnle_train import MNLETrainer
+    N = 1 << 18
+    p = random_mnle_params(0)
+    z = build_workload(N, 0, dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.stack([torch.exp(torch.rand(N, device=dev, generator=g) * 5.1 - 3.0),
+                     torch.randint(0, 3, (N,), device=dev, generator=g).float()], 1).contiguous()
+    tr = MNLETrainer(3, cond_mean=p["cond_mean"], cond_std=p["cond_std"], mu_y=0.35, sigma_y=1.1, init=p, device=dev)
+    cd = tr.standardise(z)
+    idx = [torch.randperm(N, device=dev, generator=g)[:rows].contiguous() for _ in range(8)]
+    for i in range(5):
+        tr.nll(x, cd, idx[i % 8])
+        tr.adam()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 50
+    e0.record()
+    for i in range(steps):
+        tr.nll(x, cd, idx[i % 8])
+        tr.adam()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / steps
+    e0.record()
+    for i in range(steps):
+        tr.nll(x, cd, idx[i % 8], grad=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_fwd = e0.elapsed_time(e1) / steps
+    out = {"workload": f"row f4: MNLE training step, {rows}-row minibatch gathered from {N} resident rows, "
+                       "loss + gradient of all 412 489 parameters + clip + Adam",
+           "rows": rows, "ms_per_step": ms_step, "ms_loss_only": ms_fwd, "rows_per_s": rows / (ms_step * 1e-3),
+           "fp32_dense_tflops": 3 * 0.818e6 * rows / (ms_step * 1e-3) / 1e12,
+           "note": "dense work = forward + backward-data + weight-gradient products, 3 x 0.818 MFLOP per row, fp32 CUDA cores",
+           "loss_after": float(tr.stats[0])}
+    if with_cpu:
+        from oracle import mnle_spec
+        frozen = ("cond_mean", "cond_std", "flow.mu_y", "flow.sigma_y")
+        pc = {k: v.clone().requires_grad_(k not in frozen) for k, v in p.items()}
+        opt = torch.optim.Adam([v for k, v in pc.items() if k not in frozen], lr=5e-4)
+        xs, cs = x[:rows].cpu(), z[:rows].cpu()
+        ts = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            loss = -mnle_spec.log_prob(pc, xs, cs).mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_([v for k, v in pc.items() if k not in frozen], 5.0)
+            opt.step()
+            ts.append(time.perf_counter() - t0)
+        out["cpu_spec_autograd_fp32"] = {"ms_per_step": 1e3 * float(np.median(ts[1:])), "cores": torch.get_num_threads(),
+                                         "kind": "port (oracle/mnle_spec.py under torch autograd; sbi is not installable offline)"}
+    return out
+
+
 def run_native(args):
     import numpy as np
     import torch
@@ -499,6 +559,10 @@ def run_native(args):
                 line["mnle_potential"] = mnle_bench(dev, with_cpu=not args.no_cpu_baseline)
             except Exception as e:  # the headline metric must still print
                 line["mnle_potential"] = {"error": repr(e)}
+            try:
+                line["mnle_train_step"] = mnle_train_bench(dev, with_cpu=not args.no_cpu_baseline)
+            except Exception as e:
+                line["mnle_train_step"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

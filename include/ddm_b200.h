@@ -86,8 +86,9 @@ size_t ddm_sim_workspace_bytes(void);
  *               (float)(T_MAX - 1e-6), (float)(mu_sensory * sqrt(DT_CHOICE)).
  *   seed, trial_offset
  *               native noise: Philox4x32-10 with key = seed and counter
- *               (trial_offset + i, step / 4): results do not depend on how trials are
- *               split over launches, streams or GPUs.
+ *               (trial_offset + i, step / 6) -- one 128-bit block gives six 21-bit fields =
+ *               three Box-Muller pairs = the normals of six consecutive steps: results do
+ *               not depend on how trials are split over launches, streams or GPUs.
  *   noise_dev   NULL for native noise; otherwise (n_max, >=N) fp32 standard normals,
  *               step-major with row stride ld_noise floats (the reference draws one (N,)
  *               vector per step), consumed INSTEAD of Philox.  With shared noise the

@@ -34,7 +34,8 @@ int cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 // ---- Philox4x32-10 (Salmon et al., SC'11) -------------------------------------------
-// counter = (lo32(trial), hi32(trial), step / 4, 0), key = (lo32(seed), hi32(seed)).
+// counter = (lo32(trial), hi32(trial), block, 0), key = (lo32(seed), hi32(seed)); the simulator draws
+// the normals of steps 6 * block .. 6 * block + 5 from one block (see normals6 below).
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
 constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
@@ -105,38 +106,49 @@ __device__ __forceinline__ float mufu_cos(float x)
     return y;
 }
 
-// (w & 0x007FFFFF) | one in ONE LOP3: `one` (= 0x3F800000) must sit in a register, because a
-// LOP3 can carry only one immediate; callers pass it from a kernel parameter so that the
-// compiler cannot fold it back into a second immediate (and a second instruction).
-__device__ __forceinline__ float mantissa_to_1_2(uint32_t w, uint32_t one)
+// One Philox block (128 bits) feeds SIX normals: six 21-bit fields at bit offsets 0, 21, ..., 105,
+// i.e. three Box-Muller pairs (radius field, angle field).  A field is dropped into the low mantissa
+// bits of 1.0f with ONE LOP3: (w & 0x001FFFFF) | one gives f in [1, 1.25) on a 2^-23 grid.  `one`
+// (= 0x3F800000) must sit in a register, because a LOP3 can carry only one immediate; callers pass
+// it from a kernel parameter so that the compiler cannot fold it back into a second immediate.
+constexpr int kNormalsPerBlock = 6;
+
+__device__ __forceinline__ float field_to_1_125(uint32_t w, uint32_t one)
 {
     uint32_t r;
-    asm("lop3.b32 %0, %1, 0x007FFFFF, %2, 0xEA;" : "=r"(r) : "r"(w), "r"(one));
+    asm("lop3.b32 %0, %1, 0x001FFFFF, %2, 0xEA;" : "=r"(r) : "r"(w), "r"(one));
     return __uint_as_float(r);
 }
 
-// Two 32-bit words -> two independent N(0,1) draws.
-//   radius word: low 23 bits -> f in [1,2) -> u = 2 - f in (0,1] -> r = sqrt(-2 ln u)
-//   angle  word: low 23 bits -> g in [1,2) -> phi = 2 pi (g - 1.5) in [-pi, pi)
+// Two 21-bit fields -> two independent N(0,1) draws.
+//   radius field: f in [1,1.25) -> u = 5 - 4f in [2^-21, 1] (exact) -> r = sqrt(-2 ln u) <= 5.4
+//   angle  field: g in [1,1.25) -> phi = 2 pi (4 (g - 1) - 0.5) = 8 pi g - 9 pi in [-pi, pi)
 __device__ __forceinline__ void box_muller(uint32_t wr, uint32_t wa, uint32_t one, float &z0, float &z1)
 {
-    const float f = mantissa_to_1_2(wr, one);
-    const float u = __fsub_rn(2.0f, f);
+    const float f = field_to_1_125(wr, one);
+    const float u = __fmaf_rn(f, -4.0f, 5.0f);
     const float r = mufu_sqrt(__fmul_rn(mufu_lg2(u), -1.3862943611198906f));  // -2 ln 2 * lg2 u
-    const float g = mantissa_to_1_2(wa, one);
-    const float phi = __fmaf_rn(g, 6.283185307179586f, -9.42477796076938f);
+    const float g = field_to_1_125(wa, one);
+    const float phi = __fmaf_rn(g, 25.132741228718345f, -28.274333882308138f);
     z0 = __fmul_rn(r, mufu_cos(phi));
     z1 = __fmul_rn(r, mufu_sin(phi));
 }
 
-// The four normals of steps 4*blk .. 4*blk+3 of global trial `trial`.
-__device__ __forceinline__ void philox_normals4(uint32_t trial_lo, uint32_t trial_hi, uint32_t blk,
-                                                const PhiloxKey &key, uint32_t one, float (&z)[4])
+// 128 bits -> six normals (fields that straddle two words come out of one funnel shift)
+__device__ __forceinline__ void normals6(const uint32_t (&w)[4], uint32_t one, float (&z)[6])
+{
+    box_muller(w[0], __funnelshift_r(w[0], w[1], 21), one, z[0], z[1]);
+    box_muller(__funnelshift_r(w[1], w[2], 10), __funnelshift_r(w[1], w[2], 31), one, z[2], z[3]);
+    box_muller(__funnelshift_r(w[2], w[3], 20), w[3] >> 9, one, z[4], z[5]);
+}
+
+// The six normals of steps 6*blk .. 6*blk+5 of global trial `trial`.
+__device__ __forceinline__ void philox_normals6(uint32_t trial_lo, uint32_t trial_hi, uint32_t blk,
+                                                const PhiloxKey &key, uint32_t one, float (&z)[6])
 {
     uint32_t w[4];
     philox4x32_10(trial_lo, trial_hi, blk, 0u, key, w);
-    box_muller(w[0], w[1], one, z[0], z[1]);
-    box_muller(w[2], w[3], one, z[2], z[3]);
+    normals6(w, one, z);
 }
 
 // ---- Philox with the trial-constant part of rounds 1-2 hoisted -------------------------
@@ -194,13 +206,12 @@ __device__ __forceinline__ void philox4x32_10_trial(const PhiloxTrial &t, uint32
     out[3] = c3;
 }
 
-__device__ __forceinline__ void philox_normals4_trial(const PhiloxTrial &t, uint32_t blk, const PhiloxKey &key,
-                                                      uint32_t one, float (&z)[4])
+__device__ __forceinline__ void philox_normals6_trial(const PhiloxTrial &t, uint32_t blk, const PhiloxKey &key,
+                                                      uint32_t one, float (&z)[6])
 {
     uint32_t w[4];
     philox4x32_10_trial(t, blk, key, w);
-    box_muller(w[0], w[1], one, z[0], z[1]);
-    box_muller(w[2], w[3], one, z[2], z[3]);
+    normals6(w, one, z);
 }
 
 }  // namespace ddm

@@ -9,7 +9,7 @@
 //     queue at the next chunk boundary, so warps stay full although trial lengths vary
 //     from 1 to n_max steps (mean ~5e3 of 16000 under the pipeline prior);
 //   * noise is counter-based: Philox4x32-10 keyed by the seed with counter
-//     (global trial index, step / 4) -> Box-Muller on the MUFU unit.  Which lane, warp,
+//     (global trial index, step / 6) -> six 21-bit fields -> Box-Muller on the MUFU unit.  Which lane, warp,
 //     launch or GPU runs a trial does not change its result;
 //   * the fp32 arithmetic of a step is the reference's, operation for operation, with FMA
 //     contraction forbidden (explicit *_rn intrinsics), so that feeding the same normals
@@ -18,7 +18,7 @@
 //     and packed to sign bits with warp ballots (80 pulses -> three registers);  a row that
 //     holds anything other than +-1 is flagged and read back from global memory at kick
 //     time instead, still bit-exact;
-//   * a chunk is 8 Euler steps (two Philox blocks).  The fast path only tracks the running
+//   * a chunk is 24 Euler steps (four Philox blocks of six normals each).  The fast path only tracks the running
 //     max / min of the accumulator; the per-step first-passage search runs once per trial,
 //     in the chunk where max >= B, min <= 0 or the window ends.
 #include "ddm_common.cuh"
@@ -59,7 +59,7 @@ struct SimParams {
 };
 
 #ifndef DDM_SIM_NB
-#define DDM_SIM_NB 4  // Philox blocks (x4 Euler steps) per chunk: 16 steps (measured +4 % over 8)
+#define DDM_SIM_NB 4  // Philox blocks (x6 Euler steps) per chunk: 24 steps
 #endif
 
 // torch.clamp: NaN propagates (fminf/fmaxf would drop it)
@@ -93,7 +93,9 @@ __device__ __forceinline__ int wait_for_rows(const unsigned long long *ready, un
 template <int MASKW, bool INJECT, bool ALIGNED, int NB, bool STREAM>
 __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim_kernel(const SimParams p)
 {
-    constexpr int STEPS = 4 * NB;
+    constexpr int NPB = kNormalsPerBlock;
+    constexpr int STEPS = NPB * NB;
+    static_assert(STEPS % 8 == 0, "chunks must keep pulse kicks on multiples of 8 steps");
     constexpr int MW = MASKW > 0 ? MASKW : 1;
     const unsigned lane = threadIdx.x & 31u;
 
@@ -103,7 +105,9 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
     int nsteps = 0;  // decision window in steps
     int tk = 0;      // step index of the next pulse kick
     int pidx = 0;    // column of the next pulse
+    uint32_t blk = 0u;  // Philox block of the chunk's first step (= t / 6)
     uint32_t cur = 0u;  // sign bits of pulses pidx.. (bit 0 = next pulse)
+    float kv = 0.f;     // ALIGNED: signed value v * s[pidx] of the next kick
     PhiloxTrial pt{0u, 0u, 0u, 0u};
     uint32_t mask[MW];
 #pragma unroll
@@ -178,9 +182,18 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 nsteps = !(win > 0.0f) ? 0 : (win >= (float)p.n_max ? p.n_max : (int)win);
                 a = __fmul_rn(a0, B);  // :144
                 t = 0;
+                blk = 0u;
                 tk = 0;
                 pidx = 0;
                 cur = mask[0];
+                if (ALIGNED) {
+                    if (MASKW == 0 || generic) {
+                        const float s0 = (p.n_pulses > 0) ? __ldcg(p.pulses + (long long)trial * p.ld_pulses) : 0.0f;
+                        kv = __fmul_rn(v, s0);
+                    } else {
+                        kv = (cur & 1u) ? v : -v;
+                    }
+                }
                 if (!INJECT) {
                     const unsigned long long g = p.trial_offset + (unsigned long long)trial;
                     pt = philox_trial_setup((uint32_t)g, (uint32_t)(g >> 32), p.key);
@@ -210,30 +223,39 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
             return __fadd_rn(acc, kv);
         };
 
+        // ALIGNED (steps_per_pulse % 8 == 0 and >= STEPS): at most one kick per chunk, at i = dk, a
+        // multiple of 8.  The kick sites are branch-free selects; the pulse bookkeeping runs once per
+        // chunk instead of once per site.
+        const int dk = tk - t;
         float av[STEPS];
         float acc = a;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            float z[4];
+            float z[NPB];
             if (INJECT) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int step = t + 4 * b + j;
+                for (int j = 0; j < NPB; ++j) {
+                    const int step = t + NPB * b + j;
                     z[j] = (busy && step < p.n_max)
                                ? __ldg(p.noise + (long long)step * p.ld_noise + trial)
                                : 0.0f;
                 }
             } else {
-                philox_normals4_trial(pt, (uint32_t)(t >> 2) + (uint32_t)b, p.key, p.one_bits, z);
+                philox_normals6_trial(pt, blk + (uint32_t)b, p.key, p.one_bits, z);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = 4 * b + j;
+            for (int j = 0; j < NPB; ++j) {
+                const int i = NPB * b + j;
                 const float nz = __fmul_rn(z[j], p.noise_scale);                // :186
                 const float leak = __fmul_rn(__fmul_rn(nlam, acc), p.dt);      // (-lam*a)*dt
                 acc = __fadd_rn(__fadd_rn(acc, leak), nz);                     // :187
                 // :190-192; with steps_per_pulse % 8 == 0 a kick can only fall on i % 8 == 0
-                if (!ALIGNED || (i & 7) == 0) {
+                if (ALIGNED) {
+                    if ((i & 7) == 0) {
+                        const float kicked_acc = __fadd_rn(acc, kv);  // a += v * s[:, p_idx] * active
+                        acc = (dk == i) ? kicked_acc : acc;
+                    }
+                } else {
                     if (t + i == tk) acc = kick(acc);
                 }
                 av[i] = acc;
@@ -241,6 +263,23 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
         }
         a = acc;
         chunks += 1u;
+        if (ALIGNED) {  // advance to the next pulse if this chunk held a kick
+            const bool kicked = dk < STEPS;
+            const uint32_t shifted = cur >> 1;
+            cur = kicked ? shifted : cur;
+            pidx += kicked ? 1 : 0;
+            tk += kicked ? p.spp : 0;
+            if (MASKW > 1 && kicked && (pidx & 31) == 0) cur = (pidx == 32) ? mask[1 % MW] : mask[2 % MW];
+            if (MASKW == 0 || generic) {
+                if (kicked) {
+                    float s = 0.0f;
+                    if (busy && pidx < p.n_pulses) s = __ldcg(p.pulses + (long long)trial * p.ld_pulses + pidx);
+                    kv = __fmul_rn(v, s);
+                }
+            } else {
+                kv = (cur & 1u) ? v : -v;  // v * (+-1) exactly
+            }
+        }
 
         // fmaxf / fminf ignore NaN operands, like the reference's comparisons (always false)
         float hi = -CUDART_INF_F, lo = CUDART_INF_F;
@@ -278,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
             busy = false;
         }
         t += STEPS;
+        blk += (uint32_t)NB;
     }
 
     // ---- counters --------------------------------------------------------------------
@@ -295,7 +335,8 @@ __global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, uint32_
                                                           long long n_trials, long long n_steps,
                                                           void *out, long long ld)
 {
-    const long long n_blk = (n_steps + 3) / 4;
+    constexpr int PER = WORDS ? 4 : kNormalsPerBlock;
+    const long long n_blk = (n_steps + PER - 1) / PER;
     const long long total = n_blk * n_trials;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -309,11 +350,12 @@ __global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, uint32_
             for (int j = 0; j < 4; ++j)
                 if (blk * 4 + j < n_steps) static_cast<uint32_t *>(out)[(blk * 4 + j) * ld + i] = w[j];
         } else {
-            float z[4];
-            philox_normals4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)blk, key, one, z);
+            float z[kNormalsPerBlock];
+            philox_normals6((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)blk, key, one, z);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (blk * 4 + j < n_steps) static_cast<float *>(out)[(blk * 4 + j) * ld + i] = z[j];
+            for (int j = 0; j < kNormalsPerBlock; ++j)
+                if (blk * kNormalsPerBlock + j < n_steps)
+                    static_cast<float *>(out)[(blk * kNormalsPerBlock + j) * ld + i] = z[j];
         }
     }
 }
@@ -409,7 +451,7 @@ static int sim_impl(const float *theta_dev, int64_t ld_theta, const float *pulse
     p.ready = reinterpret_cast<const unsigned long long *>(ready_dev);
 
     const bool inject = noise_dev != nullptr;
-    const bool aligned = (steps_per_pulse % 8) == 0;
+    const bool aligned = (steps_per_pulse % 8) == 0 && steps_per_pulse >= kNormalsPerBlock * DDM_SIM_NB;
     const bool packed = need <= 96;
 #define DDM_PICK(MW, INJ, AL, ST) return launch_sim<MW, INJ, AL, ST>(p, sms, st)
     if (ready_dev != nullptr) {  // streaming ingest: native noise only
@@ -458,7 +500,8 @@ static int dump_common(bool words, uint64_t seed, uint64_t trial_offset, int64_t
     DDM_REQUIRE(ld_out >= N, "philox dump: ld_out=%lld < N=%lld", (long long)ld_out, (long long)N);
     if (N == 0 || n_steps == 0) return DDM_OK;
     DDM_REQUIRE(out_dev != nullptr, "philox dump: null output");
-    const long long total = ((n_steps + 3) / 4) * N;
+    const long long per = words ? 4 : kNormalsPerBlock;
+    const long long total = ((n_steps + per - 1) / per) * N;
     long long grid = (total + 255) / 256;
     if (grid > 148 * 64) grid = 148 * 64;
     const PhiloxKey key = make_philox_key(seed);
