@@ -533,7 +533,7 @@ def run_native(args):
                                    "schedule (n_max=16000, steps_per_pulse=200, P=80)" if n == 100_000_000 else
                                    f"configs[1] shape at {n} trials per GPU (default schedule, P=80)",
                        "trials_per_gpu_per_step": n, "z_bytes_per_gpu": n * 340,
-                       "l2": "inputs (z) larger than L2; new Philox key each step", "rng": "Philox4x32-10 + Box-Muller",
+                       "l2": "inputs (z) larger than L2; new Philox key each step", "rng": "Philox4x32-10, six 21-bit Box-Muller fields per block",
                        "exchange": "all_gather(x) per step" if world > 1 else "none"},
             "trials_per_s": world * n * args.steps / (elapsed_ms * 1e-3),
             "mean_steps_per_trial": useful_all / (world * n * args.steps),

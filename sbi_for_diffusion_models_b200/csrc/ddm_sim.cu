@@ -31,7 +31,7 @@ namespace ddm {
 #define DDM_SIM_THREADS 256
 #endif
 #ifndef DDM_SIM_MIN_BLOCKS
-#define DDM_SIM_MIN_BLOCKS 4  // measured on B200: 4 blocks (<= 64 regs, no spills) 9.40e11 steps/s, 5: 9.23e11, 6: 9.12e11
+#define DDM_SIM_MIN_BLOCKS 3  // measured on B200 (24-step chunks): 3 blocks (66 regs) 1.156e12 steps/s, 4: 1.143e12, 5 (spills): 1.105e12
 #endif
 constexpr int kThreads = DDM_SIM_THREADS;  // small CTAs retire sooner in the drain phase of a launch
 constexpr unsigned kFull = 0xFFFFFFFFu;
