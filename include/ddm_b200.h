@@ -268,7 +268,7 @@ int mnle_train_adam_f32(float *params_dev, const float *grad_dev, float *m_dev, 
                         float max_grad_norm, void *stream);
 
 /* Debug aid: when trace_dev != NULL, CTA 0 of every following mnle_loglik_sum_tc_f32 launch writes
- * 34 stages x 2 tiles x 4 clock64() stamps there (issuer saw A operand / had the weights, epilogue
+ * 34 stages x 2 tiles x 8 clock64() stamps there (issuer saw A operand / had the weights, epilogue
  * saw the accumulators / finished).  NULL switches it off (the default). */
 int mnle_tc_set_trace(long long *trace_dev);
 

@@ -336,7 +336,8 @@ constexpr int kTcM = 128;                        // rows per tile = UMMA M
 constexpr int kTcTiles = 2;                      // tiles per CTA
 constexpr int kTcEpiWarps = 16;                  // warp w: lane quarter w & 3, tile (w >> 2) & 1, column half w >> 3
 constexpr int kTcEpiThreads = kTcEpiWarps * 32;
-constexpr int kTcThreads = kTcEpiThreads + 32;   // + the issuer warp
+constexpr int kTcIssuers = 2;                    // issuer warps: warp kTcEpiWarps + i owns stages s = i (mod 2)
+constexpr int kTcThreads = kTcEpiThreads + 32 * kTcIssuers;
 constexpr int kTcSlots = 3;
 constexpr uint32_t kImgBytes = kTcM * 256;       // one bf16 image of 128 rows x 128 k
 constexpr uint32_t kKGroupBytes = kTcM * 16;     // 8 k's of all 128 rows
@@ -496,6 +497,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint64_t *dfull = wfull + kTcSlots;                                // [kTcTiles]
     uint64_t *aready = dfull + kTcTiles;                               // [kTcTiles]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBars + 96);
+    // passed[X] = number of stages whose issuer has consumed its aready[X] phase (issuer warps only)
+    volatile int *passed = reinterpret_cast<volatile int *>(smem + kSmemBars + 112);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
@@ -505,6 +508,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     if (warp == kTcEpiWarps) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
+        passed[0] = 0;
+        passed[1] = 0;
         for (int i = 0; i < kTcSlots; ++i) mbar_init(&wfull[i], 1);
         for (int i = 0; i < kTcTiles; ++i) {
             mbar_init(&dfull[i], 1);
@@ -517,9 +522,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == kTcEpiWarps) {
-        // ================= issuer: bulk copies of the stage blobs + every tcgen05.mma =========
-        // The whole warp walks the (uniform) stage loop; one elected lane issues.
+    if (warp >= kTcEpiWarps) {
+        // ================= issuers: bulk copies of the stage blobs + every tcgen05.mma =========
+        // The whole warp walks the (uniform) stage loop; one elected lane issues.  Two issuer warps take
+        // alternate stages.  Per stage an issuer spends ~700 cycles building the sixteen operand
+        // descriptors on the uniform datapath, ~220 in the commit and 300-500 issuing the next bulk copies
+        // (measured with the clock64 trace); a single issuer did that with the tensor pipe idle between
+        // stages.  Now one warp prepares stage s + 1 while the other is blocked in the MMA queue of stage s.
+        // A stage's MMAs wait for its A operand (aready), which exists only after the previous stage's
+        // accumulators were committed and drained; the only extra ordering is `passed` (below).
+        const int iw = warp - kTcEpiWarps;
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
         const int t_of[2] = {tile0 / CB, (tile0 + 1) / CB};
         auto load = [&](int s) {
@@ -538,20 +550,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             __syncwarp();
         };
-        load(0);
-        load(1);
+        load(iw);
 #pragma unroll 1
-        for (int s = 0; s < kTcStages; ++s) {
+        for (int s = iw; s < kTcStages; s += kTcIssuers) {
             const TcStage &st = plan.st[s];
             const uint32_t slot = smem_u32(smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes);
             const uint32_t n = st.n, idesc = umma_idesc_bf16_f32(kTcM, (int)n);
 #pragma unroll 1
             for (int X = 0; X < n_active; ++X) {
+                if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 8 + 5] = clock64();
+                // A parity wait cannot tell phase s from phase s - 2: first make sure the other issuer has
+                // consumed phase s - 1 (then the barrier is in phase s or s + 1 and the parity is unambiguous)
+                while (passed[X] < s) {
+                }
                 mbar_wait(&aready[X], s & 1);  // A operand of this stage written, D drained
+                if (lane == 0) passed[X] = s + 1;
                 tc_fence_after_sync();
-                if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 4 + 0] = clock64();
+                if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 8 + 0] = clock64();
                 if (X == 0) mbar_wait(&wfull[s % kTcSlots], (s / kTcSlots) & 1);
-                if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 4 + 1] = clock64();
+                if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 8 + 1] = clock64();
                 const uint32_t tm = tmem_u + (uint32_t)X * kTmemTile;
                 if (elect_one_sync()) {
                     if (st.kind == kStageInput) {
@@ -584,12 +601,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                                              umma_desc_kmajor(w + ks * 2 * w_kg, w_kg, 128), idesc, (pass | ks) != 0);
                         }
                     }
+                    if (trace && blockIdx.x == 0) trace[(s * 2 + X) * 8 + 4] = clock64();
                     umma_commit(&dfull[X]);
                 }
                 __syncwarp();
                 // every tile is past stage s-1, so its slot can take stage s+2 (issued after the
                 // MMAs: the copy has a whole stage of slack, the MMA issue is on the critical path)
                 if (X == n_active - 1 && s + 2 < kTcStages) load(s + 2);
+                if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 8 + 6] = clock64();
             }
         }
     } else if (((warp >> 2) & 1) < n_active) {
@@ -671,13 +690,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_wait(&dfull[X], s & 1);
             tc_fence_after_sync();
             const bool tracer = trace && blockIdx.x == 0 && q == 0 && lane == 0 && hf == (st.kind != kStageTheta ? 0 : 1);
-            if (tracer) trace[(s * 2 + X) * 4 + 2] = clock64();
+            if (tracer) trace[(s * 2 + X) * 8 + 2] = clock64();
             if (st.kind == kStageTheta) {
                 if (st.epi == kEpiRelu) tc_epilogue_act<kEpiRelu>(trow, 0, kHidden, bias);
                 else tc_epilogue_act<kEpiSigmoid>(trow, 0, kHidden, bias);
                 tc_fence_before_sync();
                 mbar_arrive_n(&aready[X], 2);
-                if (tracer) trace[(s * 2 + X) * 4 + 3] = clock64();
+                if (tracer) trace[(s * 2 + X) * 8 + 3] = clock64();
                 continue;
             }
             if (st.epi == kEpiRelu) {
@@ -686,7 +705,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, 64, bias);
             } else if (st.epi == kEpiSpline) {
                 tc_epilogue_spline(trow, bias, u, logdet, &aready[X]);
-                if (tracer) trace[(s * 2 + X) * 4 + 3] = clock64();
+                if (tracer) trace[(s * 2 + X) * 8 + 3] = clock64();
                 continue;
             } else {
                 uint32_t v[16];
@@ -712,7 +731,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             tc_fence_before_sync();
             mbar_arrive(&aready[X]);
-            if (tracer) trace[(s * 2 + X) * 4 + 3] = clock64();
+            if (tracer) trace[(s * 2 + X) * 8 + 3] = clock64();
         }
         if (ROWS) {
             if (hf == 0 && live) out[c_glob] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
@@ -758,9 +777,10 @@ DDM_API int mnle_tc_selftest(const float *a_dev, const float *b_dev, int N, int 
     return DDM_OK;
 }
 
-// Debug aid (tools/trace_mnle_tc.py): device buffer of kTcStages * 2 * 4 clock64 stamps written by
-// CTA 0 -- per (stage, tile): issuer saw the A operand, issuer had the weights, epilogue saw the
-// accumulators, epilogue finished.  nullptr (default) = off.
+// Debug aid (tools/trace_mnle_tc.py): device buffer of kTcStages * 2 * 8 clock64 stamps written by
+// CTA 0 -- per (stage, tile): [0] issuer saw the A operand, [1] issuer had the weights, [2] epilogue saw
+// the accumulators, [3] epilogue finished, [4] MMAs issued, [5] issuer reached the stage, [6] next bulk
+// copies issued.  nullptr (default) = off.
 static long long *g_tc_trace = nullptr;
 DDM_API int mnle_tc_set_trace(long long *trace_dev)
 {
