@@ -453,6 +453,7 @@ def run_native(args):
                             trial_offset=rank * n)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    link0 = ds.host_pipeline_counters()["h2d_bytes"]
     e0.record()
     wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -463,6 +464,7 @@ def run_native(args):
     e1.record()
     torch.cuda.synchronize()
     wall_e2e = time.perf_counter() - wall0
+    link_bytes_per_step = (ds.host_pipeline_counters()["h2d_bytes"] - link0) // args.steps
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), wall_e2e * 1e3)
     # useful steps of the timed calls: the same keys again, untimed (results are deterministic)
@@ -539,7 +541,10 @@ def run_native(args):
             "mean_steps_per_trial": useful_all / (world * n * args.steps),
             "choice_frac": choice_frac,
             "roofline": roofline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * 340, "d2h_bytes_per_step": n_e2e * 8,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": link_bytes_per_step,
+                    "d2h_bytes_per_step": n_e2e * 8, "host_z_bytes_per_step": n_e2e * 340,
+                    "ingest": "z rows (340 B/trial, pinned host) are packed to 32-byte records by the host cores "
+                              "(ddm_pack_z_host) chunk by chunk while the streaming kernel runs; the link carries the records",
                     "trials_per_step_per_gpu": n_e2e, "api": "data_simulator.sim_wrapper(z pinned host) -> x host",
                     "ms_per_step": float(e2e_t.item()) / args.steps},
             "gpu_launches": args.steps * world,

@@ -129,6 +129,24 @@ int ddm_sim_stream_f32(const float *theta_dev, int64_t ld_theta,
                        float *x_out_dev, void *workspace_dev,
                        const uint64_t *ready_dev, void *stream);
 
+/*
+ * PCIe ingest path for HOST-resident z.  Pulse sides are +-1, so a 340-byte fp32 row carries 32 bytes
+ * of information; over a ~55 GB/s PCIe 5 x16 link the fp32 rows take longer to copy than the kernel
+ * needs to simulate them.  ddm_pack_z_host (host code, n_threads CPU threads, no CUDA) turns rows
+ * [theta (5), pulses (n_pulses <= 96)] of z_host (row stride ld floats) into 32-byte records
+ * [theta bits x 5, sign masks x 3] (bit j of mask w = pulses[32 w + j] > 0; bits past n_pulses = 1) in
+ * packed_host (N x 8 uint32) and returns the number of rows holding a pulse value other than +-1
+ * (such batches must take the fp32 entry points), or a negative DDM_ERR_*.
+ * ddm_sim_packed_f32 simulates from the records (device copy, 16-byte aligned): same arguments and
+ * bit-identical results as ddm_sim_f32 / ddm_sim_stream_f32 (ready_dev != NULL: streaming ingest).
+ */
+int64_t ddm_pack_z_host(const float *z_host, int64_t ld, int64_t N, int64_t n_pulses, uint32_t *packed_host,
+                        int n_threads);
+int ddm_sim_packed_f32(const uint32_t *packed_dev, int64_t N, int64_t n_max, int64_t steps_per_pulse, float dt,
+                       float t_max, float t_nd_hi, float noise_scale, uint64_t seed, uint64_t trial_offset,
+                       int log_rt, float *x_out_dev, int32_t *steps_out_dev, void *workspace_dev,
+                       const uint64_t *ready_dev, void *stream);
+
 /* The standard normals ddm_sim_f32 consumes under native noise for trials
  * [trial_offset, trial_offset + N) and steps [0, n_steps): out (n_steps, N) step-major,
  * row stride ld_out floats. */

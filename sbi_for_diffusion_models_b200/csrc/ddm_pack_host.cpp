@@ -1,0 +1,205 @@
+// Host-side packing of z rows for the PCIe-bound ingest path.
+//
+// The reference hands the simulator z = [theta (5), pulse sides (P)] as fp32 rows (340 bytes per
+// trial at P = 80; data_simulator.py:22-29).  Pulse sides are +-1, so when z lives in HOST memory
+// the link carries 10x more bytes than information: 1e8 trials are 34 GB over a ~55 GB/s PCIe 5 x16
+// link, longer than the kernel needs to simulate them.  ddm_pack_z_host turns each row into one
+// 32-byte record [theta bits x 5, pulse sign masks x 3] on the host cores (multi-threaded, SSE2 /
+// AVX2 compares + movemask) so that the copy engine moves 32 bytes per trial;
+// ddm_sim_packed_f32 (ddm_sim.cu) consumes the records directly.  Rows holding anything other than
+// +-1 are counted: the caller sends such batches through the fp32 path instead.
+#include <immintrin.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/ddm_b200.h"
+
+#define DDM_API extern "C" __attribute__((visibility("default")))
+namespace ddm {
+void set_error(const char *fmt, ...);  // ddm_common.cu
+}
+
+#include <unistd.h>
+
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace ddm {
+
+// bit j of the result = (s[j] > 0) for j < n (n <= 32), bits n..31 = 1 (the kernel's default for
+// columns past the schedule); *odd |= any |s[j]| != 1
+static inline uint32_t sign_mask_scalar(const float *s, int n, bool *odd)
+{
+    uint32_t m = 0xFFFFFFFFu;
+    for (int j = 0; j < n; ++j) {
+        const float v = s[j];
+        if (!(v > 0.0f)) m &= ~(1u << j);
+        if (!(v == 1.0f || v == -1.0f)) *odd = true;
+    }
+    return m;
+}
+
+static void pack_rows_sse2(const float *z, int64_t ld, int64_t r0, int64_t r1, int n_pulses, uint32_t *out,
+                           int64_t *generic_rows)
+{
+    const __m128 zero = _mm_setzero_ps(), one = _mm_set1_ps(1.0f);
+    const __m128 absmask = _mm_castsi128_ps(_mm_set1_epi32(0x7FFFFFFF));
+    int64_t gen = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const float *row = z + r * ld;
+        uint32_t *rec = out + r * 8;
+        for (int i = 0; i < 5; ++i) memcpy(&rec[i], &row[i], 4);
+        const float *s = row + 5;
+        bool odd = false;
+        for (int w = 0; w < 3; ++w) {
+            const int base = 32 * w;
+            const int n = n_pulses - base < 0 ? 0 : (n_pulses - base > 32 ? 32 : n_pulses - base);
+            uint32_t m = 0xFFFFFFFFu;
+            int j = 0;
+            if (n > 0) m = (n == 32) ? 0u : (0xFFFFFFFFu << n);
+            int oddbits = 0;
+            for (; j + 4 <= n; j += 4) {
+                const __m128 v = _mm_loadu_ps(s + base + j);
+                m |= (uint32_t)_mm_movemask_ps(_mm_cmpgt_ps(v, zero)) << j;
+                oddbits |= _mm_movemask_ps(_mm_cmpneq_ps(_mm_and_ps(v, absmask), one));
+            }
+            if (j < n) {
+                bool o = false;
+                const uint32_t tail = sign_mask_scalar(s + base + j, n - j, &o);
+                m |= (tail & ((1u << (n - j)) - 1u)) << j;
+                odd = odd || o;
+            }
+            odd = odd || oddbits != 0;
+            rec[5 + w] = m;
+        }
+        gen += odd ? 1 : 0;
+    }
+    *generic_rows = gen;
+}
+
+__attribute__((target("avx2"))) static void pack_rows_avx2(const float *z, int64_t ld, int64_t r0, int64_t r1,
+                                                           int n_pulses, uint32_t *out, int64_t *generic_rows)
+{
+    const __m256 zero = _mm256_setzero_ps(), one = _mm256_set1_ps(1.0f);
+    const __m256 absmask = _mm256_castsi256_ps(_mm256_set1_epi32(0x7FFFFFFF));
+    int64_t gen = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const float *row = z + r * ld;
+        uint32_t *rec = out + r * 8;
+        for (int i = 0; i < 5; ++i) memcpy(&rec[i], &row[i], 4);
+        const float *s = row + 5;
+        bool odd = false;
+        for (int w = 0; w < 3; ++w) {
+            const int base = 32 * w;
+            const int n = n_pulses - base < 0 ? 0 : (n_pulses - base > 32 ? 32 : n_pulses - base);
+            uint32_t m = 0xFFFFFFFFu;
+            if (n > 0) m = (n == 32) ? 0u : (0xFFFFFFFFu << n);
+            int j = 0, oddbits = 0;
+            for (; j + 8 <= n; j += 8) {
+                const __m256 v = _mm256_loadu_ps(s + base + j);
+                m |= (uint32_t)_mm256_movemask_ps(_mm256_cmp_ps(v, zero, _CMP_GT_OQ)) << j;
+                oddbits |= _mm256_movemask_ps(_mm256_cmp_ps(_mm256_and_ps(v, absmask), one, _CMP_NEQ_UQ));
+            }
+            if (j < n) {
+                bool o = false;
+                const uint32_t tail = sign_mask_scalar(s + base + j, n - j, &o);
+                m |= (tail & ((1u << (n - j)) - 1u)) << j;
+                odd = odd || o;
+            }
+            odd = odd || oddbits != 0;
+            rec[5 + w] = m;
+        }
+        gen += odd ? 1 : 0;
+    }
+    *generic_rows = gen;
+}
+
+// Persistent worker pool: a chunk of 2^18 rows packs in about a millisecond, so spawning threads per
+// call (~30-50 us each) would cost as much as the work.  Workers sleep on a condition variable between
+// calls; the calling thread takes jobs too.  A forked child starts a fresh pool.
+class Pool {
+public:
+    void run(int n_jobs, int n_threads, const std::function<void(int)> &f)
+    {
+        std::lock_guard<std::mutex> call(call_mutex_);
+        std::unique_lock<std::mutex> lk(m_);
+        if (pid_ != getpid()) {  // after fork(): the parent's workers do not exist here
+            for (auto &t : threads_) t.detach();
+            threads_.clear();
+            pid_ = getpid();
+        }
+        while ((int)threads_.size() < n_threads - 1) threads_.emplace_back([this] { worker(); });
+        job_ = &f;
+        n_jobs_ = n_jobs;
+        next_ = 0;
+        pending_ = n_jobs;
+        cv_work_.notify_all();
+        while (next_ < n_jobs_) {
+            const int j = next_++;
+            lk.unlock();
+            f(j);
+            lk.lock();
+            --pending_;
+        }
+        cv_done_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void worker()
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cv_work_.wait(lk, [this] { return job_ != nullptr && next_ < n_jobs_; });
+            const int j = next_++;
+            const std::function<void(int)> *f = job_;
+            lk.unlock();
+            (*f)(j);
+            lk.lock();
+            if (--pending_ == 0) cv_done_.notify_all();
+        }
+    }
+    std::mutex call_mutex_, m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> threads_;
+    const std::function<void(int)> *job_ = nullptr;
+    int n_jobs_ = 0, next_ = 0, pending_ = 0;
+    pid_t pid_ = getpid();
+};
+
+static Pool &pool()
+{
+    static Pool *p = new Pool();  // never destroyed: workers may be asleep in it at exit
+    return *p;
+}
+
+}  // namespace ddm
+
+DDM_API int64_t ddm_pack_z_host(const float *z_host, int64_t ld, int64_t N, int64_t n_pulses, uint32_t *packed_host,
+                                int n_threads)
+{
+    if (N < 0 || n_pulses < 0 || n_pulses > 96 || ld < 5 + n_pulses || (N > 0 && (!z_host || !packed_host))) {
+        ddm::set_error("ddm_pack_z_host: bad arguments (N=%lld, n_pulses=%lld in [0,96], ld=%lld >= 5 + n_pulses)",
+                       (long long)N, (long long)n_pulses, (long long)ld);
+        return DDM_ERR_INVALID;
+    }
+    if (N == 0) return 0;
+    const bool avx2 = __builtin_cpu_supports("avx2");
+    int nt = n_threads < 1 ? 1 : n_threads;
+    const int64_t min_rows = 1 << 14;  // below that a thread costs more than it packs
+    if ((int64_t)nt > (N + min_rows - 1) / min_rows) nt = (int)((N + min_rows - 1) / min_rows);
+    std::vector<int64_t> gen((size_t)nt, 0);
+    auto work = [&](int t) {
+        const int64_t r0 = N * t / nt, r1 = N * (t + 1) / nt;
+        if (avx2) ddm::pack_rows_avx2(z_host, ld, r0, r1, (int)n_pulses, packed_host, &gen[(size_t)t]);
+        else ddm::pack_rows_sse2(z_host, ld, r0, r1, (int)n_pulses, packed_host, &gen[(size_t)t]);
+    };
+    if (nt == 1) work(0);
+    else ddm::pool().run(nt, nt, work);
+    int64_t total = 0;
+    for (int64_t g : gen) total += g;
+    return total;
+}

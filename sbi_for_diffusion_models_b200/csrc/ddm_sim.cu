@@ -90,9 +90,12 @@ __device__ __forceinline__ int wait_for_rows(const unsigned long long *ready, un
     return 0;
 }
 
-template <int MASKW, bool INJECT, bool ALIGNED, int NB, bool STREAM>
+// PACKED: p.theta points at 32-byte records [theta bits x 5, pulse sign masks x 3] made on the host by
+// ddm_pack_z_host (the PCIe ingest path): no pulse matrix, every lane loads its own record.
+template <int MASKW, bool INJECT, bool ALIGNED, int NB, bool STREAM, bool PACKED = false>
 __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim_kernel(const SimParams p)
 {
+    static_assert(!PACKED || (MASKW == 3 && !INJECT), "packed records carry three sign masks and native noise");
     constexpr int NPB = kNormalsPerBlock;
     constexpr int STEPS = NPB * NB;
     static_assert(STEPS % 8 == 0, "chunks must keep pulse kicks on multiples of 8 steps");
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
             const bool got = !busy && mine < (unsigned long long)p.n_trials;
             if (got) trial = (uint32_t)mine;
 
-            if (MASKW > 0) {
+            if (MASKW > 0 && !PACKED) {
                 // whole warp loads each new trial's pulse row: coalesced, then ballot -> sign bits
                 unsigned todo = __ballot_sync(kFull, got);
                 while (todo != 0u) {
@@ -167,9 +170,19 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 }
             }
             if (got) {
-                const float *th = p.theta + (long long)trial * p.ld_theta;
-                const float th0 = __ldcg(th + 0), th1 = __ldcg(th + 1), th2 = __ldcg(th + 2);
-                const float th3 = __ldcg(th + 3), th4 = __ldcg(th + 4);
+                float th0, th1, th2, th3, th4;
+                if (PACKED) {
+                    const uint4 *rec = reinterpret_cast<const uint4 *>(p.theta) + 2ll * trial;
+                    const uint4 lo = __ldcg(rec), hi = __ldcg(rec + 1);
+                    th0 = __uint_as_float(lo.x), th1 = __uint_as_float(lo.y), th2 = __uint_as_float(lo.z);
+                    th3 = __uint_as_float(lo.w), th4 = __uint_as_float(hi.x);
+                    mask[0] = hi.y, mask[1 % MW] = hi.z, mask[2 % MW] = hi.w;
+                    generic = false;
+                } else {
+                    const float *th = p.theta + (long long)trial * p.ld_theta;
+                    th0 = __ldcg(th + 0), th1 = __ldcg(th + 1), th2 = __ldcg(th + 2);
+                    th3 = __ldcg(th + 3), th4 = __ldcg(th + 4);
+                }
                 // rt_choice_model.py:131-135
                 const float a0 = clamp_keep_nan(th0, 0.0f, 1.0f);
                 nlam = -th1;
@@ -361,10 +374,10 @@ __global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, uint32_
 }
 
 // ---- launch ----------------------------------------------------------------------------
-template <int MASKW, bool INJECT, bool ALIGNED, bool STREAM>
+template <int MASKW, bool INJECT, bool ALIGNED, bool STREAM, bool PACKED = false>
 static int launch_sim(const SimParams &p, int sm_count, cudaStream_t stream)
 {
-    auto kern = sim_kernel<MASKW, INJECT, ALIGNED, DDM_SIM_NB, STREAM>;
+    auto kern = sim_kernel<MASKW, INJECT, ALIGNED, DDM_SIM_NB, STREAM, PACKED>;
     int per_sm = 0;
     DDM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
     if (per_sm < 1) per_sm = 1;
@@ -491,6 +504,66 @@ DDM_API int ddm_sim_stream_f32(const float *theta_dev, int64_t ld_theta, const f
     return sim_impl(theta_dev, ld_theta, pulses_dev, ld_pulses, N, P, n_max, steps_per_pulse, dt, t_max, t_nd_hi,
                     noise_scale, seed, trial_offset, nullptr, 0, log_rt, x_out_dev, nullptr, workspace_dev,
                     ready_dev, stream);
+}
+
+DDM_API int ddm_sim_packed_f32(const uint32_t *packed_dev, int64_t N, int64_t n_max, int64_t steps_per_pulse, float dt,
+                               float t_max, float t_nd_hi, float noise_scale, uint64_t seed, uint64_t trial_offset,
+                               int log_rt, float *x_out_dev, int32_t *steps_out_dev, void *workspace_dev,
+                               const uint64_t *ready_dev, void *stream)
+{
+    DDM_REQUIRE(N >= 0 && N <= 0x7FFFFFFFll, "ddm_sim_packed_f32: N=%lld outside [0, 2^31)", (long long)N);
+    DDM_REQUIRE(n_max >= 0 && n_max <= 0x7FFFFF00ll, "ddm_sim_packed_f32: n_max=%lld out of range", (long long)n_max);
+    DDM_REQUIRE(steps_per_pulse >= 1 && steps_per_pulse <= 0x7FFFFFFFll,
+                "ddm_sim_packed_f32: steps_per_pulse=%lld must be >= 1", (long long)steps_per_pulse);
+    const int64_t need = (n_max + steps_per_pulse - 1) / steps_per_pulse;
+    DDM_REQUIRE(need <= 96, "ddm_sim_packed_f32: the schedule needs %lld pulses, a record holds 96 sign bits",
+                (long long)need);
+    DDM_REQUIRE(dt > 0.0f && t_max > 0.0f, "ddm_sim_packed_f32: dt and t_max must be positive");
+    DDM_REQUIRE(workspace_dev != nullptr && (reinterpret_cast<uintptr_t>(workspace_dev) & 7u) == 0,
+                "ddm_sim_packed_f32: workspace must be a non-null, 8-byte aligned device pointer");
+    DDM_REQUIRE(ready_dev == nullptr || (reinterpret_cast<uintptr_t>(ready_dev) & 7u) == 0,
+                "ddm_sim_packed_f32: ready_dev must be 8-byte aligned");
+    if (N > 0) {
+        DDM_REQUIRE(packed_dev && x_out_dev, "ddm_sim_packed_f32: null records / x_out");
+        DDM_REQUIRE((reinterpret_cast<uintptr_t>(packed_dev) & 15u) == 0, "ddm_sim_packed_f32: records must be 16-byte aligned");
+        DDM_REQUIRE((reinterpret_cast<uintptr_t>(x_out_dev) & 7u) == 0, "ddm_sim_packed_f32: x_out must be 8-byte aligned");
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DDM_CUDA_TRY(cudaMemsetAsync(workspace_dev, 0, ddm_sim_workspace_bytes(), st));
+    if (N == 0) return DDM_OK;
+    int dev = 0, sms = 0;
+    DDM_CUDA_TRY(cudaGetDevice(&dev));
+    DDM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SimParams p;
+    p.theta = reinterpret_cast<const float *>(packed_dev);
+    p.ld_theta = 8;
+    p.pulses = nullptr;
+    p.ld_pulses = 0;
+    p.noise = nullptr;
+    p.ld_noise = 0;
+    p.x_out = x_out_dev;
+    p.steps_out = steps_out_dev;
+    p.ws = static_cast<unsigned long long *>(workspace_dev);
+    p.n_trials = (unsigned int)N;
+    p.n_pulses = (int)need;
+    p.n_max = (int)n_max;
+    p.spp = (int)steps_per_pulse;
+    p.dt = dt;
+    p.t_max = t_max;
+    p.t_nd_hi = t_nd_hi;
+    p.noise_scale = noise_scale;
+    p.key = make_philox_key(seed);
+    p.trial_offset = trial_offset;
+    p.log_rt = log_rt ? 1 : 0;
+    p.one_bits = 0x3F800000u;
+    p.ready = reinterpret_cast<const unsigned long long *>(ready_dev);
+    const bool aligned = (steps_per_pulse % 8) == 0 && steps_per_pulse >= kNormalsPerBlock * DDM_SIM_NB;
+    if (ready_dev != nullptr) {
+        if (aligned) return launch_sim<3, false, true, true, true>(p, sms, st);
+        return launch_sim<3, false, false, true, true>(p, sms, st);
+    }
+    if (aligned) return launch_sim<3, false, true, false, true>(p, sms, st);
+    return launch_sim<3, false, false, false, true>(p, sms, st);
 }
 
 static int dump_common(bool words, uint64_t seed, uint64_t trial_offset, int64_t N, int64_t n_steps,

@@ -19,6 +19,17 @@ _HOST_STREAM_MIN = 1 << 18   # CPU-resident z with at least this many rows is st
 _pipelines = {}
 
 
+def host_pipeline_counters() -> dict:
+    """Totals over the host-streaming pipelines of this process: launches, packed batches and the bytes
+    actually sent over the link (32 per trial with packed ingest, 4 * (5 + P) with fp32 rows)."""
+    out = {"launches": 0, "packed_batches": 0, "h2d_bytes": 0}
+    for pipe in _pipelines.values():
+        out["launches"] += pipe.launches
+        out["packed_batches"] += pipe.packed_batches
+        out["h2d_bytes"] += pipe.h2d_bytes
+    return out
+
+
 def sim_wrapper(theta_and_pulses: torch.Tensor, *, mu_sensory: float, p_success: float, P: int, log_rt: bool,
                 seed: Optional[int] = None, trial_offset: int = 0, noise: Optional[torch.Tensor] = None,
                 ) -> torch.Tensor:

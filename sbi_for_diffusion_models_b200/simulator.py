@@ -183,16 +183,34 @@ def philox_words(seed: int, n_trials: int, n_steps: int, *, trial_offset: int = 
     return out
 
 
+def pack_threads() -> int:
+    """CPU threads ``ddm_pack_z_host`` may use: DDM_PACK_THREADS, else this process's share of the cores."""
+    import os
+    env = os.environ.get("DDM_PACK_THREADS")
+    if env:
+        return max(1, int(env))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(32, cores // ranks))
+
+
 class HostPipeline:
     """Streams a host-resident z = [theta, pulses] matrix through the GPU.
 
-    Per batch (up to ``max_batch`` rows) the copy stream carries z to the device in chunks, each
-    followed by an 8-byte copy that raises a device word ``ready`` to the number of rows delivered
-    so far, while ONE persistent ``ddm_sim_stream_f32`` launch on the kernel stream consumes
-    trials as they arrive (a warp that claims rows beyond ``ready`` sleeps until the copy engine
-    catches up).  PCIe ingest and simulation overlap inside a single launch, so a batch pays one
-    drain phase instead of one per chunk.  Two slots are double-buffered across batches.
-    Global trial offsets make the result identical to a single launch over all rows."""
+    Per batch (up to ``max_batch`` rows) ONE persistent streaming launch on the kernel stream consumes
+    trials as they arrive: the copy stream carries the rows to the device in chunks, each followed by an
+    8-byte copy that raises a device word ``ready`` to the number of rows delivered so far (a warp that
+    claims rows beyond ``ready`` sleeps until the copy engine catches up).  PCIe ingest and simulation
+    overlap inside a single launch, so a batch pays one drain phase instead of one per chunk.  Two slots
+    are double-buffered across batches.  Global trial offsets make the result identical to a single
+    launch over all rows.
+
+    Packed ingest (default whenever the schedule needs <= 96 pulses): pulse sides are +-1, so the 340
+    bytes of an fp32 row carry 32 bytes of information and the PCIe link, not the kernel, bounds the
+    fp32 path.  Each chunk is packed on the host cores (``ddm_pack_z_host``) into 32-byte records while
+    the previous chunk is on the link and the kernel is already running; ``ddm_sim_packed_f32``
+    consumes the records.  Same bits out.  A batch in which some row holds a value other than +-1 is
+    re-run through the fp32 path."""
 
     def __init__(self, n_cols: int, max_batch: int = 1 << 22, chunk: int = 1 << 18, device=None):
         self.dev = compute_device(device)
@@ -204,20 +222,30 @@ class HostPipeline:
             self.slots = []
             for _ in range(2):
                 self.slots.append({
-                    "z": torch.empty((self.max_batch, n_cols), dtype=torch.float32, device=self.dev),
+                    "z": None, "pk": None, "pk_host": None,      # allocated on first use
                     "x": torch.empty((self.max_batch, 2), dtype=torch.float32, device=self.dev),
                     "ws": torch.zeros((_native.WS_WORDS,), dtype=torch.int64, device=self.dev),
                     "ready": torch.zeros((1,), dtype=torch.int64, device=self.dev),
-                    "done": None,
+                    "done": None, "host_free": None,
                 })
             # constant pinned tables the flag copies read from (never rewritten: copies run later)
             self.marks = (torch.arange(1, n_marks + 1, dtype=torch.int64) * self.chunk).pin_memory()
             self.all_rows = torch.full((1,), 1 << 62, dtype=torch.int64).pin_memory()
         self.launches = 0
+        self.packed_batches = 0
+        self.h2d_bytes = 0
         self._pending = []
 
+    def _slot_buffers(self, slot, packed: bool):
+        with torch.cuda.device(self.dev):
+            if packed and slot["pk"] is None:
+                slot["pk"] = torch.empty((self.max_batch, 8), dtype=torch.int32, device=self.dev)
+                slot["pk_host"] = torch.empty((self.max_batch, 8), dtype=torch.int32).pin_memory()
+            if not packed and slot["z"] is None:
+                slot["z"] = torch.empty((self.max_batch, self.n_cols), dtype=torch.float32, device=self.dev)
+
     def run(self, z_host: torch.Tensor, x_host: torch.Tensor, *, sched: Schedule, seed: int, log_rt: bool = False,
-            trial_offset: int = 0) -> None:
+            trial_offset: int = 0, packed: Optional[bool] = None) -> None:
         """z_host (N, 5+P) fp32 CPU (pinned for full speed) -> x_host (N,2) fp32 CPU (pinned).
         Returns after everything has been enqueued; call ``synchronize`` before reading."""
         L = _native.lib()
@@ -227,42 +255,83 @@ class HostPipeline:
         P = self.n_cols - 5
         if P < sched.n_pulses:
             raise ValueError(f"pulse_sides has P={P} pulses but simulator needs at least {sched.n_pulses}")
+        if packed is None:
+            packed = sched.n_pulses <= 96
+        elif packed and sched.n_pulses > 96:
+            raise ValueError("packed ingest holds at most 96 pulse signs per trial")
         cur = torch.cuda.current_stream(self.dev)
         cs, ks = self.copy_stream, self.kernel_stream
         cs.wait_stream(cur)
         ks.wait_stream(cur)
+        n_threads = pack_threads()
+        redo = []
         for b, start in enumerate(range(0, n, self.max_batch)):
             slot = self.slots[b % 2]
             bs = min(self.max_batch, n - start)
+            self._slot_buffers(slot, packed)
             if slot["done"] is not None:
                 cs.wait_event(slot["done"])          # the previous kernel on this slot has finished
             with torch.cuda.stream(cs):
                 slot["ready"].zero_()
                 reset = torch.cuda.Event()
                 reset.record(cs)
+            common = (sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi, sched.noise_scale,
+                      ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(trial_offset + start), int(bool(log_rt)))
+
+            def launch():
+                # the kernel may start as soon as `ready` was reset: it sleeps on rows that have not arrived
+                ks.wait_event(reset)
+                with torch.cuda.stream(ks):
+                    if packed:
+                        rc = L.ddm_sim_packed_f32(slot["pk"].data_ptr(), bs, *common, slot["x"].data_ptr(), None,
+                                                  slot["ws"].data_ptr(), slot["ready"].data_ptr(), ks.cuda_stream)
+                    else:
+                        zd = slot["z"]
+                        rc = L.ddm_sim_stream_f32(zd.data_ptr(), self.n_cols, zd.data_ptr() + 20, self.n_cols, bs, P,
+                                                  *common, slot["x"].data_ptr(), slot["ws"].data_ptr(),
+                                                  slot["ready"].data_ptr(), ks.cuda_stream)
+                    _native.check(rc, "ddm_sim_packed_f32" if packed else "ddm_sim_stream_f32")
+                    self.launches += 1
+                    x_host[start:start + bs].copy_(slot["x"][:bs], non_blocking=True)
+                    slot["done"] = torch.cuda.Event()
+                    slot["done"].record(ks)
+                    self._pending.append(slot)
+
+            if packed:
+                if slot["host_free"] is not None:
+                    slot["host_free"].synchronize()  # the copy engine has read the staging block's last contents
+                launch()                             # resident and waiting while the host packs
+                generic = 0
                 for k, a in enumerate(range(0, bs, self.chunk)):
                     e = min(a + self.chunk, bs)
-                    slot["z"][a:e].copy_(z_host[start + a:start + e], non_blocking=True)
-                    src = self.all_rows if e == bs else self.marks[k:k + 1]
-                    slot["ready"].copy_(src, non_blocking=True)
-            # every copy of this batch is enqueued: the kernel may start as soon as `ready` was reset
-            ks.wait_event(reset)
-            with torch.cuda.stream(ks):
-                zd = slot["z"]
-                rc = L.ddm_sim_stream_f32(zd.data_ptr(), self.n_cols, zd.data_ptr() + 20, self.n_cols, bs, P,
-                                          sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi,
-                                          sched.noise_scale, ctypes.c_uint64(seed & (2**64 - 1)),
-                                          ctypes.c_uint64(trial_offset + start), int(bool(log_rt)),
-                                          slot["x"].data_ptr(), slot["ws"].data_ptr(), slot["ready"].data_ptr(),
-                                          ks.cuda_stream)
-                _native.check(rc, "ddm_sim_stream_f32")
-                self.launches += 1
-                x_host[start:start + bs].copy_(slot["x"][:bs], non_blocking=True)
-                slot["done"] = torch.cuda.Event()
-                slot["done"].record(ks)
-                self._pending.append(slot)
+                    src = z_host[start + a:start + e]
+                    got = L.ddm_pack_z_host(src.data_ptr(), src.stride(0), e - a, sched.n_pulses,
+                                            slot["pk_host"][a:e].data_ptr(), n_threads)
+                    if got < 0:
+                        _native.check(int(got), "ddm_pack_z_host")
+                    generic += got
+                    with torch.cuda.stream(cs):
+                        slot["pk"][a:e].copy_(slot["pk_host"][a:e], non_blocking=True)
+                        slot["ready"].copy_(self.all_rows if e == bs else self.marks[k:k + 1], non_blocking=True)
+                slot["host_free"] = torch.cuda.Event()
+                slot["host_free"].record(cs)
+                self.h2d_bytes += bs * 32
+                self.packed_batches += 1
+                if generic:
+                    redo.append((start, bs))         # rows with pulse values other than +-1: fp32 path
+            else:
+                with torch.cuda.stream(cs):
+                    for k, a in enumerate(range(0, bs, self.chunk)):
+                        e = min(a + self.chunk, bs)
+                        slot["z"][a:e].copy_(z_host[start + a:start + e], non_blocking=True)
+                        slot["ready"].copy_(self.all_rows if e == bs else self.marks[k:k + 1], non_blocking=True)
+                launch()
+                self.h2d_bytes += bs * self.n_cols * 4
         cur.wait_stream(ks)
         cur.wait_stream(cs)
+        for start, bs in redo:
+            self.run(z_host[start:start + bs], x_host[start:start + bs], sched=sched, seed=seed, log_rt=log_rt,
+                     trial_offset=trial_offset + start, packed=False)
 
     def synchronize(self) -> None:
         torch.cuda.current_stream(self.dev).synchronize()

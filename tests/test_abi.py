@@ -96,3 +96,30 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), f"{f} reaches into oracle/"
+
+
+def test_host_packer_matches_numpy(L):
+    """ddm_pack_z_host (host code, no GPU): 32-byte records [theta bits x 5, pulse sign masks x 3]."""
+    rs = np.random.RandomState(0)
+    N, ld = 40003, 90
+    z = np.empty((N, ld), np.float32)
+    z[:, :5] = rs.randn(N, 5)
+    z[:, 5:] = np.where(rs.rand(N, ld - 5) < 0.5, 1.0, -1.0)
+    out = np.zeros((N, 8), np.uint32)
+
+    def expect(n_pulses):
+        m = np.zeros((N, 3), np.uint64)
+        for c in range(96):
+            bit = (z[:, 5 + c] > 0) if c < n_pulses else np.ones(N, bool)
+            m[:, c // 32] |= bit.astype(np.uint64) << np.uint64(c % 32)
+        return m.astype(np.uint32)
+
+    for n_pulses, threads in ((80, 1), (80, 5), (0, 2), (1, 2), (31, 3), (32, 3), (33, 1), (64, 4), (79, 2), (85, 16)):
+        assert L.ddm_pack_z_host(z.ctypes.data, ld, N, n_pulses, out.ctypes.data, threads) == 0
+        assert np.array_equal(out[:, :5].view(np.float32), z[:, :5])
+        assert np.array_equal(out[:, 5:], expect(n_pulses)), (n_pulses, threads)
+    z[7, 5 + 33], z[9, 5 + 79], z[11, 5 + 81], z[12, 5] = 0.5, -1.0000001, 3.0, np.nan
+    assert L.ddm_pack_z_host(z.ctypes.data, ld, N, 80, out.ctypes.data, 4) == 3        # column 81 is past the schedule
+    assert L.ddm_pack_z_host(z.ctypes.data, ld, 0, 80, out.ctypes.data, 4) == 0
+    assert L.ddm_pack_z_host(z.ctypes.data, ld, N, 97, out.ctypes.data, 4) == _native.DDM_ERR_INVALID
+    assert L.ddm_pack_z_host(z.ctypes.data, 60, N, 80, out.ctypes.data, 4) == _native.DDM_ERR_INVALID

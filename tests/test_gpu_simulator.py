@@ -271,18 +271,74 @@ def test_long_schedule_dt_1e_4_shared_noise_and_native():
 
 
 def test_streaming_host_pipeline_equals_resident_launch():
-    """ddm_sim_stream_f32 (copy engine feeds one persistent kernel) == ddm_sim_f32 on resident z."""
+    """Host-resident z through one persistent streaming kernel per batch == ddm_sim_f32 on resident z:
+    fp32 rows over the link (ddm_sim_stream_f32) and host-packed 32-byte records (ddm_pack_z_host +
+    ddm_sim_packed_f32), bit for bit."""
     from sbi_for_diffusion_models_b200.simulator import HostPipeline
     n = 300000 + 17
     z = torch.empty((n, 85))
     z[:, :5] = orc.prior_sample(n, seed=61)
     z[:, 5:] = torch.from_numpy(orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(13)), 0, n, 80, 0.75))
     zh = z.pin_memory()
-    xh = torch.empty((n, 2)).pin_memory()
     sched = Schedule.from_constants()
-    pipe = HostPipeline(85, max_batch=1 << 17, chunk=1 << 14)      # 3 batches, 8 chunks each, ragged tail
-    pipe.run(zh, xh, sched=sched, seed=4242, trial_offset=1000)
+    want = simulate_trials(z[:, :5], z[:, 5:], seed=4242, trial_offset=1000).cpu()
+    for packed in (False, True, None):
+        xh = torch.full((n, 2), -7.0).pin_memory()
+        pipe = HostPipeline(85, max_batch=1 << 17, chunk=1 << 14)      # 3 batches, 8 chunks each, ragged tail
+        pipe.run(zh, xh, sched=sched, seed=4242, trial_offset=1000, packed=packed)
+        pipe.synchronize()
+        assert torch.equal(xh, want), packed
+        assert pipe.launches == 3
+        assert pipe.packed_batches == (0 if packed is False else 3)
+        assert pipe.h2d_bytes == n * (340 if packed is False else 32)
+    # the same pipeline object again (slots, staging blocks and events are reused)
+    xh2 = torch.empty((n, 2)).pin_memory()
+    pipe.run(zh, xh2, sched=sched, seed=4242, trial_offset=1000)
     pipe.synchronize()
-    want = simulate_trials(z[:, :5], z[:, 5:], seed=4242, trial_offset=1000)
-    assert torch.equal(xh, want.cpu())
-    assert pipe.launches == 3
+    assert torch.equal(xh2, want)
+
+
+def test_packed_ingest_falls_back_for_non_binary_pulses():
+    """A batch with a pulse value other than +-1 cannot be packed to sign bits: it is re-run through
+    the fp32 rows (reference semantics a += v * s, rt_choice_model.py:192)."""
+    from sbi_for_diffusion_models_b200.simulator import HostPipeline
+    n = 70000
+    z = torch.empty((n, 85))
+    z[:, :5] = orc.prior_sample(n, seed=62)
+    z[:, 5:] = torch.from_numpy(orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(14)), 0, n, 80, 0.75))
+    z[40000, 5] = 0.25          # first pulse of one trial in the second batch
+    z[40001, 5 + 3] = -2.0
+    zh, xh = z.pin_memory(), torch.empty((n, 2)).pin_memory()
+    pipe = HostPipeline(85, max_batch=1 << 15, chunk=1 << 13)
+    pipe.run(zh, xh, sched=Schedule.from_constants(), seed=99)
+    pipe.synchronize()
+    want = simulate_trials(z[:, :5], z[:, 5:], seed=99).cpu()
+    assert torch.equal(xh, want)
+    assert pipe.launches == 3 + 1 and pipe.packed_batches == 3
+
+
+def test_packed_kernel_on_resident_records():
+    """ddm_sim_packed_f32 without the streaming flag (records already in HBM), incl. hit_step."""
+    import ctypes
+    from sbi_for_diffusion_models_b200 import _native
+    n = 5000
+    theta = orc.prior_sample(n, seed=63)
+    pulses = torch.from_numpy(orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(15)), 0, n, 80, 0.75))
+    z = torch.cat([theta, pulses], 1).contiguous()
+    rec = torch.empty((n, 8), dtype=torch.int32)
+    L = _native.lib()
+    assert L.ddm_pack_z_host(z.data_ptr(), 85, n, 80, rec.data_ptr(), 2) == 0
+    sched = Schedule.from_constants()
+    recd = rec.cuda()
+    x = torch.empty((n, 2), device="cuda")
+    steps = torch.empty((n,), dtype=torch.int32, device="cuda")
+    ws = torch.zeros(8, dtype=torch.int64, device="cuda")
+    rc = L.ddm_sim_packed_f32(recd.data_ptr(), n, sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi,
+                              sched.noise_scale, ctypes.c_uint64(5), ctypes.c_uint64(17), 0, x.data_ptr(), steps.data_ptr(),
+                              ws.data_ptr(), None, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    want, want_steps = simulate_trials(theta, pulses, seed=5, trial_offset=17, return_steps=True)
+    assert torch.equal(x, want) and torch.equal(steps, want_steps)
+    assert L.ddm_sim_packed_f32(recd.data_ptr(), n, 16000, 100, sched.dt, sched.t_max, sched.t_nd_hi, sched.noise_scale,
+                                ctypes.c_uint64(5), ctypes.c_uint64(0), 0, x.data_ptr(), None, ws.data_ptr(), None,
+                                None) == _native.DDM_ERR_INVALID          # 160 pulses do not fit a record
