@@ -497,8 +497,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint64_t *dfull = wfull + kTcSlots;                                // [kTcTiles]
     uint64_t *aready = dfull + kTcTiles;                               // [kTcTiles]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBars + 96);
-    // passed[X] = number of stages whose issuer has consumed its aready[X] phase (issuer warps only)
-    volatile int *passed = reinterpret_cast<volatile int *>(smem + kSmemBars + 112);
+    // turn[X]: phase s completes when the issuer of stage s has consumed its aready[X] phase (issuers only)
+    uint64_t *turn = aready + kTcTiles;                                // [kTcTiles]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
@@ -508,8 +508,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     if (warp == kTcEpiWarps) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
-        passed[0] = 0;
-        passed[1] = 0;
+        for (int i = 0; i < kTcTiles; ++i) mbar_init(&turn[i], 1);
         for (int i = 0; i < kTcSlots; ++i) mbar_init(&wfull[i], 1);
         for (int i = 0; i < kTcTiles; ++i) {
             mbar_init(&dfull[i], 1);
@@ -530,7 +529,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // (measured with the clock64 trace); a single issuer did that with the tensor pipe idle between
         // stages.  Now one warp prepares stage s + 1 while the other is blocked in the MMA queue of stage s.
         // A stage's MMAs wait for its A operand (aready), which exists only after the previous stage's
-        // accumulators were committed and drained; the only extra ordering is `passed` (below).
+        // accumulators were committed and drained; the only extra ordering is `turn` (below).
         const int iw = warp - kTcEpiWarps;
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
         const int t_of[2] = {tile0 / CB, (tile0 + 1) / CB};
@@ -560,11 +559,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int X = 0; X < n_active; ++X) {
                 if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 8 + 5] = clock64();
                 // A parity wait cannot tell phase s from phase s - 2: first make sure the other issuer has
-                // consumed phase s - 1 (then the barrier is in phase s or s + 1 and the parity is unambiguous)
-                while (passed[X] < s) {
-                }
+                // consumed phase s - 1 (then aready is in phase s or s + 1 and its parity is unambiguous;
+                // turn itself is unambiguous because this warp completed its phase s - 2)
+                if (s > 0) mbar_wait(&turn[X], (s - 1) & 1);
                 mbar_wait(&aready[X], s & 1);  // A operand of this stage written, D drained
-                if (lane == 0) passed[X] = s + 1;
+                if (elect_one_sync()) mbar_arrive(&turn[X]);
+                __syncwarp();
                 tc_fence_after_sync();
                 if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 8 + 0] = clock64();
                 if (X == 0) mbar_wait(&wfull[s % kTcSlots], (s / kTcSlots) & 1);
