@@ -543,8 +543,10 @@ def run_native(args):
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": link_bytes_per_step,
                     "d2h_bytes_per_step": n_e2e * 8, "host_z_bytes_per_step": n_e2e * 340,
-                    "ingest": "z rows (340 B/trial, pinned host) are packed to 32-byte records by the host cores "
-                              "(ddm_pack_z_host) chunk by chunk while the streaming kernel runs; the link carries the records",
+                    "ingest": ("z rows (340 B/trial, pinned host) are packed to 32-byte records by the host cores "
+                               "(ddm_pack_z_host) chunk by chunk while the streaming kernel runs; the link carries the records"
+                               if link_bytes_per_step < n_e2e * 340 else
+                               "fp32 z rows over the link (fewer than 16 host threads per rank: packing would be slower)"),
                     "trials_per_step_per_gpu": n_e2e, "api": "data_simulator.sim_wrapper(z pinned host) -> x host",
                     "ms_per_step": float(e2e_t.item()) / args.steps},
             "gpu_launches": args.steps * world,

@@ -183,6 +183,9 @@ def philox_words(seed: int, n_trials: int, n_steps: int, *, trial_offset: int = 
     return out
 
 
+PACK_MIN_THREADS = 16   # fewer host threads than this: send the fp32 rows over the link instead
+
+
 def pack_threads() -> int:
     """CPU threads ``ddm_pack_z_host`` may use: DDM_PACK_THREADS, else this process's share of the cores."""
     import os
@@ -205,7 +208,8 @@ class HostPipeline:
     are double-buffered across batches.  Global trial offsets make the result identical to a single
     launch over all rows.
 
-    Packed ingest (default whenever the schedule needs <= 96 pulses): pulse sides are +-1, so the 340
+    Packed ingest (default when the schedule needs <= 96 pulses and this process has at least
+    ``PACK_MIN_THREADS`` cores to itself): pulse sides are +-1, so the 340
     bytes of an fp32 row carry 32 bytes of information and the PCIe link, not the kernel, bounds the
     fp32 path.  Each chunk is packed on the host cores (``ddm_pack_z_host``) into 32-byte records while
     the previous chunk is on the link and the kernel is already running; ``ddm_sim_packed_f32``
@@ -256,7 +260,9 @@ class HostPipeline:
         if P < sched.n_pulses:
             raise ValueError(f"pulse_sides has P={P} pulses but simulator needs at least {sched.n_pulses}")
         if packed is None:
-            packed = sched.n_pulses <= 96
+            # measured on the B200 box: 16 host threads pack 92.6 GB/s of z (link: 55.5 GB/s of fp32 rows);
+            # with 12 threads per rank (2 ranks on 24 cores) packing was the slower path
+            packed = sched.n_pulses <= 96 and pack_threads() >= PACK_MIN_THREADS
         elif packed and sched.n_pulses > 96:
             raise ValueError("packed ingest holds at most 96 pulse signs per trial")
         cur = torch.cuda.current_stream(self.dev)

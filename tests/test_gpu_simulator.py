@@ -282,6 +282,8 @@ def test_streaming_host_pipeline_equals_resident_launch():
     zh = z.pin_memory()
     sched = Schedule.from_constants()
     want = simulate_trials(z[:, :5], z[:, 5:], seed=4242, trial_offset=1000).cpu()
+    from sbi_for_diffusion_models_b200 import simulator as simmod
+    auto_packs = simmod.pack_threads() >= simmod.PACK_MIN_THREADS
     for packed in (False, True, None):
         xh = torch.full((n, 2), -7.0).pin_memory()
         pipe = HostPipeline(85, max_batch=1 << 17, chunk=1 << 14)      # 3 batches, 8 chunks each, ragged tail
@@ -289,8 +291,9 @@ def test_streaming_host_pipeline_equals_resident_launch():
         pipe.synchronize()
         assert torch.equal(xh, want), packed
         assert pipe.launches == 3
-        assert pipe.packed_batches == (0 if packed is False else 3)
-        assert pipe.h2d_bytes == n * (340 if packed is False else 32)
+        is_packed = packed is True or (packed is None and auto_packs)
+        assert pipe.packed_batches == (3 if is_packed else 0)
+        assert pipe.h2d_bytes == n * (32 if is_packed else 340)
     # the same pipeline object again (slots, staging blocks and events are reused)
     xh2 = torch.empty((n, 2)).pin_memory()
     pipe.run(zh, xh2, sched=sched, seed=4242, trial_offset=1000)
@@ -310,7 +313,7 @@ def test_packed_ingest_falls_back_for_non_binary_pulses():
     z[40001, 5 + 3] = -2.0
     zh, xh = z.pin_memory(), torch.empty((n, 2)).pin_memory()
     pipe = HostPipeline(85, max_batch=1 << 15, chunk=1 << 13)
-    pipe.run(zh, xh, sched=Schedule.from_constants(), seed=99)
+    pipe.run(zh, xh, sched=Schedule.from_constants(), seed=99, packed=True)
     pipe.synchronize()
     want = simulate_trials(z[:, :5], z[:, 5:], seed=99).cpu()
     assert torch.equal(xh, want)
