@@ -142,6 +142,14 @@ int ddm_sim_stream_f32(const float *theta_dev, int64_t ld_theta,
  */
 int64_t ddm_pack_z_host(const float *z_host, int64_t ld, int64_t N, int64_t n_pulses, uint32_t *packed_host,
                         int n_threads);
+/* The ingest loop of one batch in one call (host code + copies on copy_stream): for every chunk of
+ * chunk_rows rows, pack it into staging_host (pinned, N x 8 uint32), enqueue its copy to packed_dev and
+ * an 8-byte copy of marks_host[k] (pinned; rows delivered once chunk k has landed, the last entry >= N)
+ * to *ready_dev -- what a ddm_sim_packed_f32 launched with ready_dev waits on.  *generic_rows = rows
+ * holding a pulse value other than +-1. */
+int ddm_ingest_packed(const float *z_host, int64_t ld, int64_t N, int64_t n_pulses, int64_t chunk_rows,
+                      uint32_t *staging_host, uint32_t *packed_dev, uint64_t *ready_dev,
+                      const uint64_t *marks_host, int n_threads, void *copy_stream, int64_t *generic_rows);
 int ddm_sim_packed_f32(const uint32_t *packed_dev, int64_t N, int64_t n_max, int64_t steps_per_pulse, float dt,
                        float t_max, float t_nd_hi, float noise_scale, uint64_t seed, uint64_t trial_offset,
                        int log_rt, float *x_out_dev, int32_t *steps_out_dev, void *workspace_dev,

@@ -12,6 +12,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <cuda_runtime.h>
+
 #include "../../include/ddm_b200.h"
 
 #define DDM_API extern "C" __attribute__((visibility("default")))
@@ -202,4 +204,35 @@ DDM_API int64_t ddm_pack_z_host(const float *z_host, int64_t ld, int64_t N, int6
     int64_t total = 0;
     for (int64_t g : gen) total += g;
     return total;
+}
+
+// The whole ingest of one batch without returning to the caller between chunks: pack chunk k on the host
+// cores, enqueue its copy and the 8-byte copy that raises *ready_dev, go on with chunk k + 1 while the
+// copy engine works.  (Driving this loop from Python cost ~150 us per chunk, a fifth of the packing time.)
+DDM_API int ddm_ingest_packed(const float *z_host, int64_t ld, int64_t N, int64_t n_pulses, int64_t chunk_rows,
+                              uint32_t *staging_host, uint32_t *packed_dev, uint64_t *ready_dev,
+                              const uint64_t *marks_host, int n_threads, void *copy_stream, int64_t *generic_rows)
+{
+    if (N < 0 || chunk_rows < 1 || (N > 0 && (!z_host || !staging_host || !packed_dev || !ready_dev || !marks_host))) {
+        ddm::set_error("ddm_ingest_packed: bad arguments (N=%lld, chunk_rows=%lld)", (long long)N, (long long)chunk_rows);
+        return DDM_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(copy_stream);
+    int64_t generic = 0;
+    int64_t k = 0;
+    for (int64_t a = 0; a < N; a += chunk_rows, ++k) {
+        const int64_t rows = (N - a < chunk_rows) ? N - a : chunk_rows;
+        const int64_t got = ddm_pack_z_host(z_host + a * ld, ld, rows, n_pulses, staging_host + a * 8, n_threads);
+        if (got < 0) return (int)got;
+        generic += got;
+        cudaError_t e = cudaMemcpyAsync(packed_dev + a * 8, staging_host + a * 8, (size_t)rows * 32, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ready_dev, marks_host + k, sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            ddm::set_error("ddm_ingest_packed: CUDA error %d (%s)", (int)e, cudaGetErrorString(e));
+            return DDM_ERR_CUDA;
+        }
+    }
+    if (generic_rows) *generic_rows = generic;
+    return DDM_OK;
 }

@@ -8,16 +8,16 @@ namespace mnle {
 
 constexpr int kTM = 64;         // rows per CTA tile
 constexpr int kThreads = 256;
-constexpr int kLdIn = 89;       // padded leading dims (bank-conflict-free broadcast reads)
-constexpr int kLdH = 132;
+constexpr int kLdIn = 92;       // padded leading dims, multiples of 4 floats: rows are read with 128-bit loads
+constexpr int kLdH = 132;       // (context tiles must be zero in columns [kCtx, kLdIn))
 constexpr int kKC = 32;         // weight k-chunk staged in shared memory
-constexpr int kLdW = 129;
+constexpr int kLdW = 36;        // w_s[n][kk]: 36 n mod 32 = 4 n -> the 16 columns of a warp's 128-bit loads tile all banks
 
 struct SimtSmem {
     float in[kTM * kLdIn];
     float ha[kTM * kLdH];
     float hb[kTM * kLdH];
-    float w[kKC * kLdW];
+    float w[kHidden * kLdW];
     float red[8];
 };
 
@@ -26,6 +26,7 @@ struct SimtSmem {
 enum Act { kNone = 0, kRelu = 1, kSigmoid = 2, kMaskRelu = 3, kMaskSigmoid = 4 };
 
 // out[r][n] = act(sum_k in[r][k] * W[n][k] + b[n]) for r < 64, n < n_valid (<= 16 * NJ).
+// in_s rows must be 16-byte aligned (ld_in a multiple of 4) and finite up to the next multiple of 4 past K.
 // DUAL: rows come in groups of kDualRows = 6 (one primal row followed by its five tangent rows
 // d/d theta_i); the layer is linear in the tangents, so they get no bias (and ACT must be kNone:
 // the caller applies the activation and its derivative afterwards).
@@ -48,34 +49,40 @@ __device__ __forceinline__ void dense(const float *__restrict__ W, const float *
 
     for (int k0 = 0; k0 < K; k0 += kKC) {
         __syncthreads();  // previous chunk consumed (and in_s / out_s hazards of the caller)
-        // stage W[:, k0:k0+32] transposed: w_s[kk][n]
+        // stage the chunk as w_s[n][kk] (zero beyond n_valid / K): thread (tx, ty) then reads four
+        // consecutive kk of column n = tx + 16 j with one 128-bit load
         if (!TRANS) {
             const int kk = tid & 31;
             for (int n = tid >> 5; n < 16 * NJ; n += kThreads / 32) {
                 float v = 0.f;
                 if (n < n_valid && k0 + kk < K) v = __ldg(W + (size_t)n * K + k0 + kk);
-                w_s[kk * kLdW + n] = v;
+                w_s[n * kLdW + kk] = v;
             }
         } else {
             const int n = tid & 127;
             for (int kk = tid >> 7; kk < kKC; kk += kThreads / 128) {
                 float v = 0.f;
                 if (n < n_valid && n < 16 * NJ && k0 + kk < K) v = W[(size_t)(k0 + kk) * ldw + n];
-                if (n < 16 * NJ) w_s[kk * kLdW + n] = v;
+                if (n < 16 * NJ) w_s[n * kLdW + kk] = v;
             }
         }
         __syncthreads();
-        const int kend = min(kKC, K - k0);
-#pragma unroll 4
-        for (int kk = 0; kk < kend; ++kk) {
-            float a[4];
+        const int kend = min(kKC, (K - k0 + 3) & ~3);  // in_s is finite (zero) up to the next multiple of 4
+#pragma unroll 2
+        for (int kk = 0; kk < kend; kk += 4) {
+            float4 a[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = in_s[(ty * 4 + i) * ld_in + k0 + kk];
+            for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(in_s + (ty * 4 + i) * ld_in + k0 + kk);
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                const float wv = w_s[kk * kLdW + tx + 16 * j];
+                const float4 wv = *reinterpret_cast<const float4 *>(w_s + (tx + 16 * j) * kLdW + kk);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(a[i], wv, acc[i][j]);
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][j] = fmaf(a[i].x, wv.x, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].y, wv.y, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].z, wv.z, acc[i][j]);
+                    acc[i][j] = fmaf(a[i].w, wv.w, acc[i][j]);
+                }
             }
         }
     }

@@ -192,11 +192,11 @@ __global__ void __launch_bounds__(kThreads) mnle_grad_kernel(const float *__rest
     const int t0 = blockIdx.x * kGradRows, c = blockIdx.y;
 
     // ---- inputs: primal row = [theta_c, pulses_t, choice_t]; tangent row i = unit vector e_i ----
-    for (int idx = tid; idx < kTM * kCtx; idx += kThreads) {
-        const int row = idx / kCtx, j = idx - row * kCtx;
+    for (int idx = tid; idx < kTM * kLdIn; idx += kThreads) {
+        const int row = idx / kLdIn, j = idx - row * kLdIn;
         const int g = row / kDualRows, k = row - g * kDualRows, t = t0 + g;
         float v = 0.f;
-        if (g < kGradRows && t < T) {
+        if (g < kGradRows && t < T && j < kCtx) {
             if (k == 0) {
                 if (j < 5) v = __ldg(theta + (long long)c * ld_theta + j);
                 else if (j < kCond) v = __ldg(pulses + (long long)t * ld_pulses + (j - 5));

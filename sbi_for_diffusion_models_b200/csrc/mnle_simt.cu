@@ -41,11 +41,11 @@ __global__ void __launch_bounds__(kThreads) mnle_simt_kernel(const float *__rest
     const long long n_rows = src.potential ? (long long)src.T : src.R;
 
     // ---- assemble the 86-wide context [cond (85), choice] ------------------------------
-    for (int idx = tid; idx < kTM * kCtx; idx += kThreads) {
-        const int i = idx / kCtx, j = idx - i * kCtx;
+    for (int idx = tid; idx < kTM * kLdIn; idx += kThreads) {
+        const int i = idx / kLdIn, j = idx - i * kLdIn;
         const long long r = row0 + i;
         float v = 0.f;
-        if (r < n_rows) {
+        if (r < n_rows && j < kCtx) {
             if (j == kCond) v = __ldg(src.x + 2 * r + 1);
             else if (!src.potential) v = __ldg(src.cond + r * src.ld_cond + j);
             else if (j < 5) v = __ldg(src.theta + (long long)c * src.ld_theta + j);

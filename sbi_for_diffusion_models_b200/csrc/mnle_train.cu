@@ -87,11 +87,11 @@ __device__ __forceinline__ long long data_row(const TrainRows &rows, long long r
 // 86-wide context [condition, choice] of the tile's rows; rows past R are zero
 __device__ __forceinline__ void load_context(const TrainRows &rows, long long row0, float *in_s)
 {
-    for (int idx = threadIdx.x; idx < kTM * kCtx; idx += kThreads) {
-        const int i = idx / kCtx, j = idx - i * kCtx;
+    for (int idx = threadIdx.x; idx < kTM * kLdIn; idx += kThreads) {
+        const int i = idx / kLdIn, j = idx - i * kLdIn;
         const long long r = row0 + i;
         float v = 0.f;
-        if (r < rows.R) {
+        if (r < rows.R && j < kCtx) {
             const long long dr = data_row(rows, r);
             v = (j == kCond) ? __ldg(rows.x + 2 * dr + 1) : __ldg(rows.cond + dr * rows.ld_cond + j);
         }
@@ -126,9 +126,10 @@ __device__ __forceinline__ void store_rows(const float *src_s, int ld, float *ds
 
 __device__ __forceinline__ void load_rows(const float *src, int ldg, long long row0, int n, float *dst_s)
 {
-    for (int idx = threadIdx.x; idx < kTM * n; idx += kThreads) {
-        const int i = idx / n, j = idx - i * n;
-        dst_s[i * kLdIn + j] = src[(size_t)(row0 + i) * ldg + j];
+    const int n4 = (n + 3) & ~3;  // dense() reads whole groups of four columns: zero the padding
+    for (int idx = threadIdx.x; idx < kTM * n4; idx += kThreads) {
+        const int i = idx / n4, j = idx - i * n4;
+        dst_s[i * kLdIn + j] = j < n ? src[(size_t)(row0 + i) * ldg + j] : 0.f;
     }
 }
 

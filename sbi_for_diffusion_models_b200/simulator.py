@@ -245,6 +245,7 @@ class HostPipeline:
             if packed and slot["pk"] is None:
                 slot["pk"] = torch.empty((self.max_batch, 8), dtype=torch.int32, device=self.dev)
                 slot["pk_host"] = torch.empty((self.max_batch, 8), dtype=torch.int32).pin_memory()
+                slot["marks"] = torch.zeros((-(-self.max_batch // self.chunk),), dtype=torch.int64).pin_memory()
             if not packed and slot["z"] is None:
                 slot["z"] = torch.empty((self.max_batch, self.n_cols), dtype=torch.float32, device=self.dev)
 
@@ -307,18 +308,18 @@ class HostPipeline:
                 if slot["host_free"] is not None:
                     slot["host_free"].synchronize()  # the copy engine has read the staging block's last contents
                 launch()                             # resident and waiting while the host packs
-                generic = 0
-                for k, a in enumerate(range(0, bs, self.chunk)):
-                    e = min(a + self.chunk, bs)
-                    src = z_host[start + a:start + e]
-                    got = L.ddm_pack_z_host(src.data_ptr(), src.stride(0), e - a, sched.n_pulses,
-                                            slot["pk_host"][a:e].data_ptr(), n_threads)
-                    if got < 0:
-                        _native.check(int(got), "ddm_pack_z_host")
-                    generic += got
-                    with torch.cuda.stream(cs):
-                        slot["pk"][a:e].copy_(slot["pk_host"][a:e], non_blocking=True)
-                        slot["ready"].copy_(self.all_rows if e == bs else self.marks[k:k + 1], non_blocking=True)
+                # marks[k] = rows delivered once chunk k has landed (the last one: "all of them")
+                n_chunks = -(-bs // self.chunk)
+                marks = slot["marks"]
+                marks[:n_chunks] = self.marks[:n_chunks]
+                marks[n_chunks - 1] = 1 << 62
+                got = ctypes.c_int64(0)
+                src = z_host[start:start + bs]
+                rc = L.ddm_ingest_packed(src.data_ptr(), src.stride(0), bs, sched.n_pulses, self.chunk,
+                                         slot["pk_host"].data_ptr(), slot["pk"].data_ptr(), slot["ready"].data_ptr(),
+                                         marks.data_ptr(), n_threads, cs.cuda_stream, ctypes.byref(got))
+                _native.check(rc, "ddm_ingest_packed")
+                generic = got.value
                 slot["host_free"] = torch.cuda.Event()
                 slot["host_free"].record(cs)
                 self.h2d_bytes += bs * 32

@@ -5,7 +5,7 @@ import torch
 import bench
 from sbi_for_diffusion_models_b200 import data_simulator as ds
 
-n = 1 << 22
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 22
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 z = bench.build_workload(n, 0, dev)
