@@ -478,8 +478,25 @@ __device__ __forceinline__ void tc_epilogue_spline(uint32_t trow, const float *b
     u = fmaf(hgt * (delta * th * th + d0 * t1), rden, bottom);
 }
 
-// grid = ceil(D * T * ceil(C / 128) / 2): tile = ((d * T + t) * CB + chain block), chain block fastest.
+// tile = ((d * T + t) * CB + chain block), chain block fastest; grid: tc_grid().
 // D independent datasets (own x, pulses and C chains each) share one launch.
+// Launch shape of the potential kernel: whole waves of two-tile CTAs (one CTA per SM), and the tiles that
+// are left over once the last FULL wave of pairs is placed go one per CTA when that fits a single wave --
+// a half-empty wave of pairs costs a whole pair time (400 tiles on 148 SMs: 148 pairs + 104 singles
+// instead of 200 pairs in two waves).  CTAs are scheduled in index order, so the singles run last.
+static void tc_grid(long long n_tiles, int sms, int *n_pairs, long long *grid)
+{
+    const long long per_wave = 2ll * sms;
+    const long long rem = n_tiles % per_wave;
+    long long pairs = n_tiles / 2, singles = n_tiles & 1;
+    if (n_tiles > per_wave && rem > 0 && rem <= sms) {
+        pairs = (n_tiles - rem) / 2;
+        singles = rem;
+    }
+    *n_pairs = (int)pairs;
+    *grid = pairs + singles;
+}
+
 // ROWS: estimator.log_prob over arbitrary rows -- `theta` is the (R, 85) condition matrix (row stride
 // ld_theta), x is (R, 2), C = R, one tile per CTA; the 86-wide context goes into TMEM columns
 // [256, 352) as bf16 hi / lo and every net's first layer is a K = 96 stage; out[row] = log-prob.
@@ -488,7 +505,8 @@ template <bool ROWS>
 __global__ void __launch_bounds__(kTcThreads, 1)
     mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
                    const float *__restrict__ theta, long long ld_theta, const float *__restrict__ x,
-                   const float *__restrict__ hoist, int D, int T, int C, float mu_y, float sigma_y, int n_choices,
+                   const float *__restrict__ hoist, int D, int T, int C, int n_pairs, float mu_y, float sigma_y,
+                   int n_choices,
                    float *__restrict__ partial, unsigned int *__restrict__ counters, float *__restrict__ out,
                    long long *__restrict__ trace)
 {
@@ -503,8 +521,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
     const int n_tiles = D * T * CB;
-    const int tile0 = ROWS ? blockIdx.x : blockIdx.x * kTcTiles;
-    const int n_active = ROWS ? 1 : min(kTcTiles, n_tiles - tile0);
+    // potential mode: CTAs [0, n_pairs) take two tiles each, the rest one tile each (see tc_grid())
+    const int bx = blockIdx.x;
+    const int tile0 = (ROWS || bx >= n_pairs) ? (ROWS ? bx : 2 * n_pairs + (bx - n_pairs)) : bx * kTcTiles;
+    const int n_active = (ROWS || bx >= n_pairs) ? 1 : kTcTiles;
 
     if (warp == kTcEpiWarps) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
@@ -834,9 +854,13 @@ DDM_API int mnle_loglik_sum_batched_tc_f32(void *handle, const float *theta_dev,
                                                                             (int)(D * T), hoist, counters, (int)(D * CB));
     DDM_CUDA_TRY(cudaGetLastError());
     DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    mnle_tc_kernel<false><<<(unsigned)((n_tiles + kTcTiles - 1) / kTcTiles), kTcThreads, kTcSmemBytes, st>>>(
+    int sms = 0, n_pairs = 0;
+    long long grid = 0;
+    DDM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, H->device));
+    tc_grid(n_tiles, sms, &n_pairs, &grid);
+    mnle_tc_kernel<false><<<(unsigned)grid, kTcThreads, kTcSmemBytes, st>>>(
         static_cast<const unsigned char *>(H->tc_pack), H->tc_plan, theta_dev, ld_theta, x_dev, hoist, (int)D, (int)T, (int)C,
-        H->mu_y, H->sigma_y, H->layout.n_choices, partial, counters, out_dev, g_tc_trace);
+        n_pairs, H->mu_y, H->sigma_y, H->layout.n_choices, partial, counters, out_dev, g_tc_trace);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }
@@ -864,7 +888,7 @@ DDM_API int mnle_log_prob_rows_tc_f32(void *handle, const float *x_dev, const fl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     mnle_tc_kernel<true><<<(unsigned)((R + kTcM - 1) / kTcM), kTcThreads, kTcSmemBytes, st>>>(
-        static_cast<const unsigned char *>(H->tc_pack), H->tc_rows_plan, cond_dev, ld_cond, x_dev, nullptr, 1, 1, (int)R,
+        static_cast<const unsigned char *>(H->tc_pack), H->tc_rows_plan, cond_dev, ld_cond, x_dev, nullptr, 1, 1, (int)R, 0,
         H->mu_y, H->sigma_y, H->layout.n_choices, nullptr, nullptr, out_dev, nullptr);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
