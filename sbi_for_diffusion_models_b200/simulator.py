@@ -197,6 +197,22 @@ def pack_threads() -> int:
     return max(1, min(32, cores // ranks))
 
 
+def launches_block() -> bool:
+    """True when kernel launches do not return until the kernel has finished (CUDA_LAUNCH_BLOCKING=1, or
+    a tool that serialises launches: Nsight Compute, compute-sanitizer).  The packed ingest normally
+    launches its persistent kernel FIRST and feeds it while it runs; under such tools the launch would
+    wait for rows nobody can enqueue any more, so the copies go first (DDM_INGEST_ORDER=copies_first /
+    launch_first overrides the detection)."""
+    import os
+    order = os.environ.get("DDM_INGEST_ORDER")
+    if order in ("copies_first", "launch_first"):
+        return order == "copies_first"
+    if os.environ.get("CUDA_LAUNCH_BLOCKING") == "1":
+        return True
+    return any(k == "NV_COMPUTE_PROFILER_PERFWORKS_DIR" or k.startswith(("NV_NSIGHT_INJECTION", "NV_SANITIZER"))
+               for k in os.environ)
+
+
 class HostPipeline:
     """Streams a host-resident z = [theta, pulses] matrix through the GPU.
 
@@ -307,7 +323,9 @@ class HostPipeline:
             if packed:
                 if slot["host_free"] is not None:
                     slot["host_free"].synchronize()  # the copy engine has read the staging block's last contents
-                launch()                             # resident and waiting while the host packs
+                copies_first = launches_block()
+                if not copies_first:
+                    launch()                         # resident and waiting while the host packs
                 # marks[k] = rows delivered once chunk k has landed (the last one: "all of them")
                 n_chunks = -(-bs // self.chunk)
                 marks = slot["marks"]
@@ -320,6 +338,8 @@ class HostPipeline:
                                          marks.data_ptr(), n_threads, cs.cuda_stream, ctypes.byref(got))
                 _native.check(rc, "ddm_ingest_packed")
                 generic = got.value
+                if copies_first:
+                    launch()
                 slot["host_free"] = torch.cuda.Event()
                 slot["host_free"].record(cs)
                 self.h2d_bytes += bs * 32

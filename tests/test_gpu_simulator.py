@@ -270,7 +270,7 @@ def test_long_schedule_dt_1e_4_shared_noise_and_native():
     _assert_same(xn, want_n, "dt=1e-4 native replay")
 
 
-def test_streaming_host_pipeline_equals_resident_launch():
+def test_streaming_host_pipeline_equals_resident_launch(monkeypatch):
     """Host-resident z through one persistent streaming kernel per batch == ddm_sim_f32 on resident z:
     fp32 rows over the link (ddm_sim_stream_f32) and host-packed 32-byte records (ddm_pack_z_host +
     ddm_sim_packed_f32), bit for bit."""
@@ -294,9 +294,12 @@ def test_streaming_host_pipeline_equals_resident_launch():
         is_packed = packed is True or (packed is None and auto_packs)
         assert pipe.packed_batches == (3 if is_packed else 0)
         assert pipe.h2d_bytes == n * (32 if is_packed else 340)
-    # the same pipeline object again (slots, staging blocks and events are reused)
+    # the same pipeline object again (slots, staging blocks and events are reused); this time in the
+    # order used under tools that serialise launches (Nsight Compute, CUDA_LAUNCH_BLOCKING=1)
+    monkeypatch.setenv("DDM_INGEST_ORDER", "copies_first")
+    assert simmod.launches_block()
     xh2 = torch.empty((n, 2)).pin_memory()
-    pipe.run(zh, xh2, sched=sched, seed=4242, trial_offset=1000)
+    pipe.run(zh, xh2, sched=sched, seed=4242, trial_offset=1000, packed=True)
     pipe.synchronize()
     assert torch.equal(xh2, want)
 
