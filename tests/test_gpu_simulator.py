@@ -270,6 +270,28 @@ def test_long_schedule_dt_1e_4_shared_noise_and_native():
     _assert_same(xn, want_n, "dt=1e-4 native replay")
 
 
+def test_stress_schedule_dt_1e_6_native_replay():
+    """SURVEY 8d stress variant: dt = 1e-6 (the unused constants.py:2 value) -> n_max = 8e6 steps,
+    steps_per_pulse = 1e5.  Native noise, replayed through the C oracle with the dumped normals;
+    censored trials run all 8e6 steps (step counters, Philox block index and kick schedule far from
+    the default's ranges)."""
+    sched = Schedule.from_constants(dt=1e-6)
+    assert sched.steps_per_pulse == 100000 and sched.n_pulses == 80 and sched.n_max >= 7999999
+    n = 12
+    theta = orc.prior_sample(n, seed=71).numpy()
+    theta[0] = [0.5, 0.0, 0.0, 1e4, 0.1]          # never reaches a bound: censored after the whole window
+    theta[1] = [0.5, 0.3, 2.0, 30.0, 7.9999]      # window of a few steps
+    pulses = orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(16)), 0, n, 80, 0.75)
+    x, steps = simulate_trials(torch.from_numpy(theta), torch.from_numpy(pulses), seed=31, schedule=sched,
+                               return_steps=True)
+    normals = sim.philox_normals(31, n, sched.n_max)
+    want, want_steps = orc.sim_scalar_c(theta, pulses, normals.cpu().numpy(), dt=1e-6)
+    del normals
+    _assert_same(x, want, "dt=1e-6 native replay")
+    assert np.array_equal(steps.cpu().numpy().astype(np.int64), want_steps)
+    assert want[0, 1] == 2.0 and want_steps[0] >= 7.8e6
+
+
 def test_streaming_host_pipeline_equals_resident_launch(monkeypatch):
     """Host-resident z through one persistent streaming kernel per batch == ddm_sim_f32 on resident z:
     fp32 rows over the link (ddm_sim_stream_f32) and host-packed 32-byte records (ddm_pack_z_host +
