@@ -520,7 +520,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
-    const int n_tiles = D * T * CB;
     // potential mode: CTAs [0, n_pairs) take two tiles each, the rest one tile each (see tc_grid())
     const int bx = blockIdx.x;
     const int tile0 = (ROWS || bx >= n_pairs) ? (ROWS ? bx : 2 * n_pairs + (bx - n_pairs)) : bx * kTcTiles;
