@@ -45,6 +45,22 @@ def init_raw_params(n_choices: int, seed: int = 0) -> Dict[str, torch.Tensor]:
     return p
 
 
+def _column_mean_std(t: torch.Tensor, chunk: int = 1 << 22):
+    """Per-column mean and unbiased std in float64 without a float64 copy of the whole (N, d) set
+    (1e8 x 85 doubles would be 68 GB): shifted sums over row chunks."""
+    n = t.shape[0]
+    shift = t[:1].double()
+    s1 = torch.zeros(t.shape[1], dtype=torch.float64, device=t.device)
+    s2 = torch.zeros_like(s1)
+    for a in range(0, n, chunk):
+        d = t[a:a + chunk].double() - shift
+        s1 += d.sum(0)
+        s2 += (d * d).sum(0)
+    mean = s1 / n
+    var = (s2 - n * mean * mean) / max(n - 1, 1)
+    return mean + shift[0], var.clamp_min(0.0).sqrt()
+
+
 class MNLETrainer:
     """Device-resident parameters, Adam state and workspace of one estimator in training."""
 
@@ -163,12 +179,10 @@ def train_mnle(cfg, proposal_z, z_train: torch.Tensor, x_train: torch.Tensor, de
         n_choices = int(choices.numel())
         if not torch.equal(choices.cpu(), torch.arange(n_choices, dtype=torch.float32)):
             raise ValueError(f"choices must be the integers 0..K-1, got {choices.cpu().tolist()}")
-        zd = z.double()
-        cond_mean, cond_std = zd.mean(0), zd.std(0)
-        y = x[:, 0].double().log()
+        cond_mean, cond_std = _column_mean_std(z)
+        y_mean, y_std = _column_mean_std(x[:, :1].log())
         z_score_x = getattr(cfg, "Z_SCORE_X", "independent")
-        mu_y, sigma_y = (float(y.mean()), float(y.std())) if z_score_x not in (None, "none") else (0.0, 1.0)
-        del zd, y
+        mu_y, sigma_y = (float(y_mean), float(y_std)) if z_score_x not in (None, "none") else (0.0, 1.0)
         tr = MNLETrainer(n_choices, cond_mean=cond_mean.cpu(), cond_std=cond_std.cpu(), mu_y=mu_y, sigma_y=max(sigma_y, 1e-7),
                          init=init, seed=seed, device=dev)
         cond = tr.standardise(z)
