@@ -250,6 +250,40 @@ def test_million_trials_properties():
     assert stats.lane_efficiency > 0.6, stats   # 3.5 trials per lane: the drain tail is ~25 %; 0.995 at 1e8 trials
 
 
+def test_full_size_training_set_properties():
+    """BASELINE configs[1] at its full size (1e8 trials, z = 34 GB resident; 2^25 trials when the device
+    has less than 60 GB free): size-independent properties, and a checksum of checksums -- the whole set
+    in one launch equals the same set simulated in eight slices with trial offsets."""
+    import bench
+    free, _ = torch.cuda.mem_get_info()
+    n = 100_000_000 if free > 60e9 else 1 << 25
+    dev = torch.device("cuda", torch.cuda.current_device())
+    z = bench.build_workload(n, 0, dev)
+    x = torch.empty((n, 2), device=dev)
+    steps, stats = simulate_trials(z[:, :5], z[:, 5:], seed=77, out=x, return_steps=True, return_stats=True)[1:]
+    assert bool(torch.isfinite(x).all())
+    ch = x[:, 1]
+    assert bool(((ch == 0) | (ch == 1) | (ch == 2)).all())
+    assert float(x[:, 0].min()) >= 1e-6 and float(x[:, 0].max()) <= 8.0
+    assert stats.useful_steps == int(steps.to(torch.int64).sum()) and stats.generic_rows == 0
+    t_nd = z[:, 4].clamp(0.0, float(np.float32(8.0 - 1e-6)))
+    rt = (t_nd + steps.to(torch.float32) * float(np.float32(5e-4))).clamp(1e-6, 8.0)
+    assert torch.equal(rt, x[:, 0])                                        # reference :218, exactly
+    del rt, t_nd
+    frac = torch.bincount(ch.to(torch.int64), minlength=3).double() / n
+    assert abs(frac[0] - 0.5651) < 2e-3 and abs(frac[1] - 0.2558) < 2e-3 and abs(frac[2] - 0.1791) < 2e-3
+    assert abs(steps.double().mean().item() - 5116) < 10
+    assert stats.lane_efficiency > (0.99 if n == 100_000_000 else 0.97)
+    whole = int(x.view(torch.int32).to(torch.int64).sum())
+    parts = 0
+    xs = torch.empty((n // 8 + 8, 2), device=dev)
+    for k in range(8):
+        a, b = n * k // 8, n * (k + 1) // 8
+        simulate_trials(z[a:b, :5], z[a:b, 5:], seed=77, trial_offset=a, out=xs[:b - a])
+        parts += int(xs[:b - a].view(torch.int32).to(torch.int64).sum())
+    assert parts == whole
+
+
 def test_long_schedule_dt_1e_4_shared_noise_and_native():
     """configs[2]'s long pulse schedule: dt = 1e-4 -> n_max = 80000, steps_per_pulse = 1000, P = 80."""
     sched = Schedule.from_constants(dt=1e-4)
