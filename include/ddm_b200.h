@@ -208,8 +208,8 @@ int mnle_log_prob_rows_f32(void *handle, const float *x_dev, const float *cond_d
                            int64_t R, float *out_dev, void *stream);
 
 /* Same call on the 5th-generation tensor cores: the 86-wide context of each row is split into bf16
- * hi + lo in tensor memory and every layer (first layers included, K padded to 96) runs as three
- * tcgen05.mma per product; 128 rows per CTA.  Per-row results within ~1e-4 of the fp32 kernel on
+ * hi + lo operand images in shared memory and every layer (first layers included, K padded to 96) runs
+ * as three tcgen05.mma per product; two 128-row tiles per CTA in ping-pong.  Per-row results within ~1e-4 of the fp32 kernel on
  * the default-init net (see mnle_loglik_sum_tc_f32 for the accuracy model). */
 int mnle_log_prob_rows_tc_f32(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond,
                               int64_t R, float *out_dev, void *stream);

@@ -338,16 +338,23 @@ constexpr int kTcEpiWarps = 16;                  // warp w: lane quarter w & 3, 
 constexpr int kTcEpiThreads = kTcEpiWarps * 32;
 constexpr int kTcIssuers = 2;                    // issuer warps: warp kTcEpiWarps + i owns stages s = i (mod 2)
 constexpr int kTcThreads = kTcEpiThreads + 32 * kTcIssuers;
-constexpr int kTcSlots = 3;
 constexpr uint32_t kImgBytes = kTcM * 256;       // one bf16 image of 128 rows x 128 k
 constexpr uint32_t kKGroupBytes = kTcM * 16;     // 8 k's of all 128 rows
 constexpr uint32_t kAThBytes = kTcM * 64;        // theta-stage A image: 128 rows x 32 k
-constexpr uint32_t kSmemATh = 0;
-constexpr uint32_t kSmemSlot0 = kTcTiles * kAThBytes;
+constexpr uint32_t kCtxImgBytes = kTcM * kInputK * 2;          // rows mode: 128 rows x 96 k of context, one bf16 term
 constexpr uint32_t kSlotBytes = 2 * kImgBytes + kHidden * 4;   // largest blob; theta blobs are 8 KB + 2 biases
-constexpr uint32_t kSmemBars = kSmemSlot0 + kTcSlots * kSlotBytes;
-constexpr uint32_t kTcSmemBytes = kSmemBars + 128;
-static_assert(kTcSmemBytes <= 227 * 1024, "tiles do not fit shared memory");
+// Shared memory.  Potential mode: theta-stage A images of the two tiles, then a ring of 3 weight slots
+// (prefetch two stages ahead).  Rows mode: the 86-wide context of both tiles as bf16 hi / lo A images
+// (4 x 24 KB; tensor memory is full with two tiles), then 2 weight slots (prefetch one stage ahead).
+template <bool ROWS>
+struct TcSmem {
+    static constexpr int kSlots = ROWS ? 2 : 3;
+    static constexpr uint32_t kA = 0;
+    static constexpr uint32_t kSlot0 = ROWS ? kTcTiles * 2 * kCtxImgBytes : kTcTiles * kAThBytes;
+    static constexpr uint32_t kBars = kSlot0 + kSlots * kSlotBytes;
+    static constexpr uint32_t kBytes = kBars + 128;
+    static_assert(kBytes <= 227 * 1024, "tiles do not fit shared memory");
+};
 constexpr uint32_t kTmemD = 0, kTmemAHi = 128, kTmemALo = 192, kTmemTile = 256;  // columns
 
 // ncols accumulator columns + bias -> activation -> packed bf16 hi / lo columns of the A operand.
@@ -498,9 +505,9 @@ static void tc_grid(long long n_tiles, int sms, int *n_pairs, long long *grid)
 }
 
 // ROWS: estimator.log_prob over arbitrary rows -- `theta` is the (R, 85) condition matrix (row stride
-// ld_theta), x is (R, 2), C = R, one tile per CTA; the 86-wide context goes into TMEM columns
-// [256, 352) as bf16 hi / lo and every net's first layer is a K = 96 stage; out[row] = log-prob.
-constexpr uint32_t kTmemInHi = 256, kTmemInLo = 256 + kInputK / 2;
+// ld_theta), x is (R, 2), C = R; the 86-wide context of each tile sits in shared memory as bf16 hi / lo
+// A images and every net's first layer is a K = 96 stage with both operands from shared memory (the
+// other stages take A from tensor memory as in potential mode); out[row] = log-prob.
 template <bool ROWS>
 __global__ void __launch_bounds__(kTcThreads, 1)
     mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
@@ -511,8 +518,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                    long long *__restrict__ trace)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
+    using SM = TcSmem<ROWS>;
+    constexpr int kTcSlots = SM::kSlots;
+    constexpr uint32_t kSmemSlot0 = SM::kSlot0, kSmemBars = SM::kBars, kSmemATh = SM::kA;
     uint64_t *wfull = reinterpret_cast<uint64_t *>(smem + kSmemBars);  // [kTcSlots]
-    uint64_t *dfull = wfull + kTcSlots;                                // [kTcTiles]
+    uint64_t *dfull = wfull + 3;                                       // [kTcTiles]
     uint64_t *aready = dfull + kTcTiles;                               // [kTcTiles]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBars + 96);
     // turn[X]: phase s completes when the issuer of stage s has consumed its aready[X] phase (issuers only)
@@ -520,10 +530,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
-    // potential mode: CTAs [0, n_pairs) take two tiles each, the rest one tile each (see tc_grid())
+    // CTAs [0, n_pairs) take two tiles each, the rest one tile each (see tc_grid())
     const int bx = blockIdx.x;
-    const int tile0 = (ROWS || bx >= n_pairs) ? (ROWS ? bx : 2 * n_pairs + (bx - n_pairs)) : bx * kTcTiles;
-    const int n_active = (ROWS || bx >= n_pairs) ? 1 : kTcTiles;
+    const int tile0 = bx >= n_pairs ? 2 * n_pairs + (bx - n_pairs) : bx * kTcTiles;
+    const int n_active = bx >= n_pairs ? 1 : kTcTiles;
 
     if (warp == kTcEpiWarps) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
@@ -568,7 +578,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             __syncwarp();
         };
-        load(iw);
+        // the ring is kTcSlots deep: stage s + kTcSlots - 1 is fetched while stage s runs
+        for (int g = iw; g < kTcSlots - 1; g += kTcIssuers) load(g);
 #pragma unroll 1
         for (int s = iw; s < kTcStages; s += kTcIssuers) {
             const TcStage &st = plan.st[s];
@@ -592,15 +603,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (elect_one_sync()) {
                     if (st.kind == kStageInput) {
                         const uint32_t w_img = kHidden * kInputK * 2u;
+                        const uint32_t ctx = smem_u32(smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes);
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
-                            const uint32_t a = tmem_u + (pass == 2 ? kTmemInLo : kTmemInHi);
+                            const uint32_t a = ctx + (pass == 2 ? kCtxImgBytes : 0u);
                             const uint32_t w = slot + (pass == 1 ? w_img : 0u);
 #pragma unroll
                             for (int ks = 0; ks < kInputK / 16; ++ks)
-                                umma_bf16_ts(tm + kTmemD, a + (uint32_t)ks * 8u,
-                                             umma_desc_kmajor(w + ks * 2 * kKGroupBytes, kKGroupBytes, 128), idesc,
-                                             (pass | ks) != 0);
+                                umma_bf16(tm + kTmemD, umma_desc_kmajor(a + ks * 2 * kKGroupBytes, kKGroupBytes, 128),
+                                          umma_desc_kmajor(w + ks * 2 * kKGroupBytes, kKGroupBytes, 128), idesc,
+                                          (pass | ks) != 0);
                         }
                     } else if (st.kind == kStageTheta) {
                         const uint32_t a = smem_u32(smem + kSmemATh + (uint32_t)X * kAThBytes);
@@ -624,9 +636,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     umma_commit(&dfull[X]);
                 }
                 __syncwarp();
-                // every tile is past stage s-1, so its slot can take stage s+2 (issued after the
-                // MMAs: the copy has a whole stage of slack, the MMA issue is on the critical path)
-                if (X == n_active - 1 && s + 2 < kTcStages) load(s + 2);
+                // every tile is past stage s-1, so its slot can take the next stage to fetch (issued after
+                // the MMAs: the copy has a whole stage of slack, the MMA issue is on the critical path)
+                if (X == n_active - 1 && s + kTcSlots - 1 < kTcStages) load(s + kTcSlots - 1);
                 if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 8 + 6] = clock64();
             }
         }
@@ -639,14 +651,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const long long c_glob = (long long)d * C + c;
         const uint32_t trow = tmem + (uint32_t)X * kTmemTile + ((uint32_t)(32 * q) << 16);
         if (ROWS) {
-            // context row [cond (85), choice, 0...] -> bf16 hi / lo in TMEM; this thread: k in [48 hf, 48 hf + 48)
+            // context row [cond (85), choice, 0...] -> bf16 hi / lo A images of this tile (K-major, like the
+            // weights); this thread: k in [48 hf, 48 hf + 48)
+            unsigned char *img_hi = smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes, *img_lo = img_hi + kCtxImgBytes;
             const float *crow = theta + c_glob * ld_theta;
             const float ch = live ? __ldg(x + 2 * c_glob + 1) : 0.f;
 #pragma unroll 1
-            for (int k0 = 48 * hf; k0 < 48 * hf + 48; k0 += 16) {
-                uint32_t hi[8], lo[8];
+            for (int k0 = 48 * hf; k0 < 48 * hf + 48; k0 += 8) {
+                uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     float v[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
@@ -655,11 +669,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     }
                     split_bf16x2(v[0], v[1], hi[j], lo[j]);
                 }
-                tmem_st8(trow - (uint32_t)X * kTmemTile + kTmemInHi + (uint32_t)(k0 >> 1), hi);
-                tmem_st8(trow - (uint32_t)X * kTmemTile + kTmemInLo + (uint32_t)(k0 >> 1), lo);
+                const uint32_t off = (uint32_t)(k0 >> 3) * kKGroupBytes + (uint32_t)r * 16u;
+                *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-            tmem_wait_st();
-            tc_fence_before_sync();
         } else {   // A image of the theta stage: k = term * 5 + i, terms t1 t1 t2 t1 t2 t3 (pairs with pack_image_theta)
             unsigned char *a_th = smem + kSmemATh + (uint32_t)X * kAThBytes;
             uint16_t tt[5][3];
@@ -852,12 +865,12 @@ DDM_API int mnle_loglik_sum_batched_tc_f32(void *handle, const float *theta_dev,
     mnle_hoist_kernel<<<dim3(kNets, (unsigned)hoist_blocks), kHidden, 0, st>>>(H->params, H->layout, x_dev, pulses_dev, ld_pulses,
                                                                             (int)(D * T), hoist, counters, (int)(D * CB));
     DDM_CUDA_TRY(cudaGetLastError());
-    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<false>::kBytes));
     int sms = 0, n_pairs = 0;
     long long grid = 0;
     DDM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, H->device));
     tc_grid(n_tiles, sms, &n_pairs, &grid);
-    mnle_tc_kernel<false><<<(unsigned)grid, kTcThreads, kTcSmemBytes, st>>>(
+    mnle_tc_kernel<false><<<(unsigned)grid, kTcThreads, TcSmem<false>::kBytes, st>>>(
         static_cast<const unsigned char *>(H->tc_pack), H->tc_plan, theta_dev, ld_theta, x_dev, hoist, (int)D, (int)T, (int)C,
         n_pairs, H->mu_y, H->sigma_y, H->layout.n_choices, partial, counters, out_dev, g_tc_trace);
     DDM_CUDA_TRY(cudaGetLastError());
@@ -885,10 +898,15 @@ DDM_API int mnle_log_prob_rows_tc_f32(void *handle, const float *x_dev, const fl
     DDM_REQUIRE(x_dev && cond_dev && out_dev, "mnle_log_prob_rows_tc_f32: null pointer");
     DDM_REQUIRE(ld_cond >= kCond, "mnle_log_prob_rows_tc_f32: ld_cond=%lld < 85", (long long)ld_cond);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-    mnle_tc_kernel<true><<<(unsigned)((R + kTcM - 1) / kTcM), kTcThreads, kTcSmemBytes, st>>>(
-        static_cast<const unsigned char *>(H->tc_pack), H->tc_rows_plan, cond_dev, ld_cond, x_dev, nullptr, 1, 1, (int)R, 0,
-        H->mu_y, H->sigma_y, H->layout.n_choices, nullptr, nullptr, out_dev, nullptr);
+    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)TcSmem<true>::kBytes));
+    int sms = 0, n_pairs = 0;
+    long long grid = 0;
+    DDM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, H->device));
+    tc_grid((R + kTcM - 1) / kTcM, sms, &n_pairs, &grid);
+    mnle_tc_kernel<true><<<(unsigned)grid, kTcThreads, TcSmem<true>::kBytes, st>>>(
+        static_cast<const unsigned char *>(H->tc_pack), H->tc_rows_plan, cond_dev, ld_cond, x_dev, nullptr, 1, 1, (int)R,
+        n_pairs, H->mu_y, H->sigma_y, H->layout.n_choices, nullptr, nullptr, out_dev, nullptr);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }
