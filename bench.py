@@ -525,6 +525,16 @@ def run_native(args):
             roofline["traffic_note"] = (f"ncu dram bytes per trial ({dram / trials_prof:.0f} B at {trials_prof} trials per launch, "
                                         "profiles/r01_sim_kernel_ncu_full.json) x trials per launch")
             roofline["ncu_issue_active_pct"] = prof["sm__issue_active.avg.pct_of_peak_sustained_elapsed"]["value"]
+            # issue-slot view of the same launch: warp-instructions per useful Euler step from that capture
+            # (all of them: RNG, physics, bookkeeping) x the live step rate, against one instruction per
+            # lane per clock
+            inst_per_step = prof["smsp__inst_executed.sum"]["value"] * 32.0 / (trials_prof * 5116.07)
+            roofline["issue"] = {"lane_inst_per_useful_step": inst_per_step,
+                                 "achieved": per_launch_steps * inst_per_step / (k_ms * 1e-3) / 1e12, "peak": lane_peak / 1e12,
+                                 "unit": "T lane-instructions/s",
+                                 "frac": per_launch_steps * inst_per_step / (k_ms * 1e-3) / lane_peak,
+                                 "note": "instructions per step from profiles/r01_sim_kernel_ncu_full.json (8388608 trials, "
+                                         "5116.07 useful steps per trial), rate measured live"}
         except Exception:
             pass
         line = {
