@@ -15,18 +15,21 @@
 //                              d loss / d (spline parameters, logits) in place.
 //   3. train_backward_kernel   one CTA per (row tile, net): back-propagates through its net
 //                              (transposed dense products with the activation derivative fused into
-//                              the epilogue) and forms the weight gradients as 64-row outer-product
-//                              sums in registers.  Each CTA owns a slice of the partial-gradient
+//                              the epilogue) and writes d loss / d (hidden pre-activations).
+//      train_wgrad_tc_kernel   the weight gradients dW = dY^T X of all 34 layers as tcgen05 GEMMs over
+//                              the rows of the minibatch (bf16 hi / lo operands, fp32 accumulation in
+//                              tensor memory); each row split owns a slice of the partial-gradient
 //                              buffer: no atomics.
 //   4. train_reduce_kernel     sums the partials in a fixed order (bit-reproducible gradients) and
 //                              the squared gradient norm; train_stats_kernel: loss and norm.
 //   5. adam_kernel             torch.optim.Adam update with clip_grad_norm_ folded in.
 #include "mnle_dense.cuh"
+#include "tc_ptx.cuh"
 
 namespace mnle {
 
 constexpr int kQRows = 72;         // 71 spline parameters per transform, padded
-constexpr int kMaxGroups = 128;    // partial-gradient slices (row tiles beyond that share slices)
+constexpr int kMaxGroups = 4;      // partial-gradient slices = row splits of the weight-gradient kernel (34 layers x 4 = 136 CTAs)
 constexpr int kReduceThreads = 256;
 
 struct TrainBufs {
@@ -34,7 +37,8 @@ struct TrainBufs {
     float *LG;   // [Rp][kMaxChoices]          choice logits -> their gradients
     float *LP;   // [Rp]                       log p per row
     float *H;    // [kNets][3][Rp][128]        hidden activations kept for the backward pass
-    float *P;    // [groups][total]            partial gradients
+    float *DH;   // [kNets][3][Rp][128]        d loss / d (hidden pre-activations)
+    float *P;    // [groups][total]            partial gradients (one slice per row split of the wgrad kernel)
     float *SS;   // [reduce blocks]            partial sums of grad^2
 };
 
@@ -49,14 +53,15 @@ static TrainDims train_dims(const Layout &L, long long R)
     d.R = R;
     d.tiles = (int)((R + kTM - 1) / kTM);
     d.Rp = (long long)d.tiles * kTM;
-    d.groups = d.tiles < kMaxGroups ? d.tiles : kMaxGroups;
+    const int chunks = (int)((R + 127) / 128);   // 128-row chunks of the weight-gradient GEMMs
+    d.groups = chunks < kMaxGroups ? chunks : kMaxGroups;
     d.reduce_blocks = (int)((L.total + kReduceThreads - 1) / kReduceThreads);
     return d;
 }
 
 static size_t train_floats(const Layout &L, const TrainDims &d)
 {
-    return (size_t)d.Rp * (kTransforms * kQRows + kMaxChoices + 1 + kNets * 3 * kHidden) + (size_t)d.groups * L.total +
+    return (size_t)d.Rp * (kTransforms * kQRows + kMaxChoices + 1 + 2 * kNets * 3 * kHidden) + (size_t)d.groups * L.total +
            (size_t)d.reduce_blocks;
 }
 
@@ -67,7 +72,8 @@ static TrainBufs carve(float *ws, const Layout &L, const TrainDims &d)
     b.LG = b.Q + (size_t)kTransforms * kQRows * d.Rp;
     b.LP = b.LG + (size_t)kMaxChoices * d.Rp;
     b.H = b.LP + d.Rp;
-    b.P = b.H + (size_t)kNets * 3 * kHidden * d.Rp;
+    b.DH = b.H + (size_t)kNets * 3 * kHidden * d.Rp;
+    b.P = b.DH + (size_t)kNets * 3 * kHidden * d.Rp;
     b.SS = b.P + (size_t)d.groups * L.total;
     return b;
 }
@@ -352,101 +358,191 @@ __global__ void __launch_bounds__(kRowWarps * 32) train_rows_kernel(const float 
 }
 
 // ---- 3. backward through the nets ------------------------------------------------------------
-// out[n][k] (+)= sum_{r < 64} dy[r][n] * x[r][k]  (n < n_valid <= 16 NI, k < K <= 16 NJ), row-major
-// with row stride K, and bias_out[n] (+)= sum_r dy[r][n].  8 x 8 accumulators per thread.
-template <int NI, int NJ>
-__device__ __forceinline__ void wgrad(const float *dy_s, int ld_dy, int n_valid, const float *x_s, int ld_x, int K,
-                                      float *__restrict__ out, float *__restrict__ bias_out, bool accumulate)
-{
-    const int tid = threadIdx.x;
-    const int tk = tid & 15, tn = tid >> 4;
-    float acc[NI][NJ];
-#pragma unroll
-    for (int i = 0; i < NI; ++i)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
-    for (int r = 0; r < kTM; ++r) {
-        float a[NI], bb[NJ];
-#pragma unroll
-        for (int i = 0; i < NI; ++i) a[i] = dy_s[r * ld_dy + tn + 16 * i];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) bb[j] = x_s[r * ld_x + tk + 16 * j];
-#pragma unroll
-        for (int i = 0; i < NI; ++i)
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        const int n = tn + 16 * i;
-        if (n < n_valid) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int k = tk + 16 * j;
-                if (k < K) {
-                    float *p = out + (size_t)n * K + k;
-                    *p = accumulate ? *p + acc[i][j] : acc[i][j];
-                }
-            }
-        }
-    }
-    if (tid < n_valid) {
-        float sb = 0.f;
-        for (int r = 0; r < kTM; ++r) sb += dy_s[r * ld_dy + tid];
-        bias_out[tid] = accumulate ? bias_out[tid] + sb : sb;
-    }
-}
-
+// 3a. backward-data on CUDA cores: one CTA per (row tile, net) turns d loss / d (net outputs) into
+// d loss / d (hidden pre-activations), layer by layer (transposed dense products with the activation
+// derivative fused into the epilogue), and writes them out for the weight-gradient GEMMs.
 __global__ void __launch_bounds__(kThreads) train_backward_kernel(const float *__restrict__ params, Layout L,
-                                                                  TrainRows rows, long long Rp, int tiles, TrainBufs B)
+                                                                  long long Rp, TrainBufs B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SimtSmem &S = *reinterpret_cast<SimtSmem *>(smem_raw);
     const int net = blockIdx.y;  // 0 = categorical head, 1 + k = conditioner of transform k
-    float *P = B.P + (size_t)blockIdx.x * L.total;
-    bool acc = false;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, acc = true) {
-        const long long row0 = (long long)tile * kTM;
-        __syncthreads();
-        if (net > 0) {
-            const int k = net - 1;
-            load_rows(B.Q + (size_t)k * kQRows * Rp, kQRows, row0, kSplineOut, S.in);
-            load_hidden(S.hb, B.H, Rp, net, 1, row0);
-            __syncthreads();
-            wgrad<5, 8>(S.in, kLdIn, kSplineOut, S.hb, kLdH, kHidden, P + L.fl_W3[k], P + L.fl_b3[k], acc);
-            dense<8, kMaskRelu, false, true>(params + L.fl_W3[k], nullptr, kSplineOut, kHidden, S.in, kLdIn, S.hb, kLdH,
-                                             S.w, kHidden);
-            load_hidden(S.ha, B.H, Rp, net, 0, row0);
-            __syncthreads();
-            wgrad<8, 8>(S.hb, kLdH, kHidden, S.ha, kLdH, kHidden, P + L.fl_W2[k], P + L.fl_b2[k], acc);
-            dense<8, kMaskRelu, false, true>(params + L.fl_W2[k], nullptr, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH,
-                                             S.w, kHidden);
-            load_context(rows, row0, S.in);
-            __syncthreads();
-            wgrad<8, 6>(S.ha, kLdH, kHidden, S.in, kLdIn, kCtx, P + L.fl_W1[k], P + L.fl_b1[k], acc);
-        } else {
-            load_rows(B.LG, kMaxChoices, row0, L.n_choices, S.in);
-            load_hidden(S.ha, B.H, Rp, 0, 2, row0);
-            __syncthreads();
-            wgrad<1, 8>(S.in, kLdIn, L.n_choices, S.ha, kLdH, kHidden, P + L.cat_Wo, P + L.cat_bo, acc);
-            dense<8, kMaskSigmoid, false, true>(params + L.cat_Wo, nullptr, L.n_choices, kHidden, S.in, kLdIn, S.ha,
-                                                kLdH, S.w, kHidden);
-            load_hidden(S.hb, B.H, Rp, 0, 1, row0);
-            __syncthreads();
-            wgrad<8, 8>(S.ha, kLdH, kHidden, S.hb, kLdH, kHidden, P + L.cat_W2, P + L.cat_b2, acc);
-            dense<8, kMaskSigmoid, false, true>(params + L.cat_W2, nullptr, kHidden, kHidden, S.ha, kLdH, S.hb, kLdH,
-                                                S.w, kHidden);
-            load_hidden(S.ha, B.H, Rp, 0, 0, row0);
-            __syncthreads();
-            wgrad<8, 8>(S.hb, kLdH, kHidden, S.ha, kLdH, kHidden, P + L.cat_W1, P + L.cat_b1, acc);
-            dense<8, kMaskSigmoid, false, true>(params + L.cat_W1, nullptr, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH,
-                                                S.w, kHidden);
-            load_context(rows, row0, S.in);
-            __syncthreads();
-            wgrad<8, 6>(S.ha, kLdH, kHidden, S.in, kLdIn, kCond, P + L.cat_W0, P + L.cat_b0, acc);
-        }
+    const long long row0 = (long long)blockIdx.x * kTM;
+    if (net > 0) {
+        const int k = net - 1;
+        load_rows(B.Q + (size_t)k * kQRows * Rp, kQRows, row0, kSplineOut, S.in);
+        load_hidden(S.hb, B.H, Rp, net, 1, row0);
+        dense<8, kMaskRelu, false, true>(params + L.fl_W3[k], nullptr, kSplineOut, kHidden, S.in, kLdIn, S.hb, kLdH, S.w,
+                                         kHidden);
+        save_hidden(S.hb, B.DH, Rp, net, 1, row0);
+        load_hidden(S.ha, B.H, Rp, net, 0, row0);
+        dense<8, kMaskRelu, false, true>(params + L.fl_W2[k], nullptr, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH, S.w,
+                                         kHidden);
+        save_hidden(S.ha, B.DH, Rp, net, 0, row0);
+    } else {
+        load_rows(B.LG, kMaxChoices, row0, L.n_choices, S.in);
+        load_hidden(S.ha, B.H, Rp, 0, 2, row0);
+        dense<8, kMaskSigmoid, false, true>(params + L.cat_Wo, nullptr, L.n_choices, kHidden, S.in, kLdIn, S.ha, kLdH,
+                                            S.w, kHidden);
+        save_hidden(S.ha, B.DH, Rp, 0, 2, row0);
+        load_hidden(S.hb, B.H, Rp, 0, 1, row0);
+        dense<8, kMaskSigmoid, false, true>(params + L.cat_W2, nullptr, kHidden, kHidden, S.ha, kLdH, S.hb, kLdH, S.w,
+                                            kHidden);
+        save_hidden(S.hb, B.DH, Rp, 0, 1, row0);
+        __syncthreads();  // everyone is done with the gradient in S.ha before the activations replace it
+        load_hidden(S.ha, B.H, Rp, 0, 0, row0);
+        dense<8, kMaskSigmoid, false, true>(params + L.cat_W1, nullptr, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH, S.w,
+                                            kHidden);
+        save_hidden(S.ha, B.DH, Rp, 0, 0, row0);
     }
+}
+
+// 3b. weight gradients on the tensor cores.  Every layer's dW[m][n] = sum_r dY[r][m] * X[r][n] is a GEMM
+// whose reduction runs over the rows of the minibatch: M, N <= 128, K = R.  One CTA owns one (layer, row
+// split): per 128-row chunk, thread c of the first four warps turns column c of dY into row c of a
+// K-major bf16 hi / lo operand image (coalesced global reads along the row, one 16-byte shared-memory
+// store per 8 rows), the other four warps do the same for X, and one elected thread issues the three
+// tcgen05.mma passes (hi*hi + hi*lo + lo*hi, fp32 accumulation in tensor memory across all chunks).  The
+// row splits write separate slices of the partial buffer: the fixed-order reduction below sums them.
+struct WJob {
+    const float *A;     // dY: (R, lda) row-major, M columns used
+    const float *B;     // X:  (R, ldb) row-major, N columns used; nullptr = the (gathered) context rows
+    int lda, ldb, M, N;
+    unsigned w_off, b_off;  // where dW (M x N, row-major) and db (M) go in a partial slice
+};
+constexpr int kMaxWJobs = 3 * kTransforms + 4;
+struct WJobs {
+    WJob j[kMaxWJobs];
+};
+constexpr int kWgThreads = 512;                  // 2 operands x 128 columns x 2 halves of the chunk's rows
+constexpr uint32_t kWgImg = 128 * 256;           // one 128 x 128 bf16 image
+constexpr uint32_t kWgSmem = 4 * kWgImg + 64 + 128 * 8;
+
+__global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __grid_constant__ WJobs jobs, TrainRows rows,
+                                                                       int chunks_total, size_t total,
+                                                                       float *__restrict__ P)
+{
+    using namespace tc;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 4 * kWgImg);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 4 * kWgImg + 16);
+    long long *drow = reinterpret_cast<long long *>(smem + 4 * kWgImg + 64);  // dataset row of each chunk row
+    const WJob &J = jobs.j[blockIdx.x];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int c_begin = (int)((long long)chunks_total * blockIdx.y / gridDim.y);
+    const int c_end = (int)((long long)chunks_total * (blockIdx.y + 1) / gridDim.y);
+    const int n_pad = (J.N + 15) & ~15;  // UMMA N
+
+    if (warp == 0) tmem_alloc<128>(tmem_slot);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    // thread = (operand, half of the chunk's rows, column): 32 independent loads in flight per thread --
+    // the operands come from HBM (they do not fit L2 next to each other) and nothing else hides its latency
+    const bool is_a = tid < 256;
+    const int half = (tid >> 7) & 1, col = tid & 127;
+    const int img_rows = is_a ? 128 : n_pad, valid = is_a ? J.M : J.N;
+    const bool is_ctx = !is_a && J.B == nullptr;
+    const float *src = is_a ? J.A : J.B;
+    const long long ld = is_a ? J.lda : J.ldb;
+    unsigned char *img_hi = smem + (is_a ? 0u : 2u * kWgImg), *img_lo = img_hi + kWgImg;
+    float bias_acc = 0.f;
+    uint32_t phase = 0;
+    for (int c = c_begin; c < c_end; ++c) {
+        const long long r0 = (long long)c * 128;
+        const int n_rows = (int)(rows.R - r0 < 128 ? rows.R - r0 : 128);
+        if (tid < 128) drow[tid] = tid < n_rows ? data_row(rows, r0 + tid) : 0;
+        __syncthreads();  // (also: the previous chunk's images have been read, see the wait below)
+        if (col < img_rows) {
+#pragma unroll 1
+            for (int kg0 = 8 * half; kg0 < 8 * half + 8; kg0 += 4) {
+                float v[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int rr = 8 * kg0 + e;  // row within the chunk
+                    float x = 0.f;
+                    if (col < valid && rr < n_rows) {
+                        if (!is_ctx) x = src[(size_t)(r0 + rr) * ld + col];
+                        else x = col == kCond ? __ldg(rows.x + 2 * drow[rr] + 1) : __ldg(rows.cond + drow[rr] * rows.ld_cond + col);
+                    }
+                    v[e] = x;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) split_bf16x2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], hi[j], lo[j]);
+                    if (is_a)
+                        bias_acc += ((v[8 * g] + v[8 * g + 1]) + (v[8 * g + 2] + v[8 * g + 3])) +
+                                    ((v[8 * g + 4] + v[8 * g + 5]) + (v[8 * g + 6] + v[8 * g + 7]));
+                    const uint32_t off = (uint32_t)(kg0 + g) * (uint32_t)img_rows * 16u + (uint32_t)col * 16u;
+                    *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+        if (warp == 0) {
+            if (elect_one_sync()) {
+                const uint32_t idesc = umma_idesc_bf16_f32(128, n_pad);
+                const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 2 * kWgImg);
+                const uint32_t lbo_b = (uint32_t)n_pad * 16u;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t pa = a0 + (pass == 2 ? kWgImg : 0u), pb = b0 + (pass == 1 ? kWgImg : 0u);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_bf16(tmem, umma_desc_kmajor(pa + ks * 2 * 128 * 16, 128 * 16, 128),
+                                  umma_desc_kmajor(pb + ks * 2 * lbo_b, lbo_b, 128), idesc,
+                                  (c > c_begin) || (pass | ks) != 0);
+                }
+                umma_commit(bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar, phase);  // the images may be rebuilt once the tensor core has read them
+        phase ^= 1;
+        tc_fence_after_sync();
+    }
+    // the two halves of a dY column add up their bias sums (fixed order)
+    float *bias_s = reinterpret_cast<float *>(smem);  // the images are dead
+    __syncthreads();
+    if (is_a && half == 1) bias_s[col] = bias_acc;
+    __syncthreads();
+    if (is_a && half == 0) bias_acc += bias_s[col];
+    // accumulators -> this split's slice: lane m of tensor memory = row m of dW
+    float *Pout = P + (size_t)blockIdx.y * total;
+    if (tid < 128) {
+        const int m = tid;
+        for (int n0 = 0; n0 < n_pad; n0 += 16) {
+            uint32_t v[16];
+            if (c_end > c_begin) {
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
+                tmem_wait_ld();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0u;
+            }
+            if (m < J.M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + j < J.N) Pout[J.w_off + (size_t)m * J.N + n0 + j] = __uint_as_float(v[j]);
+            }
+        }
+        if (m < J.M) Pout[J.b_off + m] = bias_acc;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
 // ---- 4. fixed-order reductions ---------------------------------------------------------------
@@ -556,8 +652,30 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
     if (want_grad) {
         DDM_CUDA_TRY(cudaFuncSetAttribute(train_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SimtSmem)));
-        train_backward_kernel<<<dim3(d.groups, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, rows, d.Rp,
-                                                                                         d.tiles, B);
+        train_backward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, d.Rp, B);
+        DDM_CUDA_TRY(cudaGetLastError());
+        // weight-gradient GEMMs: (dY, X) of every layer
+        WJobs jobs;
+        int nj = 0;
+        const size_t hs = (size_t)d.Rp * kHidden;  // one [Rp][128] activation block
+        auto H = [&](int net, int slot) { return B.H + ((size_t)net * 3 + slot) * hs; };
+        auto DH = [&](int net, int slot) { return B.DH + ((size_t)net * 3 + slot) * hs; };
+        auto add = [&](const float *A, int lda, int M, const float *Bm, int ldb, int N, size_t w_off, size_t b_off) {
+            jobs.j[nj++] = WJob{A, Bm, lda, ldb, M, N, (unsigned)w_off, (unsigned)b_off};
+        };
+        add(B.LG, kMaxChoices, n_choices, H(0, 2), kHidden, kHidden, L.cat_Wo, L.cat_bo);
+        add(DH(0, 2), kHidden, kHidden, H(0, 1), kHidden, kHidden, L.cat_W2, L.cat_b2);
+        add(DH(0, 1), kHidden, kHidden, H(0, 0), kHidden, kHidden, L.cat_W1, L.cat_b1);
+        add(DH(0, 0), kHidden, kHidden, nullptr, 0, kCond, L.cat_W0, L.cat_b0);
+        for (int k = 0; k < kTransforms; ++k) {
+            const int net = 1 + k;
+            add(B.Q + (size_t)k * kQRows * d.Rp, kQRows, kSplineOut, H(net, 1), kHidden, kHidden, L.fl_W3[k], L.fl_b3[k]);
+            add(DH(net, 1), kHidden, kHidden, H(net, 0), kHidden, kHidden, L.fl_W2[k], L.fl_b2[k]);
+            add(DH(net, 0), kHidden, kHidden, nullptr, 0, kCtx, L.fl_W1[k], L.fl_b1[k]);
+        }
+        DDM_CUDA_TRY(cudaFuncSetAttribute(train_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
+        train_wgrad_tc_kernel<<<dim3(nj, d.groups), kWgThreads, kWgSmem, st>>>(jobs, rows, (int)((R + 127) / 128), L.total,
+                                                                             B.P);
         DDM_CUDA_TRY(cudaGetLastError());
         train_reduce_kernel<<<d.reduce_blocks, kReduceThreads, 0, st>>>(B.P, d.groups, L.total, L.mu_y, grad_dev, B.SS);
         DDM_CUDA_TRY(cudaGetLastError());
