@@ -279,16 +279,20 @@ int mnle_loglik_sum_batched_tc_f32(void *handle, const float *theta_dev, int64_t
  *   stats_dev[0] = -mean_r log p(x_r | cond_r),  stats_dev[1] = |grad|^2
  *   grad_dev[i]  = d stats[0] / d params[i]   (NULL: loss only, e.g. the validation pass)
  * All reductions run in a fixed order: results are bit-reproducible.  workspace_dev >=
- * mnle_train_workspace_floats(K, R) floats.
+ * mnle_train_workspace_floats(K, R) floats, 16-byte aligned.  The forward pass runs on the tensor cores
+ * (tcgen05, bf16 hi/lo operands ~ 17 bits: activations within ~1e-5 of fp32, so a ReLU unit that close to
+ * its kink may be masked differently) and so do the weight-gradient GEMMs; flags = DDM_TRAIN_FP32_FORWARD
+ * runs the forward on the fp32 CUDA cores (accuracy anchor, ~0.1 ms slower per 4096 rows).
  *
  * mnle_train_adam_f32: torch.optim.Adam update (no weight decay) for step = 1, 2, ... after
  * scaling the gradient like torch.nn.utils.clip_grad_norm_(max_grad_norm) using stats_dev[1]
  * (max_grad_norm <= 0: no clipping).
  */
 size_t mnle_train_workspace_floats(int n_choices, int64_t R);
+#define DDM_TRAIN_FP32_FORWARD 1 /* flags: forward pass on the fp32 CUDA cores instead of the tensor cores */
 int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, const float *x_dev, const float *cond_dev,
                             int64_t ld_cond, const int64_t *row_index_dev, int64_t R, float *stats_dev,
-                            float *grad_dev, float *workspace_dev, void *stream);
+                            float *grad_dev, float *workspace_dev, int flags, void *stream);
 int mnle_train_adam_f32(float *params_dev, const float *grad_dev, float *m_dev, float *v_dev, int n_choices,
                         const float *stats_dev, float lr, float beta1, float beta2, float eps, int64_t step,
                         float max_grad_norm, void *stream);

@@ -80,7 +80,8 @@ struct TcStage {
     uint16_t n;           // UMMA N (multiple of 16)
     uint8_t kind;         // TcStageKind
     uint8_t epi;          // TcEpilogue
-    uint16_t net, pad;    // 0 = categorical net, 1 + k = spline conditioner k
+    uint16_t net, pad;    // net: 0 = categorical net, 1 + k = spline conditioner k; pad: 1 + activation slot the
+                          // training forward keeps this stage's output in (0: not kept)
 };
 struct TcPlan {
     TcStage st[kTcStages];
@@ -98,6 +99,19 @@ struct Handle {
     float mu_y, sigma_y;
 };
 int build_tc_pack(Handle *H, const float *packed_host);  // mnle_tc.cu
+
+// Training forward on the tensor cores (mnle_tc.cu): the rows-mode kernel over the minibatch with the
+// operand pack rebuilt on the device from the current parameters, keeping what the backward pass needs.
+struct TcTrainDump {
+    float *H;      // [kNets][3][Rp][128] hidden activations
+    float *Q;      // [kTransforms][Rp][72] raw spline parameters
+    float *LG;     // [Rp][kMaxChoices] choice logits
+    long long Rp;  // rows allocated (a multiple of 64, >= R)
+};
+size_t tc_train_pack_bytes(int n_choices);
+int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, const float *x_dev, const float *cond_dev,
+                     long long ld_cond, const long long *row_index_dev, long long R, const TcTrainDump &dump,
+                     float *lp_dev, cudaStream_t st);
 constexpr uint32_t kMagic = 0x4D4E4C45u;  // "MNLE"
 
 __device__ __forceinline__ float softplus_f(float x)

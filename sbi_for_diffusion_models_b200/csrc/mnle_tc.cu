@@ -360,8 +360,10 @@ constexpr uint32_t kTmemD = 0, kTmemAHi = 128, kTmemALo = 192, kTmemTile = 256; 
 // ncols accumulator columns + bias -> activation -> packed bf16 hi / lo columns of the A operand.
 // The CUDA-core side of this kernel is bound by the half-rate ALU pipe (min/max, selects,
 // conversions, logic), so the arithmetic is phrased for the FMA pipe wherever possible.
+// `keep` (training forward): the activations of this row also go to global memory (row-major, 128 per row).
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int ncols, const float *bias)
+__device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int ncols, const float *bias,
+                                                float *keep = nullptr)
 {
 #pragma unroll 1
     for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
@@ -382,6 +384,10 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
             }
             split_relu_bf16x2(f[0], f[1], hi[2 * g], lo[2 * g]);
             split_relu_bf16x2(f[2], f[3], hi[2 * g + 1], lo[2 * g + 1]);
+            if (keep != nullptr)  // (the ReLU is fused into the conversions above)
+                *reinterpret_cast<float4 *>(keep + c0 + 4 * g) =
+                    EPI == kEpiRelu ? make_float4(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f), fmaxf(f[2], 0.f), fmaxf(f[3], 0.f))
+                                    : make_float4(f[0], f[1], f[2], f[3]);
         }
         tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
         tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
@@ -508,15 +514,20 @@ static void tc_grid(long long n_tiles, int sms, int *n_pairs, long long *grid)
 // ld_theta), x is (R, 2), C = R; the 86-wide context of each tile sits in shared memory as bf16 hi / lo
 // A images and every net's first layer is a K = 96 stage with both operands from shared memory (the
 // other stages take A from tensor memory as in potential mode); out[row] = log-prob.
-template <bool ROWS>
+// KEEP (rows mode only, the training forward): minibatch row c reads dataset row row_index[c] (null:
+// identity), and the hidden activations, raw spline parameters and choice logits of every row below
+// keep.Rp are written out for the backward pass (TcTrainDump).
+template <bool ROWS, bool KEEP = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
     mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
                    const float *__restrict__ theta, long long ld_theta, const float *__restrict__ x,
                    const float *__restrict__ hoist, int D, int T, int C, int n_pairs, float mu_y, float sigma_y,
                    int n_choices,
                    float *__restrict__ partial, unsigned int *__restrict__ counters, float *__restrict__ out,
-                   long long *__restrict__ trace)
+                   long long *__restrict__ trace, const long long *__restrict__ row_index = nullptr,
+                   TcTrainDump keep = TcTrainDump{nullptr, nullptr, nullptr, 0})
 {
+    static_assert(ROWS || !KEEP, "only the rows-mode kernel keeps activations");
     extern __shared__ __align__(1024) unsigned char smem[];
     using SM = TcSmem<ROWS>;
     constexpr int kTcSlots = SM::kSlots;
@@ -530,6 +541,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
+    // The training forward (KEEP) does not chain the splines (the per-row kernel does), so the eleven nets
+    // are independent: blockIdx.y picks one net and the CTA runs only that net's 3 or 4 stages -- 11 x
+    // more CTAs for a minibatch that is only a few dozen row tiles.  Barrier phases count local stages.
+    const int s_off = KEEP ? (blockIdx.y == 0 ? 0 : 4 + 3 * ((int)blockIdx.y - 1)) : 0;
+    const int n_st = KEEP ? (blockIdx.y == 0 ? 4 : 3) : kTcStages;
     // CTAs [0, n_pairs) take two tiles each, the rest one tile each (see tc_grid())
     const int bx = blockIdx.x;
     const int tile0 = bx >= n_pairs ? 2 * n_pairs + (bx - n_pairs) : bx * kTcTiles;
@@ -563,7 +579,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
         const int t_of[2] = {tile0 / CB, (tile0 + 1) / CB};
         auto load = [&](int s) {
-            const TcStage &st = plan.st[s];
+            const TcStage &st = plan.st[s_off + s];
             unsigned char *slot = smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes;
             uint64_t *bar = &wfull[s % kTcSlots];
             if (elect_one_sync()) {
@@ -581,8 +597,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // the ring is kTcSlots deep: stage s + kTcSlots - 1 is fetched while stage s runs
         for (int g = iw; g < kTcSlots - 1; g += kTcIssuers) load(g);
 #pragma unroll 1
-        for (int s = iw; s < kTcStages; s += kTcIssuers) {
-            const TcStage &st = plan.st[s];
+        for (int s = iw; s < n_st; s += kTcIssuers) {
+            const TcStage &st = plan.st[s_off + s];
             const uint32_t slot = smem_u32(smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes);
             const uint32_t n = st.n, idesc = umma_idesc_bf16_f32(kTcM, (int)n);
 #pragma unroll 1
@@ -638,7 +654,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 __syncwarp();
                 // every tile is past stage s-1, so its slot can take the next stage to fetch (issued after
                 // the MMAs: the copy has a whole stage of slack, the MMA issue is on the critical path)
-                if (X == n_active - 1 && s + kTcSlots - 1 < kTcStages) load(s + kTcSlots - 1);
+                if (X == n_active - 1 && s + kTcSlots - 1 < n_st) load(s + kTcSlots - 1);
                 if (trace && blockIdx.x == 0 && lane == 0) trace[(s * 2 + X) * 8 + 6] = clock64();
             }
         }
@@ -654,8 +670,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // context row [cond (85), choice, 0...] -> bf16 hi / lo A images of this tile (K-major, like the
             // weights); this thread: k in [48 hf, 48 hf + 48)
             unsigned char *img_hi = smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes, *img_lo = img_hi + kCtxImgBytes;
-            const float *crow = theta + c_glob * ld_theta;
-            const float ch = live ? __ldg(x + 2 * c_glob + 1) : 0.f;
+            const long long drow = (KEEP && row_index != nullptr && live) ? row_index[c_glob] : c_glob;
+            const float *crow = theta + drow * ld_theta;
+            const float ch = live ? __ldg(x + 2 * drow + 1) : 0.f;
 #pragma unroll 1
             for (int k0 = 48 * hf; k0 < 48 * hf + 48; k0 += 8) {
                 uint32_t hi[4], lo[4];
@@ -696,15 +713,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         fence_proxy_async_smem();
         mbar_arrive(&aready[X]);
 
-        const long long xi = ROWS ? (live ? c_glob : 0) : t;
+        const long long xi = ROWS ? (live ? ((KEEP && row_index != nullptr) ? row_index[c_glob] : c_glob) : 0) : t;
+        const bool kept = KEEP && c_glob < keep.Rp;  // padding rows up to Rp get defined values too
         const float rt = __ldg(x + 2 * xi);
         const int choice = (int)__ldg(x + 2 * xi + 1);
         const float y = logf(rt);
-        float u = (y - mu_y) / sigma_y, logdet = -logf(sigma_y), lp = 0.f;
+        // training forward: `hoist` points at (mu_y, sigma_y) in the parameter buffer (no host round trip)
+        const float mu = KEEP ? __ldg(hoist) : mu_y, sigma = KEEP ? __ldg(hoist + 1) : sigma_y;
+        float u = (y - mu) / sigma, logdet = -logf(sigma), lp = 0.f;
 
 #pragma unroll 1
-        for (int s = 0; s < kTcStages; ++s) {
-            const TcStage &st = plan.st[s];
+        for (int s = 0; s < n_st; ++s) {
+            const TcStage &st = plan.st[s_off + s];
             if (st.epi >= kEpiSpline && hf != 0) {  // row-wise epilogues are done by the hf = 0 thread of the row
                 mbar_wait(&dfull[X], s & 1);        // (never arrive twice within one phase of aready)
                 mbar_arrive(&aready[X]);
@@ -731,12 +751,41 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (tracer) trace[(s * 2 + X) * 8 + 3] = clock64();
                 continue;
             }
+            float *keep_h = nullptr;
+            if (KEEP && kept && st.pad != 0)
+                keep_h = keep.H + (((size_t)st.net * 3 + (st.pad - 1)) * (size_t)keep.Rp + (size_t)c_glob) * kHidden;
             if (st.epi == kEpiRelu) {
-                tc_epilogue_act<kEpiRelu>(trow, 64 * hf, 64, bias);
+                tc_epilogue_act<kEpiRelu>(trow, 64 * hf, 64, bias, keep_h);
             } else if (st.epi == kEpiSigmoid) {
-                tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, 64, bias);
+                tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, 64, bias, keep_h);
             } else if (st.epi == kEpiSpline) {
-                tc_epilogue_spline(trow, bias, u, logdet, &aready[X]);
+                if (KEEP) {  // the splines are evaluated by the per-row kernel: only keep the raw parameters
+                    float *dst = keep.Q + ((size_t)(st.net - 1) * (size_t)keep.Rp + (size_t)(kept ? c_glob : 0)) * 72;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < kSplineN; c0 += 16) {  // 71 parameters in five 16-column blocks
+                        uint32_t v[16];
+                        tmem_ld16(trow + kTmemD + (uint32_t)c0, v);
+                        tmem_wait_ld();
+                        if (kept) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                if (c0 + j + 3 < kSplineOut) {
+                                    *reinterpret_cast<float4 *>(dst + c0 + j) = make_float4(
+                                        __uint_as_float(v[j]) + bias[c0 + j], __uint_as_float(v[j + 1]) + bias[c0 + j + 1],
+                                        __uint_as_float(v[j + 2]) + bias[c0 + j + 2], __uint_as_float(v[j + 3]) + bias[c0 + j + 3]);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (c0 + j + e < kSplineOut) dst[c0 + j + e] = __uint_as_float(v[j + e]) + bias[c0 + j + e];
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before_sync();
+                    mbar_arrive(&aready[X]);
+                } else {
+                    tc_epilogue_spline(trow, bias, u, logdet, &aready[X]);
+                }
                 if (tracer) trace[(s * 2 + X) * 8 + 3] = clock64();
                 continue;
             } else {
@@ -746,6 +795,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 float lg[kMaxChoices];
 #pragma unroll
                 for (int j = 0; j < kMaxChoices; ++j) lg[j] = __uint_as_float(v[j]) + bias[j];
+                if (KEEP && kept) {
+#pragma unroll
+                    for (int j = 0; j < kMaxChoices; ++j)
+                        if (j < n_choices) keep.LG[(size_t)c_glob * kMaxChoices + j] = lg[j];
+                }
                 float m = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < kMaxChoices; ++j)
@@ -766,7 +820,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (tracer) trace[(s * 2 + X) * 8 + 3] = clock64();
         }
         if (ROWS) {
-            if (hf == 0 && live) out[c_glob] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+            if (!KEEP && hf == 0 && live) out[c_glob] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
         } else if (hf == 0) {
             // ---- sum over trials, fixed order: the tile that arrives last at its chain block adds
             // the T partial rows (every run gives the same bits whichever tile that is)
@@ -789,6 +843,108 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kTcEpiWarps) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------ training forward (row f4) ---
+// The parameters change every optimisation step, so the rows-mode operand pack (bf16 hi / lo images in
+// the UMMA shared-memory layout + fp32 biases, same format as build_tc_pack's) is rebuilt on the device.
+struct PackJob {
+    uint32_t w_off, b_off;      // weight / bias position in the packed parameters (floats)
+    uint32_t dst, img_bytes;    // blob position in the pack, bytes of one image (hi; lo follows)
+    uint16_t n_valid, k_valid;  // W is [n_valid][k_valid] row-major
+    uint16_t n_img, pad;        // rows of the image (UMMA N)
+};
+struct PackJobs {
+    PackJob j[kTcStages];
+};
+
+__global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ params, const __grid_constant__ PackJobs jobs,
+                                                      unsigned char *__restrict__ pack)
+{
+    const PackJob &J = jobs.j[blockIdx.x];
+    const int total = (int)J.n_valid * (int)J.k_valid;
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
+        const int n = idx / J.k_valid, k = idx - n * J.k_valid;
+        uint16_t hi, lo;
+        split_bf16(params[J.w_off + idx], hi, lo);
+        const uint32_t off = J.dst + tile_offset(J.n_img, n, k);
+        *reinterpret_cast<uint16_t *>(pack + off) = hi;
+        *reinterpret_cast<uint16_t *>(pack + off + J.img_bytes) = lo;
+    }
+    if (blockIdx.y == 0)
+        for (int n = threadIdx.x; n < J.n_valid; n += blockDim.x)
+            reinterpret_cast<float *>(pack + J.dst + 2 * J.img_bytes)[n] = params[J.b_off + n];
+}
+
+// stage plan of the rows-mode kernel over a pack that holds exactly its stages, in order
+static size_t train_plan(const Layout &L, TcPlan *plan, PackJobs *jobs)
+{
+    size_t bytes = 0;
+    int s = 0;
+    auto stage = [&](size_t W, size_t b, int n_valid, int k_valid, int n_img, int k_img, int kind, int epi, int net, int slot) {
+        const uint32_t img = (uint32_t)n_img * (uint32_t)k_img * 2u;
+        if (plan) {
+            TcStage &st = plan->st[s];
+            st.off = (uint32_t)bytes;
+            st.bytes = 2u * img + (uint32_t)n_img * 4u;
+            st.bias_off = 2u * img;
+            st.n = (uint16_t)n_img;
+            st.kind = (uint8_t)kind;
+            st.epi = (uint8_t)epi;
+            st.net = (uint16_t)net;
+            st.pad = (uint16_t)slot;
+        }
+        if (jobs)
+            jobs->j[s] = PackJob{(uint32_t)W, (uint32_t)b, (uint32_t)bytes, img, (uint16_t)n_valid, (uint16_t)k_valid,
+                                 (uint16_t)n_img, 0};
+        bytes += 2u * img + (uint32_t)n_img * 4u;
+        ++s;
+    };
+    stage(L.cat_W0, L.cat_b0, kHidden, kCond, kHidden, kInputK, kStageInput, kEpiSigmoid, 0, 1);
+    stage(L.cat_W1, L.cat_b1, kHidden, kHidden, kHidden, kHidden, kStageK128, kEpiSigmoid, 0, 2);
+    stage(L.cat_W2, L.cat_b2, kHidden, kHidden, kHidden, kHidden, kStageK128, kEpiSigmoid, 0, 3);
+    stage(L.cat_Wo, L.cat_bo, L.n_choices, kHidden, 16, kHidden, kStageK128, kEpiCategorical, 0, 0);
+    for (int k = 0; k < kTransforms; ++k) {
+        stage(L.fl_W1[k], L.fl_b1[k], kHidden, kCtx, kHidden, kInputK, kStageInput, kEpiRelu, 1 + k, 1);
+        stage(L.fl_W2[k], L.fl_b2[k], kHidden, kHidden, kHidden, kHidden, kStageK128, kEpiRelu, 1 + k, 2);
+        stage(L.fl_W3[k], L.fl_b3[k], kSplineOut, kHidden, kSplineN, kHidden, kStageK128, kEpiSpline, 1 + k, 0);
+    }
+    return bytes;
+}
+
+size_t tc_train_pack_bytes(int n_choices)
+{
+    return train_plan(make_layout(n_choices), nullptr, nullptr);
+}
+
+int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, const float *x_dev, const float *cond_dev,
+                     long long ld_cond, const long long *row_index_dev, long long R, const TcTrainDump &dump,
+                     float *lp_dev, cudaStream_t st)
+{
+    TcPlan plan;
+    PackJobs jobs;
+    const size_t bytes = train_plan(L, &plan, &jobs);
+    DDM_REQUIRE((reinterpret_cast<uintptr_t>(pack_dev) & 15u) == 0, "tc_train_forward: pack must be 16-byte aligned");
+    // padding rows / columns of the images stay zero; everything else is rewritten from the parameters
+    DDM_CUDA_TRY(cudaMemsetAsync(pack_dev, 0, bytes, st));
+    tc_pack_kernel<<<dim3(kTcStages, 8), 256, 0, st>>>(params_dev, jobs, static_cast<unsigned char *>(pack_dev));
+    DDM_CUDA_TRY(cudaGetLastError());
+    int dev = 0, sms = 0, n_pairs = 0;
+    long long grid = 0;
+    DDM_CUDA_TRY(cudaGetDevice(&dev));
+    DDM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long n_tiles = (R + kTcM - 1) / kTcM;
+    n_pairs = (int)(n_tiles / 2);
+    grid = n_pairs + (n_tiles & 1);
+    (void)sms;
+    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)TcSmem<true>::kBytes));
+    // (mu_y, sigma_y) sit at the tail of the parameter buffer: the kernel reads them through `hoist`
+    mnle_tc_kernel<true, true><<<dim3((unsigned)grid, kNets), kTcThreads, TcSmem<true>::kBytes, st>>>(
+        static_cast<const unsigned char *>(pack_dev), plan, cond_dev, ld_cond, x_dev, params_dev + L.mu_y, 1, 1, (int)R,
+        n_pairs, 0.f, 1.f, L.n_choices, nullptr, nullptr, lp_dev, nullptr, row_index_dev, dump);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
 }
 
 }  // namespace mnle

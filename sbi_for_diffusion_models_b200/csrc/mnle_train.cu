@@ -5,10 +5,10 @@
 // autograd through the categorical net and the ten spline conditioners.  Here one call gives the
 // loss and its gradient with respect to every packed parameter (layout: mnle_common.cuh):
 //
-//   1. train_forward_kernel    one CTA per (64-row tile, net): the eleven nets depend only on the
-//                              context, so they run side by side (activations in shared memory);
-//                              keeps the 71 raw spline parameters per (row, transform), the choice
-//                              logits and the hidden activations.
+//   1. tc_train_forward        (mnle_tc.cu) the tcgen05 rows-mode kernel over the minibatch, its operand
+//                              pack rebuilt on the device from the current parameters; keeps the 71
+//                              raw spline parameters per (row, transform), the choice logits and the
+//                              hidden activations.
 //   2. train_rows_kernel       one thread per row: choice log-probability, the ten splines forward
 //                              (log p of the row), then backwards (reverse mode written out by
 //                              hand), turning the stored spline parameters and logits into
@@ -33,6 +33,7 @@ constexpr int kMaxGroups = 4;      // partial-gradient slices = row splits of th
 constexpr int kReduceThreads = 256;
 
 struct TrainBufs {
+    float *pack; // tensor-core operand pack of the current parameters (rebuilt every call)
     float *Q;    // [kTransforms][Rp][kQRows]  spline parameters -> their gradients
     float *LG;   // [Rp][kMaxChoices]          choice logits -> their gradients
     float *LP;   // [Rp]                       log p per row
@@ -59,16 +60,22 @@ static TrainDims train_dims(const Layout &L, long long R)
     return d;
 }
 
+static size_t pack_floats(const Layout &L)
+{
+    return (tc_train_pack_bytes(L.n_choices) + 63) / 64 * 16;  // whole 64-byte blocks, in floats
+}
+
 static size_t train_floats(const Layout &L, const TrainDims &d)
 {
-    return (size_t)d.Rp * (kTransforms * kQRows + kMaxChoices + 1 + 2 * kNets * 3 * kHidden) + (size_t)d.groups * L.total +
+    return pack_floats(L) + (size_t)d.Rp * (kTransforms * kQRows + kMaxChoices + 1 + 2 * kNets * 3 * kHidden) + (size_t)d.groups * L.total +
            (size_t)d.reduce_blocks;
 }
 
 static TrainBufs carve(float *ws, const Layout &L, const TrainDims &d)
 {
     TrainBufs b;
-    b.Q = ws;
+    b.pack = ws;
+    b.Q = ws + pack_floats(L);
     b.LG = b.Q + (size_t)kTransforms * kQRows * d.Rp;
     b.LP = b.LG + (size_t)kMaxChoices * d.Rp;
     b.H = b.LP + d.Rp;
@@ -139,6 +146,7 @@ __device__ __forceinline__ void load_rows(const float *src, int ldg, long long r
     }
 }
 
+// fp32 CUDA-core forward (DDM_TRAIN_FP32_FORWARD: the accuracy anchor of the tensor-core forward).
 // grid (row tiles, nets): the eleven nets depend only on the context, so they run side by side
 __global__ void __launch_bounds__(kThreads) train_forward_kernel(const float *__restrict__ params, Layout L,
                                                                  TrainRows rows, long long Rp, TrainBufs B, int keep)
@@ -625,7 +633,7 @@ DDM_API size_t mnle_train_workspace_floats(int n_choices, int64_t R)
 
 DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, const float *x_dev, const float *cond_dev,
                                     int64_t ld_cond, const int64_t *row_index_dev, int64_t R, float *stats_dev,
-                                    float *grad_dev, float *workspace_dev, void *stream)
+                                    float *grad_dev, float *workspace_dev, int flags, void *stream)
 {
     DDM_REQUIRE(n_choices >= 1 && n_choices <= kMaxChoices, "mnle_train_nll_grad_f32: n_choices=%d outside [1,%d]",
                 n_choices, kMaxChoices);
@@ -640,11 +648,18 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
     TrainRows rows{x_dev, cond_dev, reinterpret_cast<const long long *>(row_index_dev), (long long)ld_cond, (long long)R};
 
     static_assert(sizeof(SimtSmem) < 113 * 1024, "two CTAs per SM");
-    DDM_CUDA_TRY(cudaFuncSetAttribute(train_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(SimtSmem)));
     const int want_grad = grad_dev != nullptr;
-    train_forward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, rows, d.Rp, B, want_grad);
-    DDM_CUDA_TRY(cudaGetLastError());
+    if (flags & DDM_TRAIN_FP32_FORWARD) {
+        DDM_CUDA_TRY(cudaFuncSetAttribute(train_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SimtSmem)));
+        train_forward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, rows, d.Rp, B, 1);
+        DDM_CUDA_TRY(cudaGetLastError());
+    } else {  // forward on the tensor cores (mnle_tc.cu), keeping logits, spline parameters and activations
+        const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp};
+        const int rc = tc_train_forward(params_dev, L, B.pack, x_dev, cond_dev, (long long)ld_cond,
+                                        reinterpret_cast<const long long *>(row_index_dev), (long long)R, keep, B.LP, st);
+        if (rc != DDM_OK) return rc;
+    }
     train_rows_kernel<<<(unsigned)((d.Rp + kRowWarps - 1) / kRowWarps), kRowWarps * 32, 0, st>>>(
         params_dev, L, rows, d.Rp, -1.0f / (float)R, want_grad, B);
     DDM_CUDA_TRY(cudaGetLastError());

@@ -98,9 +98,12 @@ class MNLETrainer:
 
     # ---- kernels --------------------------------------------------------------------------
     def nll(self, x: torch.Tensor, cond_std: torch.Tensor, idx: Optional[torch.Tensor] = None, *,
-            grad: bool = True) -> torch.Tensor:
+            grad: bool = True, forward: str = "tc") -> torch.Tensor:
         """stats (2,) on the device: [-mean log p over the minibatch, |grad|^2]; fills ``self.grad``
-        when ``grad``.  ``x`` (N,2), ``cond_std`` (N,85) standardised, ``idx`` int64 rows or None."""
+        when ``grad``.  ``x`` (N,2), ``cond_std`` (N,85) standardised, ``idx`` int64 rows or None.
+        ``forward``: "tc" tensor cores (tcgen05), "fp32" CUDA cores (accuracy anchor)."""
+        if forward not in ("tc", "fp32"):
+            raise ValueError(f"unknown forward {forward!r}")
         if x.device != self.dev or cond_std.device != self.dev or x.dtype != torch.float32 or cond_std.dtype != torch.float32:
             raise ValueError("training data must be float32 tensors on the trainer's device")
         if x.ndim != 2 or x.shape[1] != 2 or not x.is_contiguous():
@@ -121,7 +124,7 @@ class MNLETrainer:
                 self.params.data_ptr(), self.n_choices, x.data_ptr(), cond_std.data_ptr(),
                 cond_std.stride(0) if cond_std.shape[0] > 1 else COND_DIM, idx.data_ptr() if idx is not None else None, R,
                 self.stats.data_ptr(), self.grad.data_ptr() if grad else None, ws.data_ptr(),
-                torch.cuda.current_stream(self.dev).cuda_stream)
+                1 if forward == "fp32" else 0, torch.cuda.current_stream(self.dev).cuda_stream)
         _native.check(rc, "mnle_train_nll_grad_f32")
         return self.stats
 

@@ -1,8 +1,12 @@
 """MNLE training step through the C ABI against float64 autograd of the CPU
 specification (oracle/mnle_spec.py; parity unpinned against sbi itself, see that module).
 
-Tolerances: the kernels compute in fp32 (forward + hand-written reverse mode); each gradient tensor
-must agree with float64 autograd to 2e-3 of its own largest entry, the loss to 1e-5 relative."""
+Tolerances.  forward="fp32" (CUDA-core forward, fp32 reverse mode, bf16 hi/lo tensor-core weight
+gradients): each gradient tensor within 2e-3 of its own largest entry of float64 autograd, loss within
+1e-5 relative.  forward="tc" (default: tcgen05 forward, operands carry ~17 bits): activations sit
+within ~1e-5 of fp32, so ReLU units that close to their kink get the other mask -- about a hundred
+(row, unit) pairs in these batches, each moving single gradient entries by one row's contribution:
+1e-2 of the largest entry, loss within 1e-4 relative (5e-2 / 1e-3 on the sharpened stress net)."""
 import numpy as np
 import pytest
 import torch
@@ -52,9 +56,10 @@ def _spec_loss_and_grads(p, x, cond):
     return float(loss), {k: v.grad for k, v in p64.items() if v.grad is not None}
 
 
+@pytest.mark.parametrize("forward", ["fp32", "tc"])
 @pytest.mark.parametrize("seed,scale,R", [(1, 1.0, 300), (1, 2.0, 1000), (2, 1.0, 64 * 130 + 5)],
-                         ids=["ragged", "sharp", "shared-slices"])
-def test_loss_and_gradient_match_float64_autograd(seed, scale, R):
+                         ids=["ragged", "sharp", "many-chunks"])
+def test_loss_and_gradient_match_float64_autograd(seed, scale, R, forward):
     p = ms.init_params(seed, scale=scale)
     x, cond = _data(R, seed)
     if R < 2000:
@@ -62,8 +67,10 @@ def test_loss_and_gradient_match_float64_autograd(seed, scale, R):
     want_loss, want = _spec_loss_and_grads(p, x, cond)
     tr = _trainer(p)
     xd, cd = x.cuda(), tr.standardise(cond)
-    stats = tr.nll(xd, cd).cpu()
-    assert abs(float(stats[0]) - want_loss) <= 1e-5 * abs(want_loss) + 1e-6
+    stats = tr.nll(xd, cd, forward=forward).cpu()
+    loss_tol = {("fp32", 1.0): 1e-5, ("fp32", 2.0): 1e-5, ("tc", 1.0): 1e-4, ("tc", 2.0): 1e-3}[(forward, scale)]
+    grad_tol = {("fp32", 1.0): 2e-3, ("fp32", 2.0): 2e-2, ("tc", 1.0): 1e-2, ("tc", 2.0): 5e-2}[(forward, scale)]
+    assert abs(float(stats[0]) - want_loss) <= loss_tol * abs(want_loss) + 1e-6
     got = tr.named_grads()
     assert set(want) == set(got) - {"flow.mu_y", "flow.sigma_y"}
     for name, g64 in want.items():
@@ -71,17 +78,17 @@ def test_loss_and_gradient_match_float64_autograd(seed, scale, R):
         ref = float(g64.abs().max())
         # the sharpened net (weights x 2) is the numerics stress of the forward tests too: rows next to a
         # bin edge or a ReLU kink land on the other side in fp32
-        assert err <= (2e-3 if scale == 1.0 else 2e-2) * ref + 1e-9, (name, err, ref)
+        assert err <= grad_tol * ref + 1e-9, (name, err, ref)
     assert float(got["flow.mu_y"]) == 0.0 and float(got["flow.sigma_y"]) == 0.0   # buffers, not trained
     ss = sum(float((g.double() ** 2).sum()) for g in want.values())
-    assert abs(float(stats[1]) - ss) <= (1e-3 if scale == 1.0 else 1e-2) * ss
+    assert abs(float(stats[1]) - ss) <= (1e-3 if (scale == 1.0 and forward == "fp32") else 2e-2) * ss
     # bit-reproducible (fixed-order reductions, no atomics)
     g1 = tr.grad.clone()
-    tr.nll(xd, cd)
+    tr.nll(xd, cd, forward=forward)
     assert torch.equal(g1, tr.grad)
     # loss-only pass leaves the gradient alone and agrees on the loss
     tr.grad.zero_()
-    s2 = tr.nll(xd, cd, grad=False).cpu()
+    s2 = tr.nll(xd, cd, grad=False, forward=forward).cpu()
     assert float(s2[0]) == float(stats[0]) and float(s2[1]) == 0.0 and float(tr.grad.abs().max()) == 0.0
 
 
@@ -137,7 +144,7 @@ def test_training_trajectory_follows_the_spec_under_torch_autograd():
     opt = torch.optim.Adam([v for k, v in p64.items() if k not in frozen], lr=5e-4)
     for step in range(5):
         loss = -ms.log_prob(p64, x, cond).mean()
-        got = float(tr.nll(xd, cd)[0])
+        got = float(tr.nll(xd, cd, forward="fp32")[0])
         # (units crossing a ReLU kink between the two precisions make the trajectories drift apart slowly)
         assert abs(got - float(loss)) <= (2e-5 if step < 2 else 5e-4) * abs(float(loss)), (step, got, float(loss))
         opt.zero_grad()
