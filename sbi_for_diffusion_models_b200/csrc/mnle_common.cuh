@@ -107,11 +107,15 @@ struct TcTrainDump {
     float *Q;      // [kTransforms][Rp][72] raw spline parameters
     float *LG;     // [Rp][kMaxChoices] choice logits
     long long Rp;  // rows allocated (a multiple of 64, >= R)
+    float *DH;     // backward pass only: [kNets][3][Rp][128] d loss / d (hidden pre-activations), written
 };
 size_t tc_train_pack_bytes(int n_choices);
 int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, const float *x_dev, const float *cond_dev,
                      long long ld_cond, const long long *row_index_dev, long long R, const TcTrainDump &dump,
                      float *lp_dev, cudaStream_t st);
+// Backward-data pass on the tensor cores over the same pack (tc_train_forward must have run in this call):
+// d loss / d (spline parameters, logits) in dump.Q / dump.LG and the activations dump.H give dump.DH.
+int tc_train_backward(const Layout &L, const void *pack_dev, long long R, const TcTrainDump &dump, cudaStream_t st);
 constexpr uint32_t kMagic = 0x4D4E4C45u;  // "MNLE"
 
 __device__ __forceinline__ float softplus_f(float x)

@@ -395,6 +395,39 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
     tmem_wait_st();
 }
 
+// Backward-data epilogue: ncols accumulator columns (d loss / d activations) times the derivative of the
+// activation whose output h sits in global memory -> d loss / d pre-activations, written to global memory
+// and, when another stage follows, split into the bf16 hi / lo A operand of that stage.
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int ncols, const float *h_row, float *d_row,
+                                                 bool kept, bool feeds_next)
+{
+#pragma unroll 1
+    for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + kTmemD + (uint32_t)c0, v);
+        tmem_wait_ld();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float4 h = kept ? *reinterpret_cast<const float4 *>(h_row + c0 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float f[4] = {__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                          __uint_as_float(v[4 * g + 3])};
+            const float hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] = EPI == kEpiRelu ? (hh[j] > 0.f ? f[j] : 0.f) : f[j] * hh[j] * (1.0f - hh[j]);
+            if (kept) *reinterpret_cast<float4 *>(d_row + c0 + 4 * g) = make_float4(f[0], f[1], f[2], f[3]);
+            split_bf16x2(f[0], f[1], hi[2 * g], lo[2 * g]);
+            split_bf16x2(f[2], f[3], hi[2 * g + 1], lo[2 * g + 1]);
+        }
+        if (feeds_next) {
+            tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
+            tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
+        }
+    }
+    tmem_wait_st();
+}
+
 // softmax numerators of one 24-bin block held in registers: e[j] = exp((q[j] - max q) / sqrt(128));
 // returns 1 / sum e.
 __device__ __forceinline__ float rqs_softmax(const float (&q)[kBins], float (&e)[kBins])
@@ -517,7 +550,10 @@ static void tc_grid(long long n_tiles, int sms, int *n_pairs, long long *grid)
 // KEEP (rows mode only, the training forward): minibatch row c reads dataset row row_index[c] (null:
 // identity), and the hidden activations, raw spline parameters and choice logits of every row below
 // keep.Rp are written out for the backward pass (TcTrainDump).
-template <bool ROWS, bool KEEP = false>
+// BWD (rows layout, the training backward-data pass): the A image of a net's first stage holds the
+// gradient rows (d loss / d spline parameters or logits), the weight images are the transposed ones, and
+// every epilogue multiplies by the activation derivative (tc_epilogue_mask) and writes keep.DH.
+template <bool ROWS, bool KEEP = false, bool BWD = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
     mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
                    const float *__restrict__ theta, long long ld_theta, const float *__restrict__ x,
@@ -525,9 +561,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                    int n_choices,
                    float *__restrict__ partial, unsigned int *__restrict__ counters, float *__restrict__ out,
                    long long *__restrict__ trace, const long long *__restrict__ row_index = nullptr,
-                   TcTrainDump keep = TcTrainDump{nullptr, nullptr, nullptr, 0})
+                   TcTrainDump keep = TcTrainDump{})
 {
     static_assert(ROWS || !KEEP, "only the rows-mode kernel keeps activations");
+    static_assert(!BWD || (ROWS && !KEEP), "the backward pass uses the rows-mode layout");
     extern __shared__ __align__(1024) unsigned char smem[];
     using SM = TcSmem<ROWS>;
     constexpr int kTcSlots = SM::kSlots;
@@ -544,8 +581,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // The training forward (KEEP) does not chain the splines (the per-row kernel does), so the eleven nets
     // are independent: blockIdx.y picks one net and the CTA runs only that net's 3 or 4 stages -- 11 x
     // more CTAs for a minibatch that is only a few dozen row tiles.  Barrier phases count local stages.
-    const int s_off = KEEP ? (blockIdx.y == 0 ? 0 : 4 + 3 * ((int)blockIdx.y - 1)) : 0;
-    const int n_st = KEEP ? (blockIdx.y == 0 ? 4 : 3) : kTcStages;
+    const int s_off = KEEP ? (blockIdx.y == 0 ? 0 : 4 + 3 * ((int)blockIdx.y - 1))
+                           : (BWD ? (blockIdx.y == 0 ? 0 : 3 + 2 * ((int)blockIdx.y - 1)) : 0);
+    const int n_st = KEEP ? (blockIdx.y == 0 ? 4 : 3) : (BWD ? (blockIdx.y == 0 ? 3 : 2) : kTcStages);
     // CTAs [0, n_pairs) take two tiles each, the rest one tile each (see tc_grid())
     const int bx = blockIdx.x;
     const int tile0 = bx >= n_pairs ? 2 * n_pairs + (bx - n_pairs) : bx * kTcTiles;
@@ -618,14 +656,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t tm = tmem_u + (uint32_t)X * kTmemTile;
                 if (elect_one_sync()) {
                     if (st.kind == kStageInput) {
-                        const uint32_t w_img = kHidden * kInputK * 2u;
+                        // K of the operand images: the 96 context columns, or (BWD) what the plan says
+                        const int ksteps = BWD ? (int)(st.pad >> 8) : kInputK / 16;
+                        const uint32_t w_img = kHidden * (uint32_t)ksteps * 32u;
                         const uint32_t ctx = smem_u32(smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes);
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass) {
                             const uint32_t a = ctx + (pass == 2 ? kCtxImgBytes : 0u);
                             const uint32_t w = slot + (pass == 1 ? w_img : 0u);
-#pragma unroll
-                            for (int ks = 0; ks < kInputK / 16; ++ks)
+#pragma unroll 1
+                            for (int ks = 0; ks < ksteps; ++ks)
                                 umma_bf16(tm + kTmemD, umma_desc_kmajor(a + ks * 2 * kKGroupBytes, kKGroupBytes, 128),
                                           umma_desc_kmajor(w + ks * 2 * kKGroupBytes, kKGroupBytes, 128), idesc,
                                           (pass | ks) != 0);
@@ -666,7 +706,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const bool live = c < C;
         const long long c_glob = (long long)d * C + c;
         const uint32_t trow = tmem + (uint32_t)X * kTmemTile + ((uint32_t)(32 * q) << 16);
-        if (ROWS) {
+        if (BWD) {
+            // gradient row of this net's outputs -> bf16 hi / lo A images (K-major): 71 spline parameters in
+            // K = 80 (this thread: 40 of them), or the choice logits in K = 16 (8 each)
+            unsigned char *img_hi = smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes, *img_lo = img_hi + kCtxImgBytes;
+            const int net = blockIdx.y;
+            const bool have = c_glob < keep.Rp;
+            const float *grow = net == 0 ? keep.LG + (size_t)(have ? c_glob : 0) * kMaxChoices
+                                         : keep.Q + ((size_t)(net - 1) * (size_t)keep.Rp + (size_t)(have ? c_glob : 0)) * 72;
+            const int n_src = net == 0 ? n_choices : kSplineOut, per = net == 0 ? 8 : 40;
+#pragma unroll 1
+            for (int k0 = per * hf; k0 < per * hf + per; k0 += 8) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 + 2 * j;
+                    const float v0 = (have && k < n_src) ? grow[k] : 0.f, v1 = (have && k + 1 < n_src) ? grow[k + 1] : 0.f;
+                    split_bf16x2(v0, v1, hi[j], lo[j]);
+                }
+                const uint32_t off = (uint32_t)(k0 >> 3) * kKGroupBytes + (uint32_t)r * 16u;
+                *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        } else if (ROWS) {
             // context row [cond (85), choice, 0...] -> bf16 hi / lo A images of this tile (K-major, like the
             // weights); this thread: k in [48 hf, 48 hf + 48)
             unsigned char *img_hi = smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes, *img_lo = img_hi + kCtxImgBytes;
@@ -715,8 +777,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
         const long long xi = ROWS ? (live ? ((KEEP && row_index != nullptr) ? row_index[c_glob] : c_glob) : 0) : t;
         const bool kept = KEEP && c_glob < keep.Rp;  // padding rows up to Rp get defined values too
-        const float rt = __ldg(x + 2 * xi);
-        const int choice = (int)__ldg(x + 2 * xi + 1);
+        const float rt = BWD ? 1.0f : __ldg(x + 2 * xi);
+        const int choice = BWD ? 0 : (int)__ldg(x + 2 * xi + 1);
         const float y = logf(rt);
         // training forward: `hoist` points at (mu_y, sigma_y) in the parameter buffer (no host round trip)
         const float mu = KEEP ? __ldg(hoist) : mu_y, sigma = KEEP ? __ldg(hoist + 1) : sigma_y;
@@ -725,6 +787,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll 1
         for (int s = 0; s < n_st; ++s) {
             const TcStage &st = plan.st[s_off + s];
+            if (BWD) {
+                mbar_wait(&dfull[X], s & 1);
+                tc_fence_after_sync();
+                const bool have = c_glob < keep.Rp;
+                const size_t at = (((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * (size_t)keep.Rp + (size_t)(have ? c_glob : 0)) * kHidden;
+                if (st.epi == kEpiRelu) tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, have, s + 1 < n_st);
+                else tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, have, s + 1 < n_st);
+                tc_fence_before_sync();
+                mbar_arrive(&aready[X]);
+                continue;
+            }
             if (st.epi >= kEpiSpline && hf != 0) {  // row-wise epilogues are done by the hf = 0 thread of the row
                 mbar_wait(&dfull[X], s & 1);        // (never arrive twice within one phase of aready)
                 mbar_arrive(&aready[X]);
@@ -820,7 +893,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (tracer) trace[(s * 2 + X) * 8 + 3] = clock64();
         }
         if (ROWS) {
-            if (!KEEP && hf == 0 && live) out[c_glob] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+            if (!KEEP && !BWD && hf == 0 && live) out[c_glob] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
         } else if (hf == 0) {
             // ---- sum over trials, fixed order: the tile that arrives last at its chain block adds
             // the T partial rows (every run gives the same bits whichever tile that is)
@@ -852,10 +925,11 @@ struct PackJob {
     uint32_t w_off, b_off;      // weight / bias position in the packed parameters (floats)
     uint32_t dst, img_bytes;    // blob position in the pack, bytes of one image (hi; lo follows)
     uint16_t n_valid, k_valid;  // W is [n_valid][k_valid] row-major
-    uint16_t n_img, pad;        // rows of the image (UMMA N)
+    uint16_t n_img, transpose;  // rows of the image (UMMA N); transpose: image row = column of W, k = row of W
 };
+constexpr int kTrainStages = kTcStages + 3 + 2 * kTransforms;  // forward stages + backward-data stages
 struct PackJobs {
-    PackJob j[kTcStages];
+    PackJob j[kTrainStages];
 };
 
 __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ params, const __grid_constant__ PackJobs jobs,
@@ -867,20 +941,21 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ 
         const int n = idx / J.k_valid, k = idx - n * J.k_valid;
         uint16_t hi, lo;
         split_bf16(params[J.w_off + idx], hi, lo);
-        const uint32_t off = J.dst + tile_offset(J.n_img, n, k);
+        const uint32_t off = J.dst + (J.transpose ? tile_offset(J.n_img, k, n) : tile_offset(J.n_img, n, k));
         *reinterpret_cast<uint16_t *>(pack + off) = hi;
         *reinterpret_cast<uint16_t *>(pack + off + J.img_bytes) = lo;
     }
-    if (blockIdx.y == 0)
+    if (blockIdx.y == 0 && !J.transpose)  // (the backward-data stages have no bias)
         for (int n = threadIdx.x; n < J.n_valid; n += blockDim.x)
             reinterpret_cast<float *>(pack + J.dst + 2 * J.img_bytes)[n] = params[J.b_off + n];
 }
 
-// stage plan of the rows-mode kernel over a pack that holds exactly its stages, in order
-static size_t train_plan(const Layout &L, TcPlan *plan, PackJobs *jobs)
+// stage plans of the training forward and backward-data passes over one pack that holds exactly their
+// stages, in order (forward stages first)
+static size_t train_plan(const Layout &L, TcPlan *plan, TcPlan *bplan, PackJobs *jobs)
 {
     size_t bytes = 0;
-    int s = 0;
+    int s = 0, nj = 0;
     auto stage = [&](size_t W, size_t b, int n_valid, int k_valid, int n_img, int k_img, int kind, int epi, int net, int slot) {
         const uint32_t img = (uint32_t)n_img * (uint32_t)k_img * 2u;
         if (plan) {
@@ -895,10 +970,11 @@ static size_t train_plan(const Layout &L, TcPlan *plan, PackJobs *jobs)
             st.pad = (uint16_t)slot;
         }
         if (jobs)
-            jobs->j[s] = PackJob{(uint32_t)W, (uint32_t)b, (uint32_t)bytes, img, (uint16_t)n_valid, (uint16_t)k_valid,
-                                 (uint16_t)n_img, 0};
+            jobs->j[nj] = PackJob{(uint32_t)W, (uint32_t)b, (uint32_t)bytes, img, (uint16_t)n_valid, (uint16_t)k_valid,
+                                  (uint16_t)n_img, 0};
         bytes += 2u * img + (uint32_t)n_img * 4u;
         ++s;
+        ++nj;
     };
     stage(L.cat_W0, L.cat_b0, kHidden, kCond, kHidden, kInputK, kStageInput, kEpiSigmoid, 0, 1);
     stage(L.cat_W1, L.cat_b1, kHidden, kHidden, kHidden, kHidden, kStageK128, kEpiSigmoid, 0, 2);
@@ -909,12 +985,40 @@ static size_t train_plan(const Layout &L, TcPlan *plan, PackJobs *jobs)
         stage(L.fl_W2[k], L.fl_b2[k], kHidden, kHidden, kHidden, kHidden, kStageK128, kEpiRelu, 1 + k, 2);
         stage(L.fl_W3[k], L.fl_b3[k], kSplineOut, kHidden, kSplineN, kHidden, kStageK128, kEpiSpline, 1 + k, 0);
     }
+    // backward-data: out[row][in] = sum_out g[row][out] W[out][in]  ->  B image = W transposed ([in][out], K = out)
+    int bs = 0;
+    auto bstage = [&](size_t W, int n_out, int n_in, int k_img, int kind, int epi, int net, int mask_slot) {
+        const uint32_t img = (uint32_t)kHidden * (uint32_t)k_img * 2u;  // n_in = 128 rows everywhere
+        if (bplan) {
+            TcStage &st = bplan->st[bs];
+            st.off = (uint32_t)bytes;
+            st.bytes = 2u * img;
+            st.bias_off = 2u * img;
+            st.n = (uint16_t)kHidden;
+            st.kind = (uint8_t)kind;
+            st.epi = (uint8_t)epi;
+            st.net = (uint16_t)net;
+            st.pad = (uint16_t)((mask_slot + 1) | ((k_img / 16) << 8));
+        }
+        if (jobs)
+            jobs->j[nj] = PackJob{(uint32_t)W, 0u, (uint32_t)bytes, img, (uint16_t)n_out, (uint16_t)n_in, (uint16_t)kHidden, 1};
+        bytes += 2u * img;
+        ++bs;
+        ++nj;
+    };
+    bstage(L.cat_Wo, L.n_choices, kHidden, 16, kStageInput, kEpiSigmoid, 0, 2);
+    bstage(L.cat_W2, kHidden, kHidden, kHidden, kStageK128, kEpiSigmoid, 0, 1);
+    bstage(L.cat_W1, kHidden, kHidden, kHidden, kStageK128, kEpiSigmoid, 0, 0);
+    for (int k = 0; k < kTransforms; ++k) {
+        bstage(L.fl_W3[k], kSplineOut, kHidden, kSplineN, kStageInput, kEpiRelu, 1 + k, 1);
+        bstage(L.fl_W2[k], kHidden, kHidden, kHidden, kStageK128, kEpiRelu, 1 + k, 0);
+    }
     return bytes;
 }
 
 size_t tc_train_pack_bytes(int n_choices)
 {
-    return train_plan(make_layout(n_choices), nullptr, nullptr);
+    return train_plan(make_layout(n_choices), nullptr, nullptr, nullptr);
 }
 
 int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, const float *x_dev, const float *cond_dev,
@@ -923,11 +1027,11 @@ int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, c
 {
     TcPlan plan;
     PackJobs jobs;
-    const size_t bytes = train_plan(L, &plan, &jobs);
+    const size_t bytes = train_plan(L, &plan, nullptr, &jobs);
     DDM_REQUIRE((reinterpret_cast<uintptr_t>(pack_dev) & 15u) == 0, "tc_train_forward: pack must be 16-byte aligned");
     // padding rows / columns of the images stay zero; everything else is rewritten from the parameters
     DDM_CUDA_TRY(cudaMemsetAsync(pack_dev, 0, bytes, st));
-    tc_pack_kernel<<<dim3(kTcStages, 8), 256, 0, st>>>(params_dev, jobs, static_cast<unsigned char *>(pack_dev));
+    tc_pack_kernel<<<dim3(kTrainStages, 8), 256, 0, st>>>(params_dev, jobs, static_cast<unsigned char *>(pack_dev));
     DDM_CUDA_TRY(cudaGetLastError());
     int dev = 0, sms = 0, n_pairs = 0;
     long long grid = 0;
@@ -943,6 +1047,22 @@ int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, c
     mnle_tc_kernel<true, true><<<dim3((unsigned)grid, kNets), kTcThreads, TcSmem<true>::kBytes, st>>>(
         static_cast<const unsigned char *>(pack_dev), plan, cond_dev, ld_cond, x_dev, params_dev + L.mu_y, 1, 1, (int)R,
         n_pairs, 0.f, 1.f, L.n_choices, nullptr, nullptr, lp_dev, nullptr, row_index_dev, dump);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}
+
+int tc_train_backward(const Layout &L, const void *pack_dev, long long R, const TcTrainDump &dump, cudaStream_t st)
+{
+    TcPlan bplan;
+    train_plan(L, nullptr, &bplan, nullptr);
+    const long long n_tiles = (R + kTcM - 1) / kTcM;
+    const int n_pairs = (int)(n_tiles / 2);
+    const long long grid = n_pairs + (n_tiles & 1);
+    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)TcSmem<true>::kBytes));
+    mnle_tc_kernel<true, false, true><<<dim3((unsigned)grid, kNets), kTcThreads, TcSmem<true>::kBytes, st>>>(
+        static_cast<const unsigned char *>(pack_dev), bplan, nullptr, 0, nullptr, nullptr, 1, 1, (int)R, n_pairs, 0.f, 1.f,
+        L.n_choices, nullptr, nullptr, nullptr, nullptr, nullptr, dump);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }

@@ -655,7 +655,7 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
         train_forward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, rows, d.Rp, B, 1);
         DDM_CUDA_TRY(cudaGetLastError());
     } else {  // forward on the tensor cores (mnle_tc.cu), keeping logits, spline parameters and activations
-        const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp};
+        const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp, nullptr};
         const int rc = tc_train_forward(params_dev, L, B.pack, x_dev, cond_dev, (long long)ld_cond,
                                         reinterpret_cast<const long long *>(row_index_dev), (long long)R, keep, B.LP, st);
         if (rc != DDM_OK) return rc;
@@ -667,8 +667,14 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
     if (want_grad) {
         DDM_CUDA_TRY(cudaFuncSetAttribute(train_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SimtSmem)));
-        train_backward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, d.Rp, B);
-        DDM_CUDA_TRY(cudaGetLastError());
+        if (flags & DDM_TRAIN_FP32_FORWARD) {  // the fp32 anchor keeps the whole chain on the CUDA cores
+            train_backward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, d.Rp, B);
+            DDM_CUDA_TRY(cudaGetLastError());
+        } else {  // backward-data on the tensor cores (transposed weight images of the pack built above)
+            const TcTrainDump bwd{B.H, B.Q, B.LG, d.Rp, B.DH};
+            const int rc = tc_train_backward(L, B.pack, (long long)R, bwd, st);
+            if (rc != DDM_OK) return rc;
+        }
         // weight-gradient GEMMs: (dY, X) of every layer
         WJobs jobs;
         int nj = 0;
