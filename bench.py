@@ -339,8 +339,8 @@ def mnle_train_bench(dev, with_cpu: bool, rows: int = 4096):
                        "loss + gradient of all 412 489 parameters + clip + Adam",
            "rows": rows, "ms_per_step": ms_step, "ms_loss_only": ms_fwd, "rows_per_s": rows / (ms_step * 1e-3),
            "dense_tflops": 3 * 0.818e6 * rows / (ms_step * 1e-3) / 1e12,
-           "note": "dense work = forward + backward-data + weight-gradient products, 3 x 0.818 MFLOP per row; forward and "
-                   "weight gradients on tcgen05 (bf16 hi/lo, 3 MMAs per product), backward-data on the fp32 CUDA cores",
+           "note": "dense work = forward + backward-data + weight-gradient products, 3 x 0.818 MFLOP per row, all on "
+                   "tcgen05 (bf16 hi/lo operands, 3 MMAs per product)",
            "loss_after": float(tr.stats[0])}
     if with_cpu:
         from oracle import mnle_spec

@@ -281,8 +281,9 @@ int mnle_loglik_sum_batched_tc_f32(void *handle, const float *theta_dev, int64_t
  * All reductions run in a fixed order: results are bit-reproducible.  workspace_dev >=
  * mnle_train_workspace_floats(K, R) floats, 16-byte aligned.  The forward pass runs on the tensor cores
  * (tcgen05, bf16 hi/lo operands ~ 17 bits: activations within ~1e-5 of fp32, so a ReLU unit that close to
- * its kink may be masked differently) and so do the weight-gradient GEMMs; flags = DDM_TRAIN_FP32_FORWARD
- * runs the forward on the fp32 CUDA cores (accuracy anchor, ~0.1 ms slower per 4096 rows).
+ * its kink may be masked differently) and so do the backward-data and weight-gradient GEMMs; flags =
+ * DDM_TRAIN_FP32_FORWARD runs forward and backward-data on the fp32 CUDA cores (accuracy anchor, ~0.15 ms
+ * slower per 4096 rows; the weight gradients stay on the tensor cores).
  *
  * mnle_train_adam_f32: torch.optim.Adam update (no weight decay) for step = 1, 2, ... after
  * scaling the gradient like torch.nn.utils.clip_grad_norm_(max_grad_norm) using stats_dev[1]
