@@ -715,6 +715,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const float *grow = net == 0 ? keep.LG + (size_t)(have ? c_glob : 0) * kMaxChoices
                                          : keep.Q + ((size_t)(net - 1) * (size_t)keep.Rp + (size_t)(have ? c_glob : 0)) * 72;
             const int n_src = net == 0 ? n_choices : kSplineOut, per = net == 0 ? 8 : 40;
+            // the activations every epilogue of this net multiplies by come from HBM one row per lane: start
+            // them towards L2 now (two 128-byte lines per stage for this thread's 64 columns)
+            if (have) {
+                for (int ps = 0; ps < n_st; ++ps) {
+                    const float *hp = keep.H + (((size_t)net * 3 + ((plan.st[s_off + ps].pad & 0xFF) - 1)) * (size_t)keep.Rp +
+                                                (size_t)c_glob) * kHidden + 64 * hf;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(hp));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + 32));
+                }
+            }
 #pragma unroll 1
             for (int k0 = per * hf; k0 < per * hf + per; k0 += 8) {
                 uint32_t hi[4], lo[4];
