@@ -357,6 +357,40 @@ struct TcSmem {
 };
 constexpr uint32_t kTmemD = 0, kTmemAHi = 128, kTmemALo = 192, kTmemTile = 256;  // columns
 
+// Row-per-lane <-> coalesced global traffic.  After tcgen05.ld a lane holds 32 columns of ITS row, and a
+// 16-byte access per lane touches 32 different rows (one half-filled sector each).  The backward pass,
+// which has to WAIT for such loads, transposes each 32 x 32 block through 4 KB of shared memory instead
+// (XOR-swizzled, conflict-free both ways) and moves whole 128-byte row segments: 92 -> 63 us.  (The
+// forward's kept activations are fire-and-forget stores; staging them put more work on the critical path
+// than it saved: 71 -> 83 us, so they stay direct.)
+// g = element (row 0 of the warp, first column of the block), ld = row stride in floats, rows [0, n_rows)
+// exist, columns [0, n_cols) of the block are moved.
+__device__ __forceinline__ void warp_rows_store(float *stg, const float (&v)[32], float *g, size_t ld, int n_rows,
+                                                int n_cols, int lane)
+{
+#pragma unroll
+    for (int c = 0; c < 32; ++c) stg[lane * 32 + (c ^ lane)] = v[c];
+    __syncwarp();
+    if (lane < n_cols)
+        for (int j = 0; j < n_rows; ++j) g[(size_t)j * ld + lane] = stg[j * 32 + (lane ^ j)];
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_rows_load(float *stg, float (&v)[32], const float *g, size_t ld, int n_rows, int lane)
+{
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) stg[j * 32 + (lane ^ j)] = j < n_rows ? g[(size_t)j * ld + lane] : 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = stg[lane * 32 + (c ^ lane)];
+    __syncwarp();
+}
+// what a training epilogue needs to know about the rows of its warp
+struct KeepRows {
+    float *stg;   // 4 KB of shared memory owned by this warp
+    float *base;  // element (row 0 of the warp, column 0) of the kept matrix (row stride 128), or null
+    int n_rows;   // rows of the warp below the allocated row count (0..32)
+};
+
 // ncols accumulator columns + bias -> activation -> packed bf16 hi / lo columns of the A operand.
 // The CUDA-core side of this kernel is bound by the half-rate ALU pipe (min/max, selects,
 // conversions, logic), so the arithmetic is phrased for the FMA pipe wherever possible.
@@ -399,31 +433,29 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
 // activation whose output h sits in global memory -> d loss / d pre-activations, written to global memory
 // and, when another stage follows, split into the bf16 hi / lo A operand of that stage.
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int ncols, const float *h_row, float *d_row,
-                                                 bool kept, bool feeds_next)
+__device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int ncols, const KeepRows &hrows, float *d_base,
+                                                 bool feeds_next, int lane)
 {
 #pragma unroll 1
     for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
+        float h[32];
+        warp_rows_load(hrows.stg, h, hrows.base + c0, kHidden, hrows.n_rows, lane);  // (before the wait below)
         uint32_t v[32];
         tmem_ld32(trow + kTmemD + (uint32_t)c0, v);
         tmem_wait_ld();
-        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const float4 h = kept ? *reinterpret_cast<const float4 *>(h_row + c0 + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float f[4] = {__uint_as_float(v[4 * g + 0]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
-                          __uint_as_float(v[4 * g + 3])};
-            const float hh[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) f[j] = EPI == kEpiRelu ? (hh[j] > 0.f ? f[j] : 0.f) : f[j] * hh[j] * (1.0f - hh[j]);
-            if (kept) *reinterpret_cast<float4 *>(d_row + c0 + 4 * g) = make_float4(f[0], f[1], f[2], f[3]);
-            split_bf16x2(f[0], f[1], hi[2 * g], lo[2 * g]);
-            split_bf16x2(f[2], f[3], hi[2 * g + 1], lo[2 * g + 1]);
+        for (int j = 0; j < 32; ++j) {  // h <- d loss / d pre-activation, in place
+            const float x = __uint_as_float(v[j]);
+            h[j] = EPI == kEpiRelu ? (h[j] > 0.f ? x : 0.f) : x * h[j] * (1.0f - h[j]);
         }
         if (feeds_next) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_bf16x2(h[2 * j], h[2 * j + 1], hi[j], lo[j]);
             tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
             tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
         }
+        warp_rows_store(hrows.stg, h, d_base + c0, kHidden, hrows.n_rows, 32, lane);
     }
     tmem_wait_st();
 }
@@ -787,6 +819,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
         const long long xi = ROWS ? (live ? ((KEEP && row_index != nullptr) ? row_index[c_glob] : c_glob) : 0) : t;
         const bool kept = KEEP && c_glob < keep.Rp;  // padding rows up to Rp get defined values too
+        // backward pass: rows of this warp (consecutive), and its 4 KB of transposition space -- the tile's
+        // gradient images are dead once the net's first stage has been multiplied
+        KeepRows wr{nullptr, nullptr, 0};
+        const long long warp_row0 = c_glob - lane;
+        if (BWD) {
+            wr.stg = reinterpret_cast<float *>(smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes) + (hf * 4 + q) * 1024;
+            const long long left = keep.Rp - warp_row0;
+            wr.n_rows = left <= 0 ? 0 : (left >= 32 ? 32 : (int)left);
+        }
         const float rt = BWD ? 1.0f : __ldg(x + 2 * xi);
         const int choice = BWD ? 0 : (int)__ldg(x + 2 * xi + 1);
         const float y = logf(rt);
@@ -800,10 +841,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (BWD) {
                 mbar_wait(&dfull[X], s & 1);
                 tc_fence_after_sync();
-                const bool have = c_glob < keep.Rp;
-                const size_t at = (((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * (size_t)keep.Rp + (size_t)(have ? c_glob : 0)) * kHidden;
-                if (st.epi == kEpiRelu) tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, have, s + 1 < n_st);
-                else tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, have, s + 1 < n_st);
+                const size_t at = (((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * (size_t)keep.Rp +
+                                   (size_t)(wr.n_rows > 0 ? warp_row0 : 0)) * kHidden;
+                wr.base = keep.H + at;
+                if (st.epi == kEpiRelu) tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, wr, keep.DH + at, s + 1 < n_st, lane);
+                else tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, wr, keep.DH + at, s + 1 < n_st, lane);
                 tc_fence_before_sync();
                 mbar_arrive(&aready[X]);
                 continue;
