@@ -607,6 +607,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kSmemBars + 96);
     // turn[X]: phase s completes when the issuer of stage s has consumed its aready[X] phase (issuers only)
     uint64_t *turn = aready + kTcTiles;                                // [kTcTiles]
+    uint64_t *cfull = turn + kTcTiles;                                 // [kTcTiles] KEEP: context images landed
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
@@ -624,6 +625,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (warp == kTcEpiWarps) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         for (int i = 0; i < kTcTiles; ++i) mbar_init(&turn[i], 1);
+        for (int i = 0; i < kTcTiles; ++i) mbar_init(&cfull[i], 1);
         for (int i = 0; i < kTcSlots; ++i) mbar_init(&wfull[i], 1);
         for (int i = 0; i < kTcTiles; ++i) {
             mbar_init(&dfull[i], 1);
@@ -770,6 +772,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
+        } else if (KEEP) {
+            // the tile's context images were built by tc_ctx_kernel: one bulk copy, everybody waits for it
+            unsigned char *img_hi = smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes;
+            if (q == 0 && hf == 0 && lane == 0) {
+                mbar_expect_tx(&cfull[X], 2u * kCtxImgBytes);
+                bulk_g2s(img_hi, keep.ctx + (size_t)tile * 2u * kCtxImgBytes, 2u * kCtxImgBytes, &cfull[X]);
+            }
+            mbar_wait(&cfull[X], 0);
         } else if (ROWS) {
             // context row [cond (85), choice, 0...] -> bf16 hi / lo A images of this tile (K-major, like the
             // weights); this thread: k in [48 hf, 48 hf + 48)
@@ -828,8 +838,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const long long left = keep.Rp - warp_row0;
             wr.n_rows = left <= 0 ? 0 : (left >= 32 ? 32 : (int)left);
         }
-        const float rt = BWD ? 1.0f : __ldg(x + 2 * xi);
-        const int choice = BWD ? 0 : (int)__ldg(x + 2 * xi + 1);
+        // (the training kernels evaluate neither the splines nor the choice probability: train_rows_kernel does)
+        const float rt = (BWD || KEEP) ? 1.0f : __ldg(x + 2 * xi);
+        const int choice = (BWD || KEEP) ? 0 : (int)__ldg(x + 2 * xi + 1);
         const float y = logf(rt);
         // training forward: `hoist` points at (mu_y, sigma_y) in the parameter buffer (no host round trip)
         const float mu = KEEP ? __ldg(hoist) : mu_y, sigma = KEEP ? __ldg(hoist + 1) : sigma_y;
@@ -1068,9 +1079,45 @@ static size_t train_plan(const Layout &L, TcPlan *plan, TcPlan *bplan, PackJobs 
     return bytes;
 }
 
-size_t tc_train_pack_bytes(int n_choices)
+// The eleven nets of a row tile all start from the same 86-wide context.  Instead of every CTA gathering
+// and splitting its tile's rows itself (27 k cycles before its first MMA, eleven times per tile), the
+// bf16 hi / lo A images of every tile are built once per step and the CTAs fetch them with one bulk copy.
+// grid = tiles, 384 threads: thread = (row, third of the 96 k's).
+__global__ void __launch_bounds__(384) tc_ctx_kernel(const float *__restrict__ x, const float *__restrict__ cond,
+                                                     long long ld_cond, const long long *__restrict__ row_index, long long R,
+                                                     unsigned char *__restrict__ out)
 {
-    return train_plan(make_layout(n_choices), nullptr, nullptr, nullptr);
+    const int r = threadIdx.x & 127, part = threadIdx.x >> 7;
+    const long long row = (long long)blockIdx.x * kTcM + r;
+    const bool live = row < R;
+    const long long drow = live ? (row_index ? row_index[row] : row) : 0;
+    const float *crow = cond + drow * ld_cond;
+    unsigned char *img_hi = out + (size_t)blockIdx.x * 2u * kCtxImgBytes, *img_lo = img_hi + kCtxImgBytes;
+    float v[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const int k = 32 * part + e;
+        v[e] = !live ? 0.f : (k < kCond ? __ldg(crow + k) : (k == kCond ? __ldg(x + 2 * drow + 1) : 0.f));
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_bf16x2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], hi[j], lo[j]);
+        const uint32_t off = (uint32_t)(4 * part + g) * kKGroupBytes + (uint32_t)r * 16u;
+        *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+static size_t train_pack_only_bytes(const Layout &L)
+{
+    return (train_plan(L, nullptr, nullptr, nullptr) + 127) / 128 * 128;
+}
+
+size_t tc_train_pack_bytes(int n_choices, long long R)
+{
+    return train_pack_only_bytes(make_layout(n_choices)) + (size_t)((R + kTcM - 1) / kTcM) * 2u * kCtxImgBytes;
 }
 
 int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, const float *x_dev, const float *cond_dev,
@@ -1085,6 +1132,11 @@ int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, c
     DDM_CUDA_TRY(cudaMemsetAsync(pack_dev, 0, bytes, st));
     tc_pack_kernel<<<dim3(kTrainStages, 8), 256, 0, st>>>(params_dev, jobs, static_cast<unsigned char *>(pack_dev));
     DDM_CUDA_TRY(cudaGetLastError());
+    unsigned char *ctx_dev = static_cast<unsigned char *>(pack_dev) + train_pack_only_bytes(L);
+    tc_ctx_kernel<<<(unsigned)((R + kTcM - 1) / kTcM), 384, 0, st>>>(x_dev, cond_dev, ld_cond, row_index_dev, R, ctx_dev);
+    DDM_CUDA_TRY(cudaGetLastError());
+    TcTrainDump keep = dump;
+    keep.ctx = ctx_dev;
     int dev = 0, sms = 0, n_pairs = 0;
     long long grid = 0;
     DDM_CUDA_TRY(cudaGetDevice(&dev));
@@ -1098,7 +1150,7 @@ int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, c
     // (mu_y, sigma_y) sit at the tail of the parameter buffer: the kernel reads them through `hoist`
     mnle_tc_kernel<true, true><<<dim3((unsigned)grid, kNets), kTcThreads, TcSmem<true>::kBytes, st>>>(
         static_cast<const unsigned char *>(pack_dev), plan, cond_dev, ld_cond, x_dev, params_dev + L.mu_y, 1, 1, (int)R,
-        n_pairs, 0.f, 1.f, L.n_choices, nullptr, nullptr, lp_dev, nullptr, row_index_dev, dump);
+        n_pairs, 0.f, 1.f, L.n_choices, nullptr, nullptr, lp_dev, nullptr, row_index_dev, keep);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }

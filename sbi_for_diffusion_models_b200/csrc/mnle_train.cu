@@ -60,14 +60,14 @@ static TrainDims train_dims(const Layout &L, long long R)
     return d;
 }
 
-static size_t pack_floats(const Layout &L)
+static size_t pack_floats(const Layout &L, long long R)
 {
-    return (tc_train_pack_bytes(L.n_choices) + 63) / 64 * 16;  // whole 64-byte blocks, in floats
+    return (tc_train_pack_bytes(L.n_choices, R) + 63) / 64 * 16;  // whole 64-byte blocks, in floats
 }
 
 static size_t train_floats(const Layout &L, const TrainDims &d)
 {
-    return pack_floats(L) + (size_t)d.Rp * (kTransforms * kQRows + kMaxChoices + 1 + 2 * kNets * 3 * kHidden) + (size_t)d.groups * L.total +
+    return pack_floats(L, d.R) + (size_t)d.Rp * (kTransforms * kQRows + kMaxChoices + 1 + 2 * kNets * 3 * kHidden) + (size_t)d.groups * L.total +
            (size_t)d.reduce_blocks;
 }
 
@@ -75,7 +75,7 @@ static TrainBufs carve(float *ws, const Layout &L, const TrainDims &d)
 {
     TrainBufs b;
     b.pack = ws;
-    b.Q = ws + pack_floats(L);
+    b.Q = ws + pack_floats(L, d.R);
     b.LG = b.Q + (size_t)kTransforms * kQRows * d.Rp;
     b.LP = b.LG + (size_t)kMaxChoices * d.Rp;
     b.H = b.LP + d.Rp;
@@ -655,7 +655,7 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
         train_forward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, rows, d.Rp, B, 1);
         DDM_CUDA_TRY(cudaGetLastError());
     } else {  // forward on the tensor cores (mnle_tc.cu), keeping logits, spline parameters and activations
-        const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp, nullptr};
+        const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp, nullptr, nullptr};
         const int rc = tc_train_forward(params_dev, L, B.pack, x_dev, cond_dev, (long long)ld_cond,
                                         reinterpret_cast<const long long *>(row_index_dev), (long long)R, keep, B.LP, st);
         if (rc != DDM_OK) return rc;
@@ -671,7 +671,7 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
             train_backward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, d.Rp, B);
             DDM_CUDA_TRY(cudaGetLastError());
         } else {  // backward-data on the tensor cores (transposed weight images of the pack built above)
-            const TcTrainDump bwd{B.H, B.Q, B.LG, d.Rp, B.DH};
+            const TcTrainDump bwd{B.H, B.Q, B.LG, d.Rp, B.DH, nullptr};
             const int rc = tc_train_backward(L, B.pack, (long long)R, bwd, st);
             if (rc != DDM_OK) return rc;
         }
