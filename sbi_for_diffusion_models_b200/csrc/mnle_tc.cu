@@ -377,8 +377,13 @@ __device__ __forceinline__ void warp_rows_store(float *stg, const float (&v)[32]
 }
 __device__ __forceinline__ void warp_rows_load(float *stg, float (&v)[32], const float *g, size_t ld, int n_rows, int lane)
 {
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) stg[j * 32 + (lane ^ j)] = j < n_rows ? g[(size_t)j * ld + lane] : 0.f;
+    // all 32 row segments in flight at once: the rows come from HBM, and four at a time made this load the
+    // longest part of the backward epilogue (~8 k cycles per block)
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = j < n_rows ? g[(size_t)j * ld + lane] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stg[j * 32 + (lane ^ j)] = t[j];
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 32; ++c) v[c] = stg[lane * 32 + (c ^ lane)];
