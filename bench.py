@@ -136,6 +136,22 @@ def time_cpu_port(n_trials: int, repeats: int, warmup: int):
     return sum(steps) / sum(times), times, steps
 
 
+def time_cpu_port_cfg1():
+    """configs[0] as the reference runs it (README default: NUM_SIMULATIONS = 10 000 in batches of
+    TRAIN_BATCH_SIZE = 4096, data_simulator.py:46-58): the lock-step port over 4096 + 4096 + 1808 trials."""
+    import torch
+    from oracle import ddm_oracle as orc
+    theta, pulses = cpu_sample(10_000, seed=2)
+    torch.manual_seed(0)
+    t0 = time.perf_counter()
+    steps = 0
+    for a in range(0, 10_000, 4096):
+        _, when, _ = orc.sim_lockstep_torch(theta[a:a + 4096], pulses[a:a + 4096])
+        steps += int(when.sum())
+    dt = time.perf_counter() - t0
+    return {"trials": 10_000, "batch": 4096, "seconds": dt, "steps_per_s": steps / dt, "trials_per_s": 10_000 / dt}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -299,6 +315,34 @@ def mnle_bench(dev, with_cpu: bool):
         for kernel, ll in lls.items():
             out[kernel]["max_rel_err_vs_cpu_spec"] = float(((ll.cpu() - ref).abs() / ref.abs()).max())
     return out
+
+
+def configs0_bench(dev):
+    """configs[0] through the public API on the GPU: simulate_training_set_with_conditions(ExtendedProposal,
+    NUM_SIMULATIONS = 10 000, TRAIN_BATCH_SIZE = 4096) -> CPU (z, x), proposal sampling included."""
+    import contextlib
+    import io
+    import torch
+    from sbi_for_diffusion_models_b200 import data_simulator as ds
+    from sbi_for_diffusion_models_b200.priors import build_prior_theta
+    from sbi_for_diffusion_models_b200.proposals import ExtendedProposal, PulseSequenceProposal
+
+    def once(seed):
+        prop = ExtendedProposal(build_prior_theta(), PulseSequenceProposal(P, 0.75, seed=seed, device=dev), device=dev)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return ds.simulate_training_set_with_conditions(prop, 10_000, 4096, dev, mu_sensory=1.0, p_success=0.75, P=P,
+                                                            log_rt=False, seed=seed)
+    once(0)
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        z, x = once(1 + i)
+        ts.append(time.perf_counter() - t0)
+    dt = sorted(ts)[1]
+    steps = float(torch.round((x[:, 0] - z[:, 4].clamp(0.0, 7.999999)) / 5e-4).sum())
+    return {"workload": "configs[0]: simulate_training_set_with_conditions, 10 000 trials in batches of 4096, CPU (z, x) out",
+            "seconds": dt, "trials_per_s": 10_000 / dt, "steps_per_s": steps / dt}
 
 
 def mnle_train_bench(dev, with_cpu: bool, rows: int = 4096):
@@ -571,12 +615,17 @@ def run_native(args):
                 "sample": f"1 x {args.cpu_trials} trials of the same workload through the lock-step torch port "
                           f"(oracle.sim_lockstep_torch = rt_choice_model.py:112-221 restated, torch.randn), "
                           f"{sum(times):.1f} s",
+                "configs0": time_cpu_port_cfg1(),
             }
         if world == 1:
             try:
                 line["mnle_potential"] = mnle_bench(dev, with_cpu=not args.no_cpu_baseline)
             except Exception as e:  # the headline metric must still print
                 line["mnle_potential"] = {"error": repr(e)}
+            try:
+                line["configs0_api"] = configs0_bench(dev)
+            except Exception as e:
+                line["configs0_api"] = {"error": repr(e)}
             try:
                 line["mnle_train_step"] = mnle_train_bench(dev, with_cpu=not args.no_cpu_baseline)
             except Exception as e:
