@@ -103,11 +103,11 @@ int build_tc_pack(Handle *H, const float *packed_host);  // mnle_tc.cu
 // Training forward on the tensor cores (mnle_tc.cu): the rows-mode kernel over the minibatch with the
 // operand pack rebuilt on the device from the current parameters, keeping what the backward pass needs.
 struct TcTrainDump {
-    float *H;      // [kNets][3][Rp][128] hidden activations
+    float *H;      // [kNets][3][128][Rp] hidden activations, column-major
     float *Q;      // [kTransforms][Rp][72] raw spline parameters
     float *LG;     // [Rp][kMaxChoices] choice logits
     long long Rp;  // rows allocated (a multiple of 64, >= R)
-    float *DH;     // backward pass only: [kNets][3][Rp][128] d loss / d (hidden pre-activations), written
+    float *DH;     // backward pass only: [kNets][3][128][Rp] d loss / d (hidden pre-activations), written
     const unsigned char *ctx;  // forward only: per 128-row tile the bf16 hi / lo context images (tc_ctx_kernel)
 };
 size_t tc_train_pack_bytes(int n_choices, long long R);  // operand pack + context images of R rows

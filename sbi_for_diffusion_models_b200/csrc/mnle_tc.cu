@@ -357,52 +357,15 @@ struct TcSmem {
 };
 constexpr uint32_t kTmemD = 0, kTmemAHi = 128, kTmemALo = 192, kTmemTile = 256;  // columns
 
-// Row-per-lane <-> coalesced global traffic.  After tcgen05.ld a lane holds 32 columns of ITS row, and a
-// 16-byte access per lane touches 32 different rows (one half-filled sector each).  The backward pass,
-// which has to WAIT for such loads, transposes each 32 x 32 block through 4 KB of shared memory instead
-// (XOR-swizzled, conflict-free both ways) and moves whole 128-byte row segments: 92 -> 63 us.  (The
-// forward's kept activations are fire-and-forget stores; staging them put more work on the critical path
-// than it saved: 71 -> 83 us, so they stay direct.)
-// g = element (row 0 of the warp, first column of the block), ld = row stride in floats, rows [0, n_rows)
-// exist, columns [0, n_cols) of the block are moved.
-__device__ __forceinline__ void warp_rows_store(float *stg, const float (&v)[32], float *g, size_t ld, int n_rows,
-                                                int n_cols, int lane)
-{
-#pragma unroll
-    for (int c = 0; c < 32; ++c) stg[lane * 32 + (c ^ lane)] = v[c];
-    __syncwarp();
-    if (lane < n_cols)
-        for (int j = 0; j < n_rows; ++j) g[(size_t)j * ld + lane] = stg[j * 32 + (lane ^ j)];
-    __syncwarp();
-}
-__device__ __forceinline__ void warp_rows_load(float *stg, float (&v)[32], const float *g, size_t ld, int n_rows, int lane)
-{
-    // all 32 row segments in flight at once: the rows come from HBM, and four at a time made this load the
-    // longest part of the backward epilogue (~8 k cycles per block)
-    float t[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) t[j] = j < n_rows ? g[(size_t)j * ld + lane] : 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) stg[j * 32 + (lane ^ j)] = t[j];
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] = stg[lane * 32 + (c ^ lane)];
-    __syncwarp();
-}
-// what a training epilogue needs to know about the rows of its warp
-struct KeepRows {
-    float *stg;   // 4 KB of shared memory owned by this warp
-    float *base;  // element (row 0 of the warp, column 0) of the kept matrix (row stride 128), or null
-    int n_rows;   // rows of the warp below the allocated row count (0..32)
-};
-
 // ncols accumulator columns + bias -> activation -> packed bf16 hi / lo columns of the A operand.
 // The CUDA-core side of this kernel is bound by the half-rate ALU pipe (min/max, selects,
 // conversions, logic), so the arithmetic is phrased for the FMA pipe wherever possible.
-// `keep` (training forward): the activations of this row also go to global memory (row-major, 128 per row).
+// `keep` (training forward): the activations of this row also go to global memory, COLUMN-major (element
+// (row, col) at keep[col * keep_ld], keep pointing at the row): a lane holds one row, so the 32 lanes of a
+// store instruction write 32 consecutive rows of one column = one 128-byte line.
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int ncols, const float *bias,
-                                                float *keep = nullptr)
+                                                float *keep = nullptr, size_t keep_ld = 0)
 {
 #pragma unroll 1
     for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
@@ -423,10 +386,10 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
             }
             split_relu_bf16x2(f[0], f[1], hi[2 * g], lo[2 * g]);
             split_relu_bf16x2(f[2], f[3], hi[2 * g + 1], lo[2 * g + 1]);
-            if (keep != nullptr)  // (the ReLU is fused into the conversions above)
-                *reinterpret_cast<float4 *>(keep + c0 + 4 * g) =
-                    EPI == kEpiRelu ? make_float4(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f), fmaxf(f[2], 0.f), fmaxf(f[3], 0.f))
-                                    : make_float4(f[0], f[1], f[2], f[3]);
+            if (keep != nullptr) {  // (the ReLU is fused into the conversions above)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) keep[(size_t)(c0 + 4 * g + j) * keep_ld] = EPI == kEpiRelu ? fmaxf(f[j], 0.f) : f[j];
+            }
         }
         tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
         tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
@@ -438,13 +401,14 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
 // activation whose output h sits in global memory -> d loss / d pre-activations, written to global memory
 // and, when another stage follows, split into the bf16 hi / lo A operand of that stage.
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int ncols, const KeepRows &hrows, float *d_base,
-                                                 bool feeds_next, int lane)
+__device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int ncols, const float *h_row, float *d_row, size_t ld,
+                                                 bool have, bool feeds_next)
 {
 #pragma unroll 1
     for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
-        float h[32];
-        warp_rows_load(hrows.stg, h, hrows.base + c0, kHidden, hrows.n_rows, lane);  // (before the wait below)
+        float h[32];  // column-major storage: every load / store below is one 128-byte line per warp
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = have ? h_row[(size_t)(c0 + j) * ld] : 0.f;
         uint32_t v[32];
         tmem_ld32(trow + kTmemD + (uint32_t)c0, v);
         tmem_wait_ld();
@@ -460,7 +424,10 @@ __device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int nc
             tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
             tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
         }
-        warp_rows_store(hrows.stg, h, d_base + c0, kHidden, hrows.n_rows, 32, lane);
+        if (have) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d_row[(size_t)(c0 + j) * ld] = h[j];
+        }
     }
     tmem_wait_st();
 }
@@ -754,16 +721,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const float *grow = net == 0 ? keep.LG + (size_t)(have ? c_glob : 0) * kMaxChoices
                                          : keep.Q + ((size_t)(net - 1) * (size_t)keep.Rp + (size_t)(have ? c_glob : 0)) * 72;
             const int n_src = net == 0 ? n_choices : kSplineOut, per = net == 0 ? 8 : 40;
-            // the activations every epilogue of this net multiplies by come from HBM one row per lane: start
-            // them towards L2 now (two 128-byte lines per stage for this thread's 64 columns)
-            if (have) {
-                for (int ps = 0; ps < n_st; ++ps) {
-                    const float *hp = keep.H + (((size_t)net * 3 + ((plan.st[s_off + ps].pad & 0xFF) - 1)) * (size_t)keep.Rp +
-                                                (size_t)c_glob) * kHidden + 64 * hf;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(hp));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + 32));
-                }
-            }
 #pragma unroll 1
             for (int k0 = per * hf; k0 < per * hf + per; k0 += 8) {
                 uint32_t hi[4], lo[4];
@@ -834,15 +791,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
         const long long xi = ROWS ? (live ? ((KEEP && row_index != nullptr) ? row_index[c_glob] : c_glob) : 0) : t;
         const bool kept = KEEP && c_glob < keep.Rp;  // padding rows up to Rp get defined values too
-        // backward pass: rows of this warp (consecutive), and its 4 KB of transposition space -- the tile's
-        // gradient images are dead once the net's first stage has been multiplied
-        KeepRows wr{nullptr, nullptr, 0};
-        const long long warp_row0 = c_glob - lane;
-        if (BWD) {
-            wr.stg = reinterpret_cast<float *>(smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes) + (hf * 4 + q) * 1024;
-            const long long left = keep.Rp - warp_row0;
-            wr.n_rows = left <= 0 ? 0 : (left >= 32 ? 32 : (int)left);
-        }
         // (the training kernels evaluate neither the splines nor the choice probability: train_rows_kernel does)
         const float rt = (BWD || KEEP) ? 1.0f : __ldg(x + 2 * xi);
         const int choice = (BWD || KEEP) ? 0 : (int)__ldg(x + 2 * xi + 1);
@@ -857,11 +805,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (BWD) {
                 mbar_wait(&dfull[X], s & 1);
                 tc_fence_after_sync();
-                const size_t at = (((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * (size_t)keep.Rp +
-                                   (size_t)(wr.n_rows > 0 ? warp_row0 : 0)) * kHidden;
-                wr.base = keep.H + at;
-                if (st.epi == kEpiRelu) tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, wr, keep.DH + at, s + 1 < n_st, lane);
-                else tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, wr, keep.DH + at, s + 1 < n_st, lane);
+                const bool have = c_glob < keep.Rp;
+                const size_t at = ((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * kHidden * (size_t)keep.Rp + (size_t)(have ? c_glob : 0);
+                if (st.epi == kEpiRelu)
+                    tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st);
+                else
+                    tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st);
                 tc_fence_before_sync();
                 mbar_arrive(&aready[X]);
                 continue;
@@ -894,11 +843,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             float *keep_h = nullptr;
             if (KEEP && kept && st.pad != 0)
-                keep_h = keep.H + (((size_t)st.net * 3 + (st.pad - 1)) * (size_t)keep.Rp + (size_t)c_glob) * kHidden;
+                keep_h = keep.H + ((size_t)st.net * 3 + (st.pad - 1)) * kHidden * (size_t)keep.Rp + (size_t)c_glob;
             if (st.epi == kEpiRelu) {
-                tc_epilogue_act<kEpiRelu>(trow, 64 * hf, 64, bias, keep_h);
+                tc_epilogue_act<kEpiRelu>(trow, 64 * hf, 64, bias, keep_h, (size_t)keep.Rp);
             } else if (st.epi == kEpiSigmoid) {
-                tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, 64, bias, keep_h);
+                tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, 64, bias, keep_h, (size_t)keep.Rp);
             } else if (st.epi == kEpiSpline) {
                 if (KEEP) {  // the splines are evaluated by the per-row kernel: only keep the raw parameters
                     float *dst = keep.Q + ((size_t)(st.net - 1) * (size_t)keep.Rp + (size_t)(kept ? c_glob : 0)) * 72;

@@ -37,8 +37,10 @@ struct TrainBufs {
     float *Q;    // [kTransforms][Rp][kQRows]  spline parameters -> their gradients
     float *LG;   // [Rp][kMaxChoices]          choice logits -> their gradients
     float *LP;   // [Rp]                       log p per row
-    float *H;    // [kNets][3][Rp][128]        hidden activations kept for the backward pass
-    float *DH;   // [kNets][3][Rp][128]        d loss / d (hidden pre-activations)
+    float *H;    // [kNets][3][128][Rp]        hidden activations kept for the backward pass, COLUMN-major: the
+                 //                            tensor-core epilogues hold one row per lane, so a warp's access to one
+                 //                            column of 32 consecutive rows is one 128-byte line
+    float *DH;   // [kNets][3][128][Rp]        d loss / d (hidden pre-activations), same layout
     float *P;    // [groups][total]            partial gradients (one slice per row split of the wgrad kernel)
     float *SS;   // [reduce blocks]            partial sums of grad^2
 };
@@ -116,16 +118,16 @@ __device__ __forceinline__ void load_context(const TrainRows &rows, long long ro
 // hidden activations of one net for the backward pass: [net][slot][row][128]
 __device__ __forceinline__ void save_hidden(const float *h_s, float *H, long long Rp, int net, int slot, long long row0)
 {
-    float *dst = H + (((size_t)net * 3 + slot) * Rp + row0) * kHidden;
-    for (int idx = threadIdx.x; idx < kTM * kHidden; idx += kThreads)
-        dst[idx] = h_s[(idx >> 7) * kLdH + (idx & (kHidden - 1))];
+    float *dst = H + ((size_t)net * 3 + slot) * kHidden * (size_t)Rp + row0;
+    for (int idx = threadIdx.x; idx < kTM * kHidden; idx += kThreads)  // consecutive threads = consecutive rows
+        dst[(size_t)(idx >> 6) * Rp + (idx & (kTM - 1))] = h_s[(idx & (kTM - 1)) * kLdH + (idx >> 6)];
 }
 
 __device__ __forceinline__ void load_hidden(float *h_s, const float *H, long long Rp, int net, int slot, long long row0)
 {
-    const float *src = H + (((size_t)net * 3 + slot) * Rp + row0) * kHidden;
+    const float *src = H + ((size_t)net * 3 + slot) * kHidden * (size_t)Rp + row0;
     for (int idx = threadIdx.x; idx < kTM * kHidden; idx += kThreads)
-        h_s[(idx >> 7) * kLdH + (idx & (kHidden - 1))] = src[idx];
+        h_s[(idx & (kTM - 1)) * kLdH + (idx >> 6)] = src[(size_t)(idx >> 6) * Rp + (idx & (kTM - 1))];
 }
 
 // n leading columns of a tile between shared memory [i][ld] and row-major global storage [row][ldg]
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(kThreads) train_backward_kernel(const float *_
 struct WJob {
     const float *A;     // dY: (R, lda) row-major, M columns used
     const float *B;     // X:  (R, ldb) row-major, N columns used; nullptr = the (gathered) context rows
-    int lda, ldb, M, N;
+    int lda, ldb, M, N;     // lda / ldb = 0: the operand is stored column-major with Rp rows per column
     unsigned w_off, b_off;  // where dW (M x N, row-major) and db (M) go in a partial slice
 };
 constexpr int kMaxWJobs = 3 * kTransforms + 4;
@@ -427,7 +429,7 @@ constexpr uint32_t kWgImg = 128 * 256;           // one 128 x 128 bf16 image
 constexpr uint32_t kWgSmem = 4 * kWgImg + 64 + 128 * 8;
 
 __global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __grid_constant__ WJobs jobs, TrainRows rows,
-                                                                       int chunks_total, size_t total,
+                                                                       long long Rp, int chunks_total, size_t total,
                                                                        float *__restrict__ P)
 {
     using namespace tc;
@@ -471,6 +473,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __g
 #pragma unroll 1
             for (int kg0 = 8 * half; kg0 < 8 * half + 8; kg0 += 4) {
                 float v[32];
+                if (!is_ctx && ld == 0) {
+                    // column-major operand: this thread's 32 rows are contiguous -- eight 16-byte loads
+                    const long long rbase = r0 + 8 * kg0;
+                    const float4 *p4 = reinterpret_cast<const float4 *>(src + (size_t)col * Rp + rbase);
+#pragma unroll
+                    for (int e4 = 0; e4 < 8; ++e4) {
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col < valid && rbase + 4 * e4 + 3 < Rp) t = p4[e4];
+                        const int rr = 8 * kg0 + 4 * e4;
+                        v[4 * e4 + 0] = rr + 0 < n_rows ? t.x : 0.f;
+                        v[4 * e4 + 1] = rr + 1 < n_rows ? t.y : 0.f;
+                        v[4 * e4 + 2] = rr + 2 < n_rows ? t.z : 0.f;
+                        v[4 * e4 + 3] = rr + 3 < n_rows ? t.w : 0.f;
+                    }
+                } else {
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     const int rr = 8 * kg0 + e;  // row within the chunk
@@ -480,6 +497,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __g
                         else x = col == kCond ? __ldg(rows.x + 2 * drow[rr] + 1) : __ldg(rows.cond + drow[rr] * rows.ld_cond + col);
                     }
                     v[e] = x;
+                }
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -684,18 +702,18 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
         auto add = [&](const float *A, int lda, int M, const float *Bm, int ldb, int N, size_t w_off, size_t b_off) {
             jobs.j[nj++] = WJob{A, Bm, lda, ldb, M, N, (unsigned)w_off, (unsigned)b_off};
         };
-        add(B.LG, kMaxChoices, n_choices, H(0, 2), kHidden, kHidden, L.cat_Wo, L.cat_bo);
-        add(DH(0, 2), kHidden, kHidden, H(0, 1), kHidden, kHidden, L.cat_W2, L.cat_b2);
-        add(DH(0, 1), kHidden, kHidden, H(0, 0), kHidden, kHidden, L.cat_W1, L.cat_b1);
-        add(DH(0, 0), kHidden, kHidden, nullptr, 0, kCond, L.cat_W0, L.cat_b0);
+        add(B.LG, kMaxChoices, n_choices, H(0, 2), 0, kHidden, L.cat_Wo, L.cat_bo);
+        add(DH(0, 2), 0, kHidden, H(0, 1), 0, kHidden, L.cat_W2, L.cat_b2);
+        add(DH(0, 1), 0, kHidden, H(0, 0), 0, kHidden, L.cat_W1, L.cat_b1);
+        add(DH(0, 0), 0, kHidden, nullptr, 0, kCond, L.cat_W0, L.cat_b0);
         for (int k = 0; k < kTransforms; ++k) {
             const int net = 1 + k;
-            add(B.Q + (size_t)k * kQRows * d.Rp, kQRows, kSplineOut, H(net, 1), kHidden, kHidden, L.fl_W3[k], L.fl_b3[k]);
-            add(DH(net, 1), kHidden, kHidden, H(net, 0), kHidden, kHidden, L.fl_W2[k], L.fl_b2[k]);
-            add(DH(net, 0), kHidden, kHidden, nullptr, 0, kCtx, L.fl_W1[k], L.fl_b1[k]);
+            add(B.Q + (size_t)k * kQRows * d.Rp, kQRows, kSplineOut, H(net, 1), 0, kHidden, L.fl_W3[k], L.fl_b3[k]);
+            add(DH(net, 1), 0, kHidden, H(net, 0), 0, kHidden, L.fl_W2[k], L.fl_b2[k]);
+            add(DH(net, 0), 0, kHidden, nullptr, 0, kCtx, L.fl_W1[k], L.fl_b1[k]);
         }
         DDM_CUDA_TRY(cudaFuncSetAttribute(train_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
-        train_wgrad_tc_kernel<<<dim3(nj, d.groups), kWgThreads, kWgSmem, st>>>(jobs, rows, (int)((R + 127) / 128), L.total,
+        train_wgrad_tc_kernel<<<dim3(nj, d.groups), kWgThreads, kWgSmem, st>>>(jobs, rows, d.Rp, (int)((R + 127) / 128), L.total,
                                                                              B.P);
         DDM_CUDA_TRY(cudaGetLastError());
         train_reduce_kernel<<<d.reduce_blocks, kReduceThreads, 0, st>>>(B.P, d.groups, L.total, L.mu_y, grad_dev, B.SS);
