@@ -29,7 +29,8 @@
 namespace mnle {
 
 constexpr int kQRows = 72;         // 71 spline parameters per transform, padded
-constexpr int kMaxGroups = 4;      // partial-gradient slices = row splits of the weight-gradient kernel (34 layers x 4 = 136 CTAs)
+constexpr int kMaxGroups = 8;      // partial-gradient slices = row splits of the weight-gradient kernel (34 layers x 8 = 272 CTAs, two per SM)
+constexpr int kWgRows = 64;        // rows of the minibatch per chunk (= K of one accumulation step) of that kernel
 constexpr int kReduceThreads = 256;
 
 struct TrainBufs {
@@ -56,7 +57,7 @@ static TrainDims train_dims(const Layout &L, long long R)
     d.R = R;
     d.tiles = (int)((R + kTM - 1) / kTM);
     d.Rp = (long long)d.tiles * kTM;
-    const int chunks = (int)((R + 127) / 128);   // 128-row chunks of the weight-gradient GEMMs
+    const int chunks = (int)((R + kWgRows - 1) / kWgRows);   // row chunks of the weight-gradient GEMMs
     d.groups = chunks < kMaxGroups ? chunks : kMaxGroups;
     d.reduce_blocks = (int)((L.total + kReduceThreads - 1) / kReduceThreads);
     return d;
@@ -425,10 +426,12 @@ struct WJobs {
     WJob j[kMaxWJobs];
 };
 constexpr int kWgThreads = 512;                  // 2 operands x 128 columns x 2 halves of the chunk's rows
-constexpr uint32_t kWgImg = 128 * 256;           // one 128 x 128 bf16 image
-constexpr uint32_t kWgSmem = 4 * kWgImg + 64 + 128 * 8;
+static_assert(kWgRows == 64, "thread mapping below: 32 rows (four 8-row K groups) per thread and chunk");
+constexpr uint32_t kWgImg = 128 * kWgRows * 2;   // one 128 x kWgRows bf16 image
+constexpr uint32_t kWgSmem = 4 * kWgImg + 64 + 2 * kWgRows * 8;
+static_assert(4 * kWgImg >= 128 * 128 * 4, "the epilogue stages the 128 x 128 fp32 tile in the image area");
 
-__global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __grid_constant__ WJobs jobs, TrainRows rows,
+__global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __grid_constant__ WJobs jobs, TrainRows rows,
                                                                        long long Rp, int chunks_total, size_t total,
                                                                        float *__restrict__ P)
 {
@@ -436,9 +439,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __g
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 4 * kWgImg);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 4 * kWgImg + 16);
-    long long *drow = reinterpret_cast<long long *>(smem + 4 * kWgImg + 64);  // dataset row of each chunk row
+    long long *drow = reinterpret_cast<long long *>(smem + 4 * kWgImg + 64);  // [2][kWgRows] dataset row of each chunk row
     const WJob &J = jobs.j[blockIdx.x];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c_begin = (int)((long long)chunks_total * blockIdx.y / gridDim.y);
     const int c_end = (int)((long long)chunks_total * (blockIdx.y + 1) / gridDim.y);
     const int n_pad = (J.N + 15) & ~15;  // UMMA N
@@ -448,13 +451,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __g
         mbar_init(bar, 1);
         fence_mbar_init();
     }
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
 
-    // thread = (operand, half of the chunk's rows, column): 32 independent loads in flight per thread --
-    // the operands come from HBM (they do not fit L2 next to each other) and nothing else hides its latency
+    // thread = (operand, half of the chunk's rows, column): 32 independent rows in flight per thread -- the
+    // operands come from HBM (they do not fit L2 next to each other).  The loads of chunk c + 1 are issued
+    // before the wait for the tensor core to finish chunk c, so that one chunk costs max(load, MMA) + the
+    // conversion instead of their sum; the dataset rows of the gathered context operand are fetched one
+    // chunk further ahead still.
     const bool is_a = tid < 256;
     const int half = (tid >> 7) & 1, col = tid & 127;
     const int img_rows = is_a ? 128 : n_pad, valid = is_a ? J.M : J.N;
@@ -462,55 +464,76 @@ __global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __g
     const float *src = is_a ? J.A : J.B;
     const long long ld = is_a ? J.lda : J.ldb;
     unsigned char *img_hi = smem + (is_a ? 0u : 2u * kWgImg), *img_lo = img_hi + kWgImg;
+    const int rr0 = 32 * half;  // first row of the chunk this thread converts
+    float v[32];
+
+    auto chunk_row = [&](int c) -> long long {  // dataset row of chunk row `tid` (tid < kWgRows)
+        const long long r = (long long)c * kWgRows + tid;
+        return (c < c_end && r < rows.R) ? data_row(rows, r) : 0;
+    };
+    auto load_chunk = [&](int c, const long long *dr) {
+        const long long r0 = (long long)c * kWgRows;
+        const int n_rows = (int)(rows.R - r0 < kWgRows ? rows.R - r0 : kWgRows);
+        if (col >= img_rows) return;
+        if (!is_ctx && ld == 0) {
+            // column-major operand: this thread's 32 rows are contiguous -- eight 16-byte loads
+            const long long rbase = r0 + rr0;
+            const float4 *p4 = reinterpret_cast<const float4 *>(src + (size_t)col * Rp + rbase);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col < valid && rbase + 4 * e4 + 3 < Rp) t = p4[e4];
+                const int rr = rr0 + 4 * e4;
+                v[4 * e4 + 0] = rr + 0 < n_rows ? t.x : 0.f;
+                v[4 * e4 + 1] = rr + 1 < n_rows ? t.y : 0.f;
+                v[4 * e4 + 2] = rr + 2 < n_rows ? t.z : 0.f;
+                v[4 * e4 + 3] = rr + 3 < n_rows ? t.w : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int rr = rr0 + e;  // row within the chunk
+                float x = 0.f;
+                if (col < valid && rr < n_rows) {
+                    if (!is_ctx) x = src[(size_t)(r0 + rr) * ld + col];
+                    else x = col == kCond ? __ldg(rows.x + 2 * dr[rr] + 1) : __ldg(rows.cond + dr[rr] * rows.ld_cond + col);
+                }
+                v[e] = x;
+            }
+        }
+    };
+
+    long long drow_next = 0;
+    if (tid < kWgRows) {
+        drow[tid] = chunk_row(c_begin);
+        drow_next = chunk_row(c_begin + 1);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    if (c_begin < c_end) load_chunk(c_begin, drow);
+
     float bias_acc = 0.f;
     uint32_t phase = 0;
     for (int c = c_begin; c < c_end; ++c) {
-        const long long r0 = (long long)c * 128;
-        const int n_rows = (int)(rows.R - r0 < 128 ? rows.R - r0 : 128);
-        if (tid < 128) drow[tid] = tid < n_rows ? data_row(rows, r0 + tid) : 0;
-        __syncthreads();  // (also: the previous chunk's images have been read, see the wait below)
+        long long *dr_next = drow + (((c - c_begin) & 1) ^ 1) * kWgRows;
+        if (tid < kWgRows) {
+            dr_next[tid] = drow_next;  // rows of chunk c + 1: visible after the barrier below
+            drow_next = chunk_row(c + 2);
+        }
         if (col < img_rows) {
-#pragma unroll 1
-            for (int kg0 = 8 * half; kg0 < 8 * half + 8; kg0 += 4) {
-                float v[32];
-                if (!is_ctx && ld == 0) {
-                    // column-major operand: this thread's 32 rows are contiguous -- eight 16-byte loads
-                    const long long rbase = r0 + 8 * kg0;
-                    const float4 *p4 = reinterpret_cast<const float4 *>(src + (size_t)col * Rp + rbase);
 #pragma unroll
-                    for (int e4 = 0; e4 < 8; ++e4) {
-                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (col < valid && rbase + 4 * e4 + 3 < Rp) t = p4[e4];
-                        const int rr = 8 * kg0 + 4 * e4;
-                        v[4 * e4 + 0] = rr + 0 < n_rows ? t.x : 0.f;
-                        v[4 * e4 + 1] = rr + 1 < n_rows ? t.y : 0.f;
-                        v[4 * e4 + 2] = rr + 2 < n_rows ? t.z : 0.f;
-                        v[4 * e4 + 3] = rr + 3 < n_rows ? t.w : 0.f;
-                    }
-                } else {
+            for (int g = 0; g < 4; ++g) {
+                uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int rr = 8 * kg0 + e;  // row within the chunk
-                    float x = 0.f;
-                    if (col < valid && rr < n_rows) {
-                        if (!is_ctx) x = src[(size_t)(r0 + rr) * ld + col];
-                        else x = col == kCond ? __ldg(rows.x + 2 * drow[rr] + 1) : __ldg(rows.cond + drow[rr] * rows.ld_cond + col);
-                    }
-                    v[e] = x;
-                }
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) split_bf16x2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], hi[j], lo[j]);
-                    if (is_a)
-                        bias_acc += ((v[8 * g] + v[8 * g + 1]) + (v[8 * g + 2] + v[8 * g + 3])) +
-                                    ((v[8 * g + 4] + v[8 * g + 5]) + (v[8 * g + 6] + v[8 * g + 7]));
-                    const uint32_t off = (uint32_t)(kg0 + g) * (uint32_t)img_rows * 16u + (uint32_t)col * 16u;
-                    *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                }
+                for (int j = 0; j < 4; ++j) split_bf16x2(v[8 * g + 2 * j], v[8 * g + 2 * j + 1], hi[j], lo[j]);
+                if (is_a)
+                    bias_acc += ((v[8 * g] + v[8 * g + 1]) + (v[8 * g + 2] + v[8 * g + 3])) +
+                                ((v[8 * g + 4] + v[8 * g + 5]) + (v[8 * g + 6] + v[8 * g + 7]));
+                const uint32_t off = (uint32_t)(4 * half + g) * (uint32_t)img_rows * 16u + (uint32_t)col * 16u;
+                *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
         }
         fence_proxy_async_smem();
@@ -526,7 +549,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __g
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint32_t pa = a0 + (pass == 2 ? kWgImg : 0u), pb = b0 + (pass == 1 ? kWgImg : 0u);
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
+                    for (int ks = 0; ks < kWgRows / 16; ++ks)
                         umma_bf16(tmem, umma_desc_kmajor(pa + ks * 2 * 128 * 16, 128 * 16, 128),
                                   umma_desc_kmajor(pb + ks * 2 * lbo_b, lbo_b, 128), idesc,
                                   (c > c_begin) || (pass | ks) != 0);
@@ -535,39 +558,41 @@ __global__ void __launch_bounds__(kWgThreads, 1) train_wgrad_tc_kernel(const __g
             }
             __syncwarp();
         }
+        if (c + 1 < c_end) load_chunk(c + 1, dr_next);  // in flight while the tensor core works
         mbar_wait(bar, phase);  // the images may be rebuilt once the tensor core has read them
         phase ^= 1;
         tc_fence_after_sync();
     }
     // the two halves of a dY column add up their bias sums (fixed order)
-    float *bias_s = reinterpret_cast<float *>(smem);  // the images are dead
+    float *tile = reinterpret_cast<float *>(smem);  // the images are dead
     __syncthreads();
-    if (is_a && half == 1) bias_s[col] = bias_acc;
+    if (is_a && half == 1) tile[col] = bias_acc;
     __syncthreads();
-    if (is_a && half == 0) bias_acc += bias_s[col];
-    // accumulators -> this split's slice: lane m of tensor memory = row m of dW
+    if (is_a && half == 0) bias_acc += tile[col];
+    __syncthreads();
+    // accumulators -> shared memory (lane m of tensor memory = row m of dW; warp w reads lane group w % 4,
+    // columns 32 * (w / 4) ..; XOR swizzle against bank conflicts) -> this split's slice, coalesced
     float *Pout = P + (size_t)blockIdx.y * total;
-    if (tid < 128) {
-        const int m = tid;
-        for (int n0 = 0; n0 < n_pad; n0 += 16) {
-            uint32_t v[16];
+    {
+        const int m = 32 * (warp & 3) + lane, n0 = 32 * (warp >> 2);
+        if (n0 < n_pad) {
+            uint32_t a[32];
             if (c_end > c_begin) {
-                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
+                tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)n0, a);
                 tmem_wait_ld();
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0u;
+                for (int j = 0; j < 32; ++j) a[j] = 0u;
             }
-            if (m < J.M) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n0 + j < J.N) Pout[J.w_off + (size_t)m * J.N + n0 + j] = __uint_as_float(v[j]);
-            }
+            for (int j = 0; j < 32; ++j) tile[m * 128 + ((n0 + j) ^ lane)] = __uint_as_float(a[j]);
         }
-        if (m < J.M) Pout[J.b_off + m] = bias_acc;
+        if (tid < 128 && tid < J.M) Pout[J.b_off + tid] = bias_acc;  // (tid < 128: operand A, half 0, col = tid)
     }
     tc_fence_before_sync();
     __syncthreads();
+    for (int m = warp; m < J.M; m += kWgThreads / 32)
+        for (int n = lane; n < J.N; n += 32) Pout[J.w_off + (size_t)m * J.N + n] = tile[m * 128 + (n ^ (m & 31))];
     if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
@@ -713,7 +738,7 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
             add(DH(net, 0), 0, kHidden, nullptr, 0, kCtx, L.fl_W1[k], L.fl_b1[k]);
         }
         DDM_CUDA_TRY(cudaFuncSetAttribute(train_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
-        train_wgrad_tc_kernel<<<dim3(nj, d.groups), kWgThreads, kWgSmem, st>>>(jobs, rows, d.Rp, (int)((R + 127) / 128), L.total,
+        train_wgrad_tc_kernel<<<dim3(nj, d.groups), kWgThreads, kWgSmem, st>>>(jobs, rows, d.Rp, (int)((R + kWgRows - 1) / kWgRows), L.total,
                                                                              B.P);
         DDM_CUDA_TRY(cudaGetLastError());
         train_reduce_kernel<<<d.reduce_blocks, kReduceThreads, 0, st>>>(B.P, d.groups, L.total, L.mu_y, grad_dev, B.SS);

@@ -202,3 +202,46 @@ def test_sbc_sessions_one_launch_matches_per_dataset_calls():
     # sharding: datasets 2..5 computed on their own give the same sessions
     x2, _ = simulate_sbc_sessions(thetas[2:], seeds[2:], 50, mu_sensory=1.0, p_success=0.75, noise_seed=3, first_dataset=2)
     assert torch.equal(x2, x[2:])
+
+
+def test_outputs_and_workspaces_stay_in_bounds(net, monkeypatch):
+    """Guard bands around every float32 device buffer the wrappers hand to the library (outputs and
+    workspaces of exactly the advertised size): ragged tiles must not write past either end.
+    (compute-sanitizer is not available on the GPU pool, so the bounds are checked this way.)"""
+    _, _, est, _ = net
+    real_empty, bands, G = torch.empty, [], 2048
+
+    def guarded(*size, **kw):
+        dev = kw.get("device")
+        if dev is None or torch.device(dev).type != "cuda" or kw.get("dtype") != torch.float32:
+            return real_empty(*size, **kw)
+        shape = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)) else tuple(size)
+        n = int(np.prod(shape))
+        big = torch.full((n + 2 * G,), 12345.0, device=dev)
+        bands.append((big, n))
+        return big[G:G + n].view(shape)
+
+    monkeypatch.setattr(torch, "empty", guarded)
+    rs = np.random.RandomState(3)
+    for R in (1, 127, 129, 3000):
+        theta = orc.prior_sample(R, seed=2)
+        pulses = torch.from_numpy(orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(1)), 0, R, 80, 0.75))
+        x = torch.from_numpy(np.stack([np.exp(rs.uniform(-3, 2.1, R)), rs.randint(0, 3, R)], 1).astype(np.float32))
+        for kernel in ("tc", "simt"):
+            assert bool(torch.isfinite(est.log_prob(x.cuda(), condition=torch.cat([theta, pulses], 1).cuda(), kernel=kernel)).all())
+    for T, C in [(1, 1), (65, 7), (3, 300), (50, 130), (200, 33)]:
+        x_o, pulses = _session(T)
+        theta = orc.prior_sample(C, seed=T)
+        for kernel in ("tc", "simt"):
+            assert bool(torch.isfinite(est.loglik_sum(theta.cuda(), x_o.cuda(), pulses.cuda(), kernel=kernel)).all())
+        if T * C < 2000:
+            out, grad = est.loglik_sum_and_grad(theta.cuda(), x_o.cuda(), pulses.cuda())
+            assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(grad).all())
+    for D, T, C in [(3, 5, 130), (2, 1, 1), (4, 50, 37)]:
+        xs, ps = zip(*[_session(T, seed=d) for d in range(D)])
+        theta = orc.prior_sample(D * C, seed=9).reshape(D, C, 5)
+        assert bool(torch.isfinite(est.loglik_sum_batched(theta.cuda(), torch.stack(xs).cuda(), torch.stack(ps).cuda())).all())
+    torch.cuda.synchronize()
+    assert len(bands) >= 40
+    for big, n in bands:
+        assert bool((big[:G] == 12345.0).all()) and bool((big[G + n:] == 12345.0).all()), n

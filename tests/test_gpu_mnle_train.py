@@ -191,3 +191,33 @@ def test_init_follows_torch_linear_defaults():
     assert tuple(p["cat.W0"].shape) == (128, 85) and tuple(p["flow.9.W3"].shape) == (71, 128)
     assert float(p["flow.0.W1"].abs().max()) <= 1 / np.sqrt(86) and float(p["flow.0.b1"].abs().max()) <= 1 / np.sqrt(86)
     assert float(p["cat.Wo"].abs().max()) > 0.5 / np.sqrt(128)
+
+
+@pytest.mark.parametrize("forward", ["fp32", "tc"])
+@pytest.mark.parametrize("R", [1, 127, 300, 64 * 130 + 5])
+def test_workspace_and_gradient_writes_stay_in_bounds(R, forward):
+    """Guard bands around every buffer the step writes (workspace of exactly the advertised size,
+    gradient, stats): ragged last tiles must not spill (compute-sanitizer is not available on the
+    GPU pool, so the bounds are checked this way)."""
+    from sbi_for_diffusion_models_b200 import _native
+    p = ms.init_params(5)
+    x, cond = _data(max(R, 8), 5)
+    tr = _trainer(p)
+    xd, cd = x.cuda()[:R].contiguous(), tr.standardise(cond)[:R].contiguous()
+    G = 4096
+    need = _native.lib().mnle_train_workspace_floats(tr.n_choices, R)
+    big_ws = torch.full((need + 2 * G,), 12345.0, device="cuda")
+    tr._ws = big_ws[G:G + need]
+    n = tr.grad.numel()
+    big_g = torch.full((n + 2 * G,), 12345.0, device="cuda")
+    tr.grad = big_g[G:G + n]
+    big_s = torch.full((2 + 2 * G,), 12345.0, device="cuda")
+    tr.stats = big_s[G:G + 2]
+    stats = tr.nll(xd, cd, forward=forward)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(stats).all()) and bool(torch.isfinite(tr.grad).all())
+    for big, m in ((big_ws, need), (big_g, n), (big_s, 2)):
+        assert bool((big[:G] == 12345.0).all()) and bool((big[G + m:] == 12345.0).all())
+    tr.adam()
+    torch.cuda.synchronize()
+    assert bool((big_g[:G] == 12345.0).all()) and bool((big_g[G + n:] == 12345.0).all())

@@ -404,3 +404,36 @@ def test_packed_kernel_on_resident_records():
     assert L.ddm_sim_packed_f32(recd.data_ptr(), n, 16000, 100, sched.dt, sched.t_max, sched.t_nd_hi, sched.noise_scale,
                                 ctypes.c_uint64(5), ctypes.c_uint64(0), 0, x.data_ptr(), None, ws.data_ptr(), None,
                                 None) == _native.DDM_ERR_INVALID          # 160 pulses do not fit a record
+
+
+def test_outputs_stay_in_bounds(monkeypatch):
+    """Guard bands around the device outputs of the simulator, the Philox dumps and the pulse generator
+    at ragged sizes (compute-sanitizer is not available on the GPU pool)."""
+    from sbi_for_diffusion_models_b200.pulses import generate_pulse_matrix_device
+    real_empty, bands, G = torch.empty, [], 2048
+
+    def guarded(*size, **kw):
+        dev, dt = kw.get("device"), kw.get("dtype")
+        if dev is None or torch.device(dev).type != "cuda" or dt not in (torch.float32, torch.int32):
+            return real_empty(*size, **kw)
+        shape = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)) else tuple(size)
+        n = int(np.prod(shape))
+        big = torch.full((n + 2 * G,), 12345, dtype=dt, device=dev)
+        bands.append((big, n))
+        return big[G:G + n].view(shape)
+
+    monkeypatch.setattr(torch, "empty", guarded)
+    for n in (1, 31, 33, 1000, 70001):
+        theta = orc.prior_sample(n, seed=n)
+        pulses = generate_pulse_matrix_device(np.random.default_rng(n), n, 80, p_success=0.75)
+        assert tuple(pulses.shape) == (n, 80)
+        x, steps = sim.simulate_trials(theta, pulses, seed=3, return_steps=True)
+        assert tuple(x.shape) == (n, 2) and bool(torch.isfinite(x).all())
+        x = sim.simulate_trials(theta, pulses[:, :80].cpu().repeat(1, 2)[:, :100], seed=3, log_rt=True)   # P > 80, generic path
+        assert bool(torch.isfinite(x).all())
+    sim.philox_normals(5, 77, 13)
+    sim.philox_words(5, 77, 13)
+    torch.cuda.synchronize()
+    assert len(bands) >= 20
+    for big, n in bands:
+        assert bool((big[:G] == 12345).all()) and bool((big[G + n:] == 12345).all()), n
