@@ -410,11 +410,11 @@ __global__ void __launch_bounds__(kThreads) train_backward_kernel(const float *_
 
 // 3b. weight gradients on the tensor cores.  Every layer's dW[m][n] = sum_r dY[r][m] * X[r][n] is a GEMM
 // whose reduction runs over the rows of the minibatch: M, N <= 128, K = R.  One CTA owns one (layer, row
-// split): per 128-row chunk, thread c of the first four warps turns column c of dY into row c of a
-// K-major bf16 hi / lo operand image (coalesced global reads along the row, one 16-byte shared-memory
-// store per 8 rows), the other four warps do the same for X, and one elected thread issues the three
-// tcgen05.mma passes (hi*hi + hi*lo + lo*hi, fp32 accumulation in tensor memory across all chunks).  The
-// row splits write separate slices of the partial buffer: the fixed-order reduction below sums them.
+// split): per 64-row chunk, threads (c, half) of the first eight warps turn 32 rows of column c of dY into
+// row c of a K-major bf16 hi / lo operand image (one 16-byte shared-memory store per 8 rows), the other
+// eight warps do the same for X, and one elected thread issues the three tcgen05.mma passes (hi*hi +
+// hi*lo + lo*hi, fp32 accumulation in tensor memory across all chunks).  The row splits write separate
+// slices of the partial buffer: the fixed-order reduction below sums them.
 struct WJob {
     const float *A;     // dY: (R, lda) row-major, M columns used
     const float *B;     // X:  (R, ldb) row-major, N columns used; nullptr = the (gathered) context rows
