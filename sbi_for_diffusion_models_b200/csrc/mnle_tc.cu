@@ -547,6 +547,22 @@ static void tc_grid(long long n_tiles, int sms, int *n_pairs, long long *grid)
     *grid = pairs + singles;
 }
 
+// Launch shape of the training kernels, per net (grid = (11 nets, *grid)): a 4 096-row minibatch is 32 tiles
+// x 11 nets = 176 two-tile CTAs on 148 SMs, i.e. a second wave that is 19 % full and costs a whole pair time.
+// When the pairs that do not fit whole waves can run as ONE wave of one-tile CTAs instead, they do (13 pairs
+// + 6 singles per net: 143 + 66 CTAs; a single takes about 0.6 of a pair time).
+static void train_grid(long long n_tiles, int sms, int *n_pairs, long long *grid)
+{
+    long long pairs = n_tiles / 2;
+    const long long all = pairs * kNets, rem = all % sms;
+    if (all > sms && rem > 0) {
+        const long long fewer = (all - rem) / kNets;
+        if ((n_tiles - 2 * fewer) * kNets <= sms) pairs = fewer;
+    }
+    *n_pairs = (int)pairs;
+    *grid = pairs + (n_tiles - 2 * pairs);
+}
+
 // ROWS: estimator.log_prob over arbitrary rows -- `theta` is the (R, 85) condition matrix (row stride
 // ld_theta), x is (R, 2), C = R; the 86-wide context of each tile sits in shared memory as bf16 hi / lo
 // A images and every net's first layer is a K = 96 stage with both operands from shared memory (the
@@ -584,13 +600,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
     // The training forward (KEEP) does not chain the splines (the per-row kernel does), so the eleven nets
-    // are independent: blockIdx.y picks one net and the CTA runs only that net's 3 or 4 stages -- 11 x
+    // are independent: blockIdx.x picks one net and the CTA runs only that net's 3 or 4 stages -- 11 x
     // more CTAs for a minibatch that is only a few dozen row tiles.  Barrier phases count local stages.
-    const int s_off = KEEP ? (blockIdx.y == 0 ? 0 : 4 + 3 * ((int)blockIdx.y - 1))
-                           : (BWD ? (blockIdx.y == 0 ? 0 : 3 + 2 * ((int)blockIdx.y - 1)) : 0);
-    const int n_st = KEEP ? (blockIdx.y == 0 ? 4 : 3) : (BWD ? (blockIdx.y == 0 ? 3 : 2) : kTcStages);
+    // Training grids are (net, CTA of the net): CTAs are scheduled x-fastest, so every net's two-tile CTAs
+    // start before any one-tile CTA does (see train_grid()).
+    const int net_id = (KEEP || BWD) ? (int)blockIdx.x : 0;
+    const int s_off = KEEP ? (net_id == 0 ? 0 : 4 + 3 * (net_id - 1)) : (BWD ? (net_id == 0 ? 0 : 3 + 2 * (net_id - 1)) : 0);
+    const int n_st = KEEP ? (net_id == 0 ? 4 : 3) : (BWD ? (net_id == 0 ? 3 : 2) : kTcStages);
     // CTAs [0, n_pairs) take two tiles each, the rest one tile each (see tc_grid())
-    const int bx = blockIdx.x;
+    const int bx = (KEEP || BWD) ? (int)blockIdx.y : (int)blockIdx.x;
     const int tile0 = bx >= n_pairs ? 2 * n_pairs + (bx - n_pairs) : bx * kTcTiles;
     const int n_active = bx >= n_pairs ? 1 : kTcTiles;
 
@@ -716,7 +734,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // gradient row of this net's outputs -> bf16 hi / lo A images (K-major): 71 spline parameters in
             // K = 80 (this thread: 40 of them), or the choice logits in K = 16 (8 each)
             unsigned char *img_hi = smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes, *img_lo = img_hi + kCtxImgBytes;
-            const int net = blockIdx.y;
+            const int net = net_id;
             const bool have = c_glob < keep.Rp;
             const float *grow = net == 0 ? keep.LG + (size_t)(have ? c_glob : 0) * kMaxChoices
                                          : keep.Q + ((size_t)(net - 1) * (size_t)keep.Rp + (size_t)(have ? c_glob : 0)) * 72;
@@ -1095,14 +1113,12 @@ int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, c
     long long grid = 0;
     DDM_CUDA_TRY(cudaGetDevice(&dev));
     DDM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const long long n_tiles = (R + kTcM - 1) / kTcM;
-    n_pairs = (int)(n_tiles / 2);
-    grid = n_pairs + (n_tiles & 1);
-    (void)sms;
+    train_grid((R + kTcM - 1) / kTcM, sms, &n_pairs, &grid);
+    DDM_REQUIRE(grid <= 65535, "training minibatch too large for one launch (at most ~8e6 rows)");
     DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)TcSmem<true>::kBytes));
     // (mu_y, sigma_y) sit at the tail of the parameter buffer: the kernel reads them through `hoist`
-    mnle_tc_kernel<true, true><<<dim3((unsigned)grid, kNets), kTcThreads, TcSmem<true>::kBytes, st>>>(
+    mnle_tc_kernel<true, true><<<dim3(kNets, (unsigned)grid), kTcThreads, TcSmem<true>::kBytes, st>>>(
         static_cast<const unsigned char *>(pack_dev), plan, cond_dev, ld_cond, x_dev, params_dev + L.mu_y, 1, 1, (int)R,
         n_pairs, 0.f, 1.f, L.n_choices, nullptr, nullptr, lp_dev, nullptr, row_index_dev, keep);
     DDM_CUDA_TRY(cudaGetLastError());
@@ -1113,12 +1129,15 @@ int tc_train_backward(const Layout &L, const void *pack_dev, long long R, const 
 {
     TcPlan bplan;
     train_plan(L, nullptr, &bplan, nullptr);
-    const long long n_tiles = (R + kTcM - 1) / kTcM;
-    const int n_pairs = (int)(n_tiles / 2);
-    const long long grid = n_pairs + (n_tiles & 1);
+    int dev = 0, sms = 0, n_pairs = 0;
+    long long grid = 0;
+    DDM_CUDA_TRY(cudaGetDevice(&dev));
+    DDM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    train_grid((R + kTcM - 1) / kTcM, sms, &n_pairs, &grid);
+    DDM_REQUIRE(grid <= 65535, "training minibatch too large for one launch (at most ~8e6 rows)");
     DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)TcSmem<true>::kBytes));
-    mnle_tc_kernel<true, false, true><<<dim3((unsigned)grid, kNets), kTcThreads, TcSmem<true>::kBytes, st>>>(
+    mnle_tc_kernel<true, false, true><<<dim3(kNets, (unsigned)grid), kTcThreads, TcSmem<true>::kBytes, st>>>(
         static_cast<const unsigned char *>(pack_dev), bplan, nullptr, 0, nullptr, nullptr, 1, 1, (int)R, n_pairs, 0.f, 1.f,
         L.n_choices, nullptr, nullptr, nullptr, nullptr, nullptr, dump);
     DDM_CUDA_TRY(cudaGetLastError());
