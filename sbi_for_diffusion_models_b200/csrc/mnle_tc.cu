@@ -402,13 +402,17 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
 // and, when another stage follows, split into the bf16 hi / lo A operand of that stage.
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int ncols, const float *h_row, float *d_row, size_t ld,
-                                                 bool have, bool feeds_next)
+                                                 bool have, bool feeds_next, uint64_t *dfull, uint32_t parity)
 {
 #pragma unroll 1
     for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
         float h[32];  // column-major storage: every load / store below is one 128-byte line per warp
 #pragma unroll
         for (int j = 0; j < 32; ++j) h[j] = have ? h_row[(size_t)(c0 + j) * ld] : 0.f;
+        if (c0 == col0) {  // the kept activations do not depend on the MMAs: their latency hides behind the wait
+            mbar_wait(dfull, parity);
+            tc_fence_after_sync();
+        }
         uint32_t v[32];
         tmem_ld32(trow + kTmemD + (uint32_t)c0, v);
         tmem_wait_ld();
@@ -821,14 +825,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int s = 0; s < n_st; ++s) {
             const TcStage &st = plan.st[s_off + s];
             if (BWD) {
-                mbar_wait(&dfull[X], s & 1);
-                tc_fence_after_sync();
                 const bool have = c_glob < keep.Rp;
                 const size_t at = ((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * kHidden * (size_t)keep.Rp + (size_t)(have ? c_glob : 0);
                 if (st.epi == kEpiRelu)
-                    tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st);
+                    tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st,
+                                               &dfull[X], s & 1);
                 else
-                    tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st);
+                    tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st,
+                                                  &dfull[X], s & 1);
                 tc_fence_before_sync();
                 mbar_arrive(&aready[X]);
                 continue;
