@@ -742,19 +742,36 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const bool have = c_glob < keep.Rp;
             const float *grow = net == 0 ? keep.LG + (size_t)(have ? c_glob : 0) * kMaxChoices
                                          : keep.Q + ((size_t)(net - 1) * (size_t)keep.Rp + (size_t)(have ? c_glob : 0)) * 72;
-            const int n_src = net == 0 ? n_choices : kSplineOut, per = net == 0 ? 8 : 40;
-#pragma unroll 1
-            for (int k0 = per * hf; k0 < per * hf + per; k0 += 8) {
-                uint32_t hi[4], lo[4];
+            // all loads first (ten 16-byte loads of a spline-parameter row, 288-byte row stride), then the split
+            float gv[40];
+            int n_groups;
+            if (net == 0) {
+                n_groups = 1;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = k0 + 2 * j;
-                    const float v0 = (have && k < n_src) ? grow[k] : 0.f, v1 = (have && k + 1 < n_src) ? grow[k + 1] : 0.f;
-                    split_bf16x2(v0, v1, hi[j], lo[j]);
+                for (int j = 0; j < 8; ++j) gv[j] = (have && hf == 0 && j < n_choices) ? grow[j] : 0.f;
+            } else {
+                n_groups = 5;
+                const float4 *g4 = reinterpret_cast<const float4 *>(grow + 40 * hf);
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    const float4 t = have ? g4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    gv[4 * j + 0] = t.x;
+                    gv[4 * j + 1] = t.y;
+                    gv[4 * j + 2] = t.z;
+                    gv[4 * j + 3] = (40 * hf + 4 * j + 3 < kSplineOut) ? t.w : 0.f;  // column 71 of the row is padding
                 }
-                const uint32_t off = (uint32_t)(k0 >> 3) * kKGroupBytes + (uint32_t)r * 16u;
-                *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            const int kg0 = (net == 0 ? 1 : 5) * hf;
+#pragma unroll
+            for (int g = 0; g < 5; ++g) {
+                if (g < n_groups) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) split_bf16x2(gv[8 * g + 2 * j], gv[8 * g + 2 * j + 1], hi[j], lo[j]);
+                    const uint32_t off = (uint32_t)(kg0 + g) * kKGroupBytes + (uint32_t)r * 16u;
+                    *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
             }
         } else if (KEEP) {
             // the tile's context images were built by tc_ctx_kernel: one bulk copy, everybody waits for it
