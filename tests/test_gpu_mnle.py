@@ -245,3 +245,37 @@ def test_outputs_and_workspaces_stay_in_bounds(net, monkeypatch):
     assert len(bands) >= 40
     for big, n in bands:
         assert bool((big[:G] == 12345.0).all()) and bool((big[G + n:] == 12345.0).all()), n
+
+
+@pytest.mark.parametrize("K", [2, 5, 8])
+def test_other_numbers_of_choice_categories(K):
+    """The categorical head has as many outputs as the training set has distinct choices (sbi sizes it
+    from the data): 2 when no trial was censored (the "Bernoulli" head of BASELINE.json), up to the
+    library's limit of 8.  Rows API, potential (both kernels) and the gradient kernel against the spec."""
+    p = ms.init_params(11 + K, n_choices=K)
+    p64 = ms.cast_params(p, torch.float64)
+    est = DeviceMNLE(PackedMNLE.from_params(p))
+    assert est.packed.n_choices == K
+    R = 700
+    theta = orc.prior_sample(R, seed=2)
+    pulses = torch.from_numpy(orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(1)), 0, R, 80, 0.75))
+    cond = torch.cat([theta, pulses], dim=1)
+    rs = np.random.RandomState(K)
+    x = torch.from_numpy(np.stack([np.exp(rs.uniform(-3, 2.1, R)), rs.randint(0, K, R)], 1).astype(np.float32))
+    want = ms.log_prob(p64, x, cond)
+    for kernel, tol in (("simt", 2e-3), ("tc", 4e-3)):
+        got = est.log_prob(x.unsqueeze(0), condition=cond, kernel=kernel)[0].double()
+        assert float((got - want).abs().max()) < tol, (kernel, float((got - want).abs().max()))
+    T, C = 23, 130
+    th = orc.prior_sample(C, seed=5)
+    x_o, pl = x[:T], pulses[:T]
+    want_sum = ms.loglik_sum(p64, th, x_o, pl)
+    for kernel in ("simt", "tc"):
+        got = est.loglik_sum(th, x_o, pl, kernel=kernel).double()
+        assert float(((got - want_sum).abs() / want_sum.abs()).max()) < 1e-4, kernel
+    th64 = th[:9].double().requires_grad_(True)
+    (want_grad,) = torch.autograd.grad(ms.loglik_sum(p64, th64, x_o, pl).sum(), th64)
+    val, grad = est.loglik_sum_and_grad(th[:9], x_o, pl)
+    assert float(((val.double() - want_sum[:9]).abs() / want_sum[:9].abs()).max()) < 1e-4
+    err = (grad.double() - want_grad).abs() / (want_grad.abs() + 1e-2 * want_grad.abs().max())
+    assert float(err.max()) < 2e-3, float(err.max())

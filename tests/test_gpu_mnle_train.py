@@ -221,3 +221,29 @@ def test_workspace_and_gradient_writes_stay_in_bounds(R, forward):
     tr.adam()
     torch.cuda.synchronize()
     assert bool((big_g[:G] == 12345.0).all()) and bool((big_g[G + n:] == 12345.0).all())
+
+
+@pytest.mark.parametrize("K", [2, 8])
+def test_training_step_with_other_numbers_of_choices(K):
+    """K = 2: a training set without censored trials (sbi sizes the categorical head from the data)."""
+    p = ms.init_params(20 + K, n_choices=K)
+    R = 333
+    x, cond = _data(R, {2: 8, 8: 9}[K])
+    x[:, 1] = torch.from_numpy(np.random.RandomState(K).randint(0, K, R).astype(np.float32))
+    assert _relu_margin(p, x, cond) > 5e-7       # (data seeds chosen to keep clear of the ReLU kinks)
+    want_loss, want = _spec_loss_and_grads(p, x, cond)
+    tr = _trainer(p)
+    assert tr.n_choices == K
+    xd, cd = x.cuda(), tr.standardise(cond)
+    # (tc: with only 333 rows one ReLU unit masked differently moves an entry by 1/333 of a row's gradient,
+    # see the module docstring; the categorical tensors, which are what K changes, get the tight bound)
+    for forward, loss_tol, grad_tol in (("fp32", 1e-5, 2e-3), ("tc", 1e-4, 2e-2)):
+        stats = tr.nll(xd, cd, forward=forward).cpu()
+        assert abs(float(stats[0]) - want_loss) <= loss_tol * abs(want_loss) + 1e-6, forward
+        got = tr.named_grads()
+        for name, g64 in want.items():
+            err, ref = float((got[name].double() - g64).abs().max()), float(g64.abs().max())
+            tol = 2e-3 if name.startswith("cat.") else grad_tol      # sigmoid nets have no kinks
+            assert err <= tol * ref + 1e-9, (forward, name, err, ref)
+    tr.adam()
+    assert bool(torch.isfinite(tr.params).all())
