@@ -109,3 +109,16 @@ def gather_sbc(thetas_local: torch.Tensor, ranks_local: torch.Tensor, num_datase
     """All-gather the per-dataset results of an SBC run sharded with ``shard_bounds``:
     (thetas_true (D,5) f32, ranks (D,5) i64) in dataset order on every rank."""
     return (all_gather_rows(thetas_local, num_datasets, group), all_gather_rows(ranks_local, num_datasets, group))
+
+
+def loglik_sum_sharded(loglik_sum: Callable[[torch.Tensor], torch.Tensor], theta: torch.Tensor, group=None) -> torch.Tensor:
+    """MNLE potential with the chains split over the ranks (weights replicated, no exchange
+    while computing, one all-gather of C floats).  ``loglik_sum(theta_rows) -> (n,)`` is the per-rank
+    evaluation, e.g. ``lambda th: estimator.loglik_sum(th, x_o, pulses_o)``; every rank passes the same
+    ``theta`` (C,5) and gets all C values back in chain order.  A chain's sum never leaves its rank, so
+    the result equals the single-process one bit for bit."""
+    rank, world = _world(group)
+    C = theta.shape[0]
+    lo, hi = shard_bounds(C, rank, world)
+    local = loglik_sum(theta[lo:hi]) if hi > lo else theta.new_empty((0,), dtype=torch.float32)
+    return all_gather_rows(local.reshape(-1), C, group)

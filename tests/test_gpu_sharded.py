@@ -19,3 +19,4 @@ def test_two_gpu_sharding_matches_single_gpu():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "sharded over 2 GPUs == single GPU: True" in r.stdout
     assert "SBC sharded over 2 GPUs == single GPU: True" in r.stdout
+    assert "potential sharded over 2 GPUs == single GPU: True" in r.stdout

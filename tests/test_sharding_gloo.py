@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import ddm_oracle as orc
-from sbi_for_diffusion_models_b200.sharding import all_gather_rows, gather_sbc, shard_bounds
+from sbi_for_diffusion_models_b200.sharding import all_gather_rows, gather_sbc, loglik_sum_sharded, shard_bounds
 
 
 def test_shard_bounds_partition():
@@ -55,6 +55,19 @@ def _run_sharded():
     return z, x, prop.pulse_proposal.rng.random()
 
 
+def _chains():
+    return orc.prior_sample(7, seed=5)
+
+
+def _spec_potential():
+    """CPU stand-in for the device potential: the MNLE spec on a fixed 6-trial session."""
+    from oracle import mnle_spec as ms
+    p = ms.init_params(0)
+    pulses = torch.from_numpy(orc.pulses_pcg64_c(*orc.pcg64_state(np.random.default_rng(123)), 0, 6, 80, 0.75))
+    x, _ = orc.sim_rng_c(np.repeat(np.array([[0.45, 0.6, 1.3, 14.0, 0.25]], np.float32), 6, 0), pulses.numpy(), 7)
+    return lambda th: ms.loglik_sum(p, th, torch.from_numpy(x), pulses).float()
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -65,7 +78,9 @@ def _worker(rank, world, port, q):
         rk = torch.arange(lo, hi, dtype=torch.int64)[:, None].repeat(1, 5) * 3
         th_all, rk_all = gather_sbc(th, rk, 10)
         ragged = all_gather_rows(torch.full((hi - lo, 2), float(rank)), 10)
-        q.put((rank, z.numpy(), x.numpy(), nxt, th_all.numpy(), rk_all.numpy(), ragged.numpy()))
+        pot = loglik_sum_sharded(_spec_potential(), _chains(), None)
+        few = loglik_sum_sharded(_spec_potential(), _chains()[:1], None)      # fewer chains than ranks
+        q.put((rank, z.numpy(), x.numpy(), nxt, th_all.numpy(), rk_all.numpy(), ragged.numpy(), pot.numpy(), few.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -89,7 +104,8 @@ def test_sharded_equals_single_process(world):
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, z, x, nxt, th_all, rk_all, ragged in results:
+    pot1, few1 = _spec_potential()(_chains()).numpy(), _spec_potential()(_chains()[:1]).numpy()
+    for rank, z, x, nxt, th_all, rk_all, ragged, pot, few in results:
         assert np.array_equal(z, z1.numpy()), f"rank {rank}: z differs from the single-process set"
         assert np.array_equal(x, x1.numpy()), f"rank {rank}: x differs"
         assert nxt == nxt1                            # host pulse generator advanced identically
@@ -97,3 +113,4 @@ def test_sharded_equals_single_process(world):
         assert np.array_equal(rk_all[:, 0], np.arange(10) * 3) and rk_all.dtype == np.int64
         want = np.concatenate([np.full(shard_bounds(10, r, world)[1] - shard_bounds(10, r, world)[0], float(r)) for r in range(world)])
         assert np.array_equal(ragged[:, 0], want)
+        assert pot.shape == (7,) and np.allclose(pot, pot1, rtol=1e-6) and np.allclose(few, few1, rtol=1e-6)

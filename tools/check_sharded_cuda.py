@@ -62,6 +62,18 @@ def main():
         same = (out["ranks"] == one["ranks"]).all() and all(torch.equal(a, b) for a, b in zip(out["all_samples"], one["all_samples"]))
         print(f"SBC sharded over {dist.get_world_size()} GPUs == single GPU: {bool(same)}", flush=True)
         ok = ok and bool(same)
+    # potential: chains split over the ranks == all chains on one rank (configs[3] shape)
+    from sbi_for_diffusion_models_b200.sharding import loglik_sum_sharded
+    from sbi_for_diffusion_models_b200.data_simulator import simulate_observed_session
+    x_o, pulses_o = simulate_observed_session(torch.tensor([0.45, 0.6, 1.3, 14.0, 0.25]), 50, "cuda", mu_sensory=1.0,
+                                              p_success=0.75, P=80, seed=123, log_rt=False, noise_seed=11)
+    torch.manual_seed(5)
+    theta = build_prior_theta().sample((1027,)).cuda()
+    pot = loglik_sum_sharded(lambda th: est.loglik_sum(th, x_o.cuda(), pulses_o.cuda()), theta)
+    if rank == 0:
+        same = torch.equal(pot, est.loglik_sum(theta, x_o.cuda(), pulses_o.cuda()))
+        print(f"potential sharded over {dist.get_world_size()} GPUs == single GPU: {bool(same)}", flush=True)
+        ok = ok and bool(same)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
