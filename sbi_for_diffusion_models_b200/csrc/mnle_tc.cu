@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 }
             }
         } else if (KEEP) {
-            // the tile's context images were built by tc_ctx_kernel: one bulk copy, everybody waits for it
+            // the tile's context images were built by tc_prep_kernel (tc_ctx_tile): one bulk copy, everybody waits for it
             unsigned char *img_hi = smem + kSmemATh + (uint32_t)X * 2u * kCtxImgBytes;
             if (q == 0 && hf == 0 && lane == 0) {
                 mbar_expect_tx(&cfull[X], 2u * kCtxImgBytes);
@@ -988,22 +988,38 @@ struct PackJobs {
     PackJob j[kTrainStages];
 };
 
-__global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ params, const __grid_constant__ PackJobs jobs,
-                                                      unsigned char *__restrict__ pack)
+constexpr int kPackSplit = 8;  // CTAs per pack job
+
+// One launch prepares everything the step's tensor-core kernels read: CTAs [0, kTrainStages * kPackSplit)
+// rebuild the operand pack from the current parameters -- every byte of it, padding rows / columns and
+// padding biases included, so the caller's workspace needs no clearing --, the others build the context
+// images of one row tile each (tc_ctx_tile below).
+__device__ __forceinline__ void tc_pack_job(const float *__restrict__ params, const PackJob &J, int part,
+                                            unsigned char *__restrict__ pack)
 {
-    const PackJob &J = jobs.j[blockIdx.x];
-    const int total = (int)J.n_valid * (int)J.k_valid;
-    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
-        const int n = idx / J.k_valid, k = idx - n * J.k_valid;
+    const int n_img = J.n_img, k_img = (int)(J.img_bytes / (2u * J.n_img));
+    const int total = n_img * k_img;
+    for (int idx = part * blockDim.x + threadIdx.x; idx < total; idx += kPackSplit * blockDim.x) {
+        int r, k;  // image row, k; consecutive threads read consecutive parameters
+        float v = 0.f;
+        if (!J.transpose) {
+            r = idx / k_img;
+            k = idx - r * k_img;
+            if (r < J.n_valid && k < J.k_valid) v = params[J.w_off + r * J.k_valid + k];
+        } else {  // image row = column of W, k = row of W
+            k = idx / n_img;
+            r = idx - k * n_img;
+            if (k < J.n_valid && r < J.k_valid) v = params[J.w_off + k * J.k_valid + r];
+        }
         uint16_t hi, lo;
-        split_bf16(params[J.w_off + idx], hi, lo);
-        const uint32_t off = J.dst + (J.transpose ? tile_offset(J.n_img, k, n) : tile_offset(J.n_img, n, k));
+        split_bf16(v, hi, lo);
+        const uint32_t off = J.dst + tile_offset(n_img, r, k);
         *reinterpret_cast<uint16_t *>(pack + off) = hi;
         *reinterpret_cast<uint16_t *>(pack + off + J.img_bytes) = lo;
     }
-    if (blockIdx.y == 0 && !J.transpose)  // (the backward-data stages have no bias)
-        for (int n = threadIdx.x; n < J.n_valid; n += blockDim.x)
-            reinterpret_cast<float *>(pack + J.dst + 2 * J.img_bytes)[n] = params[J.b_off + n];
+    if (part == 0 && !J.transpose)  // (the backward-data stages have no bias)
+        for (int n = threadIdx.x; n < n_img; n += blockDim.x)
+            reinterpret_cast<float *>(pack + J.dst + 2 * J.img_bytes)[n] = n < J.n_valid ? params[J.b_off + n] : 0.f;
 }
 
 // stage plans of the training forward and backward-data passes over one pack that holds exactly their
@@ -1076,16 +1092,16 @@ static size_t train_plan(const Layout &L, TcPlan *plan, TcPlan *bplan, PackJobs 
 // and splitting its tile's rows itself (27 k cycles before its first MMA, eleven times per tile), the
 // bf16 hi / lo A images of every tile are built once per step and the CTAs fetch them with one bulk copy.
 // grid = tiles, 384 threads: thread = (row, third of the 96 k's).
-__global__ void __launch_bounds__(384) tc_ctx_kernel(const float *__restrict__ x, const float *__restrict__ cond,
-                                                     long long ld_cond, const long long *__restrict__ row_index, long long R,
-                                                     unsigned char *__restrict__ out)
+__device__ __forceinline__ void tc_ctx_tile(int tile, const float *__restrict__ x, const float *__restrict__ cond,
+                                            long long ld_cond, const long long *__restrict__ row_index, long long R,
+                                            unsigned char *__restrict__ out)
 {
     const int r = threadIdx.x & 127, part = threadIdx.x >> 7;
-    const long long row = (long long)blockIdx.x * kTcM + r;
+    const long long row = (long long)tile * kTcM + r;
     const bool live = row < R;
     const long long drow = live ? (row_index ? row_index[row] : row) : 0;
     const float *crow = cond + drow * ld_cond;
-    unsigned char *img_hi = out + (size_t)blockIdx.x * 2u * kCtxImgBytes, *img_lo = img_hi + kCtxImgBytes;
+    unsigned char *img_hi = out + (size_t)tile * 2u * kCtxImgBytes, *img_lo = img_hi + kCtxImgBytes;
     float v[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
@@ -1101,6 +1117,17 @@ __global__ void __launch_bounds__(384) tc_ctx_kernel(const float *__restrict__ x
         *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
+}
+
+__global__ void __launch_bounds__(384) tc_prep_kernel(const float *__restrict__ params, const __grid_constant__ PackJobs jobs,
+                                                      unsigned char *__restrict__ pack, const float *__restrict__ x,
+                                                      const float *__restrict__ cond, long long ld_cond,
+                                                      const long long *__restrict__ row_index, long long R,
+                                                      unsigned char *__restrict__ ctx)
+{
+    constexpr int kPackCtas = kTrainStages * kPackSplit;
+    if ((int)blockIdx.x < kPackCtas) tc_pack_job(params, jobs.j[blockIdx.x / kPackSplit], (int)blockIdx.x % kPackSplit, pack);
+    else tc_ctx_tile((int)blockIdx.x - kPackCtas, x, cond, ld_cond, row_index, R, ctx);
 }
 
 static size_t train_pack_only_bytes(const Layout &L)
@@ -1121,12 +1148,10 @@ int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, c
     PackJobs jobs;
     const size_t bytes = train_plan(L, &plan, nullptr, &jobs);
     DDM_REQUIRE((reinterpret_cast<uintptr_t>(pack_dev) & 15u) == 0, "tc_train_forward: pack must be 16-byte aligned");
-    // padding rows / columns of the images stay zero; everything else is rewritten from the parameters
-    DDM_CUDA_TRY(cudaMemsetAsync(pack_dev, 0, bytes, st));
-    tc_pack_kernel<<<dim3(kTrainStages, 8), 256, 0, st>>>(params_dev, jobs, static_cast<unsigned char *>(pack_dev));
-    DDM_CUDA_TRY(cudaGetLastError());
     unsigned char *ctx_dev = static_cast<unsigned char *>(pack_dev) + train_pack_only_bytes(L);
-    tc_ctx_kernel<<<(unsigned)((R + kTcM - 1) / kTcM), 384, 0, st>>>(x_dev, cond_dev, ld_cond, row_index_dev, R, ctx_dev);
+    (void)bytes;
+    tc_prep_kernel<<<(unsigned)(kTrainStages * kPackSplit + (R + kTcM - 1) / kTcM), 384, 0, st>>>(
+        params_dev, jobs, static_cast<unsigned char *>(pack_dev), x_dev, cond_dev, ld_cond, row_index_dev, R, ctx_dev);
     DDM_CUDA_TRY(cudaGetLastError());
     TcTrainDump keep = dump;
     keep.ctx = ctx_dev;
