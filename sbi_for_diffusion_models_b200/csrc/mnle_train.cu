@@ -1,4 +1,5 @@
-// MNLE training step on the device, fp32 CUDA cores (sm_100a).
+// MNLE training step on the device: every GEMM on tcgen05, the per-row spline work
+// and the reductions on the CUDA cores (sm_100a).
 //
 // The reference trains the estimator with sbi's MNLE.train (mnle.py:41-48): Adam on
 // loss = -mean log p(x | z) over minibatches of TRAIN_BATCH_SIZE = 4096 rows (run_config.py:12),
@@ -9,13 +10,15 @@
 //                              pack rebuilt on the device from the current parameters; keeps the 71
 //                              raw spline parameters per (row, transform), the choice logits and the
 //                              hidden activations.
-//   2. train_rows_kernel       one thread per row: choice log-probability, the ten splines forward
+//   2. train_rows_kernel       one warp per row (lane = bin): choice log-probability, the ten splines forward
 //                              (log p of the row), then backwards (reverse mode written out by
 //                              hand), turning the stored spline parameters and logits into
 //                              d loss / d (spline parameters, logits) in place.
-//   3. train_backward_kernel   one CTA per (row tile, net): back-propagates through its net
-//                              (transposed dense products with the activation derivative fused into
-//                              the epilogue) and writes d loss / d (hidden pre-activations).
+//   3. tc_train_backward       (mnle_tc.cu) backward-data on tcgen05, one CTA per (row tiles, net):
+//                              transposed weight images, the activation derivative fused into the
+//                              epilogue, writes d loss / d (hidden pre-activations).  (train_forward_kernel /
+//                              train_backward_kernel below: the same two passes on the fp32 CUDA cores,
+//                              the accuracy anchor behind DDM_TRAIN_FP32_FORWARD.)
 //      train_wgrad_tc_kernel   the weight gradients dW = dY^T X of all 34 layers as tcgen05 GEMMs over
 //                              the rows of the minibatch (bf16 hi / lo operands, fp32 accumulation in
 //                              tensor memory); each row split owns a slice of the partial-gradient
