@@ -467,7 +467,9 @@ __global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __g
     const float *src = is_a ? J.A : J.B;
     const long long ld = is_a ? J.lda : J.ldb;
     unsigned char *img_hi = smem + (is_a ? 0u : 2u * kWgImg), *img_lo = img_hi + kWgImg;
-    const int rr0 = 32 * half;  // first row of the chunk this thread converts
+    const int rr0 = 32 * half;  // first row of the chunk this thread converts (row-major / gathered operands)
+    const bool colmajor = !is_ctx && ld == 0;
+    const int wq = (tid & 255) >> 5, q = tid & 7, cs = (tid >> 3) & 3;  // column-major operands: see load_chunk
     float v[32];
 
     auto chunk_row = [&](int c) -> long long {  // dataset row of chunk row `tid` (tid < kWgRows)
@@ -477,22 +479,22 @@ __global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __g
     auto load_chunk = [&](int c, const long long *dr) {
         const long long r0 = (long long)c * kWgRows;
         const int n_rows = (int)(rows.R - r0 < kWgRows ? rows.R - r0 : kWgRows);
-        if (col >= img_rows) return;
-        if (!is_ctx && ld == 0) {
-            // column-major operand: this thread's 32 rows are contiguous -- eight 16-byte loads
-            const long long rbase = r0 + rr0;
-            const float4 *p4 = reinterpret_cast<const float4 *>(src + (size_t)col * Rp + rbase);
+        if (colmajor) {
+            // column-major operand: load i of the warp covers rows [32 h, 32 h + 32) of four columns, eight
+            // lanes (16 bytes each) per column = four whole 128-byte lines per request.  (One thread per
+            // column with its 32 rows contiguous asked for 32 different lines per request: same bytes, but
+            // the kernel then ran at 1.8 TB/s, bound by the tag stage of L1.)
 #pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {
+            for (int i = 0; i < 8; ++i) {
+                const int cq = 16 * wq + 4 * (i >> 1) + cs, rr = 32 * (i & 1) + 4 * q;
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col < valid && rbase + 4 * e4 + 3 < Rp) t = p4[e4];
-                const int rr = rr0 + 4 * e4;
-                v[4 * e4 + 0] = rr + 0 < n_rows ? t.x : 0.f;
-                v[4 * e4 + 1] = rr + 1 < n_rows ? t.y : 0.f;
-                v[4 * e4 + 2] = rr + 2 < n_rows ? t.z : 0.f;
-                v[4 * e4 + 3] = rr + 3 < n_rows ? t.w : 0.f;
+                if (cq < valid && r0 + rr + 3 < Rp) t = *reinterpret_cast<const float4 *>(src + (size_t)cq * Rp + r0 + rr);
+                v[4 * i + 0] = rr + 0 < n_rows ? t.x : 0.f;
+                v[4 * i + 1] = rr + 1 < n_rows ? t.y : 0.f;
+                v[4 * i + 2] = rr + 2 < n_rows ? t.z : 0.f;
+                v[4 * i + 3] = rr + 3 < n_rows ? t.w : 0.f;
             }
-        } else {
+        } else if (col < img_rows) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
                 const int rr = rr0 + e;  // row within the chunk
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __g
     const uint32_t tmem = *tmem_slot;
     if (c_begin < c_end) load_chunk(c_begin, drow);
 
-    float bias_acc = 0.f;
+    float bias_acc = 0.f, bias4[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t phase = 0;
     for (int c = c_begin; c < c_end; ++c) {
         long long *dr_next = drow + (((c - c_begin) & 1) ^ 1) * kWgRows;
@@ -525,7 +527,23 @@ __global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __g
             dr_next[tid] = drow_next;  // rows of chunk c + 1: visible after the barrier below
             drow_next = chunk_row(c + 2);
         }
-        if (col < img_rows) {
+        if (colmajor) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cq = 16 * wq + 4 * (i >> 1) + cs;
+                if (cq < img_rows) {
+                    uint32_t hi[2], lo[2];
+                    split_bf16x2(v[4 * i], v[4 * i + 1], hi[0], lo[0]);
+                    split_bf16x2(v[4 * i + 2], v[4 * i + 3], hi[1], lo[1]);
+                    if (is_a) bias4[i >> 1] += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
+                    // K group = 8 rows: rows 32 (i & 1) + 4 q .. + 3 are half q & 1 of group 4 (i & 1) + q / 2
+                    const uint32_t off = (uint32_t)(4 * (i & 1) + (q >> 1)) * (uint32_t)img_rows * 16u + (uint32_t)cq * 16u +
+                                         (uint32_t)(q & 1) * 8u;
+                    *reinterpret_cast<uint2 *>(img_hi + off) = make_uint2(hi[0], hi[1]);
+                    *reinterpret_cast<uint2 *>(img_lo + off) = make_uint2(lo[0], lo[1]);
+                }
+            }
+        } else if (col < img_rows) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 uint32_t hi[4], lo[4];
@@ -569,9 +587,9 @@ __global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __g
     // the two halves of a dY column add up their bias sums (fixed order)
     float *tile = reinterpret_cast<float *>(smem);  // the images are dead
     __syncthreads();
-    if (is_a && half == 1) tile[col] = bias_acc;
+    if (is_a && !colmajor && half == 1) tile[col] = bias_acc;
     __syncthreads();
-    if (is_a && half == 0) bias_acc += tile[col];
+    if (is_a && !colmajor && half == 0) bias_acc += tile[col];
     __syncthreads();
     // accumulators -> shared memory (lane m of tensor memory = row m of dW; warp w reads lane group w % 4,
     // columns 32 * (w / 4) ..; XOR swizzle against bank conflicts) -> this split's slice, coalesced
@@ -590,7 +608,19 @@ __global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __g
 #pragma unroll
             for (int j = 0; j < 32; ++j) tile[m * 128 + ((n0 + j) ^ lane)] = __uint_as_float(a[j]);
         }
-        if (tid < 128 && tid < J.M) Pout[J.b_off + tid] = bias_acc;  // (tid < 128: operand A, half 0, col = tid)
+        if (is_a && colmajor) {  // eight lanes share a column: fixed-order butterfly, lane q = 0 writes
+#pragma unroll
+            for (int cg = 0; cg < 4; ++cg) {
+                float b = bias4[cg];
+                b += __shfl_xor_sync(0xFFFFFFFFu, b, 1);
+                b += __shfl_xor_sync(0xFFFFFFFFu, b, 2);
+                b += __shfl_xor_sync(0xFFFFFFFFu, b, 4);
+                const int cq = 16 * wq + 4 * cg + cs;
+                if (q == 0 && cq < J.M) Pout[J.b_off + cq] = b;
+            }
+        } else if (tid < 128 && tid < J.M) {
+            Pout[J.b_off + tid] = bias_acc;  // (tid < 128: operand A, half 0, col = tid)
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
