@@ -430,7 +430,11 @@ struct WJobs {
 };
 constexpr int kWgThreads = 512;                  // 2 operands x 128 columns x 2 halves of the chunk's rows
 static_assert(kWgRows == 64, "thread mapping below: 32 rows (four 8-row K groups) per thread and chunk");
-constexpr uint32_t kWgImg = 128 * kWgRows * 2;   // one 128 x kWgRows bf16 image
+// K-major images with the stride between 8-row K groups padded by 32 bytes (the UMMA descriptor's LBO is free):
+// the eight lanes that share a column write four K groups at once, and without the pad those land in the same
+// banks
+constexpr uint32_t kWgPad = 32;
+constexpr uint32_t kWgImg = (kWgRows / 8) * (128 * 16 + kWgPad);   // one 128 x kWgRows bf16 image
 constexpr uint32_t kWgSmem = 4 * kWgImg + 64 + 2 * kWgRows * 8;
 static_assert(4 * kWgImg >= 128 * 128 * 4, "the epilogue stages the 128 x 128 fp32 tile in the image area");
 
@@ -537,8 +541,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __g
                     split_bf16x2(v[4 * i + 2], v[4 * i + 3], hi[1], lo[1]);
                     if (is_a) bias4[i >> 1] += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
                     // K group = 8 rows: rows 32 (i & 1) + 4 q .. + 3 are half q & 1 of group 4 (i & 1) + q / 2
-                    const uint32_t off = (uint32_t)(4 * (i & 1) + (q >> 1)) * (uint32_t)img_rows * 16u + (uint32_t)cq * 16u +
-                                         (uint32_t)(q & 1) * 8u;
+                    const uint32_t off = (uint32_t)(4 * (i & 1) + (q >> 1)) * ((uint32_t)img_rows * 16u + kWgPad) +
+                                         (uint32_t)cq * 16u + (uint32_t)(q & 1) * 8u;
                     *reinterpret_cast<uint2 *>(img_hi + off) = make_uint2(hi[0], hi[1]);
                     *reinterpret_cast<uint2 *>(img_lo + off) = make_uint2(lo[0], lo[1]);
                 }
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __g
                 if (is_a)
                     bias_acc += ((v[8 * g] + v[8 * g + 1]) + (v[8 * g + 2] + v[8 * g + 3])) +
                                 ((v[8 * g + 4] + v[8 * g + 5]) + (v[8 * g + 6] + v[8 * g + 7]));
-                const uint32_t off = (uint32_t)(4 * half + g) * (uint32_t)img_rows * 16u + (uint32_t)col * 16u;
+                const uint32_t off = (uint32_t)(4 * half + g) * ((uint32_t)img_rows * 16u + kWgPad) + (uint32_t)col * 16u;
                 *reinterpret_cast<uint4 *>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
@@ -565,13 +569,13 @@ __global__ void __launch_bounds__(kWgThreads, 2) train_wgrad_tc_kernel(const __g
             if (elect_one_sync()) {
                 const uint32_t idesc = umma_idesc_bf16_f32(128, n_pad);
                 const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 2 * kWgImg);
-                const uint32_t lbo_b = (uint32_t)n_pad * 16u;
+                const uint32_t lbo_a = 128u * 16u + kWgPad, lbo_b = (uint32_t)n_pad * 16u + kWgPad;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint32_t pa = a0 + (pass == 2 ? kWgImg : 0u), pb = b0 + (pass == 1 ? kWgImg : 0u);
 #pragma unroll
                     for (int ks = 0; ks < kWgRows / 16; ++ks)
-                        umma_bf16(tmem, umma_desc_kmajor(pa + ks * 2 * 128 * 16, 128 * 16, 128),
+                        umma_bf16(tmem, umma_desc_kmajor(pa + ks * 2 * lbo_a, lbo_a, 128),
                                   umma_desc_kmajor(pb + ks * 2 * lbo_b, lbo_b, 128), idesc,
                                   (c > c_begin) || (pass | ks) != 0);
                 }
