@@ -109,6 +109,8 @@ struct TcTrainDump {
     long long Rp;  // rows allocated (a multiple of 64, >= R)
     float *DH;     // backward pass only: [kNets][3][128][Rp] d loss / d (hidden pre-activations), written
     const unsigned char *ctx;  // forward only: per 128-row tile the bf16 hi / lo context images (tc_prep_kernel)
+    float *CX;     // forward only (may be null): [86][Rp] the gathered context rows [cond (85), choice], column-major --
+                   // the X operand of the first layers' weight-gradient GEMMs
 };
 size_t tc_train_pack_bytes(int n_choices, long long R);  // operand pack + context images of R rows
 int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, const float *x_dev, const float *cond_dev,

@@ -1094,7 +1094,7 @@ static size_t train_plan(const Layout &L, TcPlan *plan, TcPlan *bplan, PackJobs 
 // grid = tiles, 384 threads: thread = (row, third of the 96 k's).
 __device__ __forceinline__ void tc_ctx_tile(int tile, const float *__restrict__ x, const float *__restrict__ cond,
                                             long long ld_cond, const long long *__restrict__ row_index, long long R,
-                                            unsigned char *__restrict__ out)
+                                            unsigned char *__restrict__ out, float *__restrict__ cx, long long Rp)
 {
     const int r = threadIdx.x & 127, part = threadIdx.x >> 7;
     const long long row = (long long)tile * kTcM + r;
@@ -1107,6 +1107,11 @@ __device__ __forceinline__ void tc_ctx_tile(int tile, const float *__restrict__ 
     for (int e = 0; e < 32; ++e) {
         const int k = 32 * part + e;
         v[e] = !live ? 0.f : (k < kCond ? __ldg(crow + k) : (k == kCond ? __ldg(x + 2 * drow + 1) : 0.f));
+    }
+    if (cx != nullptr && row < Rp) {  // fp32 copy for the weight-gradient GEMMs: lanes = consecutive rows of a column
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+            if (32 * part + e <= kCond) cx[(size_t)(32 * part + e) * (size_t)Rp + (size_t)row] = v[e];
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -1123,11 +1128,11 @@ __global__ void __launch_bounds__(384) tc_prep_kernel(const float *__restrict__ 
                                                       unsigned char *__restrict__ pack, const float *__restrict__ x,
                                                       const float *__restrict__ cond, long long ld_cond,
                                                       const long long *__restrict__ row_index, long long R,
-                                                      unsigned char *__restrict__ ctx)
+                                                      unsigned char *__restrict__ ctx, float *__restrict__ cx, long long Rp)
 {
     constexpr int kPackCtas = kTrainStages * kPackSplit;
     if ((int)blockIdx.x < kPackCtas) tc_pack_job(params, jobs.j[blockIdx.x / kPackSplit], (int)blockIdx.x % kPackSplit, pack);
-    else tc_ctx_tile((int)blockIdx.x - kPackCtas, x, cond, ld_cond, row_index, R, ctx);
+    else tc_ctx_tile((int)blockIdx.x - kPackCtas, x, cond, ld_cond, row_index, R, ctx, cx, Rp);
 }
 
 static size_t train_pack_only_bytes(const Layout &L)
@@ -1151,7 +1156,8 @@ int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, c
     unsigned char *ctx_dev = static_cast<unsigned char *>(pack_dev) + train_pack_only_bytes(L);
     (void)bytes;
     tc_prep_kernel<<<(unsigned)(kTrainStages * kPackSplit + (R + kTcM - 1) / kTcM), 384, 0, st>>>(
-        params_dev, jobs, static_cast<unsigned char *>(pack_dev), x_dev, cond_dev, ld_cond, row_index_dev, R, ctx_dev);
+        params_dev, jobs, static_cast<unsigned char *>(pack_dev), x_dev, cond_dev, ld_cond, row_index_dev, R, ctx_dev, dump.CX,
+        dump.Rp);
     DDM_CUDA_TRY(cudaGetLastError());
     TcTrainDump keep = dump;
     keep.ctx = ctx_dev;

@@ -729,13 +729,16 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
 
     static_assert(sizeof(SimtSmem) < 113 * 1024, "two CTAs per SM");
     const int want_grad = grad_dev != nullptr;
+    // the gathered context rows as fp32 columns (written by the tensor-core forward's prep kernel, read by the
+    // weight-gradient GEMMs of the first layers): the flow nets keep two hidden layers, so slot 2 of net 1 is free
+    float *ctx_cols = B.H + (size_t)(1 * 3 + 2) * kHidden * (size_t)d.Rp;
     if (flags & DDM_TRAIN_FP32_FORWARD) {
         DDM_CUDA_TRY(cudaFuncSetAttribute(train_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(SimtSmem)));
         train_forward_kernel<<<dim3(d.tiles, kNets), kThreads, sizeof(SimtSmem), st>>>(params_dev, L, rows, d.Rp, B, 1);
         DDM_CUDA_TRY(cudaGetLastError());
     } else {  // forward on the tensor cores (mnle_tc.cu), keeping logits, spline parameters and activations
-        const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp, nullptr, nullptr};
+        const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp, nullptr, nullptr, want_grad ? ctx_cols : nullptr};
         const int rc = tc_train_forward(params_dev, L, B.pack, x_dev, cond_dev, (long long)ld_cond,
                                         reinterpret_cast<const long long *>(row_index_dev), (long long)R, keep, B.LP, st);
         if (rc != DDM_OK) return rc;
@@ -767,12 +770,13 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
         add(B.LG, kMaxChoices, n_choices, H(0, 2), 0, kHidden, L.cat_Wo, L.cat_bo);
         add(DH(0, 2), 0, kHidden, H(0, 1), 0, kHidden, L.cat_W2, L.cat_b2);
         add(DH(0, 1), 0, kHidden, H(0, 0), 0, kHidden, L.cat_W1, L.cat_b1);
-        add(DH(0, 0), 0, kHidden, nullptr, 0, kCond, L.cat_W0, L.cat_b0);
+        const float *ctx_x = (flags & DDM_TRAIN_FP32_FORWARD) ? nullptr : ctx_cols;  // nullptr: gather from the dataset
+        add(DH(0, 0), 0, kHidden, ctx_x, 0, kCond, L.cat_W0, L.cat_b0);
         for (int k = 0; k < kTransforms; ++k) {
             const int net = 1 + k;
             add(B.Q + (size_t)k * kQRows * d.Rp, kQRows, kSplineOut, H(net, 1), 0, kHidden, L.fl_W3[k], L.fl_b3[k]);
             add(DH(net, 1), 0, kHidden, H(net, 0), 0, kHidden, L.fl_W2[k], L.fl_b2[k]);
-            add(DH(net, 0), 0, kHidden, nullptr, 0, kCtx, L.fl_W1[k], L.fl_b1[k]);
+            add(DH(net, 0), 0, kHidden, ctx_x, 0, kCtx, L.fl_W1[k], L.fl_b1[k]);
         }
         DDM_CUDA_TRY(cudaFuncSetAttribute(train_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
         train_wgrad_tc_kernel<<<dim3(nj, d.groups), kWgThreads, kWgSmem, st>>>(jobs, rows, d.Rp, (int)((R + kWgRows - 1) / kWgRows), L.total,
