@@ -207,6 +207,13 @@ int mnle_destroy(void *handle);
 int mnle_log_prob_rows_f32(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond,
                            int64_t R, float *out_dev, void *stream);
 
+/* Same call with the per-row chain (log rt, ten splines, categorical head, final sum) in fp64 on the fp32
+ * conditioner outputs -- the accuracy anchor for TRAINED estimators: a trained flow's narrow, steep bins
+ * amplify fp32 rounding of the knot positions to ~3e-4 per row in ANY fp32 evaluation (the reference's torch
+ * CPU call included); this path sits ~1e-6 from exact arithmetic.  Same arguments and output type. */
+int mnle_log_prob_rows_precise_f32(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond,
+                                   int64_t R, float *out_dev, void *stream);
+
 /* Same call on the 5th-generation tensor cores: the 86-wide context of each row is split into bf16
  * hi + lo operand images in shared memory and every layer (first layers included, K padded to 96) runs
  * as three tcgen05.mma per product; two 128-row tiles per CTA in ping-pong.  Per-row results within ~1e-4 of the fp32 kernel on
@@ -228,6 +235,10 @@ size_t mnle_loglik_workspace_floats(int64_t T, int64_t C);
 int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
                              const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
                              float *out_dev, float *workspace_dev, void *stream);
+/* _precise: fp32 networks, fp64 spline chain (see mnle_log_prob_rows_precise_f32); same workspace. */
+int mnle_loglik_sum_precise_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
+                                float *out_dev, float *workspace_dev, void *stream);
 
 /*
  * Value and gradient with respect to theta of the same sum (what autograd gives the reference's

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "mnle_create": (ctypes.c_int, [_ptr, ctypes.c_size_t, _i32, _ptr]),
     "mnle_destroy": (ctypes.c_int, [_ptr]),
     "mnle_log_prob_rows_f32": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
+    "mnle_log_prob_rows_precise_f32": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
     "mnle_log_prob_rows_tc_f32": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
     "mnle_loglik_workspace_floats": (ctypes.c_size_t, [_i64, _i64]),
     "mnle_loglik_tc_workspace_floats": (ctypes.c_size_t, [_i64, _i64]),
@@ -54,6 +55,7 @@ _SIGNATURES = {
     "mnle_tc_set_trace": (ctypes.c_int, [_ptr]),
     "mnle_tc_selftest": (ctypes.c_int, [_ptr, _ptr, _i32, _i32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _ptr, _ptr]),
     "mnle_loglik_sum_simt_f32": (ctypes.c_int, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
+    "mnle_loglik_sum_precise_f32": (ctypes.c_int, [_ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

@@ -4,12 +4,13 @@
 // trial at P = 80; data_simulator.py:22-29).  Pulse sides are +-1, so when z lives in HOST memory
 // the link carries 10x more bytes than information: 1e8 trials are 34 GB over a ~55 GB/s PCIe 5 x16
 // link, longer than the kernel needs to simulate them.  ddm_pack_z_host turns each row into one
-// 32-byte record [theta bits x 5, pulse sign masks x 3] on the host cores (multi-threaded, SSE2 /
-// AVX2 compares + movemask) so that the copy engine moves 32 bytes per trial;
+// 32-byte record [theta bits x 5, pulse sign masks x 3] on the host cores (multi-threaded, AVX-512 mask
+// compares, else AVX2 / SSE2 compares + movemask) so that the copy engine moves 32 bytes per trial;
 // ddm_sim_packed_f32 (ddm_sim.cu) consumes the records directly.  Rows holding anything other than
 // +-1 are counted: the caller sends such batches through the fp32 path instead.
 #include <immintrin.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cuda_runtime.h>
@@ -119,6 +120,61 @@ __attribute__((target("avx2"))) static void pack_rows_avx2(const float *z, int64
     *generic_rows = gen;
 }
 
+// AVX-512 (F + DQ + VL): a compare writes its 16 result bits straight into a mask register, so a row of
+// 80 pulses is five 64-byte loads and ten compares; the record leaves as one 32-byte non-temporal store
+// (the staging block is write-only for the host: no read-for-ownership traffic).  Rows further along are
+// prefetched explicitly: the 340-byte row stride defeats the adjacent-line prefetcher on some parts.
+__attribute__((target("avx512f,avx512dq,avx512vl,avx2"))) static void pack_rows_avx512(
+    const float *z, int64_t ld, int64_t r0, int64_t r1, int n_pulses, uint32_t *out, int64_t *generic_rows)
+{
+    const __m512i absmask = _mm512_set1_epi32(0x7FFFFFFF), one = _mm512_set1_epi32(0x3F800000);
+    const __m512 zero = _mm512_setzero_ps();
+    __mmask16 lm[6];  // lanes of 16-column group g that the schedule reaches
+    for (int g = 0; g < 6; ++g) {
+        const int n = n_pulses - 16 * g;
+        lm[g] = (__mmask16)(n >= 16 ? 0xFFFF : (n <= 0 ? 0 : ((1u << n) - 1u)));
+    }
+    const int groups = (n_pulses + 15) / 16;
+    const bool aligned_out = (reinterpret_cast<uintptr_t>(out) & 31u) == 0;
+    constexpr int64_t kAhead = 12;  // rows (~4 KB)
+    int64_t gen = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const float *row = z + r * ld;
+        if (r + kAhead < r1) {
+            const char *pf = reinterpret_cast<const char *>(row + kAhead * ld);
+            _mm_prefetch(pf, _MM_HINT_T0);
+            _mm_prefetch(pf + 64, _MM_HINT_T0);
+            _mm_prefetch(pf + 128, _MM_HINT_T0);
+            _mm_prefetch(pf + 192, _MM_HINT_T0);
+            _mm_prefetch(pf + 256, _MM_HINT_T0);
+            _mm_prefetch(pf + 320, _MM_HINT_T0);
+        }
+        const float *s = row + 5;
+        uint32_t gt[6];
+        __mmask16 odd = 0;
+#pragma GCC unroll 6
+        for (int g = 0; g < 6; ++g) {
+            if (g < groups) {
+                const __m512 v = _mm512_maskz_loadu_ps(lm[g], s + 16 * g);  // masked-out lanes are not touched
+                gt[g] = (uint32_t)(_mm512_mask_cmp_ps_mask(lm[g], v, zero, _CMP_GT_OQ) | (__mmask16)~lm[g]);
+                odd |= _mm512_mask_cmpneq_epi32_mask(lm[g], _mm512_and_si512(_mm512_castps_si512(v), absmask), one);
+            } else {
+                gt[g] = 0xFFFFu;
+            }
+        }
+        // record: theta bits x 5 (the first 8 floats of the row, lanes 5..7 replaced), masks x 3
+        __m256i rec = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(row));
+        const __m256i masks = _mm256_setr_epi32(0, 0, 0, 0, 0, (int)(gt[0] | (gt[1] << 16)), (int)(gt[2] | (gt[3] << 16)),
+                                                (int)(gt[4] | (gt[5] << 16)));
+        rec = _mm256_mask_blend_epi32((__mmask8)0xE0, rec, masks);
+        if (aligned_out) _mm256_stream_si256(reinterpret_cast<__m256i *>(out + r * 8), rec);
+        else _mm256_storeu_si256(reinterpret_cast<__m256i *>(out + r * 8), rec);
+        gen += odd ? 1 : 0;
+    }
+    _mm_sfence();
+    *generic_rows = gen;
+}
+
 // Persistent worker pool: a chunk of 2^18 rows packs in about a millisecond, so spawning threads per
 // call (~30-50 us each) would cost as much as the work.  Workers sleep on a condition variable between
 // calls; the calling thread takes jobs too.  A forked child starts a fresh pool.
@@ -190,13 +246,17 @@ DDM_API int64_t ddm_pack_z_host(const float *z_host, int64_t ld, int64_t N, int6
     }
     if (N == 0) return 0;
     const bool avx2 = __builtin_cpu_supports("avx2");
+    // a row must hold 8 floats for the record's 32-byte load (5 + n_pulses >= 8)
+    const bool avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") &&
+                        __builtin_cpu_supports("avx512vl") && n_pulses >= 3 && getenv("DDM_PACK_NO_AVX512") == nullptr;
     int nt = n_threads < 1 ? 1 : n_threads;
     const int64_t min_rows = 1 << 14;  // below that a thread costs more than it packs
     if ((int64_t)nt > (N + min_rows - 1) / min_rows) nt = (int)((N + min_rows - 1) / min_rows);
     std::vector<int64_t> gen((size_t)nt, 0);
     auto work = [&](int t) {
         const int64_t r0 = N * t / nt, r1 = N * (t + 1) / nt;
-        if (avx2) ddm::pack_rows_avx2(z_host, ld, r0, r1, (int)n_pulses, packed_host, &gen[(size_t)t]);
+        if (avx512) ddm::pack_rows_avx512(z_host, ld, r0, r1, (int)n_pulses, packed_host, &gen[(size_t)t]);
+        else if (avx2) ddm::pack_rows_avx2(z_host, ld, r0, r1, (int)n_pulses, packed_host, &gen[(size_t)t]);
         else ddm::pack_rows_sse2(z_host, ld, r0, r1, (int)n_pulses, packed_host, &gen[(size_t)t]);
     };
     if (nt == 1) work(0);

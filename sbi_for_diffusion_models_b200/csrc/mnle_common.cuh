@@ -125,29 +125,43 @@ __device__ __forceinline__ float softplus_f(float x)
 {
     return x > 20.0f ? x : log1pf(expf(x));  // torch.nn.functional.softplus, threshold 20
 }
+__device__ __forceinline__ double softplus_f(double x) { return x > 20.0 ? x : log1p(exp(x)); }
+
+// scalar helpers so that the spline below reads the same in fp32 and fp64
+__device__ __forceinline__ float rexp(float x) { return expf(x); }
+__device__ __forceinline__ double rexp(double x) { return exp(x); }
+__device__ __forceinline__ float rlog(float x) { return logf(x); }
+__device__ __forceinline__ double rlog(double x) { return log(x); }
 
 // One rational-quadratic spline transform with linear tails (Durkan et al. 2019) on a scalar.
 // q points at the 71 raw conditioner outputs of this row (stride qs floats between them).
-template <typename Stride>
-__device__ __forceinline__ void rqs_forward(float &u, float &logdet, const float *q, Stride qs)
+// Real = float: the arithmetic of the fp32 kernels (and of the reference, which evaluates sbi's
+// estimator in fp32).  Real = double: the "precise" path.  On a TRAINED estimator the knots of narrow,
+// steep bins amplify the rounding of the softmax / cumulative-sum stage by 2-3 orders of magnitude: any
+// fp32 evaluation (torch on the CPU included) sits ~3e-4 per row from exact arithmetic, a float64 spline on
+// fp32 conditioner outputs ~1e-6.
+template <typename Real, typename Stride>
+__device__ __forceinline__ void rqs_forward(Real &u, Real &logdet, const float *q, Stride qs)
 {
-    if (!(u >= -kTail && u <= kTail)) return;  // identity outside the tail bound
-    const float inv_sqrt_h = 0.08838834764831845f;  // 1/sqrt(128)
+    const Real tail = (Real)kTail, min_bin = (Real)1e-3, min_deriv = (Real)1e-3, one = (Real)1, two = (Real)2;
+    if (!(u >= -tail && u <= tail)) return;  // identity outside the tail bound
+    const Real inv_sqrt_h = (Real)0.08838834764831844055;  // 1/sqrt(128)
+    const Real span = one - min_bin * (Real)kBins;
     // ---- widths: softmax -> cumulative knots, locate the bin -------------------------
-    float m = -INFINITY;
+    Real m = -(Real)INFINITY;
 #pragma unroll 4
-    for (int j = 0; j < kBins; ++j) m = fmaxf(m, q[j * qs] * inv_sqrt_h);
-    float s = 0.f;
+    for (int j = 0; j < kBins; ++j) m = fmax(m, (Real)q[j * qs] * inv_sqrt_h);
+    Real s = 0;
 #pragma unroll 4
-    for (int j = 0; j < kBins; ++j) s += expf(q[j * qs] * inv_sqrt_h - m);
-    const float inv_s = 1.0f / s;
-    float cs = 0.f, prev = -kTail, left = -kTail, right = kTail;
+    for (int j = 0; j < kBins; ++j) s += rexp((Real)q[j * qs] * inv_sqrt_h - m);
+    const Real inv_s = one / s;
+    Real cs = 0, prev = -tail, left = -tail, right = tail;
     int b = 0;
 #pragma unroll 4
     for (int j = 0; j < kBins; ++j) {
-        const float w = kMinBin + (1.0f - kMinBin * kBins) * (expf(q[j * qs] * inv_sqrt_h - m) * inv_s);
+        const Real w = min_bin + span * (rexp((Real)q[j * qs] * inv_sqrt_h - m) * inv_s);
         cs += w;
-        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
+        const Real edge = (j == kBins - 1) ? tail : (two * tail * cs - tail);
         if (u >= prev) {
             b = j;
             left = prev;
@@ -157,21 +171,21 @@ __device__ __forceinline__ void rqs_forward(float &u, float &logdet, const float
     }
     // ---- heights: same construction, read knots b and b+1 -----------------------------
     const float *qh = q + kBins * qs;
-    m = -INFINITY;
+    m = -(Real)INFINITY;
 #pragma unroll 4
-    for (int j = 0; j < kBins; ++j) m = fmaxf(m, qh[j * qs] * inv_sqrt_h);
-    s = 0.f;
+    for (int j = 0; j < kBins; ++j) m = fmax(m, (Real)qh[j * qs] * inv_sqrt_h);
+    s = 0;
 #pragma unroll 4
-    for (int j = 0; j < kBins; ++j) s += expf(qh[j * qs] * inv_sqrt_h - m);
-    const float inv_sh = 1.0f / s;
-    cs = 0.f;
-    prev = -kTail;
-    float bottom = -kTail, top = kTail;
+    for (int j = 0; j < kBins; ++j) s += rexp((Real)qh[j * qs] * inv_sqrt_h - m);
+    const Real inv_sh = one / s;
+    cs = 0;
+    prev = -tail;
+    Real bottom = -tail, top = tail;
 #pragma unroll 4
     for (int j = 0; j < kBins; ++j) {
-        const float h = kMinBin + (1.0f - kMinBin * kBins) * (expf(qh[j * qs] * inv_sqrt_h - m) * inv_sh);
+        const Real h = min_bin + span * (rexp((Real)qh[j * qs] * inv_sqrt_h - m) * inv_sh);
         cs += h;
-        const float edge = (j == kBins - 1) ? kTail : (2.0f * kTail * cs - kTail);
+        const Real edge = (j == kBins - 1) ? tail : (two * tail * cs - tail);
         if (j == b) {
             bottom = prev;
             top = edge;
@@ -182,36 +196,37 @@ __device__ __forceinline__ void rqs_forward(float &u, float &logdet, const float
     const float *qd = q + 2 * kBins * qs;
     // nflows pads the derivative logits with log(exp(1 - min_derivative) - 1), i.e.
     // min_derivative + softplus(pad) == 1: the spline meets the linear tails with slope 1.
-    const float edge_d = 1.0f;
-    const float d0 = (b == 0) ? edge_d : kMinDeriv + softplus_f(qd[(b - 1) * qs]);
-    const float d1 = (b == kBins - 1) ? edge_d : kMinDeriv + softplus_f(qd[b * qs]);
+    const Real edge_d = one;
+    const Real d0 = (b == 0) ? edge_d : min_deriv + softplus_f((Real)qd[(b - 1) * qs]);
+    const Real d1 = (b == kBins - 1) ? edge_d : min_deriv + softplus_f((Real)qd[b * qs]);
 
-    const float w = right - left, h = top - bottom;
-    const float delta = h / w;
-    const float th = (u - left) / w;
-    const float t1 = th * (1.0f - th);
-    const float den = delta + (d0 + d1 - 2.0f * delta) * t1;
-    const float out = bottom + h * (delta * th * th + d0 * t1) / den;
-    const float dnum = delta * delta * (d1 * th * th + 2.0f * delta * t1 + d0 * (1.0f - th) * (1.0f - th));
-    logdet += logf(dnum) - 2.0f * logf(den);
+    const Real w = right - left, h = top - bottom;
+    const Real delta = h / w;
+    const Real th = (u - left) / w;
+    const Real t1 = th * (one - th);
+    const Real den = delta + (d0 + d1 - two * delta) * t1;
+    const Real out = bottom + h * (delta * th * th + d0 * t1) / den;
+    const Real dnum = delta * delta * (d1 * th * th + two * delta * t1 + d0 * (one - th) * (one - th));
+    logdet += rlog(dnum) - two * rlog(den);
     u = out;
 }
 
 // log Categorical(choice | softmax(logits)) with torch's probs clamp to [eps, 1 - eps].
-__device__ __forceinline__ float categorical_logp(const float *logits, int ls, int n_choices, int choice)
+template <typename Real = float>
+__device__ __forceinline__ Real categorical_logp(const float *logits, int ls, int n_choices, int choice)
 {
-    float m = -INFINITY;
-    for (int j = 0; j < n_choices; ++j) m = fmaxf(m, logits[j * ls]);
-    float s = 0.f, pc = 0.f;
+    Real m = -(Real)INFINITY;
+    for (int j = 0; j < n_choices; ++j) m = fmax(m, (Real)logits[j * ls]);
+    Real s = 0, pc = 0;
     for (int j = 0; j < n_choices; ++j) {
-        const float e = expf(logits[j * ls] - m);
+        const Real e = rexp((Real)logits[j * ls] - m);
         s += e;
         if (j == choice) pc = e;
     }
-    float p = pc / s;
-    const float eps = 1.1920928955078125e-07f;
-    p = fminf(fmaxf(p, eps), 1.0f - eps);
-    return logf(p);
+    Real p = pc / s;
+    const Real eps = (Real)1.1920928955078125e-07;
+    p = fmin(fmax(p, eps), (Real)1 - eps);
+    return rlog(p);
 }
 
 }  // namespace mnle

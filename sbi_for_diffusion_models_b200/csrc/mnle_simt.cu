@@ -10,6 +10,8 @@
 // materialises a (T*C, 85) condition matrix and a (1, T*C, 2) x tensor per call (17.8 MB at
 // T=50, C=1024) and runs estimator.log_prob over it; here row r = t*C + c is assembled on the
 // fly from theta[c], pulses[t], x[t].
+#include <type_traits>
+
 #include "mnle_dense.cuh"
 
 namespace mnle {
@@ -26,9 +28,13 @@ struct RowSource {
     int potential;
 };
 
+// PRECISE: the per-row chain (log rt, the ten splines, the categorical head, the final sum) runs in fp64 on the
+// fp32 conditioner outputs.  This is the accuracy anchor for trained estimators (see rqs_forward).
+template <bool PRECISE>
 __global__ void __launch_bounds__(kThreads) mnle_simt_kernel(const float *__restrict__ params, Layout L, RowSource src,
                                                              float mu_y, float sigma_y, float *__restrict__ out)
 {
+    using Real = typename std::conditional<PRECISE, double, float>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SimtSmem &S = *reinterpret_cast<SimtSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -59,14 +65,14 @@ __global__ void __launch_bounds__(kThreads) mnle_simt_kernel(const float *__rest
     const bool owner = tid < kTM;
     const long long my_row = row0 + tid;
     const bool live = owner && my_row < n_rows;
-    float lp = 0.f, u = 0.f, logdet = 0.f, y = 0.f;
+    Real lp = 0, u = 0, logdet = 0, y = 0;
     int choice = 0;
     if (live) {
         const float rt = __ldg(src.x + 2 * my_row);
         choice = (int)__ldg(src.x + 2 * my_row + 1);
-        y = logf(rt);
-        u = (y - mu_y) / sigma_y;
-        logdet = -logf(sigma_y);
+        y = rlog((Real)rt);
+        u = (y - (Real)mu_y) / (Real)sigma_y;
+        logdet = -rlog((Real)sigma_y);
     }
 
     // ---- categorical head: 85 -> 128 -> 128 -> 128 -> K, sigmoid ------------------------
@@ -74,21 +80,21 @@ __global__ void __launch_bounds__(kThreads) mnle_simt_kernel(const float *__rest
     dense<8, kSigmoid>(params + L.cat_W1, params + L.cat_b1, kHidden, kHidden, S.ha, kLdH, S.hb, kLdH, S.w);
     dense<8, kSigmoid>(params + L.cat_W2, params + L.cat_b2, kHidden, kHidden, S.hb, kLdH, S.ha, kLdH, S.w);
     dense<1, kNone>(params + L.cat_Wo, params + L.cat_bo, kHidden, L.n_choices, S.ha, kLdH, S.hb, kLdH, S.w);
-    if (live) lp = categorical_logp(S.hb + tid * kLdH, 1, L.n_choices, choice);
+    if (live) lp = categorical_logp<Real>(S.hb + tid * kLdH, 1, L.n_choices, choice);
 
     // ---- ten spline conditioners: 86 -> 128 -> 128 -> 71, relu --------------------------
     for (int k = 0; k < kTransforms; ++k) {
         dense<8, kRelu>(params + L.fl_W1[k], params + L.fl_b1[k], kCtx, kHidden, S.in, kLdIn, S.ha, kLdH, S.w);
         dense<8, kRelu>(params + L.fl_W2[k], params + L.fl_b2[k], kHidden, kHidden, S.ha, kLdH, S.hb, kLdH, S.w);
         dense<5, kNone>(params + L.fl_W3[k], params + L.fl_b3[k], kHidden, kSplineOut, S.hb, kLdH, S.ha, kLdH, S.w);
-        if (live) rqs_forward(u, logdet, S.ha + tid * kLdH, 1);
+        if (live) rqs_forward<Real>(u, logdet, S.ha + tid * kLdH, 1);
     }
 
-    float total = 0.f;
-    if (live) total = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+    Real total = 0;
+    if (live) total = lp + ((Real)-0.5 * u * u - (Real)0.91893853320467274178) + logdet - y;
 
     if (!src.potential) {
-        if (live) out[my_row] = total;
+        if (live) out[my_row] = (float)total;
         return;
     }
     // potential mode: deterministic reduction over the tile's trials (warps 0 and 1)
@@ -118,12 +124,12 @@ static Handle *check_handle(void *h)
     return H;
 }
 
-static int launch(Handle *H, const RowSource &src, dim3 grid, float *out, cudaStream_t st)
+static int launch(Handle *H, const RowSource &src, dim3 grid, float *out, cudaStream_t st, bool precise = false)
 {
     static_assert(sizeof(SimtSmem) < 227 * 1024, "tile does not fit shared memory");
-    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(SimtSmem)));
-    mnle_simt_kernel<<<grid, kThreads, sizeof(SimtSmem), st>>>(H->params, H->layout, src, H->mu_y, H->sigma_y, out);
+    auto kern = precise ? mnle_simt_kernel<true> : mnle_simt_kernel<false>;
+    DDM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimtSmem)));
+    kern<<<grid, kThreads, sizeof(SimtSmem), st>>>(H->params, H->layout, src, H->mu_y, H->sigma_y, out);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }
@@ -187,8 +193,8 @@ DDM_API int mnle_destroy(void *handle)
     return DDM_OK;
 }
 
-DDM_API int mnle_log_prob_rows_f32(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond, int64_t R,
-                                   float *out_dev, void *stream)
+static int rows_impl(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond, int64_t R, float *out_dev,
+                     void *stream, bool precise)
 {
     Handle *H = check_handle(handle);
     if (H == nullptr) {
@@ -205,7 +211,19 @@ DDM_API int mnle_log_prob_rows_f32(void *handle, const float *x_dev, const float
     src.ld_cond = ld_cond;
     src.R = R;
     src.potential = 0;
-    return launch(H, src, dim3((unsigned)((R + kTM - 1) / kTM), 1, 1), out_dev, static_cast<cudaStream_t>(stream));
+    return launch(H, src, dim3((unsigned)((R + kTM - 1) / kTM), 1, 1), out_dev, static_cast<cudaStream_t>(stream), precise);
+}
+
+DDM_API int mnle_log_prob_rows_f32(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond, int64_t R,
+                                   float *out_dev, void *stream)
+{
+    return rows_impl(handle, x_dev, cond_dev, ld_cond, R, out_dev, stream, false);
+}
+
+DDM_API int mnle_log_prob_rows_precise_f32(void *handle, const float *x_dev, const float *cond_dev, int64_t ld_cond,
+                                           int64_t R, float *out_dev, void *stream)
+{
+    return rows_impl(handle, x_dev, cond_dev, ld_cond, R, out_dev, stream, true);
 }
 
 DDM_API size_t mnle_loglik_workspace_floats(int64_t T, int64_t C)
@@ -214,9 +232,9 @@ DDM_API size_t mnle_loglik_workspace_floats(int64_t T, int64_t C)
     return (size_t)C * (size_t)((T + kTM - 1) / kTM);
 }
 
-DDM_API int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
-                                     const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
-                                     float *out_dev, float *workspace_dev, void *stream)
+static int loglik_sum_impl(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                           const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C, float *out_dev,
+                           float *workspace_dev, void *stream, bool precise)
 {
     Handle *H = check_handle(handle);
     if (H == nullptr) {
@@ -245,9 +263,25 @@ DDM_API int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64
     src.C = (int)C;
     src.potential = 1;
     const int n_tiles = (int)((T + kTM - 1) / kTM);
-    int rc = launch(H, src, dim3((unsigned)n_tiles, (unsigned)C, 1), workspace_dev, st);
+    int rc = launch(H, src, dim3((unsigned)n_tiles, (unsigned)C, 1), workspace_dev, st, precise);
     if (rc != DDM_OK) return rc;
     reduce_tiles_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(workspace_dev, n_tiles, (int)C, out_dev);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
+}
+
+DDM_API int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                     const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
+                                     float *out_dev, float *workspace_dev, void *stream)
+{
+    return loglik_sum_impl(handle, theta_dev, ld_theta, x_dev, pulses_dev, ld_pulses, T, C, out_dev, workspace_dev, stream,
+                           false);
+}
+
+DDM_API int mnle_loglik_sum_precise_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                        const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
+                                        float *out_dev, float *workspace_dev, void *stream)
+{
+    return loglik_sum_impl(handle, theta_dev, ld_theta, x_dev, pulses_dev, ld_pulses, T, C, out_dev, workspace_dev, stream,
+                           true);
 }

@@ -191,8 +191,9 @@ class DeviceMNLE(torch.nn.Module):
 
     def log_prob(self, x: torch.Tensor, condition: torch.Tensor, *, kernel: str = "auto") -> torch.Tensor:
         """x (1,R,2) or (R,2) = [rt seconds, choice], condition (R,85) -> (1,R).
-        ``kernel``: "tc" / "auto" tensor cores (tcgen05), "simt" fp32 CUDA cores."""
-        if kernel not in ("auto", "tc", "simt"):
+        ``kernel``: "tc" / "auto" tensor cores (tcgen05), "simt" fp32 CUDA cores, "precise" fp32 networks with
+        the spline chain in fp64 (accuracy anchor for trained estimators)."""
+        if kernel not in ("auto", "tc", "simt", "precise"):
             raise ValueError(f"unknown kernel {kernel!r}")
         dev = self._dev(condition)
         xr = x.reshape(-1, 2).to(device=dev, dtype=torch.float32).contiguous()
@@ -205,7 +206,8 @@ class DeviceMNLE(torch.nn.Module):
         with torch.cuda.device(dev):
             out = torch.empty((R,), dtype=torch.float32, device=dev)
             L = _native.lib()
-            fn = L.mnle_log_prob_rows_f32 if kernel == "simt" else L.mnle_log_prob_rows_tc_f32
+            fn = {"simt": L.mnle_log_prob_rows_f32, "precise": L.mnle_log_prob_rows_precise_f32}.get(
+                kernel, L.mnle_log_prob_rows_tc_f32)
             rc = fn(self.packed.handle(dev), xr.data_ptr(), cond.data_ptr(), cond.stride(0) if R > 1 else COND_DIM, R,
                     out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
             _native.check(rc, "mnle_log_prob_rows")
@@ -288,8 +290,8 @@ class DeviceMNLE(torch.nn.Module):
 
     @staticmethod
     def _pick_kernel(kernel: str, T: int):
-        """"tc": tcgen05 tensor-core kernel; "simt": fp32 CUDA-core kernel (accuracy anchor);
-        "auto": tensor cores whenever the shape is covered."""
+        """"tc": tcgen05 tensor-core kernel; "simt": fp32 CUDA-core kernel; "precise": fp32 networks + fp64
+        spline chain (accuracy anchor); "auto": tensor cores whenever the shape is covered."""
         L = _native.lib()
         if kernel == "auto":
             kernel = "tc" if T <= 524280 else "simt"
@@ -297,4 +299,6 @@ class DeviceMNLE(torch.nn.Module):
             return L.mnle_loglik_sum_tc_f32, L.mnle_loglik_tc_workspace_floats
         if kernel == "simt":
             return L.mnle_loglik_sum_simt_f32, L.mnle_loglik_workspace_floats
+        if kernel == "precise":
+            return L.mnle_loglik_sum_precise_f32, L.mnle_loglik_workspace_floats
         raise ValueError(f"unknown kernel {kernel!r}")
