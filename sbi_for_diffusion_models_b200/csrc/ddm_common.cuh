@@ -151,6 +151,79 @@ __device__ __forceinline__ void philox_normals6(uint32_t trial_lo, uint32_t tria
     normals6(w, one, z);
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2) -----------------------------------
+// One instruction, two IEEE round-to-nearest results (no flush to zero): per lane the same bits as the
+// scalar __fmaf_rn / __fmul_rn / __fadd_rn, at half the issue slots.  The simulator kernel is
+// issue-bound, so the Box-Muller affine steps and products of TWO pairs of fields go through these.
+struct f32x2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 a, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+
+// Two Box-Muller transforms side by side: the same arithmetic as box_muller() on (wr0, wa0) and on
+// (wr1, wa1), with the five affine / product steps of both issued as packed pairs, and the result already
+// multiplied by the simulator's noise scale (one more packed product: nz = z * scale, rt_choice_model.py:186).
+//   out: (z(wr0,wa0).cos, z(wr1,wa1).cos) in zc, (..sin, ..sin) in zs -- scaled.
+struct BmConsts {  // constant pairs, built once per kernel (registers or the constant bank)
+    f32x2 m4, p5, lg, ang_a, ang_b, scale;
+};
+__device__ __forceinline__ BmConsts make_bm_consts(float noise_scale)
+{
+    BmConsts c;
+    c.m4 = pack2(-4.0f, -4.0f);
+    c.p5 = pack2(5.0f, 5.0f);
+    c.lg = pack2(-1.3862943611198906f, -1.3862943611198906f);
+    c.ang_a = pack2(25.132741228718345f, 25.132741228718345f);
+    c.ang_b = pack2(-28.274333882308138f, -28.274333882308138f);
+    c.scale = pack2(noise_scale, noise_scale);
+    return c;
+}
+__device__ __forceinline__ void box_muller_x2_scaled(uint32_t wr0, uint32_t wa0, uint32_t wr1, uint32_t wa1, uint32_t one,
+                                                     const BmConsts &k, float &c0, float &s0, float &c1, float &s1)
+{
+    const f32x2 u = fma2(pack2(field_to_1_125(wr0, one), field_to_1_125(wr1, one)), k.m4, k.p5);
+    float u0, u1;
+    unpack2(u, u0, u1);
+    const f32x2 t = mul2(pack2(mufu_lg2(u0), mufu_lg2(u1)), k.lg);
+    float t0, t1;
+    unpack2(t, t0, t1);
+    const f32x2 r = pack2(mufu_sqrt(t0), mufu_sqrt(t1));
+    const f32x2 phi = fma2(pack2(field_to_1_125(wa0, one), field_to_1_125(wa1, one)), k.ang_a, k.ang_b);
+    float p0, p1;
+    unpack2(phi, p0, p1);
+    const f32x2 zc = mul2(mul2(r, pack2(mufu_cos(p0), mufu_cos(p1))), k.scale);
+    const f32x2 zs = mul2(mul2(r, pack2(mufu_sin(p0), mufu_sin(p1))), k.scale);
+    unpack2(zc, c0, c1);
+    unpack2(zs, s0, s1);
+}
+
 // ---- Philox with the trial-constant part of rounds 1-2 hoisted -------------------------
 // With counter (g_lo, g_hi, blk, 0) only `blk` changes along a trial.  Round 1 multiplies
 // M0 * g_lo (constant per trial) and round 2 multiplies M1 * (hi(M0 g_lo) ^ k1) (also constant),
@@ -212,6 +285,23 @@ __device__ __forceinline__ void philox_normals6_trial(const PhiloxTrial &t, uint
     uint32_t w[4];
     philox4x32_10_trial(t, blk, key, w);
     normals6(w, one, z);
+}
+
+// Blocks blk and blk + 1 -> the twelve SCALED normals (z * noise_scale) of steps 6 blk .. 6 blk + 11, same
+// bits as philox_normals6_trial + __fmul_rn per normal: Box-Muller pair j of the first block runs side by
+// side with pair j of the second one.
+__device__ __forceinline__ void philox_scaled_normals12_trial(const PhiloxTrial &t, uint32_t blk, const PhiloxKey &key,
+                                                              uint32_t one, const BmConsts &k, float (&nz)[12])
+{
+    uint32_t a[4], b[4];
+    philox4x32_10_trial(t, blk, key, a);
+    philox4x32_10_trial(t, blk + 1u, key, b);
+    box_muller_x2_scaled(a[0], __funnelshift_r(a[0], a[1], 21), b[0], __funnelshift_r(b[0], b[1], 21), one, k, nz[0], nz[1],
+                         nz[6], nz[7]);
+    box_muller_x2_scaled(__funnelshift_r(a[1], a[2], 10), __funnelshift_r(a[1], a[2], 31), __funnelshift_r(b[1], b[2], 10),
+                         __funnelshift_r(b[1], b[2], 31), one, k, nz[2], nz[3], nz[8], nz[9]);
+    box_muller_x2_scaled(__funnelshift_r(a[2], a[3], 20), a[3] >> 9, __funnelshift_r(b[2], b[3], 20), b[3] >> 9, one, k, nz[4],
+                         nz[5], nz[10], nz[11]);
 }
 
 }  // namespace ddm

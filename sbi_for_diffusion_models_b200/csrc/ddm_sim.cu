@@ -99,8 +99,11 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
     constexpr int NPB = kNormalsPerBlock;
     constexpr int STEPS = NPB * NB;
     static_assert(STEPS % 8 == 0, "chunks must keep pulse kicks on multiples of 8 steps");
+    static_assert(NB % 2 == 0, "Philox blocks are consumed in pairs");
     constexpr int MW = MASKW > 0 ? MASKW : 1;
     const unsigned lane = threadIdx.x & 31u;
+    const BmConsts bm = make_bm_consts(p.noise_scale);
+    float nz12[2 * NPB];
 
     // ---- per-lane trial state ---------------------------------------------------------
     float a = 0.f, nlam = 0.f, B = 1.f, v = 0.f, tnd = 0.f;
@@ -253,13 +256,14 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                                ? __ldg(p.noise + (long long)step * p.ld_noise + trial)
                                : 0.0f;
                 }
-            } else {
-                philox_normals6_trial(pt, blk + (uint32_t)b, p.key, p.one_bits, z);
+            } else if ((b & 1) == 0) {
+                // two Philox blocks at a time: their Box-Muller pairs run as packed fp32 pairs, noise scale included
+                philox_scaled_normals12_trial(pt, blk + (uint32_t)b, p.key, p.one_bits, bm, nz12);
             }
 #pragma unroll
             for (int j = 0; j < NPB; ++j) {
                 const int i = NPB * b + j;
-                const float nz = __fmul_rn(z[j], p.noise_scale);                // :186
+                const float nz = INJECT ? __fmul_rn(z[j], p.noise_scale) : nz12[NPB * (b & 1) + j];  // :186
                 const float leak = __fmul_rn(__fmul_rn(nlam, acc), p.dt);      // (-lam*a)*dt
                 acc = __fadd_rn(__fadd_rn(acc, leak), nz);                     // :187
                 // :190-192; with steps_per_pulse % 8 == 0 a kick can only fall on i % 8 == 0
@@ -294,40 +298,65 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
             }
         }
 
-        // fmaxf / fminf ignore NaN operands, like the reference's comparisons (always false)
-        float hi = -CUDART_INF_F, lo = CUDART_INF_F;
+        // fmaxf / fminf ignore NaN operands, like the reference's comparisons (always false).  Running max / min
+        // per group of 8 steps: the exact search below only visits the group(s) that can hold the crossing.
+        constexpr int G = STEPS / 8;
+        float ghi[G], glo[G];
 #pragma unroll
-        for (int i = 0; i < STEPS; ++i) {
-            hi = fmaxf(hi, av[i]);
-            lo = fminf(lo, av[i]);
+        for (int g = 0; g < G; ++g) {
+            ghi[g] = fmaxf(fmaxf(av[8 * g], av[8 * g + 1]), av[8 * g + 2]);
+            glo[g] = fminf(fminf(av[8 * g], av[8 * g + 1]), av[8 * g + 2]);
+#pragma unroll
+            for (int i = 3; i < 7; i += 2) {
+                ghi[g] = fmaxf(fmaxf(ghi[g], av[8 * g + i]), av[8 * g + i + 1]);
+                glo[g] = fminf(fminf(glo[g], av[8 * g + i]), av[8 * g + i + 1]);
+            }
+            ghi[g] = fmaxf(ghi[g], av[8 * g + 7]);
+            glo[g] = fminf(glo[g], av[8 * g + 7]);
+        }
+        float hi = ghi[0], lo = glo[0];
+#pragma unroll
+        for (int g = 1; g < G; ++g) {
+            hi = fmaxf(hi, ghi[g]);
+            lo = fminf(lo, glo[g]);
         }
 
-        if (busy && (hi >= B || lo <= 0.0f || t + STEPS >= nsteps)) {
-            // ---- this trial ends inside the chunk: exact first-passage search ---------
+        const bool ending = busy && (hi >= B || lo <= 0.0f || t + STEPS >= nsteps);
+        if (__any_sync(kFull, ending)) {
+            // ---- some trial of the warp ends inside the chunk: exact first-passage search -------
+            // (warp-uniform control flow: typically ONE lane ends, in ONE group of 8 steps)
             int hit_step = -1;
             int choice = 2;
 #pragma unroll
-            for (int i = STEPS - 1; i >= 0; --i) {
-                const bool up = av[i] >= B;      // :195
-                const bool dn = av[i] <= 0.0f;   // :196
-                if ((t + i < nsteps) && (up || dn)) {
-                    hit_step = t + i + 1;        // :201
-                    choice = dn ? 0 : 1;         // lower bound wins ties, :202-203
+            for (int g = 0; g < G; ++g) {
+                const bool look = ending && hit_step < 0 && (ghi[g] >= B || glo[g] <= 0.0f);
+                if (__any_sync(kFull, look)) {
+#pragma unroll
+                    for (int i = 8 * g + 7; i >= 8 * g; --i) {
+                        const bool up = av[i] >= B;      // :195
+                        const bool dn = av[i] <= 0.0f;   // :196
+                        if (look && (t + i < nsteps) && (up || dn)) {
+                            hit_step = t + i + 1;        // :201
+                            choice = dn ? 0 : 1;         // lower bound wins ties, :202-203
+                        }
+                    }
                 }
             }
-            if (hit_step < 0) {  // window over without a crossing, :206-215
-                hit_step = nsteps;
-                choice = 2;
+            if (ending) {
+                if (hit_step < 0) {  // window over without a crossing, :206-215
+                    hit_step = nsteps;
+                    choice = 2;
+                }
+                // :218, then pack_x_rt_choice :338-342
+                float rt = __fadd_rn(tnd, __fmul_rn((float)hit_step, p.dt));
+                rt = clamp_keep_nan(rt, 1e-6f, p.t_max);
+                rt = (rt < 1e-6f) ? 1e-6f : rt;
+                if (p.log_rt) rt = logf(rt);
+                reinterpret_cast<float2 *>(p.x_out)[trial] = make_float2(rt, (float)choice);
+                if (p.steps_out) p.steps_out[trial] = hit_step;
+                useful += (unsigned long long)hit_step;
+                busy = false;
             }
-            // :218, then pack_x_rt_choice :338-342
-            float rt = __fadd_rn(tnd, __fmul_rn((float)hit_step, p.dt));
-            rt = clamp_keep_nan(rt, 1e-6f, p.t_max);
-            rt = (rt < 1e-6f) ? 1e-6f : rt;
-            if (p.log_rt) rt = logf(rt);
-            reinterpret_cast<float2 *>(p.x_out)[trial] = make_float2(rt, (float)choice);
-            if (p.steps_out) p.steps_out[trial] = hit_step;
-            useful += (unsigned long long)hit_step;
-            busy = false;
         }
         t += STEPS;
         blk += (uint32_t)NB;
