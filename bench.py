@@ -9,8 +9,15 @@ ExtendedProposal (pipeline prior for theta, PulseSequenceProposal(P=80, p=0.75, 
 pulses) with the default schedule (n_max=16000, steps_per_pulse=200), resident in HBM as
 z (1e8, 85) fp32 = 34 GB.  A "step" is one pass of the simulator over all of it (one
 ``ddm_sim_f32`` launch; new Philox key every step).  With N>1 every rank owns its own 1e8-trial
-shard of one global trial index space (weak scaling) and the step ends with the NCCL all-gather
-of x, the only exchange the path has.
+shard of one global trial index space (weak scaling); the all-gather of x -- the only exchange the
+path has -- is fused into the simulator kernel: every finished trial's 8 bytes are stored into all ranks'
+gathered array over NVLink peer memory (``ddm_sim_gather_f32``, ``sharding.PeerGather``), with a stream barrier
+per step; NCCL ``all_gather_into_tensor`` is the fallback when symmetric memory cannot be set up.
+
+Besides the headline line the N > 1 arm checks on the device that the gathered x equals a single-rank
+recomputation of another rank's rows (``sharded_equals_single``) and measures BASELINE configs[2] (long
+schedule, 1.25e8 trials per GPU), configs[3] with the chains split over the ranks and configs[4] (run_sbc, 125
+datasets per GPU = 1000 on 8 GPUs), each with its own sharded-equals-single check.
 
 Metric: useful Euler steps per second (sum over trials of the first-passage / censoring step,
 the count the reference's loop would have had to execute for those trials), whole job.
@@ -51,6 +58,12 @@ def parse():
                     help="trials per CPU step: the lock-step reference algorithm only amortises its ~19 tensor-op "
                          "dispatches per Euler step at large batches (2x the per-trial rate of the 4096 batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--long-trials", type=int, default=int(os.environ.get("DDM_BENCH_LONG_TRIALS", 125_000_000)),
+                    help="configs[2]: trials per GPU on the long schedule dt=1e-4 (1e9 on 8 GPUs); 0 skips it")
+    ap.add_argument("--sbc-datasets", type=int, default=int(os.environ.get("DDM_BENCH_SBC_DATASETS", 125)),
+                    help="configs[4]: SBC datasets per GPU (1000 on 8 GPUs); 0 skips it")
+    ap.add_argument("--train-set-trials", type=int, default=int(os.environ.get("DDM_BENCH_TRAINSET_TRIALS", 10_000_000)),
+                    help="end-to-end simulate_training_set_with_conditions leg (N=1 only); 0 skips it")
     return ap.parse_args()
 
 
@@ -239,25 +252,67 @@ def random_mnle_params(seed: int = 0):
     return p
 
 
-def mnle_bench(dev, with_cpu: bool):
-    """configs[3]: MNLE log-likelihood sum over T=50 trials x C=1024 chains, device-resident."""
+def trained_mnle():
+    """(DeviceMNLE, spec parameter dict) of the committed TRAINED estimator (tests/golden/mnle_trained.npz,
+    made by tools/train_reference_net.py with this repository's simulator and trainer): the reference only ever
+    evaluates a trained net (mnle.py:41-48).  The packed buffer has the z-scoring folded in, so the spec gets
+    identity z-scoring and the very same fp32 numbers."""
+    import numpy as np
     import torch
-    from sbi_for_diffusion_models_b200.mnle_net import DeviceMNLE, PackedMNLE
+    from sbi_for_diffusion_models_b200.mnle_net import DeviceMNLE, PackedMNLE, unpack_params
+    d = np.load(os.path.join(ROOT, "tests", "golden", "mnle_trained.npz"))
+    packed, K = d["packed"], int(d["n_choices"])
+    p = {k: v.clone() for k, v in unpack_params(torch.from_numpy(packed.copy()), K).items()}
+    p["cond_mean"], p["cond_std"] = torch.zeros(85), torch.ones(85)
+    return DeviceMNLE(PackedMNLE(packed, K)), p
+
+
+def potential_inputs(dev, T=50, C=1024):
+    import torch
     from sbi_for_diffusion_models_b200.data_simulator import simulate_observed_session
-    T, C = 50, 1024
-    params = random_mnle_params(0)
-    est = DeviceMNLE(PackedMNLE.from_params(params))
+    from sbi_for_diffusion_models_b200.priors import build_prior_theta
     x_o, pulses_o = simulate_observed_session(torch.tensor([0.45, 0.6, 1.3, 14.0, 0.25]), T, "cpu", mu_sensory=1.0,
                                               p_success=0.75, P=P, seed=123, log_rt=False, noise_seed=1)
     torch.manual_seed(0)
-    theta = torch.stack([torch.distributions.Beta(2.0, 2.0).sample((C,)), torch.distributions.LogNormal(-1.0, 1.0).sample((C,)),
-                         torch.distributions.LogNormal(0.0, 1.0).sample((C,)), torch.distributions.LogNormal(2.75, 0.5).sample((C,)),
-                         torch.distributions.Beta(2.0, 2.0).sample((C,))], dim=1)
+    theta = build_prior_theta().sample((C,)).to(torch.float32)
+    return theta, x_o, pulses_o
+
+
+def _time_graph(fn, reps=20, replays=5):
+    """ms per call of ``fn`` captured in a CUDA graph (device time without the Python / ctypes launch path)."""
+    import torch
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(reps):
+                fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (replays * reps)
+
+
+def mnle_bench(dev, with_cpu: bool):
+    """configs[3]: MNLE log-likelihood sum over T=50 trials x C=1024 chains on the TRAINED estimator,
+    device-resident; the potential's gradient (row f2) at C=1024 and at the reference's NUM_CHAINS=2."""
+    import torch
+    T, C = 50, 1024
+    est, params = trained_mnle()
+    theta, x_o, pulses_o = potential_inputs(dev, T, C)
     th, xo, pl = theta.to(dev), x_o.to(dev), pulses_o.to(dev)
-    out = {"workload": f"configs[3]: MNLE log_prob sum over T={T} trials x C={C} chains, weights random-init (seed 0)",
-           "rows": T * C, "dense_mflop_per_row": 0.818}
+    out = {"workload": f"configs[3]: MNLE log_prob sum over T={T} trials x C={C} chains, trained estimator "
+                       "(tests/golden/mnle_trained.npz)", "rows": T * C, "dense_mflop_per_row": 0.818}
     lls = {}
-    for kernel in ("tc", "simt"):
+    for kernel in ("tc", "simt", "precise"):
         for _ in range(3):
             est.loglik_sum(th, xo, pl, kernel=kernel)
         torch.cuda.synchronize()
@@ -270,25 +325,7 @@ def mnle_bench(dev, with_cpu: bool):
         torch.cuda.synchronize()
         ms_call = e0.elapsed_time(e1) / reps
         lls[kernel] = ll
-        # the same call captured in a CUDA graph (20 calls per replay): device time without the
-        # Python / ctypes launch path, which is comparable to the kernel at this size
-        g = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            est.loglik_sum(th, xo, pl, kernel=kernel)
-            with torch.cuda.graph(g, stream=side):
-                for _ in range(reps):
-                    est.loglik_sum(th, xo, pl, kernel=kernel)
-        torch.cuda.current_stream().wait_stream(side)
-        g.replay()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(5):
-            g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        ms_graph = e0.elapsed_time(e1) / (5 * reps)
+        ms_graph = _time_graph(lambda: est.loglik_sum(th, xo, pl, kernel=kernel))
         out[kernel] = {"ms_per_call": ms_call, "ms_per_call_graph": ms_graph, "rows_per_s": T * C / (ms_graph * 1e-3),
                        "dense_tflops": 0.818e6 * T * C / (ms_graph * 1e-3) / 1e12}
     # tensor-core work actually issued: hi/lo split = 3 bf16 MMAs per product, N padded (71 -> 80, K -> 16)
@@ -302,18 +339,30 @@ def mnle_bench(dev, with_cpu: bool):
     out["tc"]["roofline"] = {"bound": "tensor", "achieved": out["tc"]["bf16_mma_tflops"], "peak": peak, "unit": "TFLOP/s",
                              "frac": out["tc"]["bf16_mma_tflops"] / peak, "peak_source": src,
                              "flop_per_row": tc_flop_row,
+                             "frac_algorithmic": 0.818e6 * T * C / (out["tc"]["ms_per_call_graph"] * 1e-3) / 1e12 / peak,
                              "note": "bf16 MMA flops issued per (trial, chain) row: 3 passes (hi*hi, hi*lo, lo*hi) over "
-                                     "the 128x128 / 128x80 layers + the K=32 theta stage; the algorithmic fp32 dense work "
-                                     "after hoisting the first layers is 0.576 MFLOP per row (SURVEY 8d)"}
-    out["max_rel_diff_tc_vs_simt"] = float(((lls["tc"] - lls["simt"]).abs() / lls["simt"].abs()).max())
+                                     "the 128x128 / 128x80 layers + the K=32 theta stage; frac_algorithmic counts the "
+                                     "0.818 MFLOP of fp32 dense work per row of SURVEY 8d instead"}
+    # row f2: value + d/d theta (what NUTS asks the potential for, potentials.py:112) at C = 1024 and C = 2
+    grad = {}
+    for Cg in (C, 2):
+        thg = th[:Cg].contiguous()
+        for _ in range(3):
+            est.loglik_sum_and_grad(thg, xo, pl)
+        grad[f"C{Cg}"] = {"ms_per_call_graph": _time_graph(lambda: est.loglik_sum_and_grad(thg, xo, pl), reps=5),
+                          "ms_forward_only_graph": _time_graph(lambda: est.loglik_sum(thg, xo, pl), reps=5)}
+    out["grad"] = grad
     if with_cpu:
         from oracle import mnle_spec
         t0 = time.perf_counter()
-        ref = mnle_spec.loglik_sum(params, theta, x_o, pulses_o)
+        ref32 = mnle_spec.loglik_sum(params, theta, x_o, pulses_o).double()
         out["cpu_spec_fp32"] = {"ms_per_call": (time.perf_counter() - t0) * 1e3, "cores": torch.get_num_threads(),
                                 "kind": "port (oracle/mnle_spec.py; sbi itself is not installable offline)"}
+        ref64 = mnle_spec.loglik_sum(mnle_spec.cast_params(params, torch.float64), theta, x_o, pulses_o)
+        rel = lambda v: ((v.double().cpu() - ref64).abs() / ref64.abs())
+        out["cpu_spec_fp32"]["rel_err_vs_float64"] = {"max": float(rel(ref32).max()), "median": float(rel(ref32).median())}
         for kernel, ll in lls.items():
-            out[kernel]["max_rel_err_vs_cpu_spec"] = float(((ll.cpu() - ref).abs() / ref.abs()).max())
+            out[kernel]["rel_err_vs_float64"] = {"max": float(rel(ll).max()), "median": float(rel(ll).median())}
     return out
 
 
@@ -343,6 +392,176 @@ def configs0_bench(dev):
     steps = float(torch.round((x[:, 0] - z[:, 4].clamp(0.0, 7.999999)) / 5e-4).sum())
     return {"workload": "configs[0]: simulate_training_set_with_conditions, 10 000 trials in batches of 4096, CPU (z, x) out",
             "seconds": dt, "trials_per_s": 10_000 / dt, "steps_per_s": steps / dt}
+
+
+def long_schedule_bench(args, z, rank, world, dev, gather):
+    """BASELINE configs[2]: the long pulse schedule (dt = 1e-4: n_max = 80 000, steps_per_pulse = 1000, P = 80),
+    ``--long-trials`` trials per GPU (1.25e8: 1e9 on 8 GPUs), gather of x included.  One warm-up + two timed
+    launches, device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from sbi_for_diffusion_models_b200.simulator import Schedule, simulate_trials
+    n = min(args.long_trials, z.shape[0])
+    sched = Schedule.from_constants(1.0, dt=1e-4)
+    zz = z[:n]
+    pg = gather(n)
+    x = pg.local if pg is not None else torch.empty((n, 2), dtype=torch.float32, device=dev)
+    x_all = None if pg is not None or world == 1 else torch.empty((world * n, 2), dtype=torch.float32, device=dev)
+
+    def launch(seed):
+        simulate_trials(zz[:, :5], zz[:, 5:], seed=seed, trial_offset=rank * n, out=x, schedule=sched,
+                        peer_blocks=pg.peers if pg is not None else None)
+        if pg is not None:
+            pg.barrier()
+        elif world > 1:
+            dist.all_gather_into_tensor(x_all, x)
+
+    launch(900)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    e0.record()
+    for i in range(reps):
+        launch(901 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    useful = 0
+    for i in range(reps):       # exact useful-step totals of the timed keys (untimed, plain launch)
+        _, st = simulate_trials(zz[:, :5], zz[:, 5:], seed=901 + i, trial_offset=rank * n, schedule=sched, return_stats=True)
+        useful += st.useful_steps
+    t = torch.tensor([ms, float(useful)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, useful = float(tm[0]), float(t[1])
+    else:
+        useful = float(useful)
+    return {"workload": f"configs[2]: {world} x {n} trials, long schedule dt=1e-4 (n_max={sched.n_max}, "
+                        f"steps_per_pulse={sched.steps_per_pulse}, P={sched.n_pulses}), gather of x included",
+            "trials_total": world * n, "ms_per_launch": ms, "useful_steps_per_s": useful / reps / (ms * 1e-3),
+            "trials_per_s": world * n / (ms * 1e-3), "mean_steps_per_trial": useful / reps / (world * n),
+            "exchange": "fused peer stores" if pg is not None else ("all_gather(x)" if world > 1 else "none")}
+
+
+def sbc_bench(args, rank, world, dev):
+    """BASELINE configs[4]: run_sbc (reference mnle.py:128-237) over ``--sbc-datasets`` datasets per GPU (125: 1000
+    on 8 GPUs) with the reference's own settings -- NUM_TRIALS_OBS = 50, WARMUP_STEPS = 100, SBC_POST_SAMPLES = 1500 --
+    on the trained estimator: per dataset a prior draw, a simulated session, a posterior sample (128 chains of the
+    device slice sampler in lock-step over all datasets of the rank) and the ranks; datasets sharded over the
+    GPUs, ranks and samples all-gathered.  Then the check: every rank recomputes three datasets of ANOTHER rank's
+    shard on its own and must find the very same ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sbi_for_diffusion_models_b200 import mnle
+    from sbi_for_diffusion_models_b200.priors import build_prior_theta
+    from sbi_for_diffusion_models_b200.run_config import RunConfig
+    from sbi_for_diffusion_models_b200.sbc import draw_sbc_datasets
+    from sbi_for_diffusion_models_b200.sharding import shard_bounds
+    est, _ = trained_mnle()
+    cfg = RunConfig()
+    prior = build_prior_theta()
+    D, S, chains, seed = args.sbc_datasets * world, int(cfg.SBC_POST_SAMPLES), 128, 0
+    small = RunConfig(WARMUP_STEPS=2)
+    mnle.run_sbc(small, prior_theta=prior, density_estimator=est, num_datasets=2 * world, posterior_samples_per_dataset=128,
+                 save=False)                                                   # warm-up: allocator, graphs
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    out = mnle.run_sbc(cfg, prior_theta=prior, density_estimator=est, num_datasets=D, posterior_samples_per_dataset=S,
+                       seed=seed, chains_per_dataset=chains, save=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    ok = True
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        # datasets [lo, lo + 3) of the next rank's shard, recomputed here without any other dataset around
+        thetas_true, ds_seeds = draw_sbc_datasets(prior, D, seed)
+        init_all = prior.sample((D * chains,)).to(torch.float32)
+        lo, _ = shard_bounds(D, (rank + 1) % world, world)
+        ranks_again, _ = mnle.sbc_shard(cfg, prior, est, thetas_true, ds_seeds, init_all, lo, lo + 3, S, seed, dev)
+        ok = bool(np.array_equal(ranks_again.numpy(), out["ranks"][lo:lo + 3]))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    dt = float(tt.item())
+    ranks = out["ranks"].astype(np.float64) / S
+    return {"workload": f"configs[4]: run_sbc, {D} datasets over {world} GPU(s), T={cfg.NUM_TRIALS_OBS} trials each, "
+                        f"{chains} chains x ({cfg.WARMUP_STEPS} warm-up sweeps + {-(-S // chains)} draws), {S} posterior "
+                        "samples per dataset, trained estimator",
+            "datasets": D, "seconds": dt, "datasets_per_s": D / dt,
+            "rank_mean_over_S": ranks.mean(0).tolist(), "rank_std_over_S": ranks.std(0).tolist(),
+            "sharded_equals_single": ok if world > 1 else None,
+            "note": "uniform ranks have mean 0.5 and std 0.289; the estimator was trained on 1e6 simulated trials"}
+
+
+def potential_sharded_bench(rank, world, dev):
+    """configs[3] with the chains split over the ranks: weights replicated, every rank sums its own
+    chains, one all-gather of C floats; must equal the single-GPU call bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from sbi_for_diffusion_models_b200.sharding import loglik_sum_sharded
+    est, _ = trained_mnle()
+    theta, x_o, pulses_o = potential_inputs(dev)
+    th, xo, pl = theta.to(dev), x_o.to(dev), pulses_o.to(dev)
+    fn = lambda t: est.loglik_sum(t, xo, pl)
+    for _ in range(3):
+        got = loglik_sum_sharded(fn, th)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        got = loglik_sum_sharded(fn, th)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    flag = torch.tensor([1 if torch.equal(got, fn(th)) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"workload": f"configs[3]: T=50 x C=1024 chains split over {world} GPUs, all-gather of the C sums",
+            "ms_per_call": float(t.item()), "rows_per_s": 51200 / (float(t.item()) * 1e-3),
+            "sharded_equals_single": bool(flag.item())}
+
+
+def training_set_e2e_bench(args, dev):
+    """The entry point north_star names, end to end at size: simulate_training_set_with_conditions(ExtendedProposal
+    on the device, N trials, batch 2^18) -> CPU (z (N,85), x (N,2)) -- proposal draws, simulation and the
+    device->host copy of z and x (348 B per trial) all inside the timed region."""
+    import contextlib
+    import io
+    import torch
+    from sbi_for_diffusion_models_b200 import data_simulator as ds
+    from sbi_for_diffusion_models_b200.priors import build_prior_theta
+    from sbi_for_diffusion_models_b200.proposals import ExtendedProposal, PulseSequenceProposal
+    N = args.train_set_trials
+
+    def once(seed, n):
+        prop = ExtendedProposal(build_prior_theta(dev), PulseSequenceProposal(P, 0.75, seed=seed, device=dev), device=dev)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return ds.simulate_training_set_with_conditions(prop, n, 1 << 18, dev, mu_sensory=1.0, p_success=0.75, P=P,
+                                                            log_rt=False, seed=seed)
+    once(0, 1 << 20)
+    torch.cuda.synchronize()
+    ts, steps = [], 0.0
+    for i in range(2):
+        t0 = time.perf_counter()
+        z, x = once(1 + i, N)
+        ts.append(time.perf_counter() - t0)
+        steps = float(torch.round((x[:, 0].double() - z[:, 4].double().clamp(0.0, 7.999999)) / 5e-4).sum())
+        del z, x
+    dt = min(ts)
+    return {"api": "data_simulator.simulate_training_set_with_conditions(ExtendedProposal on cuda) -> CPU (z, x)",
+            "trials": N, "seconds": dt, "trials_per_s": N / dt, "value": steps / dt, "unit": UNIT,
+            "d2h_bytes": N * BYTES_PER_TRIAL, "h2d_bytes": 0,
+            "note": "bound by the device->host copy of z (340 B per trial over PCIe 5 x16), not by the simulator"}
 
 
 def mnle_train_bench(dev, with_cpu: bool, rows: int = 4096):
@@ -427,21 +646,55 @@ def run_native(args):
 
     n = args.trials
     sched = Schedule.from_constants(1.0)
-    z = build_workload(n, rank, dev)
-    x = torch.empty((n, 2), dtype=torch.float32, device=dev)
-    x_all = torch.empty((world * n, 2), dtype=torch.float32, device=dev) if world > 1 else None
+    z_big = build_workload(max(n, args.long_trials), rank, dev)   # configs[2] re-uses (and extends) the same z
+    z = z_big[:n]
+    torch.cuda.synchronize()
+
+    # ---- the exchange: fused into the kernel over peer memory, NCCL as the fallback --------------------
+    gather_note = "none"
+    peer_ok = world > 1 and os.environ.get("DDM_BENCH_EXCHANGE", "peer") == "peer"
+
+    def make_gather(rows):
+        """PeerGather over `rows` trials per rank, or None (single GPU / symmetric memory unavailable)."""
+        nonlocal peer_ok
+        if not peer_ok:
+            return None
+        try:
+            from sbi_for_diffusion_models_b200.sharding import PeerGather
+            return PeerGather(rows)
+        except Exception as e:   # every rank must take the same branch: agree below
+            print(f"[rank {rank}] symmetric memory unavailable, falling back to NCCL all_gather: {e!r}", file=sys.stderr)
+            return None
+
+    pg = make_gather(n)
+    if world > 1:
+        agree = torch.tensor([1 if pg is not None else 0], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) == 0:
+            pg, peer_ok = None, False
+    if pg is not None:
+        x, x_all = pg.local, pg.x_all
+        gather_note = ("fused into the kernel: 8-byte peer stores over NVLink into every rank's gathered x "
+                       "(ddm_sim_gather_f32), one stream barrier per step")
+    else:
+        x = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        x_all = torch.empty((world * n, 2), dtype=torch.float32, device=dev) if world > 1 else None
+        if world > 1:
+            gather_note = "NCCL all_gather_into_tensor(x) after each launch"
     torch.cuda.synchronize()
 
     base_seed = 20261018
-    stats_log = []
 
     def step(i, events=None):
         if events is not None:
             events[0].record()
-        simulate_trials(z[:, :5], z[:, 5:], seed=base_seed + i, trial_offset=rank * n, out=x, schedule=sched)
+        simulate_trials(z[:, :5], z[:, 5:], seed=base_seed + i, trial_offset=rank * n, out=x, schedule=sched,
+                        peer_blocks=pg.peers if pg is not None else None)
         if events is not None:
             events[1].record()
-        if world > 1:
+        if pg is not None:
+            pg.barrier()
+        elif world > 1:
             dist.all_gather_into_tensor(x_all, x)
 
     def barrier():
@@ -468,6 +721,24 @@ def run_native(args):
     clock_info = clocks.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
     kernel_ms = [a.elapsed_time(b) for a, b in kernel_events]
+
+    # ---- N > 1: the gathered x of the last timed step equals a single-rank recomputation -------------
+    # Every rank takes 65 536 rows of the NEXT rank's z (all-gathered), simulates them alone with that
+    # rank's global trial offsets and compares with what the exchange delivered here.
+    sharded_equals_single = None
+    if world > 1:
+        m = min(65536, n)
+        z_heads = torch.empty((world * m, 5 + P), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(z_heads, z[:m].contiguous())
+        nb = (rank + 1) % world
+        zn = z_heads[nb * m:(nb + 1) * m]
+        again = simulate_trials(zn[:, :5], zn[:, 5:], seed=base_seed + args.steps - 1, trial_offset=nb * n, schedule=sched)
+        flag = torch.tensor([1 if torch.equal(again, x_all[nb * n:nb * n + m]) else 0], device=dev)
+        mine = torch.tensor([1 if torch.equal(x_all[rank * n:(rank + 1) * n], x) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.all_reduce(mine, op=dist.ReduceOp.MIN)
+        sharded_equals_single = bool(flag.item()) and bool(mine.item())
+        del z_heads
 
     # recount useful steps per timed key (same launches, untimed) to get exact totals
     useful, lane = 0, 0
@@ -528,6 +799,38 @@ def run_native(args):
         dist.all_reduce(e2e_tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = float(e2e_tot.item()) / (float(e2e_t.item()) * 1e-3)
+
+    # ---- the other BASELINE configs, on every rank (they contain collectives) ---------------------------
+    # A watchdog makes sure the headline line is printed even if one of these legs should hang on some box.
+    extras, headline = {}, {}
+
+    def bail():
+        if rank == 0 and headline:
+            headline["line"]["extras_timeout"] = True
+            headline["line"].update(extras)
+            print(json.dumps(headline["line"]), flush=True)
+        os._exit(0)
+
+    def leg(name, fn):
+        try:
+            extras[name] = fn()
+        except Exception as e:   # the headline metric must still print
+            extras[name] = {"error": repr(e)}
+
+    def run_extras():
+        if args.long_trials > 0:
+            leg("long_schedule", lambda: long_schedule_bench(args, z_big, rank, world, dev, make_gather))
+        if world > 1:
+            leg("mnle_potential_sharded", lambda: potential_sharded_bench(rank, world, dev))
+        if args.sbc_datasets > 0:
+            leg("sbc", lambda: sbc_bench(args, rank, world, dev))
+
+    if rank != 0:
+        watchdog = threading.Timer(float(os.environ.get("DDM_BENCH_EXTRAS_TIMEOUT", 900)), bail)
+        watchdog.daemon = True
+        watchdog.start()
+        run_extras()
+        watchdog.cancel()
 
     if rank == 0:
         sms, khz = np.zeros(1, np.int32), np.zeros(1, np.int32)
@@ -591,7 +894,7 @@ def run_native(args):
                                    f"configs[1] shape at {n} trials per GPU (default schedule, P=80)",
                        "trials_per_gpu_per_step": n, "z_bytes_per_gpu": n * 340,
                        "l2": "inputs (z) larger than L2; new Philox key each step", "rng": "Philox4x32-10, six 21-bit Box-Muller fields per block",
-                       "exchange": "all_gather(x) per step" if world > 1 else "none"},
+                       "exchange": gather_note},
             "trials_per_s": world * n * args.steps / (elapsed_ms * 1e-3),
             "mean_steps_per_trial": useful_all / (world * n * args.steps),
             "choice_frac": choice_frac,
@@ -601,12 +904,26 @@ def run_native(args):
                     "ingest": ("z rows (340 B/trial, pinned host) are packed to 32-byte records by the host cores "
                                "(ddm_pack_z_host) chunk by chunk while the streaming kernel runs; the link carries the records"
                                if link_bytes_per_step < n_e2e * 340 else
-                               "fp32 z rows over the link (fewer than 16 host threads per rank: packing would be slower)"),
+                               "fp32 z rows over the link (too few host threads per rank for packing to beat the link)"),
                     "trials_per_step_per_gpu": n_e2e, "api": "data_simulator.sim_wrapper(z pinned host) -> x host",
                     "ms_per_step": float(e2e_t.item()) / args.steps},
             "gpu_launches": args.steps * world,
             "clocks": clock_info,
         }
+        if sharded_equals_single is not None:
+            line["sharded_equals_single"] = sharded_equals_single
+        headline["line"] = line
+        watchdog = threading.Timer(float(os.environ.get("DDM_BENCH_EXTRAS_TIMEOUT", 900)), bail)
+        watchdog.daemon = True
+        watchdog.start()
+        run_extras()
+        watchdog.cancel()
+        line.update(extras)
+        if world == 1 and args.train_set_trials > 0:
+            try:
+                line["e2e_training_set"] = training_set_e2e_bench(args, dev)
+            except Exception as e:
+                line["e2e_training_set"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             import torch as _t
             rate, times, _ = time_cpu_port(args.cpu_trials, 1, 1)

@@ -53,6 +53,16 @@ const char *ddm_last_error(void);
 /* sm_count, SM clock (kHz, cudaDevAttrClockRate) and compute capability of `device`. */
 int ddm_device_info(int device, int *sm_count, int *sm_clock_khz, int *cc_major, int *cc_minor);
 
+/* Do kernel launches in this process return before the kernel has finished?  Launches a one-thread kernel that
+ * waits (at most timeout_us) for a word the host raises as soon as the launch call is back; *blocking = 1 when
+ * the kernel timed out instead (CUDA_LAUNCH_BLOCKING=1, Nsight Compute, compute-sanitizer, a debugger: any tool
+ * that serialises launches).  The streaming ingest (ddm_sim_stream_f32 / ddm_sim_packed_f32 with ready_dev)
+ * launches its persistent kernel BEFORE the copies it consumes only when this reports 0. */
+int ddm_probe_launch_blocking(int64_t timeout_us, int *blocking);
+
+/* Widest SIMD path ddm_pack_z_host uses on this CPU: 512 (AVX-512 F+DQ+VL), 256 (AVX2) or 128 (SSE2). */
+int ddm_pack_simd_bits(void);
+
 /* ---------------------------------------------------------------- simulator --- */
 
 /* Device scratch the simulator needs per call (work queue + counters). */
@@ -69,6 +79,7 @@ size_t ddm_sim_workspace_bytes(void);
 #define DDM_WS_LANE_STEPS 3
 #define DDM_WS_ERROR 4 /* non-zero: streaming launch timed out waiting for data */
 #define DDM_WS_WORDS 8
+#define DDM_MAX_PEERS 15 /* other GPUs a fused-gather launch can write to */
 
 /*
  * Simulate N pulse-driven DDM trials.
@@ -109,6 +120,26 @@ int ddm_sim_f32(const float *theta_dev, int64_t ld_theta,
                 int log_rt,
                 float *x_out_dev, int32_t *steps_out_dev,
                 void *workspace_dev, void *stream);
+
+/*
+ * ddm_sim_f32 with the all-gather of x fused into the kernel (native noise): every finished trial's (rt, choice)
+ * is stored to x_out_dev[i] AND to x_peer_blocks[d][i] for d < n_peers -- blocks in OTHER GPUs' memory mapped into
+ * this process (CUDA peer access / symmetric memory), normally "rank r's slot" of each peer's gathered (world*N, 2)
+ * array.  8 bytes per trial and peer travel over NVLink as posted stores while the kernel keeps simulating, so
+ * sharded runs (the path's only exchange is this gather) need no separate collective and no second pass
+ * over x.  x_peer_blocks is a HOST array of n_peers device pointers (n_peers <= DDM_MAX_PEERS).  The stores are
+ * visible to a peer once this launch has completed and the ranks have synchronised (a barrier on the stream).
+ */
+int ddm_sim_gather_f32(const float *theta_dev, int64_t ld_theta, const float *pulses_dev,
+                       int64_t ld_pulses, int64_t N, int64_t P, int64_t n_max,
+                       int64_t steps_per_pulse, float dt, float t_max, float t_nd_hi,
+                       float noise_scale, uint64_t seed, uint64_t trial_offset, int log_rt,
+                       float *x_out_dev, float *const *x_peer_blocks, int n_peers, void *workspace_dev,
+                       void *stream);
+
+/* How long a streaming launch (ready_dev != NULL) waits for rows that have not arrived before it sets
+ * workspace[DDM_WS_ERROR] and gives the remaining trials up (process-wide, default 20 s; [1 ms, 600 s]). */
+int ddm_sim_set_stream_timeout_us(int64_t timeout_us);
 
 /*
  * Streaming variant for HOST-resident inputs: the caller enqueues the host->device copies of z

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("DDM_B200_LIB") or os.path.join(PKG, "_lib", "libddm_b
 
 DDM_OK, DDM_ERR_INVALID, DDM_ERR_CUDA, DDM_ERR_STATE = 0, -1, -2, -3
 WS_QUEUE, WS_USEFUL_STEPS, WS_GENERIC_ROWS, WS_LANE_STEPS, WS_ERROR, WS_WORDS = 0, 1, 2, 3, 4, 8
+MAX_PEERS = 15
 
 _i64, _u64, _f32, _i32 = ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_int
 _ptr = ctypes.c_void_p
@@ -23,9 +24,14 @@ _SIGNATURES = {
     "ddm_abi_version": (ctypes.c_int, []),
     "ddm_last_error": (ctypes.c_char_p, []),
     "ddm_device_info": (ctypes.c_int, [_i32, _ptr, _ptr, _ptr, _ptr]),
+    "ddm_probe_launch_blocking": (ctypes.c_int, [_i64, _ptr]),
+    "ddm_pack_simd_bits": (ctypes.c_int, []),
+    "ddm_sim_set_stream_timeout_us": (ctypes.c_int, [_i64]),
     "ddm_sim_workspace_bytes": (ctypes.c_size_t, []),
     "ddm_sim_f32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _f32, _f32,
                                    _u64, _u64, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "ddm_sim_gather_f32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _f32, _f32,
+                                          _u64, _u64, _i32, _ptr, _ptr, _i32, _ptr, _ptr]),
     "ddm_sim_stream_f32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _f32, _f32,
                                           _u64, _u64, _i32, _ptr, _ptr, _ptr, _ptr]),
     "ddm_pack_z_host": (ctypes.c_int64, [_ptr, _i64, _i64, _i64, _ptr, _i32]),

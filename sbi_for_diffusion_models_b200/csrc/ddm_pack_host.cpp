@@ -236,6 +236,14 @@ static Pool &pool()
 
 }  // namespace ddm
 
+static bool have_avx512()
+{
+    return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512vl") &&
+           getenv("DDM_PACK_NO_AVX512") == nullptr;
+}
+
+DDM_API int ddm_pack_simd_bits(void) { return have_avx512() ? 512 : (__builtin_cpu_supports("avx2") ? 256 : 128); }
+
 DDM_API int64_t ddm_pack_z_host(const float *z_host, int64_t ld, int64_t N, int64_t n_pulses, uint32_t *packed_host,
                                 int n_threads)
 {
@@ -247,8 +255,7 @@ DDM_API int64_t ddm_pack_z_host(const float *z_host, int64_t ld, int64_t N, int6
     if (N == 0) return 0;
     const bool avx2 = __builtin_cpu_supports("avx2");
     // a row must hold 8 floats for the record's 32-byte load (5 + n_pulses >= 8)
-    const bool avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq") &&
-                        __builtin_cpu_supports("avx512vl") && n_pulses >= 3 && getenv("DDM_PACK_NO_AVX512") == nullptr;
+    const bool avx512 = have_avx512() && n_pulses >= 3;
     int nt = n_threads < 1 ? 1 : n_threads;
     const int64_t min_rows = 1 << 14;  // below that a thread costs more than it packs
     if ((int64_t)nt > (N + min_rows - 1) / min_rows) nt = (int)((N + min_rows - 1) / min_rows);

@@ -55,6 +55,9 @@ struct SimParams {
     unsigned long long trial_offset;
     int log_rt;
     const unsigned long long *ready;  // streaming mode: trials [0, *ready) have arrived in HBM (else null)
+    unsigned long long wait_timeout_ns;  // streaming mode: give up on rows that have not arrived after this long
+    float *x_peers[DDM_MAX_PEERS];  // fused all-gather: the same (rt, choice) also goes to these (peer-mapped) blocks
+    int n_peers;
     uint32_t one_bits;  // 0x3F800000, kept in a register for the one-LOP3 mantissa insert
 };
 
@@ -68,12 +71,12 @@ __device__ __forceinline__ float clamp_keep_nan(float x, float lo, float hi)
     return x < lo ? lo : (x > hi ? hi : x);
 }
 
-// Streaming mode: sleep until the copy engine has delivered `need` rows (bounded: 20 s without
-// progress sets the error word).  Only the STREAM instantiation of the kernel contains this spin
+// Streaming mode: sleep until the copy engine has delivered `need` rows (bounded: by default 20 s without
+// progress sets the error word; ddm_sim_set_stream_timeout_us).  Only the STREAM instantiation of the kernel contains this spin
 // loop: its presence makes ptxas give up uniform-register round keys in the hot loop (+3
 // instructions per Euler step), which the resident-input kernel must not pay.
 __device__ __forceinline__ int wait_for_rows(const unsigned long long *ready, unsigned long long need,
-                                          unsigned long long *error_word)
+                                          unsigned long long *error_word, unsigned long long timeout_ns)
 {
     const volatile unsigned long long *rdy = ready;
     unsigned long long t0 = 0ull, now;
@@ -81,7 +84,7 @@ __device__ __forceinline__ int wait_for_rows(const unsigned long long *ready, un
     while (*rdy < need) {
         __nanosleep(500);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (now - t0 > 20000000000ull) {
+        if (now - t0 > timeout_ns) {
             atomicExch(error_word, 1ull);
             return 1;
         }
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 unsigned long long need = base + (unsigned long long)want;
                 if (need > (unsigned long long)p.n_trials) need = (unsigned long long)p.n_trials;
                 int failed = 0;
-                if (lane == 0) failed = wait_for_rows(p.ready, need, &p.ws[DDM_WS_ERROR]);
+                if (lane == 0) failed = wait_for_rows(p.ready, need, &p.ws[DDM_WS_ERROR], p.wait_timeout_ns);
                 failed = __shfl_sync(kFull, failed, 0);
                 if (failed) {
                     exhausted = true;
@@ -352,7 +355,10 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 rt = clamp_keep_nan(rt, 1e-6f, p.t_max);
                 rt = (rt < 1e-6f) ? 1e-6f : rt;
                 if (p.log_rt) rt = logf(rt);
-                reinterpret_cast<float2 *>(p.x_out)[trial] = make_float2(rt, (float)choice);
+                const float2 res = make_float2(rt, (float)choice);
+                reinterpret_cast<float2 *>(p.x_out)[trial] = res;
+                // fused all-gather (ddm_sim_gather_f32): 8 bytes per trial and peer over NVLink, posted stores
+                for (int d = 0; d < p.n_peers; ++d) reinterpret_cast<float2 *>(p.x_peers[d])[trial] = res;
                 if (p.steps_out) p.steps_out[trial] = hit_step;
                 useful += (unsigned long long)hit_step;
                 busy = false;
@@ -433,6 +439,16 @@ static int launch_sim(const SimParams &p, int sm_count, cudaStream_t stream)
 
 using namespace ddm;
 
+static unsigned long long g_stream_timeout_ns = 20000000000ull;
+
+DDM_API int ddm_sim_set_stream_timeout_us(int64_t timeout_us)
+{
+    DDM_REQUIRE(timeout_us >= 1000 && timeout_us <= 600000000ll, "ddm_sim_set_stream_timeout_us: %lld outside [1 ms, 600 s]",
+                (long long)timeout_us);
+    g_stream_timeout_ns = (unsigned long long)timeout_us * 1000ull;
+    return DDM_OK;
+}
+
 DDM_API size_t ddm_sim_workspace_bytes(void) { return DDM_WS_WORDS * sizeof(unsigned long long); }
 
 static int sim_impl(const float *theta_dev, int64_t ld_theta, const float *pulses_dev,
@@ -440,8 +456,14 @@ static int sim_impl(const float *theta_dev, int64_t ld_theta, const float *pulse
                     int64_t steps_per_pulse, float dt, float t_max, float t_nd_hi,
                     float noise_scale, uint64_t seed, uint64_t trial_offset,
                     const float *noise_dev, int64_t ld_noise, int log_rt, float *x_out_dev,
-                    int32_t *steps_out_dev, void *workspace_dev, const uint64_t *ready_dev, void *stream)
+                    int32_t *steps_out_dev, void *workspace_dev, const uint64_t *ready_dev, void *stream,
+                    float *const *x_peers = nullptr, int n_peers = 0)
 {
+    DDM_REQUIRE(n_peers >= 0 && n_peers <= DDM_MAX_PEERS && (n_peers == 0 || x_peers != nullptr),
+                "ddm_sim_gather_f32: n_peers=%d outside [0, %d]", n_peers, DDM_MAX_PEERS);
+    for (int d = 0; d < n_peers; ++d)
+        DDM_REQUIRE(x_peers[d] != nullptr && (reinterpret_cast<uintptr_t>(x_peers[d]) & 7u) == 0,
+                    "ddm_sim_gather_f32: peer block %d must be a non-null, 8-byte aligned device pointer", d);
     DDM_REQUIRE(N >= 0 && N <= 0x7FFFFFFFll, "ddm_sim_f32: N=%lld outside [0, 2^31)", (long long)N);
     DDM_REQUIRE(n_max >= 0 && n_max <= 0x7FFFFF00ll, "ddm_sim_f32: n_max=%lld out of range", (long long)n_max);
     DDM_REQUIRE(steps_per_pulse >= 1 && steps_per_pulse <= 0x7FFFFFFFll,
@@ -491,6 +513,9 @@ static int sim_impl(const float *theta_dev, int64_t ld_theta, const float *pulse
     p.log_rt = log_rt ? 1 : 0;
     p.one_bits = 0x3F800000u;
     p.ready = reinterpret_cast<const unsigned long long *>(ready_dev);
+    p.wait_timeout_ns = g_stream_timeout_ns;
+    p.n_peers = n_peers;
+    for (int d = 0; d < DDM_MAX_PEERS; ++d) p.x_peers[d] = d < n_peers ? x_peers[d] : nullptr;
 
     const bool inject = noise_dev != nullptr;
     const bool aligned = (steps_per_pulse % 8) == 0 && steps_per_pulse >= kNormalsPerBlock * DDM_SIM_NB;
@@ -520,6 +545,18 @@ DDM_API int ddm_sim_f32(const float *theta_dev, int64_t ld_theta, const float *p
     return sim_impl(theta_dev, ld_theta, pulses_dev, ld_pulses, N, P, n_max, steps_per_pulse, dt, t_max, t_nd_hi,
                     noise_scale, seed, trial_offset, noise_dev, ld_noise, log_rt, x_out_dev, steps_out_dev,
                     workspace_dev, nullptr, stream);
+}
+
+DDM_API int ddm_sim_gather_f32(const float *theta_dev, int64_t ld_theta, const float *pulses_dev,
+                               int64_t ld_pulses, int64_t N, int64_t P, int64_t n_max,
+                               int64_t steps_per_pulse, float dt, float t_max, float t_nd_hi,
+                               float noise_scale, uint64_t seed, uint64_t trial_offset, int log_rt,
+                               float *x_out_dev, float *const *x_peer_blocks, int n_peers, void *workspace_dev,
+                               void *stream)
+{
+    return sim_impl(theta_dev, ld_theta, pulses_dev, ld_pulses, N, P, n_max, steps_per_pulse, dt, t_max, t_nd_hi,
+                    noise_scale, seed, trial_offset, nullptr, 0, log_rt, x_out_dev, nullptr, workspace_dev, nullptr, stream,
+                    x_peer_blocks, n_peers);
 }
 
 DDM_API int ddm_sim_stream_f32(const float *theta_dev, int64_t ld_theta, const float *pulses_dev,
@@ -586,6 +623,9 @@ DDM_API int ddm_sim_packed_f32(const uint32_t *packed_dev, int64_t N, int64_t n_
     p.log_rt = log_rt ? 1 : 0;
     p.one_bits = 0x3F800000u;
     p.ready = reinterpret_cast<const unsigned long long *>(ready_dev);
+    p.wait_timeout_ns = g_stream_timeout_ns;
+    p.n_peers = 0;
+    for (int d = 0; d < DDM_MAX_PEERS; ++d) p.x_peers[d] = nullptr;
     const bool aligned = (steps_per_pulse % 8) == 0 && steps_per_pulse >= kNormalsPerBlock * DDM_SIM_NB;
     if (ready_dev != nullptr) {
         if (aligned) return launch_sim<3, false, true, true, true>(p, sms, st);

@@ -600,6 +600,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // turn[X]: phase s completes when the issuer of stage s has consumed its aready[X] phase (issuers only)
     uint64_t *turn = aready + kTcTiles;                                // [kTcTiles]
     uint64_t *cfull = turn + kTcTiles;                                 // [kTcTiles] KEEP: context images landed
+    // dth[X]: accumulators of a THETA stage are complete.  Theta stages have a barrier of their own because only
+    // the hf = 1 warps take part in them: were they counted on dfull, an hf = 0 warp still in the tail of the
+    // previous spline could find dfull TWO phases ahead (theta stage and the next layer both committed), take
+    // the parity of the newer phase for the one it waits for and block for good -- a deadlock seen once in
+    // ~1e7 tiles.  Every thread waits for every phase of the barriers it uses; phases are counted per barrier.
+    uint64_t *dth = reinterpret_cast<uint64_t *>(smem + kSmemBars + 104);  // [kTcTiles]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CB = (C + kTcM - 1) / kTcM;
@@ -620,6 +626,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (tid == 0) {
         for (int i = 0; i < kTcTiles; ++i) mbar_init(&turn[i], 1);
         for (int i = 0; i < kTcTiles; ++i) mbar_init(&cfull[i], 1);
+        for (int i = 0; i < kTcTiles; ++i) mbar_init(&dth[i], 1);
         for (int i = 0; i < kTcSlots; ++i) mbar_init(&wfull[i], 1);
         for (int i = 0; i < kTcTiles; ++i) {
             mbar_init(&dfull[i], 1);
@@ -717,7 +724,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         }
                     }
                     if (trace && blockIdx.x == 0) trace[(s * 2 + X) * 8 + 4] = clock64();
-                    umma_commit(&dfull[X]);
+                    umma_commit(st.kind == kStageTheta ? &dth[X] : &dfull[X]);
                 }
                 __syncwarp();
                 // every tile is past stage s-1, so its slot can take the next stage to fetch (issued after
@@ -837,6 +844,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // training forward: `hoist` points at (mu_y, sigma_y) in the parameter buffer (no host round trip)
         const float mu = KEEP ? __ldg(hoist) : mu_y, sigma = KEEP ? __ldg(hoist + 1) : sigma_y;
         float u = (y - mu) / sigma, logdet = -logf(sigma), lp = 0.f;
+        uint32_t ph_d = 0u, ph_t = 0u;  // phases of dfull[X] / dth[X] this thread has waited for
 
 #pragma unroll 1
         for (int s = 0; s < n_st; ++s) {
@@ -846,29 +854,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const size_t at = ((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * kHidden * (size_t)keep.Rp + (size_t)(have ? c_glob : 0);
                 if (st.epi == kEpiRelu)
                     tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st,
-                                               &dfull[X], s & 1);
+                                               &dfull[X], ph_d & 1u);
                 else
                     tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st,
-                                                  &dfull[X], s & 1);
+                                                  &dfull[X], ph_d & 1u);
+                ++ph_d;
                 tc_fence_before_sync();
                 mbar_arrive(&aready[X]);
                 continue;
             }
             if (st.epi >= kEpiSpline && hf != 0) {  // row-wise epilogues are done by the hf = 0 thread of the row
-                mbar_wait(&dfull[X], s & 1);        // (never arrive twice within one phase of aready)
+                mbar_wait(&dfull[X], ph_d++ & 1u);  // (never arrive twice within one phase of aready)
                 mbar_arrive(&aready[X]);
                 continue;
             }
             if (st.kind == kStageTheta && hf == 0) {
                 // theta stages belong to the hf = 1 warps (all 128 columns, arriving for both halves):
-                // the stage follows a spline, whose tail the hf = 0 warps are still computing
-                mbar_wait(&dfull[X], s & 1);        // keep in step with the barrier's phases
+                // the stage follows a spline, whose tail the hf = 0 warps are still computing.  They do not
+                // touch dth at all (see its declaration).
                 continue;
             }
             mbar_wait(&wfull[s % kTcSlots], (s / kTcSlots) & 1);  // the bias travelled with the stage blob
             const float *bias = reinterpret_cast<const float *>(smem + kSmemSlot0 + (uint32_t)(s % kTcSlots) * kSlotBytes +
                                                                 st.bias_off + (st.kind != kStageTheta ? 0u : (uint32_t)X * kHidden * 4u));
-            mbar_wait(&dfull[X], s & 1);
+            if (st.kind == kStageTheta) mbar_wait(&dth[X], ph_t++ & 1u);
+            else mbar_wait(&dfull[X], ph_d++ & 1u);
             tc_fence_after_sync();
             const bool tracer = trace && blockIdx.x == 0 && q == 0 && lane == 0 && hf == (st.kind != kStageTheta ? 0 : 1);
             if (tracer) trace[(s * 2 + X) * 8 + 2] = clock64();

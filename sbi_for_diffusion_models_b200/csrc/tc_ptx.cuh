@@ -49,6 +49,33 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+#ifdef DDM_MBAR_TIMEOUT_NS
+// Debug build (-DDDM_MBAR_TIMEOUT_NS=...): a wait that lasts longer reports which barrier is stuck and traps.
+static __device__ __noinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    unsigned long long t0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > (unsigned long long)(DDM_MBAR_TIMEOUT_NS)) {
+            printf("mbar_wait stuck: block (%d,%d) thread %d bar smem offset %u parity %u\n", (int)blockIdx.x, (int)blockIdx.y,
+                   (int)threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
@@ -63,6 +90,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+#endif
 
 // ---- async proxy ---------------------------------------------------------------------------
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / bulk copies)

@@ -57,43 +57,63 @@ def sim_wrapper(theta_and_pulses: torch.Tensor, *, mu_sensory: float, p_success:
     return x.to(z.device)
 
 
+_LAUNCH_ROWS = 1 << 22   # rows simulated per launch by simulate_training_set_with_conditions
+
+
 @torch.no_grad()
 def simulate_training_set_with_conditions(proposal: Distribution, num_simulations: int, batch_size: int, device, *,
                                           mu_sensory: float, p_success: float, P: int, log_rt: bool,
                                           seed: Optional[int] = None):
     """Draw z ~ proposal in batches, simulate x | z, return CPU (z_all (N,5+P), x_all (N,2))
-    (reference :33-71).  One Philox key covers the whole set; batches use trial offsets, so the
-    result does not depend on ``batch_size`` for a given z."""
+    (reference :33-71).  ``proposal.sample((bs,))`` is called batch by batch exactly as in the reference (so the
+    proposal's random streams advance the same way), but the draws of up to 2^22 rows are gathered into one device
+    block and simulated by ONE launch: with the reference's default batch of 4096 a launch per batch would drain
+    to its longest trial (16 000 serial Euler steps) every time.  One Philox key covers the whole set and trials
+    are indexed globally, so the result does not depend on ``batch_size`` or on this grouping for a given z."""
     dev = compute_device(device)
     if seed is None:
         seed = next_seed()
     z_all = torch.empty((num_simulations, 5 + P), dtype=torch.float32, pin_memory=True)
     x_all = torch.empty((num_simulations, 2), dtype=torch.float32, pin_memory=True)
-    copies = []
-    for start in range(0, num_simulations, batch_size):
-        bs = min(batch_size, num_simulations - start)
-        z = proposal.sample((bs,)).to(device=dev, dtype=torch.float32, non_blocking=True)
-        x = sim_wrapper(z, mu_sensory=mu_sensory, p_success=p_success, P=P, log_rt=log_rt, seed=seed,
-                        trial_offset=start)
-        z_all[start:start + bs].copy_(z, non_blocking=True)
-        x_all[start:start + bs].copy_(x, non_blocking=True)
-        copies.append((z, x))  # keep device buffers alive until the copies have run
-        if (start // batch_size) % 50 == 0:
-            print(f"Simulated {start + bs:,}/{num_simulations:,}")
-            torch.cuda.current_stream(dev).synchronize()
-            copies.clear()
-    torch.cuda.current_stream(dev).synchronize()
-    copies.clear()
+    stream = torch.cuda.current_stream(dev)
+    in_flight = []       # (event, device blocks) until their device->host copies have run
+    checks, outcomes = [], torch.zeros(3, dtype=torch.int64, device=dev)
+    group = max(int(batch_size), _LAUNCH_ROWS)
+    for g0 in range(0, num_simulations, group):
+        g1 = min(g0 + group, num_simulations)
+        with torch.cuda.device(dev):
+            z = torch.empty((g1 - g0, 5 + P), dtype=torch.float32, device=dev)
+        for start in range(g0, g1, batch_size):
+            bs = min(batch_size, g1 - start)
+            z[start - g0:start - g0 + bs].copy_(proposal.sample((bs,)), non_blocking=True)
+            if (start // batch_size) % 50 == 0:
+                print(f"Simulated {start + bs:,}/{num_simulations:,}")
+        x = sim_wrapper(z, mu_sensory=mu_sensory, p_success=p_success, P=P, log_rt=log_rt, seed=seed, trial_offset=g0)
+        z_all[g0:g1].copy_(z, non_blocking=True)
+        x_all[g0:g1].copy_(x, non_blocking=True)
+        # the reference's sanity checks (:62-66), evaluated where the data is: one flag word per block
+        choice = x[:, -1]
+        checks.append(torch.stack([torch.isfinite(z).all(), torch.isfinite(x).all(),
+                                   ((choice == 0) | (choice == 1) | (choice == 2)).all()]))
+        outcomes += torch.bincount(choice.clamp(0, 2).to(torch.int64), minlength=3)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        in_flight.append((ev, z, x))
+        while len(in_flight) > 2:      # bound the device memory held by blocks whose copies are still queued
+            in_flight.pop(0)[0].synchronize()
+    stream.synchronize()
+    in_flight.clear()
 
     assert z_all.shape[0] == num_simulations
     assert x_all.shape[0] == num_simulations
-    assert torch.isfinite(z_all).all()
-    assert torch.isfinite(x_all).all()
-    assert torch.all((x_all[:, -1] == 0) | (x_all[:, -1] == 1) | (x_all[:, -1] == 2))
+    ok = torch.stack(checks).all(0).tolist() if checks else [True, True, True]
+    assert ok[0], "non-finite values in z"
+    assert ok[1], "non-finite values in x"
+    assert ok[2], "choice outside {0, 1, 2}"
 
     print("Training x shape:", tuple(x_all.shape), " (N,2) = [rt(or log rt), choice]")
     print("Training z shape:", tuple(z_all.shape), " (N, 5+P) = [theta, pulses]")
-    print("Unique outcomes in training (choice):", x_all[:, -1].unique().tolist())
+    print("Unique outcomes in training (choice):", [float(c) for c, k in enumerate(outcomes.tolist()) if k > 0])
     return z_all, x_all
 
 

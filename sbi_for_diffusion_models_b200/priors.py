@@ -112,13 +112,16 @@ def _interior_point(d: Distribution) -> float:
     return float(d.mean.reshape(()).detach())
 
 
-def build_prior_theta() -> MultipleIndependentPrior:
+def build_prior_theta(device=None) -> MultipleIndependentPrior:
     """a0 ~ Beta(2,2), lam ~ LogNormal(-1,1), v ~ LogNormal(0,1), B ~ LogNormal(2.75,0.5),
-    tau ~ Beta(2,2)  (reference rt_choice_model_pipeline.py:38-46)."""
+    tau ~ Beta(2,2)  (reference rt_choice_model_pipeline.py:38-46).  ``device``: where the components'
+    parameters live, i.e. where ``sample`` draws (the reference's prior is a CPU object; a CUDA one keeps
+    1e7-1e9-trial proposal draws off the host)."""
+    t = lambda v: torch.tensor([v], device=device)
     return MultipleIndependentPrior([
-        Beta(torch.tensor([2.0]), torch.tensor([2.0])),
-        LogNormal(torch.tensor([-1.0]), torch.tensor([1.0])),
-        LogNormal(torch.tensor([0.0]), torch.tensor([1.0])),
-        LogNormal(torch.tensor([2.75]), torch.tensor([0.5])),
-        Beta(torch.tensor([2.0]), torch.tensor([2.0])),
+        Beta(t(2.0), t(2.0)),
+        LogNormal(t(-1.0), t(1.0)),
+        LogNormal(t(0.0), t(1.0)),
+        LogNormal(t(2.75), t(0.5)),
+        Beta(t(2.0), t(2.0)),
     ])

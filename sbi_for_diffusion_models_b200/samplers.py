@@ -123,7 +123,7 @@ class VectorizedSliceSampler:
         return y
 
     def _update_dim(self, d: int) -> torch.Tensor:
-        """One slice update of coordinate ``d`` for all chains; returns the bracket sizes."""
+        """One slice update of coordinate ``d`` for all chains; returns the final bracket sizes."""
         x0 = self.x[:, d]
         w = self.width[:, d].repeat_interleave(self.N // self.groups)        # per-chain width of its group
         base = self._updates * (2 + self.max_shrink)
@@ -144,7 +144,6 @@ class VectorizedSliceSampler:
             if not bool(grow.any()):
                 break
             hi = torch.where(grow, hi + w, hi)
-        size = hi - lo
         # shrinkage
         todo = torch.ones_like(x0, dtype=torch.bool)
         new_x, new_lp = x0.clone(), self.lp.clone()
@@ -163,7 +162,10 @@ class VectorizedSliceSampler:
         # chains that never found a point keep their state (probability ~0 with max_shrink = 64)
         self.x = self._with(d, new_x)
         self.lp = new_lp
-        return size
+        # the bracket as it stood when the chain accepted (shrunk around the slice): this is what sbi's slice
+        # samplers average into the width while tuning.  (The stepped-out bracket is never smaller than the
+        # width, so averaging THAT only ratchets the width up: 35 evaluations per update instead of ~15.)
+        return hi - lo
 
     def sweep(self, tune: bool = False) -> None:
         for d in range(self.D):

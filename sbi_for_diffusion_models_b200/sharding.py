@@ -52,6 +52,33 @@ def all_gather_rows(local: torch.Tensor, total: int, group=None) -> torch.Tensor
     return torch.cat([parts[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
 
 
+class PeerGather:
+    """The gathered output of a sharded simulation, filled by the simulator kernels themselves.
+
+    Every rank owns ``x_all`` (sum of all shards, 2) fp32 in symmetric memory (``torch.distributed._symmetric_memory``:
+    CUDA virtual-memory handles exchanged once, every rank's block mapped into every process over NVLink).  A
+    rank simulates its shard with ``simulate_trials(..., out=pg.local, peer_blocks=pg.peers)``: each finished trial's
+    8 bytes are stored to the local slot and to the same slot of every peer's ``x_all`` while the kernel keeps
+    running (``ddm_sim_gather_f32``), so the path's only exchange costs no collective, no extra pass over
+    x and no SMs.  ``barrier()`` (enqueued on the current stream) after the launch makes all slots of ``x_all``
+    complete on every rank."""
+
+    def __init__(self, shard_rows: int, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world = _world(group)
+        self.rows = int(shard_rows)                     # equal shards: rank r owns rows [r * rows, (r + 1) * rows)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        shape = (self.world * self.rows, 2)
+        self.x_all = symm.empty(shape, dtype=torch.float32, device=dev)
+        self.handle = symm.rendezvous(self.x_all, group if group is not None else dist.group.WORLD)
+        lo, hi = self.rank * self.rows, (self.rank + 1) * self.rows
+        self.local = self.x_all[lo:hi]
+        self.peers = [self.handle.get_buffer(r, shape, torch.float32)[lo:hi] for r in range(self.world) if r != self.rank]
+
+    def barrier(self) -> None:
+        self.handle.barrier(channel=0)
+
+
 def _cuda_simulate(z, *, P, mu_sensory, log_rt, seed, trial_offset):
     from .simulator import simulate_trials
     return simulate_trials(z[:, :5], z[:, 5:5 + P], mu_sensory=mu_sensory, log_rt=log_rt, seed=seed,

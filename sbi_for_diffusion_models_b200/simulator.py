@@ -101,7 +101,8 @@ def normalise_pulses(pulse_sides, n_trials: int, sched: Schedule, dev: torch.dev
 def simulate_trials(theta: torch.Tensor, pulse_sides, *, mu_sensory: float = 1.0, log_rt: bool = False,
                     seed: Optional[int] = None, trial_offset: int = 0, noise: Optional[torch.Tensor] = None,
                     return_steps: bool = False, return_stats: bool = False, device=None,
-                    schedule: Optional[Schedule] = None, out: Optional[torch.Tensor] = None):
+                    schedule: Optional[Schedule] = None, out: Optional[torch.Tensor] = None,
+                    peer_blocks=None):
     """Simulate one trial per row of ``theta`` on the GPU.
 
     theta (N,5) any float dtype, CPU or CUDA; pulse_sides (N,P) / (1,P) / (P,).
@@ -111,6 +112,10 @@ def simulate_trials(theta: torch.Tensor, pulse_sides, *, mu_sensory: float = 1.0
     ``noise`` (n_max, N) fp32 replaces the native Philox stream with shared noise: the
     output then equals the reference's bit for bit.  ``seed`` defaults to a draw from torch's
     global generator.
+
+    ``peer_blocks``: (N,2) fp32 blocks in OTHER GPUs' memory (peer-mapped views, see
+    ``sharding.PeerGather``); the kernel stores every result there as well -- the all-gather of a sharded run
+    fused into the launch (``ddm_sim_gather_f32``).
     """
     L = _native.lib()
     dev = compute_device(device if device is not None else (theta.device if theta.is_cuda else None))
@@ -137,14 +142,29 @@ def simulate_trials(theta: torch.Tensor, pulse_sides, *, mu_sensory: float = 1.0
             noise_ptr, ld_noise = noise.data_ptr(), noise.stride(0)
         if seed is None:
             seed = 0 if noise is not None else next_seed()
-        rc = L.ddm_sim_f32(th.data_ptr() if n else None, th.stride(0) if n else 5,
-                           s.data_ptr(), ld_pulses, n, s.shape[1],
-                           sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi,
-                           sched.noise_scale, ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(trial_offset),
-                           noise_ptr, ld_noise, int(bool(log_rt)), out.data_ptr() if n else None,
-                           steps.data_ptr() if steps is not None and n else None,
-                           ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-        _native.check(rc, "ddm_sim_f32")
+        if peer_blocks:
+            if noise is not None or return_steps:
+                raise ValueError("the fused gather launch takes native noise and does not return hit steps")
+            for b in peer_blocks:
+                if tuple(b.shape) != (n, 2) or b.dtype != torch.float32 or not b.is_contiguous():
+                    raise ValueError(f"peer blocks must be contiguous (N,2) fp32 with N={n}, got {tuple(b.shape)}")
+            ptrs = (ctypes.c_void_p * len(peer_blocks))(*[b.data_ptr() for b in peer_blocks])
+            rc = L.ddm_sim_gather_f32(th.data_ptr() if n else None, th.stride(0) if n else 5,
+                                      s.data_ptr(), ld_pulses, n, s.shape[1],
+                                      sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi,
+                                      sched.noise_scale, ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(trial_offset),
+                                      int(bool(log_rt)), out.data_ptr() if n else None, ptrs, len(peer_blocks),
+                                      ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _native.check(rc, "ddm_sim_gather_f32")
+        else:
+            rc = L.ddm_sim_f32(th.data_ptr() if n else None, th.stride(0) if n else 5,
+                               s.data_ptr(), ld_pulses, n, s.shape[1],
+                               sched.n_max, sched.steps_per_pulse, sched.dt, sched.t_max, sched.t_nd_hi,
+                               sched.noise_scale, ctypes.c_uint64(seed & (2**64 - 1)), ctypes.c_uint64(trial_offset),
+                               noise_ptr, ld_noise, int(bool(log_rt)), out.data_ptr() if n else None,
+                               steps.data_ptr() if steps is not None and n else None,
+                               ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+            _native.check(rc, "ddm_sim_f32")
         # keep inputs alive until the stream has consumed them
         for t in (th, s, noise):
             if t is not None:
@@ -183,7 +203,16 @@ def philox_words(seed: int, n_trials: int, n_steps: int, *, trial_offset: int = 
     return out
 
 
-PACK_MIN_THREADS = 16   # fewer host threads than this: send the fp32 rows over the link instead
+def pack_min_threads() -> int:
+    """Fewer host threads than this per process: send the fp32 rows over the link instead of packing.
+    Measured on the B200 host (Xeon, 16 vCPU): the AVX-512 packer reads 16.6 GB/s of z per thread, 62 GB/s on 4
+    threads and 165 GB/s on 16; the AVX2 one 9.9 / 37 / 94 GB/s -- against 55.6 GB/s of fp32 rows over PCIe 5 x16
+    (``tools/pack_bw.py``).  So packing beats the link from 4 threads (AVX-512) or 8 threads (AVX2) up."""
+    import os
+    env = os.environ.get("DDM_PACK_MIN_THREADS")
+    if env:
+        return max(1, int(env))
+    return 4 if _native.lib().ddm_pack_simd_bits() >= 512 else 8
 
 
 def pack_threads() -> int:
@@ -197,20 +226,28 @@ def pack_threads() -> int:
     return max(1, min(32, cores // ranks))
 
 
+_launches_block = None   # probed once per process; set to True for good after a streaming launch timed out
+
+
 def launches_block() -> bool:
-    """True when kernel launches do not return until the kernel has finished (CUDA_LAUNCH_BLOCKING=1, or
-    a tool that serialises launches: Nsight Compute, compute-sanitizer).  The packed ingest normally
-    launches its persistent kernel FIRST and feeds it while it runs; under such tools the launch would
-    wait for rows nobody can enqueue any more, so the copies go first (DDM_INGEST_ORDER=copies_first /
-    launch_first overrides the detection)."""
+    """True when a kernel launch does not return until the kernel has finished (CUDA_LAUNCH_BLOCKING=1, or a
+    tool that serialises launches: Nsight Compute, compute-sanitizer, a debugger).  The streaming ingest
+    normally launches its persistent kernel FIRST and feeds it while it runs; when launches block, the launch
+    would wait for rows nobody can enqueue any more, so the copies go first.  Decided by asking the driver, not
+    by guessing from the environment: ``ddm_probe_launch_blocking`` launches a one-thread kernel that waits up to
+    50 ms for a word the host raises the moment the launch call is back.  DDM_INGEST_ORDER=copies_first /
+    launch_first overrides the probe; a streaming launch that ever times out waiting for its rows (any other cause
+    of starvation) also switches the process to copies-first for good (``HostPipeline._check_slot``)."""
     import os
+    global _launches_block
     order = os.environ.get("DDM_INGEST_ORDER")
     if order in ("copies_first", "launch_first"):
         return order == "copies_first"
-    if os.environ.get("CUDA_LAUNCH_BLOCKING") == "1":
-        return True
-    return any(k == "NV_COMPUTE_PROFILER_PERFWORKS_DIR" or k.startswith(("NV_NSIGHT_INJECTION", "NV_SANITIZER"))
-               for k in os.environ)
+    if _launches_block is None:
+        out = ctypes.c_int(0)
+        _native.check(_native.lib().ddm_probe_launch_blocking(50_000, ctypes.byref(out)), "ddm_probe_launch_blocking")
+        _launches_block = bool(out.value)
+    return _launches_block
 
 
 class HostPipeline:
@@ -225,7 +262,7 @@ class HostPipeline:
     launch over all rows.
 
     Packed ingest (default when the schedule needs <= 96 pulses and this process has at least
-    ``PACK_MIN_THREADS`` cores to itself): pulse sides are +-1, so the 340
+    ``pack_min_threads()`` cores to itself): pulse sides are +-1, so the 340
     bytes of an fp32 row carry 32 bytes of information and the PCIe link, not the kernel, bounds the
     fp32 path.  Each chunk is packed on the host cores (``ddm_pack_z_host``) into 32-byte records while
     the previous chunk is on the link and the kernel is already running; ``ddm_sim_packed_f32``
@@ -277,9 +314,7 @@ class HostPipeline:
         if P < sched.n_pulses:
             raise ValueError(f"pulse_sides has P={P} pulses but simulator needs at least {sched.n_pulses}")
         if packed is None:
-            # measured on the B200 box: 16 host threads pack 92.6 GB/s of z (link: 55.5 GB/s of fp32 rows);
-            # with 12 threads per rank (2 ranks on 24 cores) packing was the slower path
-            packed = sched.n_pulses <= 96 and pack_threads() >= PACK_MIN_THREADS
+            packed = sched.n_pulses <= 96 and pack_threads() >= pack_min_threads()
         elif packed and sched.n_pulses > 96:
             raise ValueError("packed ingest holds at most 96 pulse signs per trial")
         cur = torch.cuda.current_stream(self.dev)
@@ -293,6 +328,7 @@ class HostPipeline:
             bs = min(self.max_batch, n - start)
             self._slot_buffers(slot, packed)
             if slot["done"] is not None:
+                self._check_slot(slot)               # its previous batch: finished, and without a starved launch
                 cs.wait_event(slot["done"])          # the previous kernel on this slot has finished
             with torch.cuda.stream(cs):
                 slot["ready"].zero_()
@@ -360,9 +396,19 @@ class HostPipeline:
             self.run(z_host[start:start + bs], x_host[start:start + bs], sched=sched, seed=seed, log_rt=log_rt,
                      trial_offset=trial_offset + start, packed=False)
 
+    def _check_slot(self, slot) -> None:
+        """Raise if the batch that last ran on ``slot`` gave up waiting for its rows (DDM_WS_ERROR), and make
+        every later batch of this process enqueue its copies before its launch."""
+        global _launches_block
+        slot["done"].synchronize()
+        self._pending = [q for q in self._pending if q is not slot]
+        if int(slot["ws"][_native.WS_ERROR].item()) != 0:
+            _launches_block = True
+            raise RuntimeError("streaming simulator launch timed out waiting for host->device copies "
+                               "(its outputs are incomplete); later batches enqueue their copies first")
+
     def synchronize(self) -> None:
         torch.cuda.current_stream(self.dev).synchronize()
-        failed = any(int(s["ws"][_native.WS_ERROR].item()) != 0 for s in self._pending)
-        self._pending.clear()
-        if failed:
-            raise RuntimeError("ddm_sim_stream_f32 timed out waiting for host->device copies")
+        pending, self._pending = self._pending, []
+        for slot in pending:
+            self._check_slot(slot)

@@ -20,3 +20,4 @@ def test_two_gpu_sharding_matches_single_gpu():
     assert "sharded over 2 GPUs == single GPU: True" in r.stdout
     assert "SBC sharded over 2 GPUs == single GPU: True" in r.stdout
     assert "potential sharded over 2 GPUs == single GPU: True" in r.stdout
+    assert r.stdout.count("fused peer-store gather over 2 GPUs == single GPU: True") == 2

@@ -1,5 +1,7 @@
 """Parity of the CUDA simulator (through the C ABI) with the CPU oracle and the reference's
 golden vectors.  Run on the B200 box: ``pytest -m gpu``."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -339,7 +341,7 @@ def test_streaming_host_pipeline_equals_resident_launch(monkeypatch):
     sched = Schedule.from_constants()
     want = simulate_trials(z[:, :5], z[:, 5:], seed=4242, trial_offset=1000).cpu()
     from sbi_for_diffusion_models_b200 import simulator as simmod
-    auto_packs = simmod.pack_threads() >= simmod.PACK_MIN_THREADS
+    auto_packs = simmod.pack_threads() >= simmod.pack_min_threads()
     for packed in (False, True, None):
         xh = torch.full((n, 2), -7.0).pin_memory()
         pipe = HostPipeline(85, max_batch=1 << 17, chunk=1 << 14)      # 3 batches, 8 chunks each, ragged tail
@@ -358,6 +360,50 @@ def test_streaming_host_pipeline_equals_resident_launch(monkeypatch):
     pipe.run(zh, xh2, sched=sched, seed=4242, trial_offset=1000, packed=True)
     pipe.synchronize()
     assert torch.equal(xh2, want)
+
+
+def test_launch_blocking_probe_and_starved_launch(monkeypatch):
+    """The ingest order is decided by a probe, not by sniffing the environment: a one-thread kernel waits for a
+    word the host raises once the launch call has returned.  Here launches do not block; in a child process with
+    CUDA_LAUNCH_BLOCKING=1 they do.  And a streaming launch whose rows never arrive (copies enqueued too late, for
+    whatever reason) gives up after the timeout, is reported when its slot is checked, and switches the process to
+    copies-first."""
+    import ctypes
+    import subprocess
+    import sys
+    from sbi_for_diffusion_models_b200 import _native
+    from sbi_for_diffusion_models_b200 import simulator as simmod
+    L = _native.lib()
+    out = ctypes.c_int(-1)
+    assert L.ddm_probe_launch_blocking(50_000, ctypes.byref(out)) == 0 and out.value == 0
+    monkeypatch.delenv("DDM_INGEST_ORDER", raising=False)
+    monkeypatch.setattr(simmod, "_launches_block", None)
+    assert simmod.launches_block() is False
+    code = ("import ctypes; from sbi_for_diffusion_models_b200 import _native; o = ctypes.c_int(-1); "
+            "assert _native.lib().ddm_probe_launch_blocking(50000, ctypes.byref(o)) == 0; print('blocking', o.value)")
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert "blocking 1" in res.stdout, res.stdout + res.stderr
+    # a starved launch: `ready` is never raised; 50 ms timeout instead of the default 20 s
+    n = 4096
+    z = torch.cat([orc.prior_sample(n, seed=5), torch.ones(n, 80)], 1).pin_memory()
+    xh = torch.empty((n, 2)).pin_memory()
+    pipe = simmod.HostPipeline(85, max_batch=1 << 12, chunk=1 << 12)
+    assert L.ddm_sim_set_stream_timeout_us(50_000) == 0
+    try:
+        real = L.ddm_ingest_packed
+        monkeypatch.setattr(L, "ddm_ingest_packed", lambda *a: 0)      # the copies "never" get enqueued
+        pipe.run(z, xh, sched=Schedule.from_constants(), seed=1, packed=True)
+        with pytest.raises(RuntimeError, match="timed out waiting"):
+            pipe.synchronize()
+        assert simmod.launches_block() is True                         # copies first from now on
+        monkeypatch.setattr(L, "ddm_ingest_packed", real)
+        pipe.run(z, xh, sched=Schedule.from_constants(), seed=1, packed=True)
+        pipe.synchronize()
+        assert torch.equal(xh, simulate_trials(z[:, :5], z[:, 5:], seed=1).cpu())
+    finally:
+        assert L.ddm_sim_set_stream_timeout_us(20_000_000) == 0
+        monkeypatch.setattr(simmod, "_launches_block", None)
 
 
 def test_packed_ingest_falls_back_for_non_binary_pulses():

@@ -74,6 +74,25 @@ def main():
         same = torch.equal(pot, est.loglik_sum(theta, x_o.cuda(), pulses_o.cuda()))
         print(f"potential sharded over {dist.get_world_size()} GPUs == single GPU: {bool(same)}", flush=True)
         ok = ok and bool(same)
+    # fused all-gather: the kernels store every result into all ranks' gathered array (peer memory over NVLink)
+    from sbi_for_diffusion_models_b200.sharding import PeerGather
+    from sbi_for_diffusion_models_b200.simulator import simulate_trials
+    world = dist.get_world_size()
+    m = 50000
+    torch.manual_seed(9)
+    z_full = make().sample((world * m,)).cuda()                 # same z on every rank
+    pg = PeerGather(m)
+    pg.x_all.fill_(-1.0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    mine = z_full[rank * m:(rank + 1) * m]
+    simulate_trials(mine[:, :5], mine[:, 5:], seed=31, trial_offset=rank * m, out=pg.local, peer_blocks=pg.peers)
+    pg.barrier()
+    torch.cuda.synchronize()
+    want = simulate_trials(z_full[:, :5], z_full[:, 5:], seed=31)
+    same = torch.equal(pg.x_all, want)
+    print(f"[rank {rank}] fused peer-store gather over {world} GPUs == single GPU: {bool(same)}", flush=True)
+    ok = ok and bool(same)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
