@@ -144,29 +144,37 @@ def run_sbc(cfg, *, prior_theta, density_estimator, device: str = "cpu", num_dat
     if save and rank == 0:
         os.makedirs(outdir, exist_ok=True)
         np.save(os.path.join(outdir, "sbc_thetas_true.npy"), out["thetas_true"])
-        np.save(os.path.join(outdir, "sbc_ranks.npy"), out["ranks"])
-        _plot_sbc_rank_histograms(out["ranks"], param_names=param_names,
-                                  outpath=os.path.join(outdir, "sbc_rank_histograms.png"), bins=plot_bins)
+        np.save(os.path.join(outdir, "sbc_ranks.npy"), out["ranks"])   # (the reference also draws a histogram: not on this path)
     return out
 
 
-def _plot_sbc_rank_histograms(ranks: np.ndarray, *, param_names: Sequence[str], outpath: Optional[str] = None, bins: int = 30):
-    """Rank histograms (reference mnle.py:107-126); skipped when matplotlib is not installed."""
-    try:
-        import matplotlib
-        matplotlib.use("Agg")
-        import matplotlib.pyplot as plt
-    except Exception:
+# ---- checkpoints (reference mnle.py:241-297) ---------------------------------------------------------------
+
+def _model_dir() -> str:
+    path = os.path.join(os.path.expanduser("~"), "models")
+    os.makedirs(path, exist_ok=True)
+    return path
+
+
+def save_model(density_estimator, cfg, filename: str = "mnle_rt_choice_model.pt") -> str:
+    """``torch.save({"state_dict": ..., "config": ...})`` under ``~/models`` like the reference (mnle.py:247-259);
+    the state of a device estimator is its packed parameter buffer.  Returns the path."""
+    est = as_device_estimator(density_estimator)
+    path = os.path.join(_model_dir(), filename)
+    torch.save({"state_dict": est.state_dict(), "config": cfg}, path)
+    return path
+
+
+def load_model(cfg=None, filename: str = "mnle_rt_choice.pt"):
+    """The estimator saved by ``save_model`` (``None`` when the file does not exist, as the reference's
+    mnle.py:262-266; its default file names differ between save and load, which is kept).  ``cfg`` is accepted for
+    signature compatibility: the architecture is fixed by the packed layout, nothing has to be rebuilt."""
+    from .mnle_net import DeviceMNLE, PackedMNLE
+    path = os.path.join(_model_dir(), filename)
+    if not os.path.exists(path):
         return None
-    D = ranks.shape[1]
-    fig, axes = plt.subplots(D, 1, figsize=(8, 2.5 * D), constrained_layout=True)
-    axes = [axes] if D == 1 else axes
-    for d, ax in enumerate(axes):
-        ax.hist(ranks[:, d], bins=bins)
-        ax.set_title(f"SBC ranks: {param_names[d]}")
-        ax.set_xlabel("rank")
-        ax.set_ylabel("count")
-    if outpath is not None:
-        os.makedirs(os.path.dirname(outpath) or ".", exist_ok=True)
-        fig.savefig(outpath, dpi=150, bbox_inches="tight")
-    return fig
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    sd = blob["state_dict"]
+    if "packed_params" in sd:
+        return DeviceMNLE(PackedMNLE(sd["packed_params"].numpy(), int(sd["n_choices"])))
+    return DeviceMNLE(PackedMNLE.from_state_dict(sd))      # a checkpoint written by sbi itself (see from_state_dict)

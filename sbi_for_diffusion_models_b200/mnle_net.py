@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from typing import Dict, Optional
 
 import numpy as np
@@ -57,6 +58,18 @@ class PackedMNLE:
             raise ValueError(f"packed MNLE buffer has shape {packed.shape}, expected ({need},)")
         self.packed, self.n_choices = packed, int(n_choices)
         self._handles: Dict[tuple, int] = {}
+        # device copies (cudaMalloc'd by mnle_create) are released when the object is collected
+        self._finalizer = weakref.finalize(self, PackedMNLE._release, self._handles)
+
+    @staticmethod
+    def _release(handles: Dict[tuple, int]) -> None:
+        for (pid, _), h in list(handles.items()):
+            if pid == os.getpid():           # a forked child does not own its parent's device memory
+                try:
+                    _native.lib().mnle_destroy(h)
+                except Exception:
+                    pass
+        handles.clear()
 
     @staticmethod
     def packed_floats(n_choices: int) -> int:
@@ -74,9 +87,17 @@ class PackedMNLE:
         if mean.shape != (COND_DIM,) or std.shape != (COND_DIM,):
             raise ValueError("condition mean/std must have 85 entries")
 
-        def fold(W, b):
+        # optional: a flow that standardises ALL 86 context columns itself (choice column included)
+        ctx_mean = f64(p["flow.ctx_mean"]) if "flow.ctx_mean" in p else None
+        ctx_std = np.maximum(f64(p["flow.ctx_std"]), 1e-7) if "flow.ctx_std" in p else None
+        if (ctx_mean is None) != (ctx_std is None) or (ctx_mean is not None and ctx_mean.shape != (CTX_DIM,)):
+            raise ValueError("flow.ctx_mean / flow.ctx_std must both be given with 86 entries")
+
+        def fold(W, b, flow=False):
             W, b = f64(W), f64(b)
             Wf = W.copy()
+            if flow and ctx_mean is not None:   # z-scoring of the 86-wide context owned by the flow
+                return W / ctx_std[None, :], b - W @ (ctx_mean / ctx_std)
             Wf[:, :COND_DIM] = W[:, :COND_DIM] / std[None, :]
             return Wf, b - W[:, :COND_DIM] @ (mean / std)
 
@@ -92,7 +113,7 @@ class PackedMNLE:
                   f64(shape(p["cat.W2"], (HIDDEN, HIDDEN), "cat.W2")), f64(p["cat.b2"]),
                   f64(shape(p["cat.Wo"], (n_choices, HIDDEN), "cat.Wo")), f64(p["cat.bo"])]
         for k in range(NUM_TRANSFORMS):
-            W1, b1 = fold(shape(p[f"flow.{k}.W1"], (HIDDEN, CTX_DIM), f"flow.{k}.W1"), p[f"flow.{k}.b1"])
+            W1, b1 = fold(shape(p[f"flow.{k}.W1"], (HIDDEN, CTX_DIM), f"flow.{k}.W1"), p[f"flow.{k}.b1"], flow=True)
             parts += [W1, b1, f64(shape(p[f"flow.{k}.W2"], (HIDDEN, HIDDEN), f"flow.{k}.W2")), f64(p[f"flow.{k}.b2"]),
                       f64(shape(p[f"flow.{k}.W3"], (SPLINE_OUT, HIDDEN), f"flow.{k}.W3")), f64(p[f"flow.{k}.b3"])]
         parts += [f64(p["flow.mu_y"]).reshape(1), f64(p["flow.sigma_y"]).reshape(1)]
@@ -101,11 +122,24 @@ class PackedMNLE:
 
     @classmethod
     def from_state_dict(cls, sd: Dict[str, torch.Tensor]) -> "PackedMNLE":
-        """Shape-driven import of an sbi MNLE ``state_dict`` (the only way weights leave sbi,
-        reference mnle.py:247-259).  Key names are sbi/nflows internals, so layers are
-        recognised by their shapes in registration order and anything unexpected is refused.
-        UNVERIFIED against a real sbi checkpoint (sbi is not installable here)."""
-        layers, buffers = [], {}
+        """Import of an sbi MNLE ``state_dict`` (the only way weights leave sbi, reference mnle.py:247-259).
+
+        UNVERIFIED against a real sbi 0.25.0 checkpoint (sbi is not installable in this repository's build
+        environment; ``tools/compare_with_sbi.py`` is the check to run where it is).  Key names are sbi / nflows
+        internals, so layers are recognised by SHAPE in registration order -- exactly one categorical net
+        ``(128,85) (128,128) (128,128) (K,128)`` and exactly ten conditioners ``(128,86) (128,128) (71,128)`` --
+        and the standardisation buffers by name AND width:
+
+        * ``*mean*`` / ``*std*`` pairs (sbi ``Standardize``: (x - mean) / std) or ``*_shift`` / ``*_scale`` pairs
+          (nflows ``AffineTransform``: x * scale + shift, i.e. mean = -shift / scale, std = 1 / scale);
+        * one 85-wide pair = z-scoring of the condition, shared by both nets;
+        * optionally one 86-wide pair = the flow's own z-scoring of [condition, choice]; it is folded into the
+          conditioners' first layers (then the 85-wide pair feeds the categorical net only);
+        * exactly one 1-wide pair = z-scoring of log rt.
+
+        Anything else -- extra or missing layers, more than one candidate for a buffer, widths that do not fit --
+        raises ``ValueError`` naming what was found; nothing is guessed."""
+        layers, stats = [], []
         items = list(sd.items())
         i = 0
         while i < len(items):
@@ -115,34 +149,50 @@ class PackedMNLE:
                 layers.append((k, v, items[i + 1][1]))
                 i += 2
                 continue
-            if v.ndim == 1 and ("mean" in k or "std" in k):
-                buffers[k] = v
+            if v.ndim <= 1 and v.numel() in (1, COND_DIM, CTX_DIM) and v.dtype.is_floating_point:
+                stats.append((k, v.reshape(-1)))
             i += 1
         shapes = [tuple(w.shape) for _, w, _ in layers]
 
         def find_run(first, rest):
-            hits = [j for j, s in enumerate(shapes) if s == first and
+            return [j for j, s in enumerate(shapes) if s == first and
                     all(j + 1 + m < len(shapes) and (shapes[j + 1 + m] == r or (r is None and shapes[j + 1 + m][1] == HIDDEN))
                         for m, r in enumerate(rest))]
-            return hits
 
         cat = find_run((HIDDEN, COND_DIM), [(HIDDEN, HIDDEN), (HIDDEN, HIDDEN), None])
         flows = find_run((HIDDEN, CTX_DIM), [(HIDDEN, HIDDEN), (SPLINE_OUT, HIDDEN)])
-        if len(cat) != 1 or len(flows) != NUM_TRANSFORMS:
+        if len(cat) != 1 or len(flows) != NUM_TRANSFORMS or len(layers) != 4 + 3 * NUM_TRANSFORMS:
             raise ValueError(f"state_dict does not look like the reference's MNLE: found {len(cat)} categorical "
-                             f"nets and {len(flows)} spline conditioners (expected 1 and {NUM_TRANSFORMS}); "
-                             f"layer shapes {shapes}")
-        means = [v for k, v in buffers.items() if "mean" in k]
-        stds = [v for k, v in buffers.items() if "std" in k]
-        m85 = [v for v in means if v.shape[0] == COND_DIM]
-        s85 = [v for v in stds if v.shape[0] == COND_DIM]
-        m1 = [v for v in means if v.shape[0] == 1]
-        s1 = [v for v in stds if v.shape[0] == 1]
-        if not (m85 and s85 and len(m1) == 1 and len(s1) == 1):
-            raise ValueError("state_dict lacks the expected standardisation buffers (85-wide condition, 1-wide log rt); "
-                             "a flow that standardises all 86 context columns is not supported")
-        p: Dict[str, torch.Tensor] = {"cond_mean": m85[0], "cond_std": s85[0], "flow.mu_y": m1[0][0],
-                                      "flow.sigma_y": s1[0][0]}
+                             f"nets, {len(flows)} spline conditioners and {len(layers)} linear layers (expected 1, "
+                             f"{NUM_TRANSFORMS} and {4 + 3 * NUM_TRANSFORMS}); layer shapes {shapes}")
+
+        def pair(width):
+            """(mean, std) of the one standardisation of this width, or None if there is none."""
+            def named(*tags):
+                return [(k, v) for k, v in stats if v.numel() == width and any(t in k.lower() for t in tags)]
+            means, stds = named("mean"), named("std")
+            shifts, scales = named("shift"), named("scale")
+            if len(means) == 1 and len(stds) == 1 and not shifts and not scales:
+                return means[0][1].double(), stds[0][1].double()
+            if len(shifts) == 1 and len(scales) == 1 and not means and not stds:
+                scale = scales[0][1].double()
+                return -shifts[0][1].double() / scale, 1.0 / scale
+            if not (means or stds or shifts or scales):
+                return None
+            raise ValueError(f"ambiguous standardisation buffers of width {width}: "
+                             f"{[k for k, _ in means + stds + shifts + scales]}")
+
+        cond, ctx, y = pair(COND_DIM), pair(CTX_DIM), pair(1)
+        if y is None or (cond is None and ctx is None):
+            raise ValueError("state_dict lacks the standardisation buffers of the reference's MNLE "
+                             f"(condition: 85- or 86-wide, log rt: 1-wide); candidates seen: {[k for k, _ in stats]}")
+        p: Dict[str, torch.Tensor] = {"flow.mu_y": y[0][0], "flow.sigma_y": y[1][0]}
+        if cond is not None:
+            p["cond_mean"], p["cond_std"] = cond
+        else:   # only the flow standardises; the categorical net then sees the first 85 columns' statistics
+            p["cond_mean"], p["cond_std"] = ctx[0][:COND_DIM], ctx[1][:COND_DIM]
+        if ctx is not None:
+            p["flow.ctx_mean"], p["flow.ctx_std"] = ctx
         j = cat[0]
         for n, name in enumerate(("0", "1", "2", "o")):
             p[f"cat.W{name}"], p[f"cat.b{name}"] = layers[j + n][1], layers[j + n][2]
@@ -165,16 +215,14 @@ class PackedMNLE:
         return h
 
     def close(self) -> None:
-        for (pid, _), h in list(self._handles.items()):
-            if pid == os.getpid():
-                _native.lib().mnle_destroy(h)
-        self._handles.clear()
+        PackedMNLE._release(self._handles)
 
     def __getstate__(self):
         return {"packed": self.packed, "n_choices": self.n_choices}
 
     def __setstate__(self, st):
         self.packed, self.n_choices, self._handles = st["packed"], st["n_choices"], {}
+        self._finalizer = weakref.finalize(self, PackedMNLE._release, self._handles)
 
 
 class DeviceMNLE(torch.nn.Module):
@@ -185,6 +233,27 @@ class DeviceMNLE(torch.nn.Module):
         super().__init__()
         self.packed = packed
         self._device = device
+        # the reference checkpoints an estimator as {"state_dict": est.state_dict(), "config": cfg}
+        # (mnle.py:241-259): the packed parameters are the state (z-scoring already folded in)
+        self.register_buffer("packed_params", torch.from_numpy(packed.packed.copy()))
+        self.register_buffer("n_choices", torch.tensor(packed.n_choices, dtype=torch.int64))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        key_p, key_k = prefix + "packed_params", prefix + "n_choices"
+        if key_p in state_dict and key_k in state_dict:
+            K = int(state_dict[key_k])
+            new = PackedMNLE(state_dict[key_p].detach().cpu().numpy().astype(np.float32, copy=True), K)   # validates the size
+            if self.packed_params.numel() != new.packed.size:   # a different number of choice categories
+                self.packed_params = torch.empty(new.packed.size, dtype=torch.float32, device=self.packed_params.device)
+            self.packed.close()
+            self.packed = new
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def __getstate__(self):
+        return {"packed": self.packed, "device": self._device}
+
+    def __setstate__(self, st):
+        self.__init__(st["packed"], st["device"])
 
     def _dev(self, t: Optional[torch.Tensor] = None) -> torch.device:
         return compute_device(self._device if self._device is not None else (t.device if t is not None and t.is_cuda else None))

@@ -22,14 +22,26 @@ from torch.distributions import Distribution
 from .mnle_net import DeviceMNLE, PackedMNLE
 
 
+_converted = {}   # id(source object) -> (weak reference to it, its DeviceMNLE): convert a foreign estimator once
+
+
 def as_device_estimator(estimator) -> DeviceMNLE:
-    """Accept our estimator types, or anything exposing an MNLE-shaped ``state_dict()``."""
+    """Accept our estimator types, or anything exposing an MNLE-shaped ``state_dict()`` (converted once per
+    source object: every conversion allocates device copies of the weights)."""
+    import weakref
     if isinstance(estimator, DeviceMNLE):
         return estimator
-    if isinstance(estimator, PackedMNLE):
-        return DeviceMNLE(estimator)
-    if hasattr(estimator, "state_dict"):
-        return DeviceMNLE(PackedMNLE.from_state_dict(estimator.state_dict()))
+    if isinstance(estimator, PackedMNLE) or hasattr(estimator, "state_dict"):
+        hit = _converted.get(id(estimator))
+        if hit is not None and hit[0]() is estimator:
+            return hit[1]
+        dev = DeviceMNLE(estimator if isinstance(estimator, PackedMNLE) else PackedMNLE.from_state_dict(estimator.state_dict()))
+        try:
+            key = id(estimator)
+            _converted[key] = (weakref.ref(estimator, lambda _r, key=key: _converted.pop(key, None)), dev)
+        except TypeError:     # not weak-referenceable: no cache
+            pass
+        return dev
     raise TypeError(f"cannot run {type(estimator).__name__} on the GPU: expected DeviceMNLE, PackedMNLE or a module "
                     "whose state_dict() holds the reference's MNLE architecture")
 

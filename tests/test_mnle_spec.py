@@ -79,14 +79,23 @@ def test_packer_folds_zscoring_exactly():
     assert pk.packed[-2] == np.float32(p["flow.mu_y"]) and pk.packed[-1] == np.float32(p["flow.sigma_y"])
 
 
-def _fake_sbi_state_dict(p):
+def _fake_sbi_state_dict(p, y_as="affine", ctx86=None):
+    """A state_dict laid out the way sbi 0.25.0 / nflows are believed to (UNVERIFIED, see from_state_dict):
+    ``Standardize`` modules carry ``_mean`` / ``_std``, nflows ``AffineTransform`` carries ``_shift`` / ``_scale``
+    with x -> x * scale + shift."""
     sd = {}
     sd["net.discrete_net.embedding._mean"] = p["cond_mean"]
     sd["net.discrete_net.embedding._std"] = p["cond_std"]
     for i, n in enumerate(("0", "1", "2", "o")):
         sd[f"net.discrete_net.layers.{i}.weight"], sd[f"net.discrete_net.layers.{i}.bias"] = p[f"cat.W{n}"], p[f"cat.b{n}"]
-    sd["net.continuous_net._transform.0._shift_mean"] = p["flow.mu_y"].reshape(1)
-    sd["net.continuous_net._transform.0._scale_std"] = p["flow.sigma_y"].reshape(1)
+    if y_as == "affine":
+        sd["net.continuous_net._transform.0._shift"] = (-p["flow.mu_y"] / p["flow.sigma_y"]).reshape(1)
+        sd["net.continuous_net._transform.0._scale"] = (1.0 / p["flow.sigma_y"]).reshape(1)
+    else:
+        sd["net.continuous_net._transform.0._mean"] = p["flow.mu_y"].reshape(1)
+        sd["net.continuous_net._transform.0._std"] = p["flow.sigma_y"].reshape(1)
+    if ctx86 is not None:
+        sd["net.continuous_net._embedding_net.0._mean"], sd["net.continuous_net._embedding_net.0._std"] = ctx86
     for k in range(10):
         base = f"net.continuous_net._transform.{k + 1}.conditioner"
         for i in range(3):
@@ -95,19 +104,72 @@ def _fake_sbi_state_dict(p):
 
 
 def test_state_dict_import_is_shape_driven_and_strict():
-    p = ms.init_params(6)
+    p = ms.cast_params(ms.init_params(6), torch.float64)
     a = PackedMNLE.from_params(p)
-    b = PackedMNLE.from_state_dict(_fake_sbi_state_dict(p))
-    assert np.array_equal(a.packed, b.packed) and b.n_choices == 3
+    for y_as in ("affine", "standardize"):          # (x * scale + shift) or ((x - mean) / std) for log rt
+        b = PackedMNLE.from_state_dict(_fake_sbi_state_dict(p, y_as))
+        assert np.array_equal(a.packed, b.packed) and b.n_choices == 3
     broken = _fake_sbi_state_dict(p)
     del broken["net.continuous_net._transform.4.conditioner.0.weight"]
     with pytest.raises(ValueError, match="does not look like"):
         PackedMNLE.from_state_dict(broken)
-    no_std = {k: v for k, v in _fake_sbi_state_dict(p).items() if "_std" not in k}
+    extra = _fake_sbi_state_dict(p)
+    extra["head.weight"], extra["head.bias"] = torch.zeros(7, 128), torch.zeros(7)      # a layer the layout has no place for
+    with pytest.raises(ValueError, match="does not look like"):
+        PackedMNLE.from_state_dict(extra)
+    no_std = {k: v for k, v in _fake_sbi_state_dict(p, "standardize").items() if "_std" not in k}
     with pytest.raises(ValueError, match="standardisation"):
         PackedMNLE.from_state_dict(no_std)
+    twice = _fake_sbi_state_dict(p)
+    twice["other._mean"], twice["other._std"] = p["cond_mean"], p["cond_std"]           # two 85-wide candidates: refuse
+    with pytest.raises(ValueError, match="ambiguous"):
+        PackedMNLE.from_state_dict(twice)
     with pytest.raises(ValueError):
         PackedMNLE(np.zeros(10, np.float32), 3)
+
+
+def test_flow_side_context_standardisation_is_folded_into_the_conditioners():
+    """A flow that z-scores all 86 context columns itself (choice included): first layers W (c - m) / s + b."""
+    p = ms.cast_params(ms.init_params(8), torch.float64)
+    g = torch.Generator().manual_seed(1)
+    m86 = torch.randn(86, generator=g, dtype=torch.float64)
+    s86 = torch.rand(86, generator=g, dtype=torch.float64) + 0.5
+    pk = PackedMNLE.from_state_dict(_fake_sbi_state_dict(p, ctx86=(m86, s86)))
+    from sbi_for_diffusion_models_b200.mnle_net import unpack_params
+    u = unpack_params(torch.from_numpy(pk.packed.copy()), 3)
+    ctx = torch.randn(86, generator=g, dtype=torch.float64)
+    for k in (0, 9):
+        want = p[f"flow.{k}.W1"] @ ((ctx - m86) / s86) + p[f"flow.{k}.b1"]
+        got = u[f"flow.{k}.W1"].double() @ ctx + u[f"flow.{k}.b1"].double()
+        assert float((got - want).abs().max()) < 5e-6
+    z = ctx[:85]                                     # the categorical net keeps the 85-wide z-scoring
+    want = p["cat.W0"] @ ((z - p["cond_mean"]) / p["cond_std"]) + p["cat.b0"]
+    assert float((u["cat.W0"].double() @ z + u["cat.b0"].double() - want).abs().max()) < 5e-6
+
+
+def test_estimator_state_round_trips_like_the_reference_checkpoints(tmp_path, monkeypatch):
+    """reference mnle.py:241-297: torch.save({"state_dict": est.state_dict(), "config": cfg}) / load_state_dict."""
+    import pickle
+    from sbi_for_diffusion_models_b200 import mnle
+    from sbi_for_diffusion_models_b200.mnle_net import DeviceMNLE
+    from sbi_for_diffusion_models_b200.run_config import RUN_CONFIG_PARAMS as cfg
+    est = DeviceMNLE(PackedMNLE.from_params(ms.init_params(2)))
+    sd = est.state_dict()
+    assert set(sd) == {"packed_params", "n_choices"} and sd["packed_params"].numel() == 412491
+    other = DeviceMNLE(PackedMNLE.from_params(ms.init_params(3)))
+    other.load_state_dict(sd)
+    assert np.array_equal(other.packed.packed, est.packed.packed)
+    two = DeviceMNLE(PackedMNLE.from_params(ms.init_params(4, n_choices=2)))     # a different head size loads too
+    two.load_state_dict(sd)
+    assert two.packed.n_choices == 3 and np.array_equal(two.packed.packed, est.packed.packed)
+    clone = pickle.loads(pickle.dumps(est))
+    assert np.array_equal(clone.packed.packed, est.packed.packed) and set(clone.state_dict()) == set(sd)
+    monkeypatch.setenv("HOME", str(tmp_path))
+    assert mnle.load_model(cfg) is None                                          # nothing saved yet (mnle.py:264-266)
+    path = mnle.save_model(est, cfg, "net.pt")
+    assert path == str(tmp_path / "models" / "net.pt")
+    back = mnle.load_model(cfg, "net.pt")
+    assert np.array_equal(back.packed.packed, est.packed.packed) and back.packed.n_choices == 3
 
 
 def test_sbc_helpers_cpu():

@@ -10,12 +10,18 @@ machine with sbi (and a B200 for the CUDA columns):
     python tools/compare_with_sbi.py [--no-cuda]
 
 It builds the estimator exactly as the reference does (mnle.py:31-39), on a small simulated
-training set (for the z-scoring buffers and the number of choice categories), evaluates
+training set (for the z-scoring buffers and the number of choice categories), optionally trains it
+for a few epochs (``--train-epochs``, so that the weights are not at their initial values), evaluates
 ``estimator.log_prob`` on held-out rows, imports the ``state_dict`` with
 ``PackedMNLE.from_state_dict`` and prints the largest differences of (a) the CPU spec, (b) the fp32
 CUDA kernel, (c) the tcgen05 kernel against sbi's own numbers.  Expected: ~1e-5 (fp32 noise).
 Anything larger means the restatement (or the shape-driven state_dict import) does not match that
 sbi version and must be fixed before trusting MNLE numbers from this package.
+
+It also WRITES ``tests/golden/mnle_sbi.npz`` (``--out``): the estimator's ``state_dict`` (keys in registration
+order + tensors), the held-out rows and sbi's own log-probs.  Commit that file and
+``tests/test_mnle_sbi_fixture.py`` turns from "skipped: parity unpinned" into the pin of the whole MNLE path
+(spec on the CPU; fp32, precise and tcgen05 kernels on the GPU) against real sbi numbers.
 
 NOT run in this repository's CI: it cannot be (sbi is absent).  It is shipped, not claimed.
 """
@@ -34,6 +40,9 @@ def main():
     ap.add_argument("--no-cuda", action="store_true")
     ap.add_argument("--train-rows", type=int, default=4096)
     ap.add_argument("--test-rows", type=int, default=2048)
+    ap.add_argument("--train-epochs", type=int, default=0, help="train with sbi for this many epochs first")
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                  "tests", "golden", "mnle_sbi.npz"))
     args = ap.parse_args()
     try:
         from sbi.neural_nets import likelihood_nn
@@ -56,12 +65,29 @@ def main():
     build = likelihood_nn(model="mnle", log_transform_x=True, z_score_theta="independent", z_score_x="independent",
                           hidden_features=128, num_transforms=10, num_bins=24)
     est = build(z[tr], x[tr])           # sbi: builder(batch_theta, batch_x) with theta := condition z
+    if args.train_epochs > 0:           # a few optimiser steps the way sbi's trainer takes them (-mean log_prob, Adam)
+        opt = torch.optim.Adam(est.parameters(), lr=5e-4)
+        est.train()
+        for _ in range(args.train_epochs):
+            for a in range(0, args.train_rows, 512):
+                opt.zero_grad()
+                loss = -est.log_prob(x[tr][a:a + 512].unsqueeze(0), condition=z[tr][a:a + 512]).mean()
+                loss.backward()
+                opt.step()
     est.eval()
     with torch.no_grad():
         want = est.log_prob(x[te].unsqueeze(0), condition=z[te]).reshape(-1).double()
 
+    sd = est.state_dict()
+    keys = list(sd.keys())
+    import sbi
+    np.savez_compressed(args.out, keys=np.array(keys), x=x[te].numpy(), z=z[te].numpy(), log_prob=want.numpy(),
+                        sbi_version=np.array(getattr(sbi, "__version__", "unknown")),
+                        **{f"t{i}": sd[k].detach().cpu().numpy() for i, k in enumerate(keys)})
+    print(f"wrote {args.out}: {len(keys)} state_dict tensors, {want.numel()} rows (sbi {getattr(sbi, '__version__', '?')})")
+
     from sbi_for_diffusion_models_b200.mnle_net import DeviceMNLE, PackedMNLE
-    packed = PackedMNLE.from_state_dict(est.state_dict())
+    packed = PackedMNLE.from_state_dict(sd)
     print(f"imported state_dict: {packed.packed.size} packed floats, {packed.n_choices} choice categories")
 
     # (a) CPU spec on the imported parameters: unpack the folded buffer back into spec names
@@ -70,7 +96,7 @@ def main():
     report("CPU spec (float64)", got, want)
     if not args.no_cuda:
         dev = DeviceMNLE(packed)
-        for kernel in ("simt", "tc"):
+        for kernel in ("precise", "simt", "tc"):
             got = dev.log_prob(x[te], condition=z[te], kernel=kernel)[0].double()
             report(f"CUDA {kernel}", got, want)
 
