@@ -284,6 +284,19 @@ int mnle_loglik_sum_grad_f32(void *handle, const float *theta_dev, int64_t ld_th
                              float *out_dev, float *grad_dev, float *workspace_dev, void *stream);
 
 /*
+ * The same value and gradient in REVERSE mode on the tensor cores (what autograd does for the reference, with
+ * the MNLE training step's kernels): the (T*C, 85) rows of the reference's expansion go through the tcgen05
+ * forward with activations kept, the per-row spline sweep, the tcgen05 backward-data pass, and the five theta
+ * columns of every first layer are contracted and summed over the trials in a fixed order.  Same arguments as
+ * mnle_loglik_sum_grad_f32; T*C <= 8e6 rows; workspace_dev 256-byte aligned with at least
+ * mnle_loglik_grad_tc_workspace_floats(n_choices, T, C) floats (~9.6 KB per row).
+ */
+size_t mnle_loglik_grad_tc_workspace_floats(int n_choices, int64_t T, int64_t C);
+int mnle_loglik_sum_grad_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C, float *out_dev,
+                                float *grad_dev, float *workspace_dev, void *stream);
+
+/*
  * Same contract on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM): the
  * 128x128 / 128x71 layers run as bf16 hi/lo split GEMMs (three MMAs per product, fp32
  * accumulate), the five global parameters enter through a K = 32 six-term stage, and the

@@ -26,6 +26,8 @@
 //   4. train_reduce_kernel     sums the partials in a fixed order (bit-reproducible gradients) and
 //                              the squared gradient norm; train_stats_kernel: loss and norm.
 //   5. adam_kernel             torch.optim.Adam update with clip_grad_norm_ folded in.
+#include <algorithm>
+
 #include "mnle_dense.cuh"
 #include "tc_ptx.cuh"
 
@@ -806,6 +808,147 @@ DDM_API int mnle_train_adam_f32(float *params_dev, const float *grad_dev, float 
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         params_dev, grad_dev, m_dev, v_dev, n, stats_dev, lr, beta1, beta2, eps, bc1, bc2_sqrt, max_grad_norm);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}
+
+// ---- potential: value and d/d theta in reverse mode on the tensor cores (row f2) ------------------------
+// What autograd does for the reference's NUTS (potentials.py:112 with track_gradients=True), with the training
+// step's kernels: the (T*C, 85) rows of the reference's expansion (row r = t*C + c) go through the tcgen05
+// forward (activations kept), the per-row spline sweep leaves d log p / d (spline parameters, logits), the
+// tcgen05 backward-data pass turns them into d log p / d (first-layer pre-activations), and only the five theta
+// columns of every first layer are contracted: grad[c][i] = sum_t sum_net sum_j DH[net][0][j][t*C+c] W1_net[j][i].
+namespace mnle {
+
+__global__ void __launch_bounds__(256) potential_rows_kernel(const float *__restrict__ theta, long long ld_theta,
+                                                             const float *__restrict__ x, const float *__restrict__ pulses,
+                                                             long long ld_pulses, int T, int C, float *__restrict__ cond,
+                                                             float *__restrict__ xr)
+{
+    const long long total = (long long)T * C * kCond;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / kCond;
+        const int j = (int)(idx - r * kCond);
+        const int t = (int)(r / C), c = (int)(r - (long long)t * C);
+        cond[idx] = j < 5 ? __ldg(theta + (long long)c * ld_theta + j) : __ldg(pulses + (long long)t * ld_pulses + (j - 5));
+        if (j < 2) xr[2 * r + j] = __ldg(x + 2 * t + j);
+    }
+}
+
+constexpr int kGradTSplit = 8;  // trial ranges summed separately (fixed order afterwards: reproducible)
+
+// grid (chain blocks of 128, nets, trial splits): part[(net * kGradTSplit + ts) * C + c][5]
+__global__ void __launch_bounds__(128) potential_grad_partial_kernel(const float *__restrict__ params, Layout L,
+                                                                     const float *__restrict__ DH, long long Rp, int T, int C,
+                                                                     float *__restrict__ part)
+{
+    __shared__ float w_s[kHidden][5];
+    const int net = blockIdx.y, ts = blockIdx.z, c = blockIdx.x * 128 + threadIdx.x;
+    const int K = net == 0 ? kCond : kCtx;
+    const float *W = params + (net == 0 ? L.cat_W0 : L.fl_W1[net - 1]);
+    for (int idx = threadIdx.x; idx < kHidden * 5; idx += 128) w_s[idx / 5][idx % 5] = __ldg(W + (size_t)(idx / 5) * K + idx % 5);
+    __syncthreads();
+    if (c >= C) return;
+    const float *dh = DH + ((size_t)net * 3 + 0) * kHidden * (size_t)Rp;
+    const int t0 = (int)((long long)T * ts / kGradTSplit), t1 = (int)((long long)T * (ts + 1) / kGradTSplit);
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = t0; t < t1; ++t) {
+        const float *col = dh + (size_t)t * C + c;
+#pragma unroll 8
+        for (int j = 0; j < kHidden; ++j) {
+            const float g = __ldcg(col + (size_t)j * Rp);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) acc[i] = fmaf(g, w_s[j][i], acc[i]);
+        }
+    }
+    float *dst = part + ((size_t)(net * kGradTSplit + ts) * C + c) * 5;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dst[i] = acc[i];
+}
+
+__global__ void __launch_bounds__(128) potential_grad_final_kernel(const float *__restrict__ part, const float *__restrict__ LP, int T,
+                                                                   int C, float *__restrict__ out, float *__restrict__ grad)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < kNets * kGradTSplit; ++s)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) acc[i] += part[((size_t)s * C + c) * 5 + i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) grad[(size_t)c * 5 + i] = acc[i];
+    float sum = 0.f;
+    for (int t = 0; t < T; ++t) sum += LP[(size_t)t * C + c];
+    out[c] = sum;
+}
+
+static size_t potential_grad_floats(const Layout &L, long long T, long long C)
+{
+    const long long R = T * C;
+    const TrainDims d = train_dims(L, R);
+    auto up = [](size_t v) { return (v + 63) / 64 * 64; };
+    size_t n = up(train_floats(L, d));
+    n += up((size_t)R * kCond) + up(2 * (size_t)R);         // the expanded rows
+    n += (size_t)kNets * kGradTSplit * (size_t)C * 5;       // partial gradients
+    return n;
+}
+
+}  // namespace mnle
+
+DDM_API size_t mnle_loglik_grad_tc_workspace_floats(int n_choices, int64_t T, int64_t C)
+{
+    if (n_choices < 1 || n_choices > kMaxChoices || T <= 0 || C <= 0) return 0;
+    return potential_grad_floats(make_layout(n_choices), T, C);
+}
+
+DDM_API int mnle_loglik_sum_grad_tc_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                        const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C, float *out_dev,
+                                        float *grad_dev, float *workspace_dev, void *stream)
+{
+    Handle *H = static_cast<Handle *>(handle);
+    if (H == nullptr || H->magic != kMagic) {
+        ddm::set_error("mnle_loglik_sum_grad_tc_f32: bad handle");
+        return DDM_ERR_STATE;
+    }
+    DDM_REQUIRE(T >= 0 && C >= 0 && T * C <= 8000000ll, "mnle_loglik_sum_grad_tc_f32: T=%lld x C=%lld rows (at most 8e6 per call)",
+                (long long)T, (long long)C);
+    if (C == 0) return DDM_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DDM_REQUIRE(out_dev && grad_dev, "mnle_loglik_sum_grad_tc_f32: null output");
+    if (T == 0) {
+        DDM_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)C * sizeof(float), st));
+        DDM_CUDA_TRY(cudaMemsetAsync(grad_dev, 0, (size_t)C * 5 * sizeof(float), st));
+        return DDM_OK;
+    }
+    DDM_REQUIRE(theta_dev && x_dev && pulses_dev && workspace_dev, "mnle_loglik_sum_grad_tc_f32: null pointer");
+    DDM_REQUIRE(ld_theta >= 5 && ld_pulses >= kCond - 5, "mnle_loglik_sum_grad_tc_f32: ld_theta=%lld ld_pulses=%lld too small",
+                (long long)ld_theta, (long long)ld_pulses);
+    DDM_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 255u) == 0, "mnle_loglik_sum_grad_tc_f32: workspace must be 256-byte aligned");
+    const Layout &L = H->layout;
+    const long long R = T * C;
+    const TrainDims d = train_dims(L, R);
+    const TrainBufs B = carve(workspace_dev, L, d);
+    auto up = [](size_t v) { return (v + 63) / 64 * 64; };
+    float *cond = workspace_dev + up(train_floats(L, d));
+    float *xr = cond + up((size_t)R * kCond);
+    float *part = xr + up(2 * (size_t)R);
+    potential_rows_kernel<<<(unsigned)std::min<long long>((R * kCond + 255) / 256, 148 * 16), 256, 0, st>>>(
+        theta_dev, ld_theta, x_dev, pulses_dev, ld_pulses, (int)T, (int)C, cond, xr);
+    DDM_CUDA_TRY(cudaGetLastError());
+    TrainRows rows{xr, cond, nullptr, (long long)kCond, R};
+    const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp, nullptr, nullptr, nullptr};
+    int rc = tc_train_forward(H->params, L, B.pack, xr, cond, (long long)kCond, nullptr, R, keep, B.LP, st);
+    if (rc != DDM_OK) return rc;
+    // scale = +1: the "loss" is the sum of the rows' log-probabilities
+    train_rows_kernel<<<(unsigned)((d.Rp + kRowWarps - 1) / kRowWarps), kRowWarps * 32, 0, st>>>(H->params, L, rows, d.Rp, 1.0f, 1, B);
+    DDM_CUDA_TRY(cudaGetLastError());
+    const TcTrainDump bwd{B.H, B.Q, B.LG, d.Rp, B.DH, nullptr};
+    rc = tc_train_backward(L, B.pack, R, bwd, st);
+    if (rc != DDM_OK) return rc;
+    const unsigned cb = (unsigned)((C + 127) / 128);
+    potential_grad_partial_kernel<<<dim3(cb, kNets, kGradTSplit), 128, 0, st>>>(H->params, L, B.DH, d.Rp, (int)T, (int)C, part);
+    DDM_CUDA_TRY(cudaGetLastError());
+    potential_grad_final_kernel<<<cb, 128, 0, st>>>(part, B.LP, (int)T, (int)C, out_dev, grad_dev);
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }

@@ -309,8 +309,15 @@ class DeviceMNLE(torch.nn.Module):
             _native.check(rc, "mnle_loglik_sum")
         return out.to(theta.device)
 
-    def loglik_sum_and_grad(self, theta: torch.Tensor, x_o: torch.Tensor, pulses: torch.Tensor):
-        """(out (C,), grad (C,5)) with grad[c] = d out[c] / d theta[c]: forward-mode kernel."""
+    GRAD_TC_MIN_ROWS = 2048   # below this the forward-mode CUDA-core kernel (one launch) wins on latency
+
+    def loglik_sum_and_grad(self, theta: torch.Tensor, x_o: torch.Tensor, pulses: torch.Tensor, *, kernel: str = "auto"):
+        """(out (C,), grad (C,5)) with grad[c] = d out[c] / d theta[c].
+        ``kernel``: "tc" reverse mode on the tensor cores (the training step's tcgen05 forward / backward-data
+        kernels over the T*C expanded rows), "simt" forward mode on the CUDA cores (five tangents per row, fp32),
+        "auto" picks by the number of rows."""
+        if kernel not in ("auto", "tc", "simt"):
+            raise ValueError(f"unknown kernel {kernel!r}")
         L = _native.lib()
         dev = self._dev(theta)
         th = theta.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -321,14 +328,24 @@ class DeviceMNLE(torch.nn.Module):
         if pl.ndim != 2 or pl.shape[0] != xo.shape[0] or pl.shape[1] < COND_DIM - 5:
             raise ValueError(f"pulses must be (T,>=80) with T={xo.shape[0]}, got {tuple(pl.shape)}")
         C, T = th.shape[0], xo.shape[0]
+        if kernel == "auto":
+            kernel = "tc" if self.GRAD_TC_MIN_ROWS <= T * C <= 8_000_000 else "simt"
         with torch.cuda.device(dev):
             out = torch.empty((C,), dtype=torch.float32, device=dev)
             grad = torch.empty((C, 5), dtype=torch.float32, device=dev)
-            ws = torch.empty((max(L.mnle_loglik_grad_workspace_floats(T, C), 1),), dtype=torch.float32, device=dev)
-            rc = L.mnle_loglik_sum_grad_f32(self.packed.handle(dev), th.data_ptr(), 5, xo.data_ptr(), pl.data_ptr(),
-                                            pl.shape[1], T, C, out.data_ptr(), grad.data_ptr(), ws.data_ptr(),
-                                            torch.cuda.current_stream(dev).cuda_stream)
-            _native.check(rc, "mnle_loglik_sum_grad_f32")
+            if kernel == "tc":
+                ws = torch.empty((max(L.mnle_loglik_grad_tc_workspace_floats(self.packed.n_choices, T, C), 1),),
+                                 dtype=torch.float32, device=dev)
+                rc = L.mnle_loglik_sum_grad_tc_f32(self.packed.handle(dev), th.data_ptr(), 5, xo.data_ptr(), pl.data_ptr(),
+                                                   pl.shape[1], T, C, out.data_ptr(), grad.data_ptr(), ws.data_ptr(),
+                                                   torch.cuda.current_stream(dev).cuda_stream)
+                _native.check(rc, "mnle_loglik_sum_grad_tc_f32")
+            else:
+                ws = torch.empty((max(L.mnle_loglik_grad_workspace_floats(T, C), 1),), dtype=torch.float32, device=dev)
+                rc = L.mnle_loglik_sum_grad_f32(self.packed.handle(dev), th.data_ptr(), 5, xo.data_ptr(), pl.data_ptr(),
+                                                pl.shape[1], T, C, out.data_ptr(), grad.data_ptr(), ws.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream)
+                _native.check(rc, "mnle_loglik_sum_grad_f32")
         return out.to(theta.device), grad.to(theta.device)
 
     def loglik_sum_batched(self, theta: torch.Tensor, x_o: torch.Tensor, pulses: torch.Tensor) -> torch.Tensor:

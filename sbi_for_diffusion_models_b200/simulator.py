@@ -354,6 +354,7 @@ class HostPipeline:
                     x_host[start:start + bs].copy_(slot["x"][:bs], non_blocking=True)
                     slot["done"] = torch.cuda.Event()
                     slot["done"].record(ks)
+                    slot["checked"] = False
                     self._pending.append(slot)
 
             if packed:
@@ -400,8 +401,11 @@ class HostPipeline:
         """Raise if the batch that last ran on ``slot`` gave up waiting for its rows (DDM_WS_ERROR), and make
         every later batch of this process enqueue its copies before its launch."""
         global _launches_block
-        slot["done"].synchronize()
         self._pending = [q for q in self._pending if q is not slot]
+        if slot.get("checked", True):
+            return
+        slot["done"].synchronize()
+        slot["checked"] = True
         if int(slot["ws"][_native.WS_ERROR].item()) != 0:
             _launches_block = True
             raise RuntimeError("streaming simulator launch timed out waiting for host->device copies "
