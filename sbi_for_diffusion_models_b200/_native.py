@@ -27,6 +27,7 @@ _SIGNATURES = {
     "ddm_probe_launch_blocking": (ctypes.c_int, [_i64, _ptr]),
     "ddm_pack_simd_bits": (ctypes.c_int, []),
     "ddm_sim_set_stream_timeout_us": (ctypes.c_int, [_i64]),
+    "ddm_sim_set_small_batch_max": (ctypes.c_int, [_i64]),
     "ddm_sim_workspace_bytes": (ctypes.c_size_t, []),
     "ddm_sim_f32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _f32, _f32,
                                    _u64, _u64, _ptr, _i64, _i32, _ptr, _ptr, _ptr, _ptr]),

@@ -406,6 +406,40 @@ def test_launch_blocking_probe_and_starved_launch(monkeypatch):
         monkeypatch.setattr(simmod, "_launches_block", None)
 
 
+def test_small_batch_kernel_is_bit_identical_to_the_throughput_kernel():
+    """Launches of <= 8192 trials run producer / consumer CTAs (one warp integrates 32 trials in lock-step, seven
+    warps generate the noise of the next 42 steps into shared memory); larger ones the persistent lane-per-trial
+    kernel.  Same Philox indexing, same operations: identical bits, hit steps and step counts -- default, long and
+    unaligned schedules, broadcast and non-binary pulses, log rt, ragged sizes."""
+    from sbi_for_diffusion_models_b200 import _native
+    L = _native.lib()
+    rs = np.random.RandomState(3)
+    cases = [(1, {}), (31, {}), (33, {}), (1000, {}), (10007, {}), (40000, {}),
+             (3000, {"dt": 1e-4}), (2000, {"dt": 7e-4, "pulse_interval": 0.0497}), (500, {"t_max": 1.0})]
+    try:
+        for n, kw in cases:
+            sched = Schedule.from_constants(1.0, **kw)
+            theta = orc.prior_sample(n, seed=70 + n)
+            theta[: min(n, 4)] = torch.tensor([[0.5, 0.2, 0.3, 1e-7, 0.1], [0.0, -0.5, 2.0, 5.0, 7.9999995], [1.0, 3.0, 0.0, 30.0, 0.0],
+                                               [0.3, 0.7, 1.0, 12.0, 9.0]])[: min(n, 4)]
+            pulses = torch.from_numpy(np.where(rs.rand(n, sched.n_pulses) < 0.75, 1.0, -1.0).astype(np.float32))
+            variants = [("rows", pulses, False), ("log rt", pulses, True), ("broadcast", pulses[:1], False)]
+            odd = pulses.clone()
+            odd[::7, ::5] = 0.25
+            variants.append(("non-binary", odd, False))
+            for name, pl, log_rt in variants:
+                out = {}
+                for mode, cap in (("small", 1 << 20), ("throughput", 0)):
+                    assert L.ddm_sim_set_small_batch_max(cap) == 0
+                    out[mode] = sim.simulate_trials(theta, pl, seed=5 + n, trial_offset=11, schedule=sched, log_rt=log_rt,
+                                                    return_steps=True, return_stats=True)
+                (xa, sa, ta), (xb, sb, tb) = out["small"], out["throughput"]
+                assert torch.equal(xa.view(torch.int32), xb.view(torch.int32)), (n, kw, name)
+                assert torch.equal(sa, sb) and ta.useful_steps == tb.useful_steps, (n, kw, name)
+    finally:
+        assert L.ddm_sim_set_small_batch_max(8192) == 0
+
+
 def test_packed_ingest_falls_back_for_non_binary_pulses():
     """A batch with a pulse value other than +-1 cannot be packed to sign bits: it is re-run through
     the fp32 rows (reference semantics a += v * s, rt_choice_model.py:192)."""
