@@ -863,26 +863,28 @@ def run_native(args):
         # evidence from the committed ncu --set full capture of this kernel (profiles/): issue-slot
         # utilisation (what BASELINE's ">= 60 % of FP32 issue" refers to) and DRAM bytes per trial
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_sim_kernel_ncu_full.json")))["launches"][0]
-            trials_prof = 8388608
+            prof_file = json.load(open(os.path.join(ROOT, "profiles", "r02_sim_kernel_ncu_full.json")))
+            prof, cap = prof_file["launches"][0], prof_file["capture"]
+            trials_prof = int(cap["trials_per_launch"])
             dram = 0.0
             for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[prof[key]["unit"]]
                 dram += prof[key]["value"] * scale
             roofline["traffic"] = dram / trials_prof * n
             roofline["traffic_note"] = (f"ncu dram bytes per trial ({dram / trials_prof:.0f} B at {trials_prof} trials per launch, "
-                                        "profiles/r01_sim_kernel_ncu_full.json) x trials per launch")
-            roofline["ncu_issue_active_pct"] = prof["sm__issue_active.avg.pct_of_peak_sustained_elapsed"]["value"]
+                                        "profiles/r02_sim_kernel_ncu_full.json) x trials per launch; a constant of that capture, not "
+                                        "measured in this run")
+            roofline["ncu_issue_active_pct"] = prof["sm__issue_active.avg.pct_of_peak_sustained_elapsed"]["value"]   # (of that capture)
             # issue-slot view of the same launch: warp-instructions per useful Euler step from that capture
             # (all of them: RNG, physics, bookkeeping) x the live step rate, against one instruction per
             # lane per clock
-            inst_per_step = prof["smsp__inst_executed.sum"]["value"] * 32.0 / (trials_prof * 5116.07)
+            inst_per_step = prof["smsp__inst_executed.sum"]["value"] * 32.0 / (trials_prof * float(cap["useful_steps_per_trial"]))
             roofline["issue"] = {"lane_inst_per_useful_step": inst_per_step,
                                  "achieved": per_launch_steps * inst_per_step / (k_ms * 1e-3) / 1e12, "peak": lane_peak / 1e12,
                                  "unit": "T lane-instructions/s",
                                  "frac": per_launch_steps * inst_per_step / (k_ms * 1e-3) / lane_peak,
-                                 "note": "instructions per step from profiles/r01_sim_kernel_ncu_full.json (8388608 trials, "
-                                         "5116.07 useful steps per trial), rate measured live"}
+                                 "note": "instructions per step from profiles/r02_sim_kernel_ncu_full.json (8388608 trials, "
+                                         "5116.72 useful steps per trial: a constant of that capture), step rate measured live"}
         except Exception:
             pass
         line = {
