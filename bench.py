@@ -376,22 +376,28 @@ def configs0_bench(dev):
     from sbi_for_diffusion_models_b200.priors import build_prior_theta
     from sbi_for_diffusion_models_b200.proposals import ExtendedProposal, PulseSequenceProposal
 
-    def once(seed):
-        prop = ExtendedProposal(build_prior_theta(), PulseSequenceProposal(P, 0.75, seed=seed, device=dev), device=dev)
+    def once(seed, prior_dev=None):
+        prop = ExtendedProposal(build_prior_theta(prior_dev), PulseSequenceProposal(P, 0.75, seed=seed, device=dev), device=dev)
         with contextlib.redirect_stdout(io.StringIO()):
             return ds.simulate_training_set_with_conditions(prop, 10_000, 4096, dev, mu_sensory=1.0, p_success=0.75, P=P,
                                                             log_rt=False, seed=seed)
-    once(0)
-    torch.cuda.synchronize()
-    ts = []
-    for i in range(3):
-        t0 = time.perf_counter()
-        z, x = once(1 + i)
-        ts.append(time.perf_counter() - t0)
-    dt = sorted(ts)[1]
+
+    def timed(prior_dev):
+        once(0, prior_dev)
+        torch.cuda.synchronize()
+        ts = []
+        for i in range(5):
+            t0 = time.perf_counter()
+            z, x = once(1 + i, prior_dev)
+            ts.append(time.perf_counter() - t0)
+        return sorted(ts)[2], z, x
+    dt, z, x = timed(None)
+    dt_dev, _, _ = timed(dev)
     steps = float(torch.round((x[:, 0] - z[:, 4].clamp(0.0, 7.999999)) / 5e-4).sum())
     return {"workload": "configs[0]: simulate_training_set_with_conditions, 10 000 trials in batches of 4096, CPU (z, x) out",
-            "seconds": dt, "trials_per_s": 10_000 / dt, "steps_per_s": steps / dt}
+            "seconds": dt, "trials_per_s": 10_000 / dt, "steps_per_s": steps / dt, "seconds_with_cuda_prior": dt_dev,
+            "note": "seconds: the reference's CPU prior object -- ~3 ms of it are torch's CPU Beta sampler "
+                    "(tools/time_configs0.py); seconds_with_cuda_prior: the same call with the prior's parameters on the GPU"}
 
 
 def long_schedule_bench(args, z, rank, world, dev, gather):

@@ -58,6 +58,14 @@ def sim_wrapper(theta_and_pulses: torch.Tensor, *, mu_sensory: float, p_success:
 
 
 _LAUNCH_ROWS = 1 << 22   # rows simulated per launch by simulate_training_set_with_conditions
+_copy_streams = {}
+
+
+def _copy_stream(dev) -> "torch.cuda.Stream":
+    s = _copy_streams.get(dev)
+    if s is None:
+        s = _copy_streams[dev] = torch.cuda.Stream(dev)
+    return s
 
 
 @torch.no_grad()
@@ -73,9 +81,13 @@ def simulate_training_set_with_conditions(proposal: Distribution, num_simulation
     dev = compute_device(device)
     if seed is None:
         seed = next_seed()
-    z_all = torch.empty((num_simulations, 5 + P), dtype=torch.float32, pin_memory=True)
-    x_all = torch.empty((num_simulations, 2), dtype=torch.float32, pin_memory=True)
+    # results go to pinned memory (asynchronous device->host copies on their own stream, overlapped with the next
+    # block's draws and simulation) unless the whole set is small: pinning a few megabytes costs more than it saves
+    pinned = num_simulations * (7 + P) * 4 >= (8 << 20)
+    z_all = torch.empty((num_simulations, 5 + P), dtype=torch.float32, pin_memory=pinned)
+    x_all = torch.empty((num_simulations, 2), dtype=torch.float32, pin_memory=pinned)
     stream = torch.cuda.current_stream(dev)
+    copier = _copy_stream(dev) if pinned else stream
     in_flight = []       # (event, device blocks) until their device->host copies have run
     checks, outcomes = [], torch.zeros(3, dtype=torch.int64, device=dev)
     group = max(int(batch_size), _LAUNCH_ROWS)
@@ -89,19 +101,26 @@ def simulate_training_set_with_conditions(proposal: Distribution, num_simulation
             if (start // batch_size) % 50 == 0:
                 print(f"Simulated {start + bs:,}/{num_simulations:,}")
         x = sim_wrapper(z, mu_sensory=mu_sensory, p_success=p_success, P=P, log_rt=log_rt, seed=seed, trial_offset=g0)
-        z_all[g0:g1].copy_(z, non_blocking=True)
-        x_all[g0:g1].copy_(x, non_blocking=True)
         # the reference's sanity checks (:62-66), evaluated where the data is: one flag word per block
         choice = x[:, -1]
         checks.append(torch.stack([torch.isfinite(z).all(), torch.isfinite(x).all(),
                                    ((choice == 0) | (choice == 1) | (choice == 2)).all()]))
         outcomes += torch.bincount(choice.clamp(0, 2).to(torch.int64), minlength=3)
-        ev = torch.cuda.Event()
-        ev.record(stream)
+        if copier is not stream:
+            copier.wait_stream(stream)
+        with torch.cuda.stream(copier):
+            z_all[g0:g1].copy_(z, non_blocking=True)
+            x_all[g0:g1].copy_(x, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copier)
+        if copier is not stream:
+            z.record_stream(copier)
+            x.record_stream(copier)
         in_flight.append((ev, z, x))
         while len(in_flight) > 2:      # bound the device memory held by blocks whose copies are still queued
             in_flight.pop(0)[0].synchronize()
-    stream.synchronize()
+    for ev, _, _ in in_flight:
+        ev.synchronize()
     in_flight.clear()
 
     assert z_all.shape[0] == num_simulations

@@ -31,7 +31,7 @@ class MultipleIndependentPrior(Distribution):
 
     def sample(self, sample_shape=torch.Size()) -> torch.Tensor:
         shape = torch.Size(sample_shape)
-        cols = [d.sample(shape).reshape(shape + (1,)) for d in self.dists]
+        cols = [_sample_component(d, shape).reshape(shape + (1,)) for d in self.dists]
         return torch.cat(cols, dim=-1)
 
     def log_prob(self, value: torch.Tensor) -> torch.Tensor:
@@ -93,6 +93,23 @@ class MultipleIndependentPrior(Distribution):
     @property
     def support(self):
         raise NotImplementedError("use log_prob(...) == -inf to test the support")
+
+
+def _sample_component(d: Distribution, shape: torch.Size) -> torch.Tensor:
+    """``d.sample(shape)``.  One exception: a Beta(a, b) with small integer parameters that lives on a CUDA
+    device is drawn as the a-th smallest of a + b - 1 uniforms (its exact law): torch's CUDA Beta sampler goes
+    through per-element gamma rejection loops and costs ~15 ns per draw, which made the prior -- not the
+    simulator or the PCIe link -- the bottleneck of a 1e7-trial training set.  CPU priors (the reference's)
+    keep torch's sampler and therefore torch's random stream."""
+    if isinstance(d, Beta) and d.concentration1.is_cuda and d.concentration1.numel() == 1:
+        a, b = float(d.concentration1.reshape(-1)[0]), float(d.concentration0.reshape(-1)[0])
+        if a == int(a) and b == int(b) and 1 <= a and 1 <= b and a + b <= 6:
+            n = int(a + b - 1)
+            u = torch.rand(tuple(shape) + (n,), device=d.concentration1.device, dtype=d.concentration1.dtype)
+            if n == 1:
+                return u[..., 0]
+            return torch.sort(u, dim=-1).values[..., int(a) - 1]
+    return d.sample(shape)
 
 
 def _on_device(d: Distribution, device) -> Distribution:
