@@ -312,7 +312,7 @@ def mnle_bench(dev, with_cpu: bool):
     out = {"workload": f"configs[3]: MNLE log_prob sum over T={T} trials x C={C} chains, trained estimator "
                        "(tests/golden/mnle_trained.npz)", "rows": T * C, "dense_mflop_per_row": 0.818}
     lls = {}
-    for kernel in ("tc", "simt", "precise"):
+    for kernel in ("tc", "simt", "precise", "tc64"):
         for _ in range(3):
             est.loglik_sum(th, xo, pl, kernel=kernel)
         torch.cuda.synchronize()

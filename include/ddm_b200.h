@@ -276,6 +276,14 @@ int mnle_loglik_sum_simt_f32(void *handle, const float *theta_dev, int64_t ld_th
 int mnle_loglik_sum_precise_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
                                 const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C,
                                 float *out_dev, float *workspace_dev, void *stream);
+/* _tc64: the networks on the tensor cores (rows-mode tcgen05 forward over the T*C expanded rows, writing the raw
+ * spline parameters and choice logits), then the spline chain, categorical head and the sum over trials in fp64:
+ * the accuracy of _precise at a fraction of its time.  T*C <= 8e6; workspace_dev 256-byte aligned with at least
+ * mnle_loglik_tc64_workspace_floats(n_choices, T, C) floats (~3 KB per row). */
+size_t mnle_loglik_tc64_workspace_floats(int n_choices, int64_t T, int64_t C);
+int mnle_loglik_sum_tc64_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                             const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C, float *out_dev,
+                             float *workspace_dev, void *stream);
 
 /*
  * Value and gradient with respect to theta of the same sum (what autograd gives the reference's

@@ -891,7 +891,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 continue;
             }
             float *keep_h = nullptr;
-            if (KEEP && kept && st.pad != 0)
+            if (KEEP && kept && st.pad != 0 && keep.H != nullptr)   // (H == null: only logits and spline parameters are kept)
                 keep_h = keep.H + ((size_t)st.net * 3 + (st.pad - 1)) * kHidden * (size_t)keep.Rp + (size_t)c_glob;
             if (st.epi == kEpiRelu) {
                 tc_epilogue_act<kEpiRelu>(trow, 64 * hf, 64, bias, keep_h, (size_t)keep.Rp);

@@ -952,3 +952,101 @@ DDM_API int mnle_loglik_sum_grad_tc_f32(void *handle, const float *theta_dev, in
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }
+
+
+// ---- potential: networks on the tensor cores, spline chain in fp64 ("tc64") ----------------------------
+// On a trained estimator the fp32 rounding of the spline arithmetic, not of the networks, is what separates an
+// fp32 evaluation from exact arithmetic (mnle_common.cuh::rqs_forward).  Here the tcgen05 rows-mode forward
+// writes the raw spline parameters and choice logits of every (trial, chain) row, and one thread per row runs
+// the ten splines, the categorical head and the final sum in fp64; the trials of a chain are added in fp64 in a
+// fixed order.
+namespace mnle {
+
+__global__ void __launch_bounds__(128) precise_rows_kernel(const float *__restrict__ Q, const float *__restrict__ LG, long long Rp,
+                                                           const float *__restrict__ xr, long long R, int n_choices, float mu_y,
+                                                           float sigma_y, double *__restrict__ LP)
+{
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= R) return;
+    const float rt = __ldg(xr + 2 * row);
+    const int choice = (int)__ldg(xr + 2 * row + 1);
+    const double y = log((double)rt);
+    double u = (y - (double)mu_y) / (double)sigma_y, logdet = -log((double)sigma_y);
+#pragma unroll 1
+    for (int k = 0; k < kTransforms; ++k) rqs_forward<double>(u, logdet, Q + ((size_t)k * Rp + row) * kQRows, 1);
+    const double lp = categorical_logp<double>(LG + (size_t)row * kMaxChoices, 1, n_choices, choice);
+    LP[row] = lp + (-0.5 * u * u - 0.91893853320467274178) + logdet - y;
+}
+
+__global__ void __launch_bounds__(128) precise_sum_kernel(const double *__restrict__ LP, int T, int C, float *__restrict__ out)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
+    double sum = 0.0;
+    for (int t = 0; t < T; ++t) sum += LP[(size_t)t * C + c];
+    out[c] = (float)sum;
+}
+
+static size_t tc64_floats(const Layout &L, long long T, long long C)
+{
+    const long long R = T * C;
+    const TrainDims d = train_dims(L, R);
+    auto up = [](size_t v) { return (v + 63) / 64 * 64; };
+    // operand pack + spline parameters + logits (the head of the training workspace), the expanded rows, fp64 log-probs
+    return up(pack_floats(L, R) + (size_t)d.Rp * (kTransforms * kQRows + kMaxChoices + 1)) + up((size_t)R * kCond) + up(2 * (size_t)R) +
+           2 * (size_t)d.Rp;
+}
+
+}  // namespace mnle
+
+DDM_API size_t mnle_loglik_tc64_workspace_floats(int n_choices, int64_t T, int64_t C)
+{
+    if (n_choices < 1 || n_choices > kMaxChoices || T <= 0 || C <= 0) return 0;
+    return tc64_floats(make_layout(n_choices), T, C);
+}
+
+DDM_API int mnle_loglik_sum_tc64_f32(void *handle, const float *theta_dev, int64_t ld_theta, const float *x_dev,
+                                     const float *pulses_dev, int64_t ld_pulses, int64_t T, int64_t C, float *out_dev,
+                                     float *workspace_dev, void *stream)
+{
+    Handle *H = static_cast<Handle *>(handle);
+    if (H == nullptr || H->magic != kMagic) {
+        ddm::set_error("mnle_loglik_sum_tc64_f32: bad handle");
+        return DDM_ERR_STATE;
+    }
+    DDM_REQUIRE(T >= 0 && C >= 0 && T * C <= 8000000ll, "mnle_loglik_sum_tc64_f32: T=%lld x C=%lld rows (at most 8e6 per call)",
+                (long long)T, (long long)C);
+    if (C == 0) return DDM_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DDM_REQUIRE(out_dev != nullptr, "mnle_loglik_sum_tc64_f32: null output");
+    if (T == 0) {
+        DDM_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)C * sizeof(float), st));
+        return DDM_OK;
+    }
+    DDM_REQUIRE(theta_dev && x_dev && pulses_dev && workspace_dev, "mnle_loglik_sum_tc64_f32: null pointer");
+    DDM_REQUIRE(ld_theta >= 5 && ld_pulses >= kCond - 5, "mnle_loglik_sum_tc64_f32: ld_theta=%lld ld_pulses=%lld too small",
+                (long long)ld_theta, (long long)ld_pulses);
+    DDM_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 255u) == 0, "mnle_loglik_sum_tc64_f32: workspace must be 256-byte aligned");
+    const Layout &L = H->layout;
+    const long long R = T * C;
+    const TrainDims d = train_dims(L, R);
+    auto up = [](size_t v) { return (v + 63) / 64 * 64; };
+    float *pack = workspace_dev;
+    float *Q = pack + pack_floats(L, R);
+    float *LG = Q + (size_t)kTransforms * kQRows * d.Rp;
+    float *lp32 = LG + (size_t)kMaxChoices * d.Rp;   // the forward kernel's own fp32 log-prob slot (unused here)
+    float *cond = workspace_dev + up(pack_floats(L, R) + (size_t)d.Rp * (kTransforms * kQRows + kMaxChoices + 1));
+    float *xr = cond + up((size_t)R * kCond);
+    double *LP = reinterpret_cast<double *>(xr + up(2 * (size_t)R));
+    potential_rows_kernel<<<(unsigned)std::min<long long>((R * kCond + 255) / 256, 148 * 16), 256, 0, st>>>(
+        theta_dev, ld_theta, x_dev, pulses_dev, ld_pulses, (int)T, (int)C, cond, xr);
+    DDM_CUDA_TRY(cudaGetLastError());
+    const TcTrainDump keep{nullptr, Q, LG, d.Rp, nullptr, nullptr, nullptr};
+    const int rc = tc_train_forward(H->params, L, pack, xr, cond, (long long)kCond, nullptr, R, keep, lp32, st);
+    if (rc != DDM_OK) return rc;
+    precise_rows_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(Q, LG, d.Rp, xr, R, L.n_choices, H->mu_y, H->sigma_y, LP);
+    DDM_CUDA_TRY(cudaGetLastError());
+    precise_sum_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(LP, (int)T, (int)C, out_dev);
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
+}

@@ -302,7 +302,8 @@ class DeviceMNLE(torch.nn.Module):
         with torch.cuda.device(dev):
             out = torch.empty((C,), dtype=torch.float32, device=dev)
             fn, ws_floats = self._pick_kernel(kernel, T)
-            ws = torch.empty((max(ws_floats(T, C), 1),), dtype=torch.float32, device=dev)
+            n_ws = ws_floats(T, C) if ws_floats is not None else L.mnle_loglik_tc64_workspace_floats(self.packed.n_choices, T, C)
+            ws = torch.empty((max(n_ws, 1),), dtype=torch.float32, device=dev)
             rc = fn(self.packed.handle(dev), th.data_ptr(), th.stride(0) if C > 1 else 5, xo.data_ptr(), pl.data_ptr(),
                     pl.stride(0) if T > 1 else pl.shape[1], T, C, out.data_ptr(), ws.data_ptr(),
                     torch.cuda.current_stream(dev).cuda_stream)
@@ -377,7 +378,8 @@ class DeviceMNLE(torch.nn.Module):
     @staticmethod
     def _pick_kernel(kernel: str, T: int):
         """"tc": tcgen05 tensor-core kernel; "simt": fp32 CUDA-core kernel; "precise": fp32 networks + fp64
-        spline chain (accuracy anchor); "auto": tensor cores whenever the shape is covered."""
+        spline chain (accuracy anchor); "tc64": tensor-core networks + fp64 spline chain; "auto": tensor cores
+        whenever the shape is covered."""
         L = _native.lib()
         if kernel == "auto":
             kernel = "tc" if T <= 524280 else "simt"
@@ -387,4 +389,6 @@ class DeviceMNLE(torch.nn.Module):
             return L.mnle_loglik_sum_simt_f32, L.mnle_loglik_workspace_floats
         if kernel == "precise":
             return L.mnle_loglik_sum_precise_f32, L.mnle_loglik_workspace_floats
+        if kernel == "tc64":
+            return L.mnle_loglik_sum_tc64_f32, None
         raise ValueError(f"unknown kernel {kernel!r}")

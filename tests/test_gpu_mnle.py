@@ -88,7 +88,7 @@ def test_rows_api_matches_spec(net, kernel):
         assert torch.equal(est.log_prob(x[:r], condition=cond[:r], kernel=kernel)[0], got[0, :r])
 
 
-@pytest.mark.parametrize("kernel", ["tc", "simt", "precise"])
+@pytest.mark.parametrize("kernel", ["tc", "simt", "precise", "tc64"])
 @pytest.mark.parametrize("T,C", [(50, 1024), (1, 1), (64, 3), (65, 7), (200, 33), (50, 1), (3, 300)])
 def test_potential_sum_matches_spec(net, T, C, kernel):
     p32, p64, est, kind = net
@@ -100,7 +100,15 @@ def test_potential_sum_matches_spec(net, T, C, kernel):
     want = want_rows.sum(0)
     err = (got - want).abs()
     rel = err / want.abs()
-    if kind == "init" or kernel == "precise":
+    if kind == "trained" and kernel == "tc64":
+        # tensor-core networks (bf16 hi/lo operands, ~1e-5 on the conditioner outputs) + fp64 spline chain: between
+        # the tcgen05 kernel and the precise one -- measured 7e-5 relative on the worst configs[3] sum of the bench's
+        # chains (tcgen05: 1.5e-3, precise: 2.4e-6), median 4e-6
+        scale = torch.maximum(want.abs(), want_rows.abs().sum(0) / 10)
+        assert float((err / scale).max()) < 5e-4, float((err / scale).max())
+        if T * C == 51200:
+            assert float(rel.median()) < 1e-5 and float((rel > 1e-4).float().mean()) < 0.01, (float(rel.median()), float(rel.max()))
+    elif kind == "init" or kernel in ("precise", "tc64"):
         # north_star tolerance: 1e-4 relative on every sum (a sum of T log-probs of either sign is compared on the
         # scale of its summands when it cancels below that: |want| -> max(|want|, sum_t |log p_t| / 10))
         scale = torch.maximum(want.abs(), want_rows.abs().sum(0) / 10)
@@ -118,7 +126,8 @@ def test_potential_sum_matches_spec(net, T, C, kernel):
             assert float(err.max()) < 4.0 * float(floor.max()), (float(err.max()), float(floor.max()))
             assert float(rel.median()) < 1e-4, float(rel.median())
     # same numbers through the rows API and the reference's row layout r = t*C + c
-    rows = est.log_prob(xr.unsqueeze(0), condition=cond, kernel=kernel)[0].reshape(T, C).sum(0).double()
+    rows_kernel = "precise" if kernel == "tc64" else kernel        # (tc64 is a potential-only path)
+    rows = est.log_prob(xr.unsqueeze(0), condition=cond, kernel=rows_kernel)[0].reshape(T, C).sum(0).double()
     if kernel != "tc":
         assert torch.allclose(rows, got, rtol=2e-6, atol=1e-3)
     else:   # bf16 hi/lo operands carry ~17 bits: per-row noise ~1e-4 (more on the trained net), random in sign
@@ -155,7 +164,7 @@ def test_potential_is_reproducible_and_handles_empty(net):
     _, _, est, _ = net
     theta = orc.prior_sample(100, seed=4)
     x, pulses = _session(50)
-    for kernel in ("tc", "simt", "precise"):
+    for kernel in ("tc", "simt", "precise", "tc64"):
         a, b = est.loglik_sum(theta, x, pulses, kernel=kernel), est.loglik_sum(theta, x, pulses, kernel=kernel)
         assert torch.equal(a, b)
     assert est.loglik_sum(theta[:0], x, pulses).shape == (0,)
