@@ -770,7 +770,7 @@ def run_native(args):
     z_host.copy_(z[:n_e2e])
     torch.cuda.synchronize()
     xo = None
-    for i in range(args.warmup):   # same hold-one-result pattern as the timed loop (both pinned blocks exist)
+    for i in range(max(args.warmup, 5)):   # (5: the ingest tries packed records and fp32 rows twice each, then keeps the faster)
         xo = ds.sim_wrapper(z_host, mu_sensory=1.0, p_success=0.75, P=P, log_rt=False, seed=base_seed - 1 - i,
                             trial_offset=rank * n)
     barrier()
@@ -912,7 +912,8 @@ def run_native(args):
                     "ingest": ("z rows (340 B/trial, pinned host) are packed to 32-byte records by the host cores "
                                "(ddm_pack_z_host) chunk by chunk while the streaming kernel runs; the link carries the records"
                                if link_bytes_per_step < n_e2e * 340 else
-                               "fp32 z rows over the link (too few host threads per rank for packing to beat the link)"),
+                               "fp32 z rows over the link (measured faster than packing on this host at this rank count: "
+                               "HostPipeline.choose_packed)"),
                     "trials_per_step_per_gpu": n_e2e, "api": "data_simulator.sim_wrapper(z pinned host) -> x host",
                     "ms_per_step": float(e2e_t.item()) / args.steps},
             "gpu_launches": args.steps * world,

@@ -5,6 +5,7 @@ and sanity asserts are the reference's; compute happens on the current CUDA devi
 """
 from __future__ import annotations
 
+import time
 from typing import Optional
 
 import numpy as np
@@ -48,9 +49,12 @@ def sim_wrapper(theta_and_pulses: torch.Tensor, *, mu_sensory: float, p_success:
         if pipe is None:
             pipe = _pipelines[key] = HostPipeline(z.shape[1], device=dev)
         x = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
+        packed = pipe.choose_packed(sched, n)
+        t0 = time.perf_counter()
         pipe.run(z, x, sched=sched, seed=next_seed() if seed is None else seed, log_rt=log_rt,
-                 trial_offset=trial_offset)
+                 trial_offset=trial_offset, packed=packed)
         pipe.synchronize()
+        pipe.report(packed, n, time.perf_counter() - t0)
         return x
     x = simulate_trials(z[:, :5], z[:, 5:5 + P], mu_sensory=mu_sensory, log_rt=log_rt, seed=seed,
                         trial_offset=trial_offset, noise=noise)
@@ -103,9 +107,9 @@ def simulate_training_set_with_conditions(proposal: Distribution, num_simulation
         x = sim_wrapper(z, mu_sensory=mu_sensory, p_success=p_success, P=P, log_rt=log_rt, seed=seed, trial_offset=g0)
         # the reference's sanity checks (:62-66), evaluated where the data is: one flag word per block
         choice = x[:, -1]
-        checks.append(torch.stack([torch.isfinite(z).all(), torch.isfinite(x).all(),
-                                   ((choice == 0) | (choice == 1) | (choice == 2)).all()]))
-        outcomes += torch.bincount(choice.clamp(0, 2).to(torch.int64), minlength=3)
+        counts = torch.stack([(choice == 0).sum(), (choice == 1).sum(), (choice == 2).sum()])    # (no host sync)
+        checks.append(torch.stack([torch.isfinite(z).all(), torch.isfinite(x).all(), counts.sum() == choice.numel()]))
+        outcomes += counts
         if copier is not stream:
             copier.wait_stream(stream)
         with torch.cuda.stream(copier):

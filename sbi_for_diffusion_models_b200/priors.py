@@ -95,20 +95,42 @@ class MultipleIndependentPrior(Distribution):
         raise NotImplementedError("use log_prob(...) == -inf to test the support")
 
 
+_cuda_params = {}   # id(distribution) -> (distribution, kind, python floats): read once, no device sync per draw
+
+
 def _sample_component(d: Distribution, shape: torch.Size) -> torch.Tensor:
-    """``d.sample(shape)``.  One exception: a Beta(a, b) with small integer parameters that lives on a CUDA
-    device is drawn as the a-th smallest of a + b - 1 uniforms (its exact law): torch's CUDA Beta sampler goes
-    through per-element gamma rejection loops and costs ~15 ns per draw, which made the prior -- not the
-    simulator or the PCIe link -- the bottleneck of a 1e7-trial training set.  CPU priors (the reference's)
-    keep torch's sampler and therefore torch's random stream."""
-    if isinstance(d, Beta) and d.concentration1.is_cuda and d.concentration1.numel() == 1:
-        a, b = float(d.concentration1.reshape(-1)[0]), float(d.concentration0.reshape(-1)[0])
-        if a == int(a) and b == int(b) and 1 <= a and 1 <= b and a + b <= 6:
-            n = int(a + b - 1)
-            u = torch.rand(tuple(shape) + (n,), device=d.concentration1.device, dtype=d.concentration1.dtype)
-            if n == 1:
-                return u[..., 0]
-            return torch.sort(u, dim=-1).values[..., int(a) - 1]
+    """``d.sample(shape)``, except for Beta / LogNormal components whose parameters live on a CUDA device:
+
+    * torch's samplers synchronise the host with the device on every call (``torch.normal`` checks ``std.min() >= 0``
+      with ``.item()``), which serialises a training-set loop that otherwise only enqueues work;
+    * torch's CUDA Beta sampler goes through per-element gamma rejection loops (~15 ns per draw) and made the prior,
+      not the simulator or the PCIe link, the bottleneck of a 1e7-trial training set.
+
+    There a LogNormal is drawn as exp(loc + scale * randn) and a Beta(a, b) with small integer parameters as the a-th
+    smallest of a + b - 1 uniforms (its exact law), from parameters read to the host once.  CPU priors (the
+    reference's) keep torch's samplers and therefore torch's random stream."""
+    if isinstance(d, (Beta, LogNormal)):
+        ref = d.concentration1 if isinstance(d, Beta) else d.loc
+        if ref.is_cuda and ref.numel() == 1:
+            hit = _cuda_params.get(id(d))
+            if hit is None or hit[0] is not d:
+                if isinstance(d, Beta):
+                    hit = (d, "beta", float(d.concentration1.reshape(-1)[0]), float(d.concentration0.reshape(-1)[0]))
+                else:
+                    hit = (d, "lognormal", float(d.loc.reshape(-1)[0]), float(d.scale.reshape(-1)[0]))
+                _cuda_params[id(d)] = hit
+            _, kind, p0, p1 = hit
+            if kind == "lognormal":
+                return torch.randn(tuple(shape), device=ref.device, dtype=ref.dtype).mul_(p1).add_(p0).exp_()
+            if p0 == int(p0) and p1 == int(p1) and 1 <= p0 and 1 <= p1 and p0 + p1 <= 6:
+                n = int(p0 + p1 - 1)
+                u = torch.rand(tuple(shape) + (n,), device=ref.device, dtype=ref.dtype)
+                if n == 1:
+                    return u[..., 0]
+                if n == 3 and p0 == 2:      # the pipeline prior's Beta(2, 2): the median of three uniforms
+                    a, b, c = u.unbind(-1)
+                    return torch.maximum(torch.minimum(a, b), torch.minimum(torch.maximum(a, b), c))
+                return torch.sort(u, dim=-1).values[..., int(p0) - 1]
     return d.sample(shape)
 
 

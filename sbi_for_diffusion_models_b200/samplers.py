@@ -81,7 +81,7 @@ class VectorizedSliceSampler:
     points with finite log-probability."""
 
     def __init__(self, log_prob_fn: Callable[[torch.Tensor], torch.Tensor], init: torch.Tensor, *,
-                 init_width: float = 0.1, max_step_out: int = 16, max_shrink: int = 64,
+                 init_width: float = 0.1, max_step_out: int = 8, max_shrink: int = 64,
                  generator: Optional[torch.Generator] = None, uniforms: Optional[Callable[[int], torch.Tensor]] = None,
                  chain_groups: int = 1):
         if init.ndim != 2:
@@ -126,24 +126,34 @@ class VectorizedSliceSampler:
         """One slice update of coordinate ``d`` for all chains; returns the final bracket sizes."""
         x0 = self.x[:, d]
         w = self.width[:, d].repeat_interleave(self.N // self.groups)        # per-chain width of its group
-        base = self._updates * (2 + self.max_shrink)
+        base = self._updates * (3 + self.max_shrink)
         self._updates += 1
         log_y = self.lp + torch.log(self._rand(base).clamp_min(1e-37))
         lo = x0 - w * self._rand(base + 1)
         hi = lo + w
-        # stepping out: only chains whose bracket end is still inside the slice move
-        grow = torch.ones_like(x0, dtype=torch.bool)
-        for _ in range(self.max_step_out):
+        # stepping out with a limit (Neal 2003, fig. 3): at most m - 1 expansions in total, split at random between
+        # the two ends (J to the left, m - 1 - J to the right), which keeps the update reversible for any m.  All
+        # chains advance in lock-step, so the number of potential calls of an update is set by its slowest chain:
+        # an uncapped search costs ~10 calls per end, every time, for the sake of a handful of chains.
+        m = self.max_step_out
+        J = torch.floor(m * self._rand(base + 2 + self.max_shrink)).clamp_(0, m - 1)
+        K = (m - 1) - J
+        grow = J > 0
+        for _ in range(m - 1):
+            if not bool(grow.any()):
+                break
             grow = grow & (self._eval(self._with(d, lo)) > log_y)
-            if not bool(grow.any()):
-                break
             lo = torch.where(grow, lo - w, lo)
-        grow = torch.ones_like(x0, dtype=torch.bool)
-        for _ in range(self.max_step_out):
-            grow = grow & (self._eval(self._with(d, hi)) > log_y)
+            J = J - grow.to(J.dtype)
+            grow = grow & (J > 0)
+        grow = K > 0
+        for _ in range(m - 1):
             if not bool(grow.any()):
                 break
+            grow = grow & (self._eval(self._with(d, hi)) > log_y)
             hi = torch.where(grow, hi + w, hi)
+            K = K - grow.to(K.dtype)
+            grow = grow & (K > 0)
         # shrinkage
         todo = torch.ones_like(x0, dtype=torch.bool)
         new_x, new_lp = x0.clone(), self.lp.clone()

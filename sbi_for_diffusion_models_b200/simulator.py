@@ -292,6 +292,47 @@ class HostPipeline:
         self.packed_batches = 0
         self.h2d_bytes = 0
         self._pending = []
+        # ingest mode chosen by measurement (choose_packed / report): seconds per row of each mode, calls so far
+        self._times = {True: [], False: []}
+        self._calls = 0
+
+    PROBE_MIN_ROWS = 1 << 20    # only batches this large say anything about the ingest rate
+    REPROBE_EVERY = 64          # the slower mode gets another look this often (the host's load may have changed)
+
+    def choose_packed(self, sched: Schedule, n_rows: int) -> bool:
+        """Packed records or fp32 rows for the next call?  Both give the same bits; which one is faster depends on
+        the HOST: packing reads z with the CPU cores (340 + 64 bytes of DRAM traffic per trial) and sends 32 bytes
+        over PCIe, fp32 rows are read by the copy engine (340 bytes of DRAM traffic and 340 over PCIe).  One process
+        with 16 cores to itself packs at 165 GB/s against a 55 GB/s link; eight ranks sharing 32 cores and ~170 GB/s
+        of host memory bandwidth are better off with the plain copies.  So: start from the thread-count rule, try
+        each mode twice on large batches (the first call of a mode also allocates its staging blocks), keep the faster
+        one, look again every REPROBE_EVERY calls."""
+        import os
+        if sched.n_pulses > 96:
+            return False
+        forced = os.environ.get("DDM_INGEST_MODE")
+        if forced in ("packed", "rows"):
+            return forced == "packed"
+        first = pack_threads() >= pack_min_threads()
+        if n_rows < self.PROBE_MIN_ROWS:
+            return first
+        # the first call of a mode also allocates its staging blocks: two samples per mode before it is judged
+        for mode in (first, not first):
+            if len(self._times[mode]) < 2:
+                return mode
+        best = min(self._times[True][1:]) <= min(self._times[False][1:])
+        if self._calls % self.REPROBE_EVERY == self.REPROBE_EVERY - 1:
+            return not best
+        return best
+
+    def report(self, packed: bool, n_rows: int, seconds: float) -> None:
+        """Wall time of one whole call (run + synchronize) in the given mode."""
+        self._calls += 1
+        if n_rows >= self.PROBE_MIN_ROWS:
+            t = self._times[packed]
+            t.append(seconds / n_rows)
+            if len(t) > 5:          # first sample (allocation) + the last four
+                del t[1]
 
     def _slot_buffers(self, slot, packed: bool):
         with torch.cuda.device(self.dev):
