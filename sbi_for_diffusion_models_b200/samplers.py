@@ -77,31 +77,46 @@ class PhiloxUniforms:
 
 
 class VectorizedSliceSampler:
-    """``log_prob_fn``: (N, D) -> (N,), ``-inf`` outside the support.  ``init``: (N, D) starting
-    points with finite log-probability."""
+    """Coordinate-wise slice sampler (Neal 2003: stepping out with a limit + shrinkage) over N chains, **every chain
+    on its own clock**.  ``log_prob_fn``: (N, D) -> (N,), ``-inf`` outside the support.  ``init``: (N, D) starting
+    points with finite log-probability.
+
+    One potential call evaluates, for each chain, whatever point THAT chain needs next -- the left or right end of
+    its bracket while stepping out, a shrinkage proposal afterwards -- for whatever coordinate it is working on.
+    (A lock-step version, where all chains step out, then all shrink, runs every phase until its slowest chain is
+    done: with 16 000 chains ~30 calls per coordinate update instead of the ~9 a single chain needs.)  Chains are
+    fully independent: own uniforms (counter-based: draw 4 * it + j of chain g), own slice widths (running mean of
+    the final bracket while tuning, as sbi's slice samplers do), own sweep count -- so a run sharded over GPUs, or
+    batched with other datasets, reproduces the unsharded one bit for bit.  On a CUDA device one iteration (the
+    potential plus ~60 elementwise ops of bookkeeping) is captured once into a CUDA graph and replayed.
+    """
 
     def __init__(self, log_prob_fn: Callable[[torch.Tensor], torch.Tensor], init: torch.Tensor, *,
                  init_width: float = 0.1, max_step_out: int = 8, max_shrink: int = 64,
                  generator: Optional[torch.Generator] = None, uniforms: Optional[Callable[[int], torch.Tensor]] = None,
-                 chain_groups: int = 1):
+                 chain_groups: int = 1, use_graph: bool = True):
         if init.ndim != 2:
             raise ValueError(f"init must be (num_chains, dim), got {tuple(init.shape)}")
-        self.f = log_prob_fn
+        # a GraphedLogProb cannot be replayed inside another capture: use the function it wraps
+        self.f = log_prob_fn.fn if isinstance(log_prob_fn, GraphedLogProb) else log_prob_fn
         self.x = init.clone()
         self.gen, self.uniforms = generator, uniforms
-        # chains come in ``chain_groups`` equal consecutive groups (SBC: one group per dataset), each
-        # with its own slice widths, so that a group's trajectory does not depend on its neighbours
-        self.groups = int(chain_groups)
-        if init.shape[0] % self.groups:
-            raise ValueError("the number of chains must be a multiple of chain_groups")
         self.N, self.D = init.shape
+        if init.shape[0] % int(chain_groups):
+            raise ValueError("the number of chains must be a multiple of chain_groups")
+        self.n_evals = 0
         self.lp = self._eval(self.x)
         if not bool(torch.isfinite(self.lp).all()):
             raise ValueError("every chain must start at a point of finite log-probability")
-        per = self.N // self.groups
-        self.width = float(init_width) * init.abs().view(self.groups, per, self.D).mean(dim=1).clamp_min(1e-3)   # (G, D)
+        # starting widths: a tenth of the typical magnitude of the coordinate within the chain's group (SBC: its
+        # dataset), then tuned per chain
+        G, per = int(chain_groups), self.N // int(chain_groups)
+        w0 = float(init_width) * init.abs().view(G, per, self.D).mean(dim=1).clamp_min(1e-3)
+        self.width = w0.repeat_interleave(per, dim=0).contiguous()                        # (N, D)
         self.max_step_out, self.max_shrink = int(max_step_out), int(max_shrink)
-        self.n_evals, self._updates = 0, 0
+        self._use_graph = bool(use_graph) and init.is_cuda
+        self._graph = None
+        self._it = 0
 
     # ------------------------------------------------------------------------------------
     def _eval(self, x: torch.Tensor) -> torch.Tensor:
@@ -109,88 +124,147 @@ class VectorizedSliceSampler:
         self.n_evals = getattr(self, "n_evals", 0) + 1
         return torch.nan_to_num(lp, nan=-float("inf"), posinf=float("inf"), neginf=-float("inf"))
 
-    def _rand(self, k: int) -> torch.Tensor:
-        """Uniform number ``k`` of every chain.  With a counter-based source the index is explicit
-        (update number, draw within the update), so chains that need more shrinkage steps than others
-        do not shift anybody's later draws."""
+    def _draw4(self, it: int) -> torch.Tensor:
+        """The four uniforms every chain may consume in iteration ``it``: (4, N) in (0, 1)."""
         if self.uniforms is not None:
-            return self.uniforms(k).to(self.x.dtype)
-        return torch.rand((self.N,), dtype=self.x.dtype, device=self.x.device, generator=self.gen)
+            return torch.stack([self.uniforms(4 * it + j) for j in range(4)]).to(self.x.dtype)
+        return torch.rand((4, self.N), dtype=self.x.dtype, device=self.x.device, generator=self.gen).clamp_(1e-12, 1 - 1e-12)
 
-    def _with(self, d: int, v: torch.Tensor) -> torch.Tensor:
-        y = self.x.clone()
-        y[:, d] = v
-        return y
-
-    def _update_dim(self, d: int) -> torch.Tensor:
-        """One slice update of coordinate ``d`` for all chains; returns the final bracket sizes."""
-        x0 = self.x[:, d]
-        w = self.width[:, d].repeat_interleave(self.N // self.groups)        # per-chain width of its group
-        base = self._updates * (3 + self.max_shrink)
-        self._updates += 1
-        log_y = self.lp + torch.log(self._rand(base).clamp_min(1e-37))
-        lo = x0 - w * self._rand(base + 1)
-        hi = lo + w
-        # stepping out with a limit (Neal 2003, fig. 3): at most m - 1 expansions in total, split at random between
-        # the two ends (J to the left, m - 1 - J to the right), which keeps the update reversible for any m.  All
-        # chains advance in lock-step, so the number of potential calls of an update is set by its slowest chain:
-        # an uncapped search costs ~10 calls per end, every time, for the sake of a handful of chains.
+    def _begin(self, mask: torch.Tensor, u: torch.Tensor) -> None:
+        """Chains in ``mask`` start the slice update of their current coordinate ``self.d`` (uniforms u[1..3])."""
         m = self.max_step_out
-        J = torch.floor(m * self._rand(base + 2 + self.max_shrink)).clamp_(0, m - 1)
+        idx = self._idx
+        w = self.width[idx, self.d]
+        x0 = self.x[idx, self.d]
+        lo = x0 - w * u[2]
+        J = torch.floor(m * u[3]).clamp_(0, m - 1)
         K = (m - 1) - J
-        grow = J > 0
-        for _ in range(m - 1):
-            if not bool(grow.any()):
-                break
-            grow = grow & (self._eval(self._with(d, lo)) > log_y)
-            lo = torch.where(grow, lo - w, lo)
-            J = J - grow.to(J.dtype)
-            grow = grow & (J > 0)
-        grow = K > 0
-        for _ in range(m - 1):
-            if not bool(grow.any()):
-                break
-            grow = grow & (self._eval(self._with(d, hi)) > log_y)
-            hi = torch.where(grow, hi + w, hi)
-            K = K - grow.to(K.dtype)
-            grow = grow & (K > 0)
-        # shrinkage
-        todo = torch.ones_like(x0, dtype=torch.bool)
-        new_x, new_lp = x0.clone(), self.lp.clone()
-        for it in range(self.max_shrink):
-            prop = lo + (hi - lo) * self._rand(base + 2 + it)
-            lp = self._eval(self._with(d, torch.where(todo, prop, new_x)))
-            ok = todo & (lp > log_y)
-            new_x = torch.where(ok, prop, new_x)
-            new_lp = torch.where(ok, lp, new_lp)
-            todo = todo & ~ok
-            if not bool(todo.any()):
-                break
-            left = todo & (prop < x0)
-            lo = torch.where(left, prop, lo)
-            hi = torch.where(todo & ~left, prop, hi)
-        # chains that never found a point keep their state (probability ~0 with max_shrink = 64)
-        self.x = self._with(d, new_x)
-        self.lp = new_lp
-        # the bracket as it stood when the chain accepted (shrunk around the slice): this is what sbi's slice
-        # samplers average into the width while tuning.  (The stepped-out bracket is never smaller than the
-        # width, so averaging THAT only ratchets the width up: 35 evaluations per update instead of ~15.)
-        return hi - lo
+        phase = torch.where(J > 0, 1, torch.where(K > 0, 2, 3)).to(self.phase.dtype)
+        self.log_y.copy_(torch.where(mask, self.lp + torch.log(u[1]), self.log_y))
+        self.lo.copy_(torch.where(mask, lo, self.lo))
+        self.hi.copy_(torch.where(mask, lo + w, self.hi))
+        self.x0.copy_(torch.where(mask, x0, self.x0))
+        self.J.copy_(torch.where(mask, J, self.J))
+        self.K.copy_(torch.where(mask, K, self.K))
+        self.phase.copy_(torch.where(mask, phase, self.phase))
+        self.nshr.copy_(torch.where(mask, torch.zeros_like(self.nshr), self.nshr))
 
-    def sweep(self, tune: bool = False) -> None:
-        for d in range(self.D):
-            size = self._update_dim(d)
-            if tune:   # running estimate of the typical slice width, as sbi's slice samplers do
-                self.width[:, d] = 0.5 * self.width[:, d] + 0.5 * size.view(self.groups, -1).mean(dim=1).clamp_min(1e-6)
+    def _step(self) -> None:
+        """One potential call for all chains, and each chain's move through its own state machine."""
+        u, idx, D = self._u, self._idx, self.D
+        ph, lo, hi = self.phase, self.lo, self.hi
+        w = self.width[idx, self.d]
+        q_val = torch.where(ph == 1, lo, torch.where(ph == 2, hi, lo + (hi - lo) * u[0]))
+        q = self.x.clone()
+        q[idx, self.d] = q_val
+        f = self._eval(q)
+        inside = f > self.log_y
+        live = self.sweeps < self._total
+        # stepping out, left end then right end, at most J resp. K expansions
+        g1 = (ph == 1) & inside
+        g2 = (ph == 2) & inside
+        J = self.J - g1.to(self.J.dtype)
+        K = self.K - g2.to(self.K.dtype)
+        leave1 = (ph == 1) & ~(g1 & (J > 0))
+        leave2 = (ph == 2) & ~(g2 & (K > 0))
+        lo = torch.where(g1, lo - w, lo)
+        hi = torch.where(g2, hi + w, hi)
+        # shrinkage
+        nshr = self.nshr + (ph == 3).to(self.nshr.dtype)
+        give_up = (ph == 3) & ~inside & (nshr >= self.max_shrink)      # (never seen; the chain keeps its point)
+        acc = (ph == 3) & inside & live
+        rej = (ph == 3) & ~inside & ~give_up
+        left = q_val < self.x0
+        lo = torch.where(rej & left, q_val, lo)
+        hi = torch.where(rej & ~left, q_val, hi)
+        self.x[idx, self.d] = torch.where(acc, q_val, self.x[idx, self.d])
+        self.lp.copy_(torch.where(acc, f, self.lp))
+        ph = torch.where(leave1, torch.where(K > 0, 2, 3).to(ph.dtype), ph)
+        ph = torch.where(leave2, torch.full_like(ph, 3), ph)
+        self.lo.copy_(lo)
+        self.hi.copy_(hi)
+        self.J.copy_(J)
+        self.K.copy_(K)
+        self.nshr.copy_(nshr)
+        self.phase.copy_(ph)
+        # a finished update: tune the width, move to the next coordinate, count sweeps, record a draw
+        fin = (acc | (give_up & live))
+        tune = fin & (self.sweeps < self._warmup)
+        cnt = self.tuned[idx, self.d]
+        self.width[idx, self.d] = torch.where(tune, w + ((hi - lo) - w) / (cnt + 1.0), w).clamp_min(1e-6)
+        self.tuned[idx, self.d] = cnt + tune.to(cnt.dtype)
+        sweep_end = fin & (self.d == D - 1)
+        self.d.copy_(torch.where(fin, (self.d + 1) % D, self.d))
+        self.sweeps.add_(sweep_end.to(self.sweeps.dtype))
+        past = self.sweeps - self._warmup
+        rec = sweep_end & (past > 0) & (past % self._thin == 0) & (self.taken < self._S)
+        slot = self.taken.clamp(max=self._S - 1)
+        cur = self.out[slot, idx]
+        self.out[slot, idx] = torch.where(rec[:, None], self.x, cur)
+        self.taken.add_(rec.to(self.taken.dtype))
+        self._begin(fin & (self.sweeps < self._total), u)
 
     @torch.no_grad()
     def run(self, num_samples_per_chain: int, *, warmup: int = 100, thin: int = 1) -> torch.Tensor:
-        """-> (num_samples_per_chain, N, D) after ``warmup`` tuning sweeps."""
-        for _ in range(int(warmup)):
-            self.sweep(tune=True)
-        out = torch.empty((int(num_samples_per_chain), self.N, self.D), dtype=self.x.dtype, device=self.x.device)
-        for s in range(int(num_samples_per_chain)):
-            for _ in range(max(int(thin), 1)):
-                self.sweep()
-            out[s] = self.x
-        return out
+        """-> (num_samples_per_chain, N, D): every chain's state after each of its post-warm-up sweeps (every
+        ``thin``-th), ``warmup`` tuning sweeps first."""
+        dev, N, D = self.x.device, self.N, self.D
+        S, thin, warmup = int(num_samples_per_chain), max(int(thin), 1), int(warmup)
+        long_, fl = dict(dtype=torch.int64, device=dev), dict(dtype=self.x.dtype, device=dev)
+        self._S, self._thin, self._warmup, self._total = S, thin, warmup, warmup + S * thin
+        self._idx = torch.arange(N, device=dev)
+        self.out = torch.empty((max(S, 1), N, D), **fl)
+        self.d, self.sweeps, self.taken = torch.zeros(N, **long_), torch.zeros(N, **long_), torch.zeros(N, **long_)
+        self.phase, self.nshr = torch.zeros(N, **long_), torch.zeros(N, **long_)
+        self.tuned = torch.zeros((N, D), **fl)
+        self.lo, self.hi, self.x0, self.log_y = (torch.zeros(N, **fl) for _ in range(4))
+        self.J, self.K = torch.zeros(N, **fl), torch.zeros(N, **fl)
+        self._u = self._draw4(self._it)
+        self._it += 1
+        self._graph = None
+        if self._total == 0:
+            return self.out[:S]
+        self._begin(torch.ones(N, dtype=torch.bool, device=dev), self._u)
+        check_every = 16
+        while True:
+            for _ in range(check_every):
+                self._u.copy_(self._draw4(self._it))
+                self._it += 1
+                self._iterate()
+            if not bool((self.sweeps < self._total).any()):
+                break
+        return self.out[:S].clone()
+
+    def _iterate(self) -> None:
+        if not self._use_graph:
+            self._step()
+            return
+        if self._graph is None:
+            dev = self.x.device
+            snap = {k: v.clone() for k, v in self._state().items()}      # the warm-up calls below must not count
+            evals = self.n_evals
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            try:
+                with torch.cuda.stream(side):
+                    self._step()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
+                        self._step()
+                self._graph = graph
+            except Exception:        # the potential synchronises or leaves the device: run eagerly
+                self._use_graph = False
+                torch.cuda.synchronize(dev)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            for k, v in self._state().items():
+                v.copy_(snap[k])
+            self.n_evals = evals
+            if not self._use_graph:
+                self._step()
+                return
+        self._graph.replay()
+        self.n_evals += 1
+
+    def _state(self):
+        return {k: getattr(self, k) for k in ("x", "lp", "width", "tuned", "d", "sweeps", "taken", "phase", "nshr", "lo", "hi",
+                                               "x0", "log_y", "J", "K", "out")}

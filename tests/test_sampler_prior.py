@@ -80,7 +80,7 @@ def test_slice_sampler_is_uniform_in_rank_for_a_known_posterior():
 
     s = VectorizedSliceSampler(logp, torch.zeros((n_data, 1), dtype=torch.float64), init_width=1.0, generator=g)
     s.width[:] = 1.0
-    assert tuple(s.width.shape) == (1, 1)
+    assert tuple(s.width.shape) == (n_data, 1)            # every chain tunes its own widths
     draws = s.run(n_draws, warmup=20, thin=3)[:, :, 0]                   # (n_draws, n_data)
     ranks = (draws < theta_true[None, :]).sum(0).numpy()
     hist = np.bincount(ranks // 4, minlength=8)[:8]                     # 32 possible ranks -> 8 bins

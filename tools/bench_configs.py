@@ -50,19 +50,20 @@ def sbc(datasets, samples, warmup):
     torch.cuda.synchronize()
     import sbi_for_diffusion_models_b200.samplers as smp
     evals = {"n": 0}
-    orig = smp.VectorizedSliceSampler._eval
+    orig = smp.VectorizedSliceSampler.run
 
-    def counting(self, x):
-        evals["n"] += 1
-        return orig(self, x)
+    def counting(self, *a, **kw):
+        out = orig(self, *a, **kw)
+        evals["n"] += self.n_evals
+        return out
 
-    smp.VectorizedSliceSampler._eval = counting
+    smp.VectorizedSliceSampler.run = counting
     t0 = time.perf_counter()
     out = run_sbc(cfg, prior_theta=prior, density_estimator=est, num_datasets=datasets,
                   posterior_samples_per_dataset=samples, save=False)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    smp.VectorizedSliceSampler._eval = orig
+    smp.VectorizedSliceSampler.run = orig
     rows = datasets * 128 * cfg.NUM_TRIALS_OBS
     return {"workload": f"configs[4] shape on one GPU: run_sbc over {datasets} datasets x 128 chains, T={cfg.NUM_TRIALS_OBS}, "
                         f"{warmup} warm-up sweeps + {-(-samples // 128)} draws per chain, random-init MNLE",
