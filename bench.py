@@ -507,6 +507,41 @@ def sbc_bench(args, rank, world, dev):
             "note": "uniform ranks have mean 0.5 and std 0.289; the estimator was trained on 1e6 simulated trials"}
 
 
+def mcmc_bench(dev):
+    """run_inference_mcmc (reference mnle.py:52-95) with the reference's run_config: one observed session of
+    NUM_TRIALS_OBS = 50 trials, WARMUP_STEPS = 100, POSTERIOR_SAMPLES = 1000, on the trained estimator.  The reference
+    runs pyro NUTS with NUM_CHAINS = 2 CPU processes; here 128 slice-sampling chains advance per potential launch."""
+    import torch
+    from sbi_for_diffusion_models_b200 import mnle, samplers
+    from sbi_for_diffusion_models_b200.priors import build_prior_theta
+    from sbi_for_diffusion_models_b200.run_config import RunConfig
+    est, _ = trained_mnle()
+    cfg, prior = RunConfig(), build_prior_theta()
+    _, x_o, pulses_o = potential_inputs(dev)
+    calls = {"n": 0}
+    orig = samplers.VectorizedSliceSampler.run
+
+    def counting(self, *a, **kw):
+        out = orig(self, *a, **kw)
+        calls["n"] += self.n_evals
+        return out
+    samplers.VectorizedSliceSampler.run = counting
+    try:
+        mnle.run_inference_mcmc(RunConfig(WARMUP_STEPS=2, POSTERIOR_SAMPLES=128), prior, est, x_o, pulses_o)   # warm-up
+        torch.cuda.synchronize()
+        calls["n"] = 0
+        t0 = time.perf_counter()
+        samples = mnle.run_inference_mcmc(cfg, prior, est, x_o, pulses_o)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        samplers.VectorizedSliceSampler.run = orig
+    return {"workload": f"run_inference_mcmc: T={cfg.NUM_TRIALS_OBS} trials, 128 chains, {cfg.WARMUP_STEPS} warm-up sweeps, "
+                        f"{cfg.POSTERIOR_SAMPLES} posterior samples, trained estimator",
+            "seconds": dt, "potential_calls": calls["n"], "ms_per_call": dt / max(calls["n"], 1) * 1e3,
+            "posterior_mean": samples.mean(0).tolist(), "theta_true": [0.45, 0.6, 1.3, 14.0, 0.25]}
+
+
 def potential_sharded_bench(rank, world, dev):
     """configs[3] with the chains split over the ranks: weights replicated, every rank sums its own
     chains, one all-gather of C floats; must equal the single-GPU call bit for bit."""
@@ -948,6 +983,10 @@ def run_native(args):
                 line["mnle_potential"] = mnle_bench(dev, with_cpu=not args.no_cpu_baseline)
             except Exception as e:  # the headline metric must still print
                 line["mnle_potential"] = {"error": repr(e)}
+            try:
+                line["mcmc"] = mcmc_bench(dev)
+            except Exception as e:
+                line["mcmc"] = {"error": repr(e)}
             try:
                 line["configs0_api"] = configs0_bench(dev)
             except Exception as e:

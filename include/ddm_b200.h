@@ -379,6 +379,23 @@ int mnle_tc_set_trace(long long *trace_dev);
 int mnle_tc_selftest(const float *a_dev, const float *b_dev, int N, int passes, uint32_t lbo_a,
                      uint32_t lbo_b, uint32_t sbo, float *d_dev, void *stream);
 
+/* ------------------------------------------------------------ slice sampler --- */
+
+/*
+ * Bookkeeping of the many-chain slice sampler that drives the potential (host side: samplers.py; the reference hands
+ * this job to sbi's MCMCPosterior, mnle.py:77-93).  Every chain runs its own state machine (Neal 2003: stepping out
+ * with a limit, then shrinkage).  Per iteration: ddm_slice_propose_f32 writes the point each chain needs evaluated next
+ * into row c of query_dev (N, D); the caller evaluates the potential there; ddm_slice_update_f32 applies f_dev (N,) --
+ * bracket moves, acceptance, width tuning, coordinate / sweep accounting, recording of draws, start of the next update.
+ * state_ptrs: HOST array of 16 device pointers [x (N,D), lp, width (N,D), tuned (N,D), lo, hi, x0, log_y, J, K (float),
+ * d, sweeps, taken, phase, nshr (int64), out (S,N,D)]; state_ints: HOST array [N, D, S, thin, warmup, total sweeps,
+ * max_step_out, max_shrink]; u_dev (4, N) uniforms in (0, 1) of this iteration.
+ */
+int ddm_slice_propose_f32(const void *const *state_ptrs, const int64_t *state_ints, const float *u_dev, float *query_dev,
+                          void *stream);
+int ddm_slice_update_f32(const void *const *state_ptrs, const int64_t *state_ints, const float *u_dev, const float *f_dev,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "ddm_philox_words_u32": (ctypes.c_int, [_u64, _u64, _i64, _i64, _ptr, _i64, _ptr]),
     "ddm_pulses_pcg64": (ctypes.c_int, [_u64, _u64, _u64, _u64, _u64, _i64, _i64, _u64, _ptr, _i64, _ptr]),
     "ddm_pcg64_advance": (ctypes.c_int, [_ptr, _ptr, _u64, _u64, _u64]),
+    "ddm_slice_propose_f32": (ctypes.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr]),
+    "ddm_slice_update_f32": (ctypes.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr]),
     "mnle_packed_floats": (ctypes.c_size_t, [_i32]),
     "mnle_create": (ctypes.c_int, [_ptr, ctypes.c_size_t, _i32, _ptr]),
     "mnle_destroy": (ctypes.c_int, [_ptr]),

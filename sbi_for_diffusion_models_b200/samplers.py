@@ -94,7 +94,7 @@ class VectorizedSliceSampler:
     def __init__(self, log_prob_fn: Callable[[torch.Tensor], torch.Tensor], init: torch.Tensor, *,
                  init_width: float = 0.1, max_step_out: int = 8, max_shrink: int = 64,
                  generator: Optional[torch.Generator] = None, uniforms: Optional[Callable[[int], torch.Tensor]] = None,
-                 chain_groups: int = 1, use_graph: bool = True):
+                 chain_groups: int = 1, use_graph: bool = True, fused: Optional[bool] = None):
         if init.ndim != 2:
             raise ValueError(f"init must be (num_chains, dim), got {tuple(init.shape)}")
         # a GraphedLogProb cannot be replayed inside another capture: use the function it wraps
@@ -115,6 +115,11 @@ class VectorizedSliceSampler:
         self.width = w0.repeat_interleave(per, dim=0).contiguous()                        # (N, D)
         self.max_step_out, self.max_shrink = int(max_step_out), int(max_shrink)
         self._use_graph = bool(use_graph) and init.is_cuda
+        # the bookkeeping of an iteration as two CUDA kernels around the potential (csrc/mnle_sampler.cu) instead of
+        # ~80 elementwise torch launches; same arithmetic in the same order, same bits (float32 chains on a GPU)
+        self._fused = (init.is_cuda and init.dtype == torch.float32) if fused is None else bool(fused)
+        if self._fused and not (init.is_cuda and init.dtype == torch.float32):
+            raise ValueError("the fused sampler kernels need float32 chains on a CUDA device")
         self._graph = None
         self._it = 0
 
@@ -149,8 +154,23 @@ class VectorizedSliceSampler:
         self.phase.copy_(torch.where(mask, phase, self.phase))
         self.nshr.copy_(torch.where(mask, torch.zeros_like(self.nshr), self.nshr))
 
+    def _step_fused(self) -> None:
+        import ctypes
+        from . import _native
+        L = _native.lib()
+        stream = torch.cuda.current_stream(self.x.device).cuda_stream
+        _native.check(L.ddm_slice_propose_f32(self._ptrs, self._ints, self._u.data_ptr(), self._q.data_ptr(), stream),
+                      "ddm_slice_propose_f32")
+        f = self.f(self._q)
+        self.n_evals += 1
+        f = f.to(torch.float32).contiguous()
+        _native.check(L.ddm_slice_update_f32(self._ptrs, self._ints, self._u.data_ptr(), f.data_ptr(), stream),
+                      "ddm_slice_update_f32")
+
     def _step(self) -> None:
         """One potential call for all chains, and each chain's move through its own state machine."""
+        if self._fused:
+            return self._step_fused()
         u, idx, D = self._u, self._idx, self.D
         ph, lo, hi = self.phase, self.lo, self.hi
         w = self.width[idx, self.d]
@@ -219,9 +239,17 @@ class VectorizedSliceSampler:
         self.tuned = torch.zeros((N, D), **fl)
         self.lo, self.hi, self.x0, self.log_y = (torch.zeros(N, **fl) for _ in range(4))
         self.J, self.K = torch.zeros(N, **fl), torch.zeros(N, **fl)
-        self._u = self._draw4(self._it)
+        self._u = self._draw4(self._it).contiguous()
         self._it += 1
         self._graph = None
+        if self._fused:
+            import ctypes
+            self.x, self.lp, self.width = self.x.contiguous(), self.lp.to(torch.float32).contiguous(), self.width.contiguous()
+            self._q = torch.empty_like(self.x)
+            order = (self.x, self.lp, self.width, self.tuned, self.lo, self.hi, self.x0, self.log_y, self.J, self.K, self.d,
+                     self.sweeps, self.taken, self.phase, self.nshr, self.out)
+            self._ptrs = (ctypes.c_void_p * 16)(*[t.data_ptr() for t in order])
+            self._ints = (ctypes.c_int64 * 8)(N, D, max(S, 1), thin, warmup, self._total, self.max_step_out, self.max_shrink)
         if self._total == 0:
             return self.out[:S]
         self._begin(torch.ones(N, dtype=torch.bool, device=dev), self._u)
