@@ -601,8 +601,9 @@ def training_set_e2e_bench(args, dev):
     dt = min(ts)
     return {"api": "data_simulator.simulate_training_set_with_conditions(ExtendedProposal on cuda) -> CPU (z, x)",
             "trials": N, "seconds": dt, "trials_per_s": N / dt, "value": steps / dt, "unit": UNIT,
-            "d2h_bytes": N * BYTES_PER_TRIAL, "h2d_bytes": 0,
-            "note": "bound by the device->host copy of z (340 B per trial over PCIe 5 x16), not by the simulator"}
+            "d2h_bytes": N * 40, "h2d_bytes": 0, "host_bytes_out": N * BYTES_PER_TRIAL,
+            "note": "z comes home as 32-byte records (theta bits + pulse sign masks, packed by the GPU) and is rebuilt to "
+                    "fp32 rows by the host cores while the next block is simulated; x as it is (8 B per trial)"}
 
 
 def mnle_train_bench(dev, with_cpu: bool, rows: int = 4096):

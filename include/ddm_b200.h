@@ -179,6 +179,15 @@ int ddm_sim_stream_f32(const float *theta_dev, int64_t ld_theta,
  */
 int64_t ddm_pack_z_host(const float *z_host, int64_t ld, int64_t N, int64_t n_pulses, uint32_t *packed_host,
                         int n_threads);
+/* The device->host mirror: ddm_pack_z_dev turns rows of a DEVICE z (row stride ld floats) into the same 32-byte
+ * records (one warp per row; *generic_rows_dev = rows holding a pulse value other than +-1, whose records must not
+ * be used), and ddm_unpack_z_host (host code, n_threads CPU threads) rebuilds z_host rows [theta (5), pulses (+-1)]
+ * from records: a caller that wants z in host memory moves 32 instead of 340 bytes per trial over the link.  With
+ * AVX-512, ld == 5 + n_pulses and a 64-byte aligned z_host the rows leave with non-temporal stores. */
+int ddm_pack_z_dev(const float *z_dev, int64_t ld, int64_t N, int64_t n_pulses, uint32_t *packed_dev,
+                   uint64_t *generic_rows_dev, void *stream);
+int ddm_unpack_z_host(const uint32_t *packed_host, int64_t N, int64_t n_pulses, float *z_host, int64_t ld, int n_threads);
+
 /* The ingest loop of one batch in one call (host code + copies on copy_stream): for every chunk of
  * chunk_rows rows, pack it into staging_host (pinned, N x 8 uint32), enqueue its copy to packed_dev and
  * an 8-byte copy of marks_host[k] (pinned; rows delivered once chunk k has landed, the last entry >= N)

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "ddm_sim_stream_f32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _f32, _f32,
                                           _u64, _u64, _i32, _ptr, _ptr, _ptr, _ptr]),
     "ddm_pack_z_host": (ctypes.c_int64, [_ptr, _i64, _i64, _i64, _ptr, _i32]),
+    "ddm_pack_z_dev": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
+    "ddm_unpack_z_host": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _i64, _i32]),
     "ddm_ingest_packed": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr]),
     "ddm_sim_packed_f32": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f32, _f32, _f32, _f32, _u64, _u64, _i32, _ptr, _ptr,
                                           _ptr, _ptr, _ptr]),

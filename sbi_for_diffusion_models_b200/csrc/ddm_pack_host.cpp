@@ -273,6 +273,78 @@ DDM_API int64_t ddm_pack_z_host(const float *z_host, int64_t ld, int64_t N, int6
     return total;
 }
 
+// ---- records -> fp32 rows on the host (device->host direction) -----------------------------------------
+// The mirror image of the packer: the GPU packs the rows it produced (ddm_pack_z_dev), 32 bytes per trial cross
+// the link, and the host cores rebuild z = [theta (5), pulses (+-1)] -- for a caller that wants the training set
+// in host memory (reference data_simulator.py:53-60) the link carries 40 bytes per trial instead of 348.
+namespace ddm {
+
+static void unpack_rows_scalar(const uint32_t *packed, int64_t r0, int64_t r1, int n_pulses, float *z, int64_t ld)
+{
+    for (int64_t r = r0; r < r1; ++r) {
+        const uint32_t *rec = packed + r * 8;
+        float *row = z + r * ld;
+        memcpy(row, rec, 20);
+        for (int j = 0; j < n_pulses; ++j) row[5 + j] = ((rec[5 + (j >> 5)] >> (j & 31)) & 1u) ? 1.0f : -1.0f;
+    }
+}
+
+// Contiguous rows of 5 + n_pulses floats: sixteen rows are a whole number of 64-byte lines whatever the row
+// length, so they are rebuilt in a line-aligned stack block and leave with non-temporal stores (no
+// read-for-ownership of the destination: 340 instead of 680 bytes of DRAM traffic per trial).
+__attribute__((target("avx512f,avx512dq,avx512vl,avx2"))) static void unpack_rows_avx512(const uint32_t *packed, int64_t r0,
+                                                                                        int64_t r1, int n_pulses, float *z)
+{
+    const int W = 5 + n_pulses;
+    const __m512 pos = _mm512_set1_ps(1.0f), neg = _mm512_set1_ps(-1.0f);
+    alignas(64) float block[16 * (5 + 96) + 16];
+    int64_t r = r0;
+    for (; r + 16 <= r1; r += 16) {
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t *rec = packed + (r + i) * 8;
+            float *row = block + i * W;
+            memcpy(row, rec, 20);
+            for (int g = 0; 16 * g < n_pulses; ++g) {
+                const __mmask16 k = (__mmask16)(rec[5 + (g >> 1)] >> (16 * (g & 1)));
+                const int left = n_pulses - 16 * g;
+                const __m512 v = _mm512_mask_blend_ps(k, neg, pos);
+                if (left >= 16) _mm512_storeu_ps(row + 5 + 16 * g, v);
+                else _mm512_mask_storeu_ps(row + 5 + 16 * g, (__mmask16)((1u << left) - 1u), v);
+            }
+        }
+        float *dst = z + r * W;   // 64-byte aligned: r is a multiple of 16 rows from an aligned base
+        for (int i = 0; i < W; ++i) _mm512_stream_ps(dst + 16 * i, _mm512_load_ps(block + 16 * i));
+    }
+    _mm_sfence();
+    if (r < r1) unpack_rows_scalar(packed, r, r1, n_pulses, z, W);
+}
+
+}  // namespace ddm
+
+DDM_API int ddm_unpack_z_host(const uint32_t *packed_host, int64_t N, int64_t n_pulses, float *z_host, int64_t ld, int n_threads)
+{
+    if (N < 0 || n_pulses < 0 || n_pulses > 96 || ld < 5 + n_pulses || (N > 0 && (!packed_host || !z_host))) {
+        ddm::set_error("ddm_unpack_z_host: bad arguments (N=%lld, n_pulses=%lld in [0,96], ld=%lld >= 5 + n_pulses)", (long long)N,
+                       (long long)n_pulses, (long long)ld);
+        return DDM_ERR_INVALID;
+    }
+    if (N == 0) return DDM_OK;
+    const bool fast = have_avx512() && ld == 5 + n_pulses && (reinterpret_cast<uintptr_t>(z_host) & 63u) == 0;
+    int nt = n_threads < 1 ? 1 : n_threads;
+    const int64_t min_rows = 1 << 14;
+    if ((int64_t)nt > (N + min_rows - 1) / min_rows) nt = (int)((N + min_rows - 1) / min_rows);
+    auto work = [&](int t) {
+        int64_t r0 = N * t / nt, r1 = N * (t + 1) / nt;
+        r0 &= ~int64_t(15);                       // thread ranges start on 16-row (= whole-line) boundaries
+        if (t + 1 < nt) r1 &= ~int64_t(15);
+        if (fast) ddm::unpack_rows_avx512(packed_host, r0, r1, (int)n_pulses, z_host);
+        else ddm::unpack_rows_scalar(packed_host, r0, r1, (int)n_pulses, z_host, ld);
+    };
+    if (nt == 1) work(0);
+    else ddm::pool().run(nt, nt, work);
+    return DDM_OK;
+}
+
 // The whole ingest of one batch without returning to the caller between chunks: pack chunk k on the host
 // cores, enqueue its copy and the 8-byte copy that raises *ready_dev, go on with chunk k + 1 while the
 // copy engine works.  (Driving this loop from Python cost ~150 us per chunk, a fifth of the packing time.)

@@ -519,6 +519,34 @@ __global__ void __launch_bounds__(kSmallThreads) sim_small_kernel(const SimParam
     }
 }
 
+// ---- z rows -> 32-byte records on the device (the device->host mirror of the packed ingest) -------------
+// One warp per row: coalesced loads of the row, ballots -> three sign masks, lane 0 writes the record
+// [theta bits x 5, masks x 3] (same format as ddm_pack_z_host); rows holding a value other than +-1 are counted.
+__global__ void __launch_bounds__(256) pack_z_kernel(const float *__restrict__ z, long long ld, long long n_rows, int n_pulses,
+                                                     uint32_t *__restrict__ packed, unsigned long long *__restrict__ generic_rows)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        const float *row = z + r * ld;
+        uint32_t m[3];
+        bool odd = false;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const int c = 32 * w + (int)lane;
+            const float s = c < n_pulses ? __ldcs(row + 5 + c) : 1.0f;
+            m[w] = __ballot_sync(kFull, s > 0.0f);
+            odd = odd || (fabsf(s) != 1.0f);
+        }
+        const bool any_odd = __any_sync(kFull, odd);
+        const float th = lane < 5 ? __ldcs(row + lane) : 0.0f;
+        uint32_t word = __float_as_uint(th);
+        if (lane >= 5 && lane < 8) word = m[lane - 5];
+        if (lane < 8) packed[r * 8 + lane] = word;
+        if (lane == 0 && any_odd) atomicAdd(generic_rows, 1ull);
+    }
+}
+
 // ---- dump kernels: the noise stream as a tensor ---------------------------------------
 template <bool WORDS>
 __global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, uint32_t one, unsigned long long trial_offset,
@@ -822,4 +850,24 @@ DDM_API int ddm_philox_words_u32(uint64_t seed, uint64_t trial_offset, int64_t N
                                  uint32_t *out_dev, int64_t ld_out, void *stream)
 {
     return dump_common(true, seed, trial_offset, N, n_steps, out_dev, ld_out, stream);
+}
+
+DDM_API int ddm_pack_z_dev(const float *z_dev, int64_t ld, int64_t N, int64_t n_pulses, uint32_t *packed_dev,
+                           uint64_t *generic_rows_dev, void *stream)
+{
+    DDM_REQUIRE(N >= 0 && n_pulses >= 0 && n_pulses <= 96 && ld >= 5 + n_pulses,
+                "ddm_pack_z_dev: bad arguments (N=%lld, n_pulses=%lld in [0,96], ld=%lld >= 5 + n_pulses)", (long long)N,
+                (long long)n_pulses, (long long)ld);
+    DDM_REQUIRE(generic_rows_dev != nullptr && (reinterpret_cast<uintptr_t>(generic_rows_dev) & 7u) == 0,
+                "ddm_pack_z_dev: generic_rows_dev must be a non-null, 8-byte aligned device pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DDM_CUDA_TRY(cudaMemsetAsync(generic_rows_dev, 0, sizeof(uint64_t), st));
+    if (N == 0) return DDM_OK;
+    DDM_REQUIRE(z_dev && packed_dev, "ddm_pack_z_dev: null pointer");
+    long long blocks = (N + 7) / 8;   // 8 warps per block, one row per warp and pass
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    pack_z_kernel<<<(unsigned)blocks, 256, 0, st>>>(z_dev, ld, N, (int)n_pulses, packed_dev,
+                                                   reinterpret_cast<unsigned long long *>(generic_rows_dev));
+    DDM_CUDA_TRY(cudaGetLastError());
+    return DDM_OK;
 }

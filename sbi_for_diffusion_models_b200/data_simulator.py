@@ -5,7 +5,9 @@ and sanity asserts are the reference's; compute happens on the current CUDA devi
 """
 from __future__ import annotations
 
+import os
 import time
+from concurrent.futures import ThreadPoolExecutor
 from typing import Optional
 
 import numpy as np
@@ -13,7 +15,8 @@ import torch
 from torch.distributions import Distribution
 
 from .pulses import generate_pulse_matrix_device
-from .simulator import HostPipeline, Schedule, compute_device, next_seed, simulate_trials
+from . import _native
+from .simulator import HostPipeline, Schedule, compute_device, next_seed, pack_threads, simulate_trials
 
 
 _HOST_STREAM_MIN = 1 << 18   # CPU-resident z with at least this many rows is streamed in chunks
@@ -92,10 +95,33 @@ def simulate_training_set_with_conditions(proposal: Distribution, num_simulation
     x_all = torch.empty((num_simulations, 2), dtype=torch.float32, pin_memory=pinned)
     stream = torch.cuda.current_stream(dev)
     copier = _copy_stream(dev) if pinned else stream
+    # Large sets: z goes home as 32-byte records (theta bits + pulse sign masks, packed by the GPU) and the host cores
+    # rebuild the fp32 rows while the GPU simulates the next block -- 40 instead of 348 bytes per trial over PCIe.
+    # A block with a pulse value other than +-1 is copied as it is.
+    as_records = pinned and P <= 96 and os.environ.get("DDM_TRAINSET_D2H", "records") == "records"
+    L = _native.lib()
+    n_threads = pack_threads()
+    rec_host = torch.empty((num_simulations, 8), dtype=torch.int32, pin_memory=True) if as_records else None
+    unpacker = ThreadPoolExecutor(max_workers=1) if as_records else None
+    jobs = []
     in_flight = []       # (event, device blocks) until their device->host copies have run
     checks, outcomes = [], torch.zeros(3, dtype=torch.int64, device=dev)
     group = max(int(batch_size), _LAUNCH_ROWS)
-    for g0 in range(0, num_simulations, group):
+    n_groups = -(-num_simulations // group)
+    generic_host = torch.zeros((max(n_groups, 1),), dtype=torch.int64, pin_memory=True) if as_records else None
+
+    def rebuild(g, g0, g1, ev, z_dev):
+        """Worker thread: block g has landed -- rebuild its rows of z_all from the records (or fetch them as they are)."""
+        ev.synchronize()
+        if int(generic_host[g]) == 0:
+            _native.check(L.ddm_unpack_z_host(rec_host[g0:g1].data_ptr(), g1 - g0, P, z_all[g0:g1].data_ptr(), 5 + P, n_threads),
+                          "ddm_unpack_z_host")
+        else:
+            with torch.cuda.stream(copier):
+                z_all[g0:g1].copy_(z_dev, non_blocking=True)
+            copier.synchronize()
+
+    for g, g0 in enumerate(range(0, num_simulations, group)):
         g1 = min(g0 + group, num_simulations)
         with torch.cuda.device(dev):
             z = torch.empty((g1 - g0, 5 + P), dtype=torch.float32, device=dev)
@@ -110,22 +136,38 @@ def simulate_training_set_with_conditions(proposal: Distribution, num_simulation
         counts = torch.stack([(choice == 0).sum(), (choice == 1).sum(), (choice == 2).sum()])    # (no host sync)
         checks.append(torch.stack([torch.isfinite(z).all(), torch.isfinite(x).all(), counts.sum() == choice.numel()]))
         outcomes += counts
+        if as_records:
+            with torch.cuda.device(dev):
+                rec = torch.empty((g1 - g0, 8), dtype=torch.int32, device=dev)
+                n_generic = torch.empty((1,), dtype=torch.int64, device=dev)
+                _native.check(L.ddm_pack_z_dev(z.data_ptr(), 5 + P, g1 - g0, P, rec.data_ptr(), n_generic.data_ptr(),
+                                               stream.cuda_stream), "ddm_pack_z_dev")
         if copier is not stream:
             copier.wait_stream(stream)
         with torch.cuda.stream(copier):
-            z_all[g0:g1].copy_(z, non_blocking=True)
+            if as_records:
+                rec_host[g0:g1].copy_(rec, non_blocking=True)
+                generic_host[g:g + 1].copy_(n_generic, non_blocking=True)
+            else:
+                z_all[g0:g1].copy_(z, non_blocking=True)
             x_all[g0:g1].copy_(x, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copier)
         if copier is not stream:
-            z.record_stream(copier)
-            x.record_stream(copier)
+            for t in (z, x) + ((rec, n_generic) if as_records else ()):
+                t.record_stream(copier)
+        if as_records:
+            jobs.append(unpacker.submit(rebuild, g, g0, g1, ev, z))
         in_flight.append((ev, z, x))
         while len(in_flight) > 2:      # bound the device memory held by blocks whose copies are still queued
             in_flight.pop(0)[0].synchronize()
     for ev, _, _ in in_flight:
         ev.synchronize()
     in_flight.clear()
+    for job in jobs:
+        job.result()
+    if unpacker is not None:
+        unpacker.shutdown()
 
     assert z_all.shape[0] == num_simulations
     assert x_all.shape[0] == num_simulations

@@ -123,3 +123,24 @@ def test_host_packer_matches_numpy(L):
     assert L.ddm_pack_z_host(z.ctypes.data, ld, 0, 80, out.ctypes.data, 4) == 0
     assert L.ddm_pack_z_host(z.ctypes.data, ld, N, 97, out.ctypes.data, 4) == _native.DDM_ERR_INVALID
     assert L.ddm_pack_z_host(z.ctypes.data, 60, N, 80, out.ctypes.data, 4) == _native.DDM_ERR_INVALID
+
+
+def test_host_unpacker_inverts_the_packer(L):
+    """ddm_unpack_z_host (host code, no GPU): records [theta bits x 5, sign masks x 3] -> fp32 rows, every alignment
+    and thread count, whole 16-row blocks (non-temporal stores) and ragged tails."""
+    rs = np.random.RandomState(1)
+    for N, P in ((1, 80), (15, 80), (16, 80), (1000, 80), (70001, 80), (333, 7), (4097, 96), (100, 0)):
+        z = np.empty((N, 5 + P), np.float32)
+        z[:, :5] = rs.randn(N, 5)
+        z[:, 5:] = np.where(rs.rand(N, P) < 0.5, 1.0, -1.0)
+        rec = np.empty((N, 8), np.uint32)
+        assert L.ddm_pack_z_host(z.ctypes.data, 5 + P, N, P, rec.ctypes.data, 4) == 0
+        buf = np.zeros(N * (5 + P) + 64, np.float32)
+        off = (-buf.ctypes.data // 4) % 16
+        for shift in (off, off + 1):                     # 64-byte aligned (fast path) and not
+            out = buf[shift:shift + N * (5 + P)].reshape(N, 5 + P)
+            for threads in (1, 5):
+                out[:] = 7.0
+                assert L.ddm_unpack_z_host(rec.ctypes.data, N, P, out.ctypes.data, 5 + P, threads) == 0
+                assert np.array_equal(out.view(np.uint32), z.view(np.uint32)), (N, P, shift - off, threads)
+    assert L.ddm_unpack_z_host(rec.ctypes.data, 10, 97, buf.ctypes.data, 200, 1) == _native.DDM_ERR_INVALID

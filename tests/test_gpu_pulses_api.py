@@ -166,3 +166,41 @@ def test_cuda_prior_draws_follow_the_prior():
         assert stats.kstest(t[:, i], law.cdf).pvalue > 1e-4, i
     assert bool(torch.isfinite(prior.log_prob(th)).all())
     assert tuple(prior.sample(()).shape) == (5,) and tuple(prior.sample((3, 2)).shape) == (3, 2, 5)
+
+
+def test_training_set_comes_home_as_records_or_rows_with_the_same_bits(monkeypatch):
+    """Large sets: z crosses the link as 32-byte records packed by the GPU (ddm_pack_z_dev) and is rebuilt by the host
+    cores (ddm_unpack_z_host); DDM_TRAINSET_D2H=rows copies the fp32 rows.  Same (z, x), also when a block holds a
+    pulse value other than +-1 (that block is copied as it is)."""
+    import contextlib
+    import io
+    from sbi_for_diffusion_models_b200 import data_simulator as ds
+    from sbi_for_diffusion_models_b200.priors import build_prior_theta
+    from sbi_for_diffusion_models_b200.proposals import ExtendedProposal, PulseSequenceProposal
+
+    class Odd(ExtendedProposal):
+        """every 7th call plants a pulse value that is not +-1"""
+        calls = 0
+
+        def sample(self, shape=torch.Size()):
+            z = super().sample(shape)
+            Odd.calls += 1
+            if Odd.calls % 7 == 0:
+                z[3, 9] = 0.5
+            return z
+
+    def run(mode, cls, n, bs):
+        monkeypatch.setenv("DDM_TRAINSET_D2H", mode)
+        monkeypatch.setattr(ds, "_LAUNCH_ROWS", 40_000)                    # several blocks, ragged tail
+        Odd.calls = 0
+        torch.manual_seed(11)
+        prop = cls(build_prior_theta("cuda"), PulseSequenceProposal(80, 0.75, seed=2, device="cuda"), device="cuda")
+        with contextlib.redirect_stdout(io.StringIO()):
+            return ds.simulate_training_set_with_conditions(prop, n, bs, "cuda", mu_sensory=1.0, p_success=0.75, P=80,
+                                                            log_rt=False, seed=5)
+    for cls in (ExtendedProposal, Odd):
+        za, xa = run("records", cls, 130_001, 10_000)
+        zb, xb = run("rows", cls, 130_001, 10_000)
+        assert torch.equal(za, zb) and torch.equal(xa, xb), cls.__name__
+        assert bool(((za[:, 5:].abs() == 1) | (za[:, 5:] == 0.5)).all())
+    assert int((za[:, 5:] == 0.5).sum()) == 2
