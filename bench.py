@@ -53,7 +53,9 @@ def parse():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--trials", type=int, default=int(os.environ.get("DDM_BENCH_TRIALS", 100_000_000)),
                     help="trials per GPU per step (default: the 1e8-trial config)")
-    ap.add_argument("--e2e-trials", type=int, default=int(os.environ.get("DDM_BENCH_E2E_TRIALS", 1 << 22)))
+    ap.add_argument("--e2e-trials", type=int, default=int(os.environ.get("DDM_BENCH_E2E_TRIALS", 1 << 24)),
+                    help="trials per end-to-end step (default 2^24 = 5.7 GB of pinned host z per rank: four batches of the "
+                         "streaming pipeline per call; the headline's 1e8 would pin 34 GB per rank, 272 GB on 8 GPUs)")
     ap.add_argument("--cpu-trials", type=int, default=int(os.environ.get("DDM_BENCH_CPU_TRIALS", 65536)),
                     help="trials per CPU step: the lock-step reference algorithm only amortises its ~19 tensor-op "
                          "dispatches per Euler step at large batches (2x the per-trial rate of the 4096 batch)")

@@ -20,6 +20,7 @@ from .simulator import HostPipeline, Schedule, compute_device, next_seed, pack_t
 
 
 _HOST_STREAM_MIN = 1 << 18   # CPU-resident z with at least this many rows is streamed in chunks
+_HOST_BATCH_ROWS = 1 << 24   # rows per persistent streaming launch (every launch ends with the drain of its longest trials)
 _pipelines = {}
 
 
@@ -50,7 +51,7 @@ def sim_wrapper(theta_and_pulses: torch.Tensor, *, mu_sensory: float, p_success:
         key = (dev, z.shape[1])
         pipe = _pipelines.get(key)
         if pipe is None:
-            pipe = _pipelines[key] = HostPipeline(z.shape[1], device=dev)
+            pipe = _pipelines[key] = HostPipeline(z.shape[1], max_batch=_HOST_BATCH_ROWS, device=dev)
         x = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
         packed = pipe.choose_packed(sched, n)
         t0 = time.perf_counter()
