@@ -352,6 +352,8 @@ def mnle_bench(dev, with_cpu: bool):
         for _ in range(3):
             est.loglik_sum_and_grad(thg, xo, pl)
         grad[f"C{Cg}"] = {"ms_per_call_graph": _time_graph(lambda: est.loglik_sum_and_grad(thg, xo, pl), reps=5),
+                          "ms_reverse_mode_tcgen05": _time_graph(lambda: est.loglik_sum_and_grad(thg, xo, pl, kernel="tc"), reps=5),
+                          "ms_forward_mode_fp32": _time_graph(lambda: est.loglik_sum_and_grad(thg, xo, pl, kernel="simt"), reps=5),
                           "ms_forward_only_graph": _time_graph(lambda: est.loglik_sum(thg, xo, pl), reps=5)}
     out["grad"] = grad
     if with_cpu:
