@@ -34,8 +34,10 @@ int cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 // ---- Philox4x32-10 (Salmon et al., SC'11) -------------------------------------------
-// counter = (lo32(trial), hi32(trial), block, 0), key = (lo32(seed), hi32(seed)); the simulator draws
-// the normals of steps 6 * block .. 6 * block + 5 from one block (see normals6 below).
+// counter = (lo32(trial), block, hi32(trial), 0), key = (lo32(seed), hi32(seed)); the simulator draws
+// the normals of steps 6 * block .. 6 * block + 5 from one block (see normals6 below).  The block index sits
+// in counter word 1 -- a word the first round only XORs -- so that most of rounds 1-3 is constant along a
+// trial (PhiloxTrial below).
 constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
 constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
@@ -45,6 +47,9 @@ constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 // kernels read the ten round keys straight from the constant bank (one LOP3 operand each).
 struct PhiloxKey {
     uint32_t k0[10], k1[10];
+    // rounds 3..9 once more, interleaved (k0[3], k1[3], k0[4], ...) and 16-byte aligned: the simulator's hot loop
+    // fetches them with four 128-bit uniform loads per chunk
+    alignas(16) uint32_t hot[16];
 };
 
 inline PhiloxKey make_philox_key(uint64_t seed)
@@ -54,6 +59,11 @@ inline PhiloxKey make_philox_key(uint64_t seed)
         k.k0[r] = (uint32_t)seed + (uint32_t)r * kPhiloxW0;
         k.k1[r] = (uint32_t)(seed >> 32) + (uint32_t)r * kPhiloxW1;
     }
+    for (int r = 3; r < 10; ++r) {
+        k.hot[2 * (r - 3)] = k.k0[r];
+        k.hot[2 * (r - 3) + 1] = k.k1[r];
+    }
+    k.hot[14] = k.hot[15] = 0u;
     return k;
 }
 
@@ -147,7 +157,7 @@ __device__ __forceinline__ void philox_normals6(uint32_t trial_lo, uint32_t tria
                                                 const PhiloxKey &key, uint32_t one, float (&z)[6])
 {
     uint32_t w[4];
-    philox4x32_10(trial_lo, trial_hi, blk, 0u, key, w);
+    philox4x32_10(trial_lo, blk, trial_hi, 0u, key, w);
     normals6(w, one, z);
 }
 
@@ -224,50 +234,60 @@ __device__ __forceinline__ void box_muller_x2_scaled(uint32_t wr0, uint32_t wa0,
     unpack2(zs, s0, s1);
 }
 
-// ---- Philox with the trial-constant part of rounds 1-2 hoisted -------------------------
-// With counter (g_lo, g_hi, blk, 0) only `blk` changes along a trial.  Round 1 multiplies
-// M0 * g_lo (constant per trial) and round 2 multiplies M1 * (hi(M0 g_lo) ^ k1) (also constant),
-// so four words per trial replace two IMAD.WIDE and one LOP3 in every block.  Same output bits
-// as philox4x32_10 (exact integer algebra).
+// ---- Philox with the trial-constant part of rounds 1-3 hoisted -------------------------
+// With counter (g_lo, blk, g_hi, 0) only `blk` changes along a trial, and round 1 merely XORs it into word 0:
+//   round 1: both products (M0 g_lo, M1 g_hi) are constant;            n0 = A ^ blk
+//   round 2: M1 * n2 is constant, M0 * n0 varies;                      m2 = hi(M0 n0) ^ F, m3 = lo(M0 n0)
+//   round 3: M0 * m0 is constant, M1 * m2 varies;                      q0 = hi(M1 m2) ^ D, q1 = lo(M1 m2), q2 = H ^ m3, q3 = E
+// so five words per trial replace four IMAD.WIDE and three LOP3 in every block (16 + 18 instructions per block
+// instead of 20 + 20).  Same output bits as philox4x32_10 on that counter (exact integer algebra).
 struct PhiloxTrial {
-    uint32_t a;  // g_hi ^ k0[0]
-    uint32_t d;  // hi(M1 * c2') ^ k0[1]          with c2' = hi(M0 g_lo) ^ k1[0]
-    uint32_t e;  // lo(M1 * c2')
+    uint32_t a;  // hi(M1 g_hi) ^ k0[0]
     uint32_t f;  // lo(M0 g_lo) ^ k1[1]
+    uint32_t d;  // lo(M1 n2) ^ k0[2]                 with n2 = hi(M0 g_lo) ^ k1[0]
+    uint32_t h;  // hi(M0 m0) ^ k1[2]                 with m0 = hi(M1 n2) ^ lo(M1 g_hi) ^ k0[1]
+    uint32_t e;  // lo(M0 m0)
 };
 
 __device__ __forceinline__ PhiloxTrial philox_trial_setup(uint32_t g_lo, uint32_t g_hi, const PhiloxKey &key)
 {
     const uint64_t p0 = (uint64_t)kPhiloxM0 * g_lo;
-    const uint32_t c2p = (uint32_t)(p0 >> 32) ^ key.k1[0];  // c3 = 0
-    const uint64_t p1 = (uint64_t)kPhiloxM1 * c2p;
+    const uint64_t p1 = (uint64_t)kPhiloxM1 * g_hi;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ key.k1[0];  // c3 = 0
+    const uint64_t r1 = (uint64_t)kPhiloxM1 * n2;
+    const uint32_t m0 = (uint32_t)(r1 >> 32) ^ n1 ^ key.k0[1];
+    const uint64_t r0 = (uint64_t)kPhiloxM0 * m0;
     PhiloxTrial t;
-    t.a = g_hi ^ key.k0[0];
-    t.d = (uint32_t)(p1 >> 32) ^ key.k0[1];
-    t.e = (uint32_t)p1;
+    t.a = (uint32_t)(p1 >> 32) ^ key.k0[0];
     t.f = (uint32_t)p0 ^ key.k1[1];
+    t.d = (uint32_t)r1 ^ key.k0[2];
+    t.h = (uint32_t)(r0 >> 32) ^ key.k1[2];
+    t.e = (uint32_t)r0;
     return t;
 }
 
+// The block index is blk ^ sub: callers whose `blk` has its low bits clear pass the small constant part as `sub`
+// (blk + sub == blk ^ sub then), which folds into the one three-input LOP3 of round 1.
 __device__ __forceinline__ void philox4x32_10_trial(const PhiloxTrial &t, uint32_t blk, const PhiloxKey &key,
-                                                    uint32_t (&out)[4])
+                                                    uint32_t (&out)[4], uint32_t sub = 0u)
 {
-    // round 1 (only M1 * blk varies)
-    const uint64_t q1 = (uint64_t)kPhiloxM1 * blk;
-    const uint32_t r1c0 = (uint32_t)(q1 >> 32) ^ t.a;
-    const uint32_t r1c1 = (uint32_t)q1;
-    // round 2 (only M0 * c0' varies)
-    const uint64_t q0 = (uint64_t)kPhiloxM0 * r1c0;
-    uint32_t c0 = t.d ^ r1c1;
-    uint32_t c1 = t.e;
-    uint32_t c2 = (uint32_t)(q0 >> 32) ^ t.f;
-    uint32_t c3 = (uint32_t)q0;
+    // round 1 (blk enters by XOR only), round 2 (only M0 * n0 varies)
+    const uint64_t q0 = (uint64_t)kPhiloxM0 * (t.a ^ blk ^ sub);
+    const uint32_t m2 = (uint32_t)(q0 >> 32) ^ t.f;
+    const uint32_t m3 = (uint32_t)q0;
+    // round 3 (only M1 * m2 varies)
+    const uint64_t q1 = (uint64_t)kPhiloxM1 * m2;
+    uint32_t c0 = (uint32_t)(q1 >> 32) ^ t.d;
+    uint32_t c1 = (uint32_t)q1;
+    uint32_t c2 = t.h ^ m3;
+    uint32_t c3 = t.e;
 #pragma unroll
-    for (int r = 2; r < 10; ++r) {
+    for (int r = 3; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r];
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k1[r];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.hot[2 * (r - 3)];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.hot[2 * (r - 3) + 1];
         c0 = n0;
         c1 = (uint32_t)p1;
         c2 = n2;
@@ -287,15 +307,17 @@ __device__ __forceinline__ void philox_normals6_trial(const PhiloxTrial &t, uint
     normals6(w, one, z);
 }
 
-// Blocks blk and blk + 1 -> the twelve SCALED normals (z * noise_scale) of steps 6 blk .. 6 blk + 11, same
-// bits as philox_normals6_trial + __fmul_rn per normal: Box-Muller pair j of the first block runs side by
-// side with pair j of the second one.
-__device__ __forceinline__ void philox_scaled_normals12_trial(const PhiloxTrial &t, uint32_t blk, const PhiloxKey &key,
-                                                              uint32_t one, const BmConsts &k, float (&nz)[12])
+// Blocks blk + sub and blk + sub + 1 -> the twelve SCALED normals (z * noise_scale) of the twelve steps from
+// 6 (blk + sub) on, same bits as philox_normals6_trial + __fmul_rn per normal: Box-Muller pair j of the first
+// block runs side by side with pair j of the second one.  Requires blk % (sub + 2) == 0 with sub + 2 a power of
+// two (the simulator: blk a multiple of its blocks per chunk, sub even).
+__device__ __forceinline__ void philox_scaled_normals12_trial(const PhiloxTrial &t, uint32_t blk, uint32_t sub,
+                                                              const PhiloxKey &key, uint32_t one, const BmConsts &k,
+                                                              float (&nz)[12])
 {
     uint32_t a[4], b[4];
-    philox4x32_10_trial(t, blk, key, a);
-    philox4x32_10_trial(t, blk + 1u, key, b);
+    philox4x32_10_trial(t, blk, key, a, sub);
+    philox4x32_10_trial(t, blk, key, b, sub + 1u);
     box_muller_x2_scaled(a[0], __funnelshift_r(a[0], a[1], 21), b[0], __funnelshift_r(b[0], b[1], 21), one, k, nz[0], nz[1],
                          nz[6], nz[7]);
     box_muller_x2_scaled(__funnelshift_r(a[1], a[2], 10), __funnelshift_r(a[1], a[2], 31), __funnelshift_r(b[1], b[2], 10),

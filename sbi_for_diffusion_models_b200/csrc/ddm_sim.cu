@@ -49,8 +49,12 @@ struct SimParams {
     unsigned int n_trials;
     int n_pulses;  // columns of the pulse matrix the schedule can reach
     int n_max;
+    float t_max, t_nd_hi;
+    // the four scalars of the hot loop side by side: one 128-bit uniform load per chunk
+    alignas(16) float dt;
+    float noise_scale;
+    uint32_t one_bits;  // 0x3F800000, kept in a register for the one-LOP3 mantissa insert
     int spp;
-    float dt, t_max, t_nd_hi, noise_scale;
     PhiloxKey key;
     unsigned long long trial_offset;
     int log_rt;
@@ -58,7 +62,6 @@ struct SimParams {
     unsigned long long wait_timeout_ns;  // streaming mode: give up on rows that have not arrived after this long
     float *x_peers[DDM_MAX_PEERS];  // fused all-gather: the same (rt, choice) also goes to these (peer-mapped) blocks
     int n_peers;
-    uint32_t one_bits;  // 0x3F800000, kept in a register for the one-LOP3 mantissa insert
 };
 
 #ifndef DDM_SIM_NB
@@ -102,36 +105,54 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
     constexpr int NPB = kNormalsPerBlock;
     constexpr int STEPS = NPB * NB;
     static_assert(STEPS % 8 == 0, "chunks must keep pulse kicks on multiples of 8 steps");
-    static_assert(NB % 2 == 0, "Philox blocks are consumed in pairs");
+    static_assert(NB % 2 == 0 && (NB & (NB - 1)) == 0, "Philox blocks are consumed in pairs; blk + b == blk ^ b needs a power of two");
     constexpr int MW = MASKW > 0 ? MASKW : 1;
     const unsigned lane = threadIdx.x & 31u;
     const BmConsts bm = make_bm_consts(p.noise_scale);
     float nz12[2 * NPB];
 
     // ---- per-lane trial state ---------------------------------------------------------
-    float a = 0.f, nlam = 0.f, B = 1.f, v = 0.f, tnd = 0.f;
-    int t = 0;       // Euler steps already taken by this lane's trial
+    // An idle lane carries a = NaN and rem = -1: none of the end-of-trial tests below can fire for it (NaN compares
+    // false, fmaxf / fminf skip NaN, (unsigned)rem is huge), so the hot loop never has to ask whether a lane is busy.
+    float a = CUDART_NAN_F, nlam = 0.f, B = 1.f, v = 0.f, tnd = 0.f;
+    int rem = -1;    // steps of the decision window still ahead at the chunk's first step (nsteps - t); < 0: idle
     int nsteps = 0;  // decision window in steps
-    int tk = 0;      // step index of the next pulse kick
-    int pidx = 0;    // column of the next pulse
+    int dk = 0;      // steps from the chunk's first step to the next pulse kick (tk - t)
+    int pidx = 0;    // column of the next pulse (maintained only where the pulse VALUE is read from memory)
     uint32_t blk = 0u;  // Philox block of the chunk's first step (= t / 6)
-    uint32_t cur = 0u;  // sign bits of pulses pidx.. (bit 0 = next pulse)
-    float kv = 0.f;     // ALIGNED: signed value v * s[pidx] of the next kick
-    PhiloxTrial pt{0u, 0u, 0u, 0u};
-    uint32_t mask[MW];
+    float kv = 0.f;     // signed value v * s[pidx] of the next kick
+    PhiloxTrial pt{0u, 0u, 0u, 0u, 0u};
+    // sign masks, REVERSED and INVERTED: bit 31 of sgn[0] is set iff the NEXT pulse is -1, then bit 30, ..., then
+    // sgn[1], sgn[2].  A kick shifts the chain left by one, so the next kick value is ONE LOP3: v ^ (sgn[0] & 2^31).
+    uint32_t sgn[MW];
 #pragma unroll
-    for (int w = 0; w < MW; ++w) mask[w] = 0u;
+    for (int w = 0; w < MW; ++w) sgn[w] = 0u;
     uint32_t trial = 0;  // index into this launch's arrays
-    bool busy = false;
     bool generic = (MASKW == 0);  // kick reads the pulse value from global memory
     bool exhausted = false;       // warp-uniform: the queue has run dry
     unsigned long long useful = 0ull;
     unsigned int chunks = 0u;
 
+    auto next_pulse = [&]() {   // a kick has happened: advance to the next pulse (rt_choice_model.py:190-192)
+        if (MASKW > 0) {
+#pragma unroll
+            for (int w = 0; w + 1 < MW; ++w) sgn[w] = __funnelshift_l(sgn[w + 1], sgn[w], 1);
+            sgn[MW - 1] <<= 1;
+        }
+    };
+    auto signed_kick = [&]() -> float { return __uint_as_float(__float_as_uint(v) ^ (sgn[0] & 0x80000000u)); };  // v * (+-1) exactly
+    auto loaded_kick = [&]() -> float {   // generic rows: the pulse value comes from memory
+        float s = 0.0f;
+        if (rem >= 0 && pidx < p.n_pulses) s = __ldcg(p.pulses + (long long)trial * p.ld_pulses + pidx);
+        return __fmul_rn(v, s);
+    };
+
     for (;;) {
         // ---- refill idle lanes from the global queue ----------------------------------
-        const unsigned idle = __ballot_sync(kFull, !busy);
-        if (idle != 0u && !exhausted) {
+        // common case (every lane busy): ONE ballot; the second one, after a refill, only when lanes were idle
+        unsigned idle = __ballot_sync(kFull, rem < 0);
+        if (idle != 0u) {
+        if (!exhausted) {
             const int want = __popc(idle);
             unsigned long long base = 0ull;
             if (lane == 0) base = atomicAdd(&p.ws[DDM_WS_QUEUE], (unsigned long long)want);
@@ -151,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 }
             }
             const unsigned long long mine = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
-            const bool got = !busy && mine < (unsigned long long)p.n_trials;
+            const bool got = rem < 0 && mine < (unsigned long long)p.n_trials;
             if (got) trial = (uint32_t)mine;
 
             if (MASKW > 0 && !PACKED) {
@@ -167,9 +188,9 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                     for (int w = 0; w < MASKW; ++w) {
                         const int c = w * 32 + (int)lane;
                         const float s = (c < p.n_pulses) ? __ldcg(row + c) : 1.0f;
-                        const unsigned bits = __ballot_sync(kFull, s > 0.0f);
+                        const unsigned neg = __ballot_sync(kFull, !(s > 0.0f));   // bit c: pulse c is not +1
                         odd = odd || (fabsf(s) != 1.0f);
-                        if ((int)lane == j) mask[w] = bits;
+                        if ((int)lane == j) sgn[w] = __brev(neg);
                     }
                     const unsigned any_odd = __ballot_sync(kFull, odd);
                     if ((int)lane == j) generic = (any_odd != 0u);
@@ -182,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                     const uint4 lo = __ldcg(rec), hi = __ldcg(rec + 1);
                     th0 = __uint_as_float(lo.x), th1 = __uint_as_float(lo.y), th2 = __uint_as_float(lo.z);
                     th3 = __uint_as_float(lo.w), th4 = __uint_as_float(hi.x);
-                    mask[0] = hi.y, mask[1 % MW] = hi.z, mask[2 % MW] = hi.w;
+                    sgn[0] = __brev(~hi.y), sgn[1 % MW] = __brev(~hi.z), sgn[2 % MW] = __brev(~hi.w);   // records: bit c set = +1
                     generic = false;
                 } else {
                     const float *th = p.theta + (long long)trial * p.ld_theta;
@@ -200,52 +221,37 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 const float win = floorf(__fdiv_rn(__fsub_rn(p.t_max, tnd), p.dt));
                 nsteps = !(win > 0.0f) ? 0 : (win >= (float)p.n_max ? p.n_max : (int)win);
                 a = __fmul_rn(a0, B);  // :144
-                t = 0;
+                rem = nsteps;
                 blk = 0u;
-                tk = 0;
+                dk = 0;
                 pidx = 0;
-                cur = mask[0];
-                if (ALIGNED) {
-                    if (MASKW == 0 || generic) {
-                        const float s0 = (p.n_pulses > 0) ? __ldcg(p.pulses + (long long)trial * p.ld_pulses) : 0.0f;
-                        kv = __fmul_rn(v, s0);
-                    } else {
-                        kv = (cur & 1u) ? v : -v;
-                    }
-                }
+                kv = (MASKW == 0 || generic) ? loaded_kick() : signed_kick();
                 if (!INJECT) {
                     const unsigned long long g = p.trial_offset + (unsigned long long)trial;
                     pt = philox_trial_setup((uint32_t)g, (uint32_t)(g >> 32), p.key);
                 }
-                busy = true;
                 if (MASKW > 0 && generic) atomicAdd(&p.ws[DDM_WS_GENERIC_ROWS], 1ull);
             }
+            idle = __ballot_sync(kFull, rem < 0);
         }
-        if (__ballot_sync(kFull, busy) == 0u) break;
+        if (idle == kFull) break;
+        }
 
         // ---- one chunk of STEPS Euler steps -------------------------------------------
         auto kick = [&](float acc) -> float {
             // rt_choice_model.py:192  a += v * s[:, p_idx] * active   (then advance to the next pulse)
-            float kv;
-            if (MASKW == 0 || generic) {
-                float s = 0.0f;
-                if (busy && pidx < p.n_pulses)
-                    s = __ldcg(p.pulses + (long long)trial * p.ld_pulses + pidx);
-                kv = __fmul_rn(v, s);
-            } else {
-                kv = (cur & 1u) ? v : -v;  // v * (+-1) exactly
-            }
-            cur >>= 1;
+            acc = __fadd_rn(acc, kv);
+            next_pulse();
             pidx += 1;
-            if (MASKW > 1 && (pidx & 31) == 0) cur = (pidx == 32) ? mask[1 % MW] : mask[2 % MW];
-            tk += p.spp;
-            return __fadd_rn(acc, kv);
+            dk += p.spp;
+            kv = (MASKW == 0 || generic) ? loaded_kick() : signed_kick();
+            return acc;
         };
 
         // ALIGNED (steps_per_pulse % 8 == 0 and >= STEPS): at most one kick per chunk, at i = dk, a
-        // multiple of 8.  The kick sites are branch-free selects; the pulse bookkeeping runs once per
+        // multiple of 8.  The kick sites are predicated adds; the pulse bookkeeping runs once per
         // chunk instead of once per site.
-        const int dk = tk - t;
+        const int dk0 = dk;
         float av[STEPS];
         float acc = a;
 #pragma unroll
@@ -254,14 +260,14 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
             if (INJECT) {
 #pragma unroll
                 for (int j = 0; j < NPB; ++j) {
-                    const int step = t + NPB * b + j;
-                    z[j] = (busy && step < p.n_max)
+                    const int step = nsteps - rem + NPB * b + j;
+                    z[j] = (rem >= 0 && step < p.n_max)
                                ? __ldg(p.noise + (long long)step * p.ld_noise + trial)
                                : 0.0f;
                 }
             } else if ((b & 1) == 0) {
                 // two Philox blocks at a time: their Box-Muller pairs run as packed fp32 pairs, noise scale included
-                philox_scaled_normals12_trial(pt, blk + (uint32_t)b, p.key, p.one_bits, bm, nz12);
+                philox_scaled_normals12_trial(pt, blk, (uint32_t)b, p.key, p.one_bits, bm, nz12);
             }
 #pragma unroll
             for (int j = 0; j < NPB; ++j) {
@@ -272,11 +278,10 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 // :190-192; with steps_per_pulse % 8 == 0 a kick can only fall on i % 8 == 0
                 if (ALIGNED) {
                     if ((i & 7) == 0) {
-                        const float kicked_acc = __fadd_rn(acc, kv);  // a += v * s[:, p_idx] * active
-                        acc = (dk == i) ? kicked_acc : acc;
+                        if (dk0 == i) acc = __fadd_rn(acc, kv);  // a += v * s[:, p_idx] * active (one predicated FADD)
                     }
                 } else {
-                    if (t + i == tk) acc = kick(acc);
+                    if (dk == i) acc = kick(acc);
                 }
                 av[i] = acc;
             }
@@ -284,22 +289,19 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
         a = acc;
         chunks += 1u;
         if (ALIGNED) {  // advance to the next pulse if this chunk held a kick
-            const bool kicked = dk < STEPS;
-            const uint32_t shifted = cur >> 1;
-            cur = kicked ? shifted : cur;
-            pidx += kicked ? 1 : 0;
-            tk += kicked ? p.spp : 0;
-            if (MASKW > 1 && kicked && (pidx & 31) == 0) cur = (pidx == 32) ? mask[1 % MW] : mask[2 % MW];
-            if (MASKW == 0 || generic) {
+            const bool kicked = dk0 < STEPS;
+            if (kicked) next_pulse();            // predicated shifts, no branch
+            dk += kicked ? p.spp : 0;
+            if (MASKW == 0 || generic) {         // rare (rows with a pulse value other than +-1) or MASKW == 0
                 if (kicked) {
-                    float s = 0.0f;
-                    if (busy && pidx < p.n_pulses) s = __ldcg(p.pulses + (long long)trial * p.ld_pulses + pidx);
-                    kv = __fmul_rn(v, s);
+                    pidx += 1;
+                    kv = loaded_kick();
                 }
             } else {
-                kv = (cur & 1u) ? v : -v;  // v * (+-1) exactly
+                kv = signed_kick();
             }
         }
+        dk -= STEPS;
 
         // fmaxf / fminf ignore NaN operands, like the reference's comparisons (always false).  Running max / min
         // per group of 8 steps: the exact search below only visits the group(s) that can hold the crossing.
@@ -324,29 +326,32 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
             lo = fminf(lo, glo[g]);
         }
 
-        const bool ending = busy && (hi >= B || lo <= 0.0f || t + STEPS >= nsteps);
+        // idle lanes: hi = lo = NaN and (unsigned)rem >= 2^31, so all three tests are false without asking
+        const bool ending = (hi >= B) | (lo <= 0.0f) | ((unsigned)rem <= (unsigned)STEPS);   // no short-circuit: no branch
         if (__any_sync(kFull, ending)) {
             // ---- some trial of the warp ends inside the chunk: exact first-passage search -------
             // (warp-uniform control flow: typically ONE lane ends, in ONE group of 8 steps)
-            int hit_step = -1;
-            int choice = 2;
+            int first = STEPS;       // first step of the chunk at which the accumulator is outside (0, B)
+            float afirst = 1.0f;     // its value there
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const bool look = ending && hit_step < 0 && (ghi[g] >= B || glo[g] <= 0.0f);
+                const bool look = ending && first == STEPS && (ghi[g] >= B || glo[g] <= 0.0f);
                 if (__any_sync(kFull, look)) {
 #pragma unroll
                     for (int i = 8 * g + 7; i >= 8 * g; --i) {
-                        const bool up = av[i] >= B;      // :195
-                        const bool dn = av[i] <= 0.0f;   // :196
-                        if (look && (t + i < nsteps) && (up || dn)) {
-                            hit_step = t + i + 1;        // :201
-                            choice = dn ? 0 : 1;         // lower bound wins ties, :202-203
+                        if (look && (av[i] >= B || av[i] <= 0.0f)) {   // :195-196
+                            first = i;
+                            afirst = av[i];
                         }
                     }
                 }
             }
             if (ending) {
-                if (hit_step < 0) {  // window over without a crossing, :206-215
+                int hit_step, choice;
+                if (first < rem) {                   // inside the decision window (t + i < n_steps)
+                    hit_step = nsteps - rem + first + 1;   // :201
+                    choice = (afirst <= 0.0f) ? 0 : 1;     // lower bound wins ties, :202-203
+                } else {                             // window over without a crossing, :206-215
                     hit_step = nsteps;
                     choice = 2;
                 }
@@ -361,10 +366,11 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 for (int d = 0; d < p.n_peers; ++d) reinterpret_cast<float2 *>(p.x_peers[d])[trial] = res;
                 if (p.steps_out) p.steps_out[trial] = hit_step;
                 useful += (unsigned long long)hit_step;
-                busy = false;
+                a = CUDART_NAN_F;   // idle (see the state comment above)
+                rem = -1 + STEPS;   // (the chunk epilogue below takes STEPS off again)
             }
         }
-        t += STEPS;
+        rem -= STEPS;
         blk += (uint32_t)NB;
     }
 
@@ -563,7 +569,7 @@ __global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, uint32_
         const unsigned long long g = trial_offset + (unsigned long long)i;
         if (WORDS) {
             uint32_t w[4];
-            philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)blk, 0u, key, w);
+            philox4x32_10((uint32_t)g, (uint32_t)blk, (uint32_t)(g >> 32), 0u, key, w);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (blk * 4 + j < n_steps) static_cast<uint32_t *>(out)[(blk * 4 + j) * ld + i] = w[j];
