@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
     constexpr int NPB = kNormalsPerBlock;
     constexpr int STEPS = NPB * NB;
     static_assert(STEPS % 8 == 0, "chunks must keep pulse kicks on multiples of 8 steps");
-    static_assert(NB % 2 == 0 && (NB & (NB - 1)) == 0, "Philox blocks are consumed in pairs; blk + b == blk ^ b needs a power of two");
+    static_assert(NB % 2 == 0 && (NB & (NB - 1)) == 0, "Philox blocks are consumed in pairs; pair + b / 2 == pair ^ (b / 2) needs a power of two");
     constexpr int MW = MASKW > 0 ? MASKW : 1;
     const unsigned lane = threadIdx.x & 31u;
     const BmConsts bm = make_bm_consts(p.noise_scale);
@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
     int nsteps = 0;  // decision window in steps
     int dk = 0;      // steps from the chunk's first step to the next pulse kick (tk - t)
     int pidx = 0;    // column of the next pulse (maintained only where the pulse VALUE is read from memory)
-    uint32_t blk = 0u;  // Philox block of the chunk's first step (= t / 6)
+    uint32_t pair = 0u;  // Philox block pair of the chunk's first step (= t / 12)
     float kv = 0.f;     // signed value v * s[pidx] of the next kick
-    PhiloxTrial pt{0u, 0u, 0u, 0u, 0u};
+    PhiloxTrial pt{0u, 0u, {0u, 0u}, {0u, 0u}, {0u, 0u}};
     // sign masks, REVERSED and INVERTED: bit 31 of sgn[0] is set iff the NEXT pulse is -1, then bit 30, ..., then
     // sgn[1], sgn[2].  A kick shifts the chain left by one, so the next kick value is ONE LOP3: v ^ (sgn[0] & 2^31).
     uint32_t sgn[MW];
@@ -147,12 +147,11 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
         return __fmul_rn(v, s);
     };
 
-    for (;;) {
-        // ---- refill idle lanes from the global queue ----------------------------------
-        // common case (every lane busy): ONE ballot; the second one, after a refill, only when lanes were idle
+    // ---- refill idle lanes from the global queue; returns true when the whole warp is (still) idle ----------
+    // Called once before the loop and then only where lanes become idle: in the end-of-trial branch of a chunk.
+    auto refill = [&]() -> bool {
         unsigned idle = __ballot_sync(kFull, rem < 0);
-        if (idle != 0u) {
-        if (!exhausted) {
+        if (idle != 0u && !exhausted) {
             const int want = __popc(idle);
             unsigned long long base = 0ull;
             if (lane == 0) base = atomicAdd(&p.ws[DDM_WS_QUEUE], (unsigned long long)want);
@@ -222,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 nsteps = !(win > 0.0f) ? 0 : (win >= (float)p.n_max ? p.n_max : (int)win);
                 a = __fmul_rn(a0, B);  // :144
                 rem = nsteps;
-                blk = 0u;
+                pair = 0u;
                 dk = 0;
                 pidx = 0;
                 kv = (MASKW == 0 || generic) ? loaded_kick() : signed_kick();
@@ -234,9 +233,11 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
             }
             idle = __ballot_sync(kFull, rem < 0);
         }
-        if (idle == kFull) break;
-        }
+        return idle == kFull;
+    };
 
+    if (refill()) goto done;
+    for (;;) {
         // ---- one chunk of STEPS Euler steps -------------------------------------------
         auto kick = [&](float acc) -> float {
             // rt_choice_model.py:192  a += v * s[:, p_idx] * active   (then advance to the next pulse)
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 }
             } else if ((b & 1) == 0) {
                 // two Philox blocks at a time: their Box-Muller pairs run as packed fp32 pairs, noise scale included
-                philox_scaled_normals12_trial(pt, blk, (uint32_t)b, p.key, p.one_bits, bm, nz12);
+                philox_scaled_normals12_trial(pt, pair, (uint32_t)(b >> 1), p.key, p.one_bits, bm, nz12);
             }
 #pragma unroll
             for (int j = 0; j < NPB; ++j) {
@@ -304,20 +305,24 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
         dk -= STEPS;
 
         // fmaxf / fminf ignore NaN operands, like the reference's comparisons (always false).  Running max / min
-        // per group of 8 steps: the exact search below only visits the group(s) that can hold the crossing.
-        constexpr int G = STEPS / 8;
+        // per group of 7 steps (three 3-input FMNMX each): the exact search below only visits the group(s) that can
+        // hold the crossing.
+        constexpr int GS = 7, G = (STEPS + GS - 1) / GS;
         float ghi[G], glo[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            ghi[g] = fmaxf(fmaxf(av[8 * g], av[8 * g + 1]), av[8 * g + 2]);
-            glo[g] = fminf(fminf(av[8 * g], av[8 * g + 1]), av[8 * g + 2]);
+            const int s0 = GS * g, s1 = (GS * g + GS < STEPS) ? GS * g + GS : STEPS;
+            ghi[g] = glo[g] = av[s0];
 #pragma unroll
-            for (int i = 3; i < 7; i += 2) {
-                ghi[g] = fmaxf(fmaxf(ghi[g], av[8 * g + i]), av[8 * g + i + 1]);
-                glo[g] = fminf(fminf(glo[g], av[8 * g + i]), av[8 * g + i + 1]);
+            for (int i = s0 + 1; i < s1; i += 2) {
+                if (i + 1 < s1) {
+                    ghi[g] = fmaxf(fmaxf(ghi[g], av[i]), av[i + 1]);
+                    glo[g] = fminf(fminf(glo[g], av[i]), av[i + 1]);
+                } else {
+                    ghi[g] = fmaxf(ghi[g], av[i]);
+                    glo[g] = fminf(glo[g], av[i]);
+                }
             }
-            ghi[g] = fmaxf(ghi[g], av[8 * g + 7]);
-            glo[g] = fminf(glo[g], av[8 * g + 7]);
         }
         float hi = ghi[0], lo = glo[0];
 #pragma unroll
@@ -328,17 +333,21 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
 
         // idle lanes: hi = lo = NaN and (unsigned)rem >= 2^31, so all three tests are false without asking
         const bool ending = (hi >= B) | (lo <= 0.0f) | ((unsigned)rem <= (unsigned)STEPS);   // no short-circuit: no branch
+        rem -= STEPS;
+        pair += (uint32_t)(NB / 2);
         if (__any_sync(kFull, ending)) {
+            const int rem0 = rem + STEPS;   // window left at the chunk's first step
             // ---- some trial of the warp ends inside the chunk: exact first-passage search -------
-            // (warp-uniform control flow: typically ONE lane ends, in ONE group of 8 steps)
+            // (warp-uniform control flow: typically ONE lane ends, in ONE group of 7 steps)
             int first = STEPS;       // first step of the chunk at which the accumulator is outside (0, B)
             float afirst = 1.0f;     // its value there
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 const bool look = ending && first == STEPS && (ghi[g] >= B || glo[g] <= 0.0f);
                 if (__any_sync(kFull, look)) {
+                    const int s0 = GS * g, s1 = (GS * g + GS < STEPS) ? GS * g + GS : STEPS;
 #pragma unroll
-                    for (int i = 8 * g + 7; i >= 8 * g; --i) {
+                    for (int i = s1 - 1; i >= s0; --i) {
                         if (look && (av[i] >= B || av[i] <= 0.0f)) {   // :195-196
                             first = i;
                             afirst = av[i];
@@ -348,8 +357,8 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
             }
             if (ending) {
                 int hit_step, choice;
-                if (first < rem) {                   // inside the decision window (t + i < n_steps)
-                    hit_step = nsteps - rem + first + 1;   // :201
+                if (first < rem0) {                  // inside the decision window (t + i < n_steps)
+                    hit_step = nsteps - rem0 + first + 1;  // :201
                     choice = (afirst <= 0.0f) ? 0 : 1;     // lower bound wins ties, :202-203
                 } else {                             // window over without a crossing, :206-215
                     hit_step = nsteps;
@@ -367,12 +376,12 @@ __global__ void __launch_bounds__(kThreads, STREAM ? 4 : DDM_SIM_MIN_BLOCKS) sim
                 if (p.steps_out) p.steps_out[trial] = hit_step;
                 useful += (unsigned long long)hit_step;
                 a = CUDART_NAN_F;   // idle (see the state comment above)
-                rem = -1 + STEPS;   // (the chunk epilogue below takes STEPS off again)
+                rem = -1;
             }
+            if (refill()) break;
         }
-        rem -= STEPS;
-        blk += (uint32_t)NB;
     }
+done:
 
     // ---- counters --------------------------------------------------------------------
 #pragma unroll
@@ -569,7 +578,7 @@ __global__ void __launch_bounds__(256) philox_dump_kernel(PhiloxKey key, uint32_
         const unsigned long long g = trial_offset + (unsigned long long)i;
         if (WORDS) {
             uint32_t w[4];
-            philox4x32_10((uint32_t)g, (uint32_t)blk, (uint32_t)(g >> 32), 0u, key, w);
+            philox4x32_10((uint32_t)g, (uint32_t)(blk >> 1), (uint32_t)(g >> 32), (uint32_t)(blk & 1), key, w);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (blk * 4 + j < n_steps) static_cast<uint32_t *>(out)[(blk * 4 + j) * ld + i] = w[j];
