@@ -310,7 +310,12 @@ class DeviceMNLE(torch.nn.Module):
             _native.check(rc, "mnle_loglik_sum")
         return out.to(theta.device)
 
-    GRAD_TC_MIN_ROWS = 2048   # below this the forward-mode CUDA-core kernel (one launch) wins on latency
+    # "auto" takes the reverse-mode tensor-core path from this many rows on.  Measured (tools/time_grad_sizes.py, trained
+    # estimator, eager calls): T=50 x C=2 (the reference's NUM_CHAINS) 0.14 ms against 0.39 ms for the forward-mode
+    # fp32 kernel, T=1 x C=1 0.10 against 0.38, T=50 x C=1024 1.27 against 9.97 -- reverse mode wins at every size.
+    # kernel="simt" remains for callers who want every gradient entry within fp32 rounding of float64 (the tensor-core
+    # path can put a ReLU unit that sits within 1e-5 of its kink on the other side, see tests/test_gpu_mnle.py).
+    GRAD_TC_MIN_ROWS = 0
 
     def loglik_sum_and_grad(self, theta: torch.Tensor, x_o: torch.Tensor, pulses: torch.Tensor, *, kernel: str = "auto"):
         """(out (C,), grad (C,5)) with grad[c] = d out[c] / d theta[c].

@@ -10,9 +10,10 @@ expands (C thetas) x (T trials) into T*C rows of 85 numbers and calls ``estimato
 from ``theta[c]``, ``local_theta[t]`` and ``x_o[t]`` and returns the sum over t.
 
 Gradients: a call that needs d loglik / d theta (NUTS: ``track_gradients=True`` with a theta that
-requires grad, reference potentials.py:33, 112) runs the forward-mode CUDA kernel
-(``mnle_loglik_sum_grad_f32``: value and the five partials in one pass) behind a
-``torch.autograd.Function``; everything else runs the tensor-core forward kernel.
+requires grad, reference potentials.py:33, 112) runs value and the five partials in reverse mode on the
+tensor cores (``mnle_loglik_sum_grad_tc_f32``; ``DeviceMNLE.loglik_sum_and_grad`` also offers the fp32
+forward-mode kernel ``mnle_loglik_sum_grad_f32``) behind a ``torch.autograd.Function``; everything else
+runs the tensor-core forward kernel.
 """
 from __future__ import annotations
 
@@ -59,8 +60,8 @@ def prior_log_prob(prior, theta: torch.Tensor) -> torch.Tensor:
 
 
 class _LoglikSumWithGrad(torch.autograd.Function):
-    """sum_t log p(x_t | theta_c, pulses_t) with its Jacobian-vector product taken from the
-    forward-mode kernel: each output depends on its own theta row only, so
+    """sum_t log p(x_t | theta_c, pulses_t) with its Jacobian taken from the gradient kernel (value and
+    d out[c] / d theta[c] in one call): each output depends on its own theta row only, so
     d L / d theta[c] = grad_output[c] * d out[c] / d theta[c]."""
 
     @staticmethod
