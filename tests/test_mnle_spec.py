@@ -188,3 +188,31 @@ def test_sbc_helpers_cpu():
     for i in range(6):                              # reference order: prior draw, then ds_seed (mnle.py:185-188)
         assert torch.equal(th[i], torch.rand((1, 5)).view(5))
         assert seeds[i] == int(rng.integers(0, 2**31 - 1))
+
+
+def test_spline_matches_the_nflows_derived_implementation_shipped_in_transformers():
+    """An independent pin for the part of A8 where the numerics are: the unconstrained rational-quadratic spline with
+    linear tails.  sbi 0.25.0 evaluates it through nflows 0.14 (``nflows.transforms.splines.rational_quadratic``),
+    which is not in this image; Hugging Face ``transformers`` IS, and its VITS model carries the same routine (VITS
+    took its ``transforms.py`` from nflows: softmax widths / heights with the 1e-3 floors, cumulative knots pinned at
+    +-tail_bound, softplus derivatives with the boundary constant log(exp(1 - 1e-3) - 1), the 1e-6 nudge of the last
+    edge in the bin search, identity outside the tails).  The spec's ``rqs_forward`` must agree with it to rounding,
+    in float64 and in float32, on random parameters at the scale of a trained net and on the edge cases."""
+    vits = pytest.importorskip("transformers.models.vits.modeling_vits")
+    ref = vits._unconstrained_rational_quadratic_spline
+    K = ms.NUM_BINS
+    g = torch.Generator().manual_seed(5)
+    for dtype, tol in ((torch.float64, 1e-13), (torch.float32, 1e-6)):   # measured: 4e-15 and 4e-6 (a few ulp at |u| ~ 10)
+        for scale in (1.0, 30.0, 120.0):      # raw conditioner outputs; 120 / sqrt(128) ~ 10: sharp bins
+            R = 4000
+            q = (torch.randn(R, 3 * K - 1, generator=g) * scale).to(dtype)
+            u = (torch.rand(R, generator=g) * 24.0 - 12.0).to(dtype)           # a sixth of them outside the tails
+            u[:8] = torch.tensor([-ms.TAIL_BOUND, ms.TAIL_BOUND, 0.0, -12.0, 12.0, 9.999999, -9.999999, 1e-30], dtype=dtype)
+            got_u, got_lad = ms.rqs_forward(u, q)
+            want_u, want_lad = ref(u.clone(), q[:, :K] / math.sqrt(ms.HIDDEN), q[:, K:2 * K] / math.sqrt(ms.HIDDEN),
+                                   q[:, 2 * K:].clone(), reverse=False, tail_bound=ms.TAIL_BOUND, min_bin_width=ms.MIN_BIN,
+                                   min_bin_height=ms.MIN_BIN, min_derivative=ms.MIN_DERIV)
+            assert torch.allclose(got_u, want_u, rtol=tol, atol=tol * 10), (dtype, scale, float((got_u - want_u).abs().max()))
+            assert torch.allclose(got_lad, want_lad, rtol=tol, atol=tol * 10), (dtype, scale, float((got_lad - want_lad).abs().max()))
+            outside = (u < -ms.TAIL_BOUND) | (u > ms.TAIL_BOUND)
+            assert torch.equal(got_u[outside], u[outside]) and float(got_lad[outside].abs().max()) == 0.0
