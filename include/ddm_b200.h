@@ -96,8 +96,9 @@ size_t ddm_sim_workspace_bytes(void);
  *               float32 tensor op sees them: (float)DT_CHOICE, (float)T_MAX,
  *               (float)(T_MAX - 1e-6), (float)(mu_sensory * sqrt(DT_CHOICE)).
  *   seed, trial_offset
- *               native noise: Philox4x32-10 with key = seed and counter
- *               (trial_offset + i, step / 6) -- one 128-bit block gives six 21-bit fields =
+ *               native noise: Philox4x32-10 with key = (lo32, hi32) of seed and counter words
+ *               (lo32(g), b >> 1, hi32(g), b & 1) for global trial g = trial_offset + i and block
+ *               b = step / 6 -- one 128-bit block gives six 21-bit fields =
  *               three Box-Muller pairs = the normals of six consecutive steps: results do
  *               not depend on how trials are split over launches, streams or GPUs.
  *   noise_dev   NULL for native noise; otherwise (n_max, >=N) fp32 standard normals,
