@@ -393,28 +393,46 @@ def configs0_bench(dev):
     from sbi_for_diffusion_models_b200.priors import build_prior_theta
     from sbi_for_diffusion_models_b200.proposals import ExtendedProposal, PulseSequenceProposal
 
+    # as in the reference's pipeline (rt_choice_model_pipeline.py:38-75) the prior is built once, outside the call
+    priors = {None: build_prior_theta(None), dev: build_prior_theta(dev)}
+
     def once(seed, prior_dev=None):
-        prop = ExtendedProposal(build_prior_theta(prior_dev), PulseSequenceProposal(P, 0.75, seed=seed, device=dev), device=dev)
+        prop = ExtendedProposal(priors[prior_dev], PulseSequenceProposal(P, 0.75, seed=seed, device=dev), device=dev)
         with contextlib.redirect_stdout(io.StringIO()):
             return ds.simulate_training_set_with_conditions(prop, 10_000, 4096, dev, mu_sensory=1.0, p_success=0.75, P=P,
                                                             log_rt=False, seed=seed)
 
     def timed(prior_dev):
-        once(0, prior_dev)
+        for i in range(3):
+            once(100 + i, prior_dev)
         torch.cuda.synchronize()
         ts = []
-        for i in range(5):
+        for i in range(9):
             t0 = time.perf_counter()
             z, x = once(1 + i, prior_dev)
             ts.append(time.perf_counter() - t0)
-        return sorted(ts)[2], z, x
+        return sorted(ts)[4], z, x
     dt, z, x = timed(None)
     dt_dev, _, _ = timed(dev)
     steps = float(torch.round((x[:, 0] - z[:, 4].clamp(0.0, 7.999999)) / 5e-4).sum())
+    # simulate_observed_session (data_simulator.py:74-99) at NUM_TRIALS_OBS = 50: what run_sbc calls once per dataset
+    theta_true = torch.tensor([0.45, 0.6, 1.3, 14.0, 0.25])
+    sess = lambda seed: ds.simulate_observed_session(theta_true, 50, dev, mu_sensory=1.0, p_success=0.75, P=P, seed=seed, log_rt=False)
+    for i in range(3):
+        sess(i)
+    ts = []
+    for i in range(9):
+        t0 = time.perf_counter()
+        sess(10 + i)
+        ts.append(time.perf_counter() - t0)
     return {"workload": "configs[0]: simulate_training_set_with_conditions, 10 000 trials in batches of 4096, CPU (z, x) out",
             "seconds": dt, "trials_per_s": 10_000 / dt, "steps_per_s": steps / dt, "seconds_with_cuda_prior": dt_dev,
-            "note": "seconds: the reference's CPU prior object -- ~3 ms of it are torch's CPU Beta sampler "
-                    "(tools/time_configs0.py); seconds_with_cuda_prior: the same call with the prior's parameters on the GPU"}
+            "observed_session_T50_seconds": sorted(ts)[4],
+            "note": "median of 9 calls, prior object built once outside the call as in the reference's pipeline.  seconds: the "
+                    "reference's CPU prior object -- most of it is torch's CPU Beta sampler (tools/time_configs0.py); "
+                    "seconds_with_cuda_prior: the same call with the prior's parameters on the GPU; observed_session_T50_seconds: "
+                    "simulate_observed_session(theta, 50 trials) -> CPU (x_o, pulses_o), one launch of the small-batch kernel "
+                    "(floor: 16 000 serial Euler steps = 0.38 ms)"}
 
 
 def long_schedule_bench(args, z, rank, world, dev, gather):
