@@ -26,7 +26,8 @@ def test_philox_words_layout():
     for i in range(5):
         g = off + i
         for t in range(10):
-            blk = orc.philox4x32_10([g & 0xFFFFFFFF, g >> 32, t // 4, 0], [seed & 0xFFFFFFFF, seed >> 32])
+            b = t // 4   # counter = (trial lo, block pair, trial hi, place in pair), see csrc/ddm_common.cuh
+            blk = orc.philox4x32_10([g & 0xFFFFFFFF, b >> 1, g >> 32, b & 1], [seed & 0xFFFFFFFF, seed >> 32])
             assert w[t, i] == blk[t % 4]
 
 
