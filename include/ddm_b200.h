@@ -90,7 +90,7 @@ size_t ddm_sim_workspace_bytes(void);
  *               broadcasts one row to every trial (rt_choice_model.py:166-168).  Only
  *               the first ceil(n_max / steps_per_pulse) columns are read (:178); P smaller
  *               than that is DDM_ERR_INVALID (:173-176).
- *   n_max, steps_per_pulse      time grid (rt_choice_model.py:45-59)
+ *   n_max, steps_per_pulse      time grid (rt_choice_model.py:45-59); 0 <= n_max <= 2^30
  *   dt, t_max, t_nd_hi, noise_scale
  *               the Python floats of the reference ALREADY ROUNDED to fp32 the way a
  *               float32 tensor op sees them: (float)DT_CHOICE, (float)T_MAX,

@@ -658,7 +658,9 @@ static int sim_impl(const float *theta_dev, int64_t ld_theta, const float *pulse
         DDM_REQUIRE(x_peers[d] != nullptr && (reinterpret_cast<uintptr_t>(x_peers[d]) & 7u) == 0,
                     "ddm_sim_gather_f32: peer block %d must be a non-null, 8-byte aligned device pointer", d);
     DDM_REQUIRE(N >= 0 && N <= 0x7FFFFFFFll, "ddm_sim_f32: N=%lld outside [0, 2^31)", (long long)N);
-    DDM_REQUIRE(n_max >= 0 && n_max <= 0x7FFFFF00ll, "ddm_sim_f32: n_max=%lld out of range", (long long)n_max);
+    // (an idle lane counts its window register down from -1 by 24 per chunk for as long as the longest trial of its
+    // warp runs: n_max <= 2^30 keeps that above INT_MIN)
+    DDM_REQUIRE(n_max >= 0 && n_max <= 0x40000000ll, "ddm_sim_f32: n_max=%lld outside [0, 2^30]", (long long)n_max);
     DDM_REQUIRE(steps_per_pulse >= 1 && steps_per_pulse <= 0x7FFFFFFFll,
                 "ddm_sim_f32: steps_per_pulse=%lld must be >= 1", (long long)steps_per_pulse);
     const int64_t need = (n_max + steps_per_pulse - 1) / steps_per_pulse;
@@ -777,7 +779,7 @@ DDM_API int ddm_sim_packed_f32(const uint32_t *packed_dev, int64_t N, int64_t n_
                                const uint64_t *ready_dev, void *stream)
 {
     DDM_REQUIRE(N >= 0 && N <= 0x7FFFFFFFll, "ddm_sim_packed_f32: N=%lld outside [0, 2^31)", (long long)N);
-    DDM_REQUIRE(n_max >= 0 && n_max <= 0x7FFFFF00ll, "ddm_sim_packed_f32: n_max=%lld out of range", (long long)n_max);
+    DDM_REQUIRE(n_max >= 0 && n_max <= 0x40000000ll, "ddm_sim_packed_f32: n_max=%lld outside [0, 2^30]", (long long)n_max);
     DDM_REQUIRE(steps_per_pulse >= 1 && steps_per_pulse <= 0x7FFFFFFFll,
                 "ddm_sim_packed_f32: steps_per_pulse=%lld must be >= 1", (long long)steps_per_pulse);
     const int64_t need = (n_max + steps_per_pulse - 1) / steps_per_pulse;
