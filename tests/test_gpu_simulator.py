@@ -415,7 +415,10 @@ def test_small_batch_kernel_is_bit_identical_to_the_throughput_kernel():
     L = _native.lib()
     rs = np.random.RandomState(3)
     cases = [(1, {}), (31, {}), (33, {}), (1000, {}), (10007, {}), (40000, {}),
-             (3000, {"dt": 1e-4}), (2000, {"dt": 7e-4, "pulse_interval": 0.0497}), (500, {"t_max": 1.0})]
+             (3000, {"dt": 1e-4}), (2000, {"dt": 7e-4, "pulse_interval": 0.0497}), (500, {"t_max": 1.0}),
+             # several kicks per 24-step chunk, sign masks (63 pulses) and memory pulses (267 pulses > 96 mask bits)
+             (1500, {"dt": 1e-3, "pulse_interval": 0.008, "t_max": 0.5}), (700, {"dt": 2.5e-3, "pulse_interval": 0.03}),
+             (900, {"dt": 1e-3, "pulse_interval": 0.001, "t_max": 0.09})]
     try:
         for n, kw in cases:
             sched = Schedule.from_constants(1.0, **kw)
