@@ -10,7 +10,7 @@
 //                              pack rebuilt on the device from the current parameters; keeps the 71
 //                              raw spline parameters per (row, transform), the choice logits and the
 //                              hidden activations.
-//   2. train_rows_kernel       one warp per row (lane = bin): choice log-probability, the ten splines forward
+//   2. train_rows_kernel       four lanes per row (six bins per lane): choice log-probability, the ten splines forward
 //                              (log p of the row), then backwards (reverse mode written out by
 //                              hand), turning the stored spline parameters and logits into
 //                              d loss / d (spline parameters, logits) in place.
@@ -184,84 +184,130 @@ __global__ void __launch_bounds__(kThreads) train_forward_kernel(const float *__
     }
 }
 
-// ---- 2. per-row work: one warp per row, lane j owns bin j ------------------------------------
+// ---- 2. per-row work: four lanes per row, six bins per lane ----------------------------------
+// (Round 1 and the first half of round 2 ran one warp per row with lane j owning bin j: 24 of 32 lanes busy, every
+// softmax / cumulative sum a pair of five-step warp scans -- ~315 warp-instructions per (row, transform) pass.  With
+// six bins per lane the scans are local, the four lanes of a row meet in two-step shuffles, and a warp carries eight
+// rows: ~55 warp-instructions per (row, transform) pass.)
 constexpr int kRowWarps = 8;
+constexpr int kRowLanes = 4;                       // lanes per row
+constexpr int kLaneBins = kBins / kRowLanes;       // 6
+constexpr int kWarpRows = 32 / kRowLanes;          // 8 rows per warp
+constexpr int kBlockRows = kRowWarps * kWarpRows;  // 64 rows per block
+static_assert(kBins == kRowLanes * kLaneBins && kSplineOut == 3 * kBins - 1, "six bins per lane");
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-__device__ __forceinline__ float warp_max(float v)
+__device__ __forceinline__ float quad_max(float v)
 {
+    v = fmaxf(v, __shfl_xor_sync(kFull, v, 1));
+    return fmaxf(v, __shfl_xor_sync(kFull, v, 2));
+}
+__device__ __forceinline__ int quad_sum(int v)
+{
+    v += __shfl_xor_sync(kFull, v, 1);
+    return v + __shfl_xor_sync(kFull, v, 2);
+}
+template <typename T>
+__device__ __forceinline__ T quad_get(T v, int base, int sub) { return __shfl_sync(kFull, v, base + sub); }
+
+// entry `i` (0..5, not known at compile time) of a register array: a select chain, no local memory
+__device__ __forceinline__ float pick6(const float (&v)[kLaneBins], int i)
+{
+    float r = v[0];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
-    return v;
+    for (int j = 1; j < kLaneBins; ++j) r = (i == j) ? v[j] : r;
+    return r;
 }
 
-__device__ __forceinline__ float warp_scan(float v, int lane)  // inclusive prefix sum over lanes
-{
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float t = __shfl_up_sync(kFull, v, o);
-        if (lane >= o) v += t;
-    }
-    return v;
-}
-
-// softmax over the 24 logits held by lanes 0..23 (one per lane) and the knot positions built from it:
-// e = softmax probability of the lane's bin, cum = sum of e over bins before it, lo / hi = the bin's
-// edges 20 * cumsum(m + c e) - 10 with both ends pinned to -+10.
-struct Knots {
-    float e, cum, lo, hi;
+// softmax over the 24 logits of a row (six per lane, bins 6 s .. 6 s + 5 on sub-lane s) and the knot positions built
+// from it: e = softmax probability of the bin, cum = sum of e over the bins before it, lo / hi = the bin's edges
+// 20 * cumsum(m + c e) - 10 with both ends pinned to -+10.
+struct Knots6 {
+    float e[kLaneBins], cum[kLaneBins], lo[kLaneBins], hi[kLaneBins];
 };
-__device__ __forceinline__ Knots knots(float logit, int lane)
+__device__ __forceinline__ void knots6(const float (&logit)[kLaneBins], int base, int sub, Knots6 &k)
 {
     const float inv_sqrt_h = 0.08838834764831845f;  // 1/sqrt(128)
     const float c = 1.0f - kMinBin * kBins;
-    const bool on = lane < kBins;
-    const float a = on ? logit * inv_sqrt_h : -INFINITY;
-    const float m = warp_max(a);
-    const float ex = on ? expf(a - m) : 0.f;
-    const float sc = warp_scan(ex, lane);
-    const float inv_s = 1.0f / __shfl_sync(kFull, sc, kBins - 1);
-    Knots k;
-    k.e = ex * inv_s;
-    const float inc = sc * inv_s;  // inclusive cumulative probability
-    k.cum = inc - k.e;
-    k.hi = (lane >= kBins - 1) ? kTail : 2.0f * kTail * (kMinBin * (float)(lane + 1) + c * inc) - kTail;
-    const float up = __shfl_up_sync(kFull, k.hi, 1);
-    k.lo = (lane == 0) ? -kTail : up;
-    return k;
+    float a[kLaneBins];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kLaneBins; ++i) {
+        a[i] = logit[i] * inv_sqrt_h;
+        m = fmaxf(m, a[i]);
+    }
+    m = quad_max(m);
+    float pre[kLaneBins];  // inclusive prefix sums within the lane
+    float run = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLaneBins; ++i) {
+        k.e[i] = expf(a[i] - m);
+        run += k.e[i];
+        pre[i] = run;
+    }
+    // totals of the four lanes, added in the same order everywhere: every lane of the row sees the same sum
+    const float t0 = quad_get(run, base, 0), t1 = quad_get(run, base, 1), t2 = quad_get(run, base, 2), t3 = quad_get(run, base, 3);
+    const float off = (sub > 0 ? t0 : 0.f) + (sub > 1 ? t1 : 0.f) + (sub > 2 ? t2 : 0.f);
+    const float inv_s = 1.0f / (((t0 + t1) + t2) + t3);
+#pragma unroll
+    for (int i = 0; i < kLaneBins; ++i) {
+        const int j = kLaneBins * sub + i;
+        k.e[i] *= inv_s;
+        const float inc = (off + pre[i]) * inv_s;  // inclusive cumulative probability
+        k.cum[i] = inc - k.e[i];
+        k.hi[i] = (j >= kBins - 1) ? kTail : 2.0f * kTail * (kMinBin * (float)(j + 1) + c * inc) - kTail;
+    }
+    const float up = __shfl_up_sync(kFull, k.hi[kLaneBins - 1], 1);  // (sub > 0: the lane below belongs to the same row)
+    k.lo[0] = (sub == 0) ? -kTail : up;
+#pragma unroll
+    for (int i = 1; i < kLaneBins; ++i) k.lo[i] = k.hi[i - 1];
 }
 
-// One rational-quadratic spline for the warp's row (Durkan et al. 2019, linear tails).  q points at the
-// row's 71 raw parameters of this transform.  Forward: u <- spline(u), logdet += log |du_out / du|.
-// BACKWARD (reverse mode written out by hand): u is the transform's INPUT, g = d l / d u_out on entry
-// (l = log p of the row, d l / d logdet = 1) and d l / d u on exit; q[j] <- scale * d l / d q[j].
+// One rational-quadratic spline for the quad's row (Durkan et al. 2019, linear tails).  q points at the row's 71 raw
+// parameters of this transform.  Forward: u <- spline(u), logdet += log |du_out / du|.
+// BACKWARD (reverse mode written out by hand): u is the transform's INPUT, g = d l / d u_out on entry (l = log p of the
+// row, d l / d logdet = 1) and d l / d u on exit; q[j] <- scale * d l / d q[j].  Rows differ within a warp, so nothing
+// here branches on the row: a row outside the tail bound (identity, no parameter dependence) computes on u = 0 and
+// discards the result.
 template <bool BACKWARD>
-__device__ __forceinline__ void rqs_warp(float &u, float &logdet, float *q, int lane, float &g, float scale)
+__device__ __forceinline__ void rqs_quad(float &u, float &logdet, float *q, int base, int sub, bool live, float &g, float scale)
 {
-    if (!(u >= -kTail && u <= kTail)) {  // identity outside the tail bound: no parameter dependence
-        if (BACKWARD) {
-            q[lane] = 0.f;
-            q[32 + lane] = 0.f;
-            if (lane < kSplineOut - 64) q[64 + lane] = 0.f;
+    const bool inside = (u >= -kTail && u <= kTail);
+    const float ui = inside ? u : 0.f;
+    float qw[kLaneBins], qh[kLaneBins], qd[kLaneBins];
+    {
+        // 6 s floats into each third of the row: 24 s bytes, 8-byte aligned
+        const float2 *pw = reinterpret_cast<const float2 *>(q + kLaneBins * sub);
+        const float2 *ph = reinterpret_cast<const float2 *>(q + kBins + kLaneBins * sub);
+        const float2 *pd = reinterpret_cast<const float2 *>(q + 2 * kBins + kLaneBins * sub);
+#pragma unroll
+        for (int i = 0; i < kLaneBins / 2; ++i) {
+            const float2 w2 = live ? pw[i] : make_float2(0.f, 0.f), h2 = live ? ph[i] : make_float2(0.f, 0.f);
+            const float2 d2 = live ? pd[i] : make_float2(0.f, 0.f);   // (element 71 of the row is padding)
+            qw[2 * i] = w2.x, qw[2 * i + 1] = w2.y, qh[2 * i] = h2.x, qh[2 * i + 1] = h2.y, qd[2 * i] = d2.x, qd[2 * i + 1] = d2.y;
         }
-        return;
     }
-    const float qw = lane < kBins ? q[lane] : 0.f;
-    const float qh = lane < kBins ? q[kBins + lane] : 0.f;
-    const float qd = lane < kBins - 1 ? q[2 * kBins + lane] : 0.f;
-    const Knots W = knots(qw, lane), H = knots(qh, lane);
+    Knots6 W, H;
+    knots6(qw, base, sub, W);
+    knots6(qh, base, sub, H);
     // bin: the last one whose left edge is <= u (left edges are increasing, the first is -10)
-    const int b = __popc(__ballot_sync(kFull, lane < kBins && u >= W.lo)) - 1;
-    const float left = __shfl_sync(kFull, W.lo, b), right = __shfl_sync(kFull, W.hi, b);
-    const float bottom = __shfl_sync(kFull, H.lo, b), top = __shfl_sync(kFull, H.hi, b);
-    const float qd0 = __shfl_sync(kFull, qd, b > 0 ? b - 1 : 0), qd1 = __shfl_sync(kFull, qd, b);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kLaneBins; ++i) cnt += (ui >= W.lo[i]) ? 1 : 0;
+    const int b = quad_sum(cnt) - 1;
+    const int sb = (b >= kLaneBins ? 1 : 0) + (b >= 2 * kLaneBins ? 1 : 0) + (b >= 3 * kLaneBins ? 1 : 0), ib = b - kLaneBins * sb;
+    const float left = quad_get(pick6(W.lo, ib), base, sb), right = quad_get(pick6(W.hi, ib), base, sb);
+    const float bottom = quad_get(pick6(H.lo, ib), base, sb), top = quad_get(pick6(H.hi, ib), base, sb);
+    const int bm = b > 0 ? b - 1 : 0;
+    const int sm = (bm >= kLaneBins ? 1 : 0) + (bm >= 2 * kLaneBins ? 1 : 0) + (bm >= 3 * kLaneBins ? 1 : 0), im = bm - kLaneBins * sm;
+    const float qd0 = quad_get(pick6(qd, im), base, sm), qd1 = quad_get(pick6(qd, ib), base, sb);
     // knot derivatives; the boundary ones are exactly 1 (min_derivative + softplus(pad) == 1)
     const float d0 = (b == 0) ? 1.0f : kMinDeriv + softplus_f(qd0);
     const float d1 = (b == kBins - 1) ? 1.0f : kMinDeriv + softplus_f(qd1);
 
     const float w = right - left, h = top - bottom;
     const float delta = h / w;
-    const float th = (u - left) / w;
+    const float th = (ui - left) / w;
     const float omt = 1.0f - th;
     const float t1 = th * omt;
     const float dd = d0 + d1 - 2.0f * delta;
@@ -271,8 +317,10 @@ __device__ __forceinline__ void rqs_warp(float &u, float &logdet, float *q, int 
     const float s2 = d1 * th * th + 2.0f * delta * t1 + d0 * omt * omt;
     const float dnum = delta * delta * s2;
     if (!BACKWARD) {
-        logdet += logf(dnum) - 2.0f * logf(den);
-        u = bottom + num / den;
+        if (inside) {
+            logdet += logf(dnum) - 2.0f * logf(den);
+            u = bottom + num / den;
+        }
         return;
     }
     const float inv_den = 1.0f / den;
@@ -295,24 +343,35 @@ __device__ __forceinline__ void rqs_warp(float &u, float &logdet, float *q, int 
     const float gl = (b >= 1) ? -g_u - g_w : 0.f, gr = (b <= kBins - 2) ? g_w : 0.f;
     const float gb = (b >= 1) ? g - g_h : 0.f, gt = (b <= kBins - 2) ? g_h : 0.f;
     const float k20 = 2.0f * kTail * (1.0f - kMinBin * kBins);
-    const float Sw = __shfl_sync(kFull, W.cum, b), ew = __shfl_sync(kFull, W.e, b);
-    const float Sh = __shfl_sync(kFull, H.cum, b), eh = __shfl_sync(kFull, H.e, b);
+    const float Sw = quad_get(pick6(W.cum, ib), base, sb), ew = quad_get(pick6(W.e, ib), base, sb);
+    const float Sh = quad_get(pick6(H.cum, ib), base, sb), eh = quad_get(pick6(H.e, ib), base, sb);
     const float dot_w = k20 * (gl * Sw + gr * (Sw + ew));
     const float dot_h = k20 * (gb * Sh + gt * (Sh + eh));
-    const float out_scale = scale * 0.08838834764831845f;
-    if (lane < kBins) {
-        const float sel_w = k20 * ((lane < b ? gl : 0.f) + (lane <= b ? gr : 0.f));
-        const float sel_h = k20 * ((lane < b ? gb : 0.f) + (lane <= b ? gt : 0.f));
-        q[lane] = out_scale * W.e * (sel_w - dot_w);
-        q[kBins + lane] = out_scale * H.e * (sel_h - dot_h);
+    const float out_scale = inside ? scale * 0.08838834764831845f : 0.f;
+    const float v0 = inside ? scale * g_d0 / (1.0f + expf(-qd0)) : 0.f;  // softplus' = sigmoid
+    const float v1 = inside ? scale * g_d1 / (1.0f + expf(-qd1)) : 0.f;
+    float ow[kLaneBins], oh[kLaneBins], od[kLaneBins];
+#pragma unroll
+    for (int i = 0; i < kLaneBins; ++i) {
+        const int j = kLaneBins * sub + i;
+        const float sel_w = k20 * ((j < b ? gl : 0.f) + (j <= b ? gr : 0.f));
+        const float sel_h = k20 * ((j < b ? gb : 0.f) + (j <= b ? gt : 0.f));
+        ow[i] = out_scale * W.e[i] * (sel_w - dot_w);
+        oh[i] = out_scale * H.e[i] * (sel_h - dot_h);
+        od[i] = (j >= kBins - 1) ? 0.f : ((j == b - 1) ? v0 : ((j == b) ? v1 : 0.f));   // (j = 23: the padding slot of the row)
     }
-    if (lane < kBins - 1) {
-        float v = 0.f;
-        if (lane == b - 1) v = g_d0 / (1.0f + expf(-qd0));  // softplus' = sigmoid
-        if (lane == b) v = g_d1 / (1.0f + expf(-qd1));
-        q[2 * kBins + lane] = scale * v;
+    if (live) {
+        float2 *pw = reinterpret_cast<float2 *>(q + kLaneBins * sub);
+        float2 *ph = reinterpret_cast<float2 *>(q + kBins + kLaneBins * sub);
+        float2 *pd = reinterpret_cast<float2 *>(q + 2 * kBins + kLaneBins * sub);
+#pragma unroll
+        for (int i = 0; i < kLaneBins / 2; ++i) {
+            pw[i] = make_float2(ow[2 * i], ow[2 * i + 1]);
+            ph[i] = make_float2(oh[2 * i], oh[2 * i + 1]);
+            pd[i] = make_float2(od[2 * i], od[2 * i + 1]);
+        }
     }
-    g = g_u;
+    if (inside) g = g_u;
 }
 
 // log p of every row (choice head + ten splines forward) and, when the gradient is wanted, the
@@ -321,55 +380,69 @@ __global__ void __launch_bounds__(kRowWarps * 32) train_rows_kernel(const float 
                                                                     TrainRows rows, long long Rp, float scale,
                                                                     int backward, TrainBufs B)
 {
-    __shared__ float u_in[kRowWarps][kTransforms];
+    __shared__ float u_in[kRowWarps][kWarpRows][kTransforms];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long row = (long long)blockIdx.x * kRowWarps + wib;
-    if (row >= Rp) return;
+    const int sub = lane & (kRowLanes - 1), base = lane & ~(kRowLanes - 1), rw = lane / kRowLanes;
+    const long long row = ((long long)blockIdx.x * kRowWarps + wib) * kWarpRows + rw;
+    const bool alloc = row < Rp;        // the row exists in the buffers (Rp is padded to whole tiles)
+    const bool live = row < rows.R;     // ... and in the minibatch
     const int n_choices = L.n_choices;
-    float *lg = B.LG + (size_t)row * kMaxChoices;
-    if (row >= rows.R) {  // padding rows of the last tile contribute nothing
-        if (backward) {
-            for (int k = 0; k < kTransforms; ++k)
-                for (int j = lane; j < kSplineOut; j += 32) B.Q[((size_t)k * Rp + row) * kQRows + j] = 0.f;
-            if (lane < n_choices) lg[lane] = 0.f;
-        }
-        return;
+    const long long rowc = alloc ? row : 0;
+    float *lg = B.LG + (size_t)rowc * kMaxChoices;
+    if (alloc && !live && backward) {   // padding rows of the last tile contribute nothing
+        for (int k = 0; k < kTransforms; ++k)
+            for (int j = sub; j < kSplineOut; j += kRowLanes) B.Q[((size_t)k * Rp + row) * kQRows + j] = 0.f;
+        for (int j = sub; j < n_choices; j += kRowLanes) lg[j] = 0.f;
     }
-    const long long dr = data_row(rows, row);
-    // categorical head: l = log clamp(softmax(logits)[choice], eps, 1 - eps)
-    float lp;
+    const long long dr = live ? data_row(rows, row) : 0;
+    // categorical head: l = log clamp(softmax(logits)[choice], eps, 1 - eps); every lane of the row computes it
+    float lp = 0.f;
     {
-        const int choice = (int)__ldg(rows.x + 2 * dr + 1);
-        const float logit = lane < n_choices ? lg[lane] : -INFINITY;
-        const float m = warp_max(logit);
-        const float e = lane < n_choices ? expf(logit - m) : 0.f;
-        const float s = __shfl_sync(kFull, warp_scan(e, lane), 31);
-        const float p = __shfl_sync(kFull, e, choice) / s;
+        const int choice = live ? (int)__ldg(rows.x + 2 * dr + 1) : 0;
+        float logit[kMaxChoices];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kMaxChoices; ++j) {
+            logit[j] = (live && j < n_choices) ? lg[j] : -INFINITY;
+            m = fmaxf(m, logit[j]);
+        }
+        float e[kMaxChoices], ssum = 0.f, ec = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxChoices; ++j) {
+            e[j] = (live && j < n_choices) ? expf(logit[j] - m) : 0.f;
+            ssum += e[j];
+            ec = (j == choice) ? e[j] : ec;
+        }
+        const float p = live ? ec / ssum : 0.5f;
         const float eps = 1.1920928955078125e-07f;
         lp = logf(fminf(fmaxf(p, eps), 1.0f - eps));
-        if (backward && lane < n_choices) {
+        if (backward) __syncwarp();   // every lane of the row has read the logits before any of them is overwritten
+        if (backward && live) {
             const bool clamped = p < eps || p > 1.0f - eps;  // torch.clamp passes no gradient outside
-            lg[lane] = clamped ? 0.f : scale * ((lane == choice ? 1.0f : 0.f) - e / s);
+#pragma unroll
+            for (int j = 0; j < kMaxChoices; ++j)
+                if (j < n_choices && (j & (kRowLanes - 1)) == sub)
+                    lg[j] = clamped ? 0.f : scale * ((j == choice ? 1.0f : 0.f) - e[j] / ssum);
         }
     }
     const float mu_y = params[L.mu_y], sigma_y = params[L.sigma_y];
-    const float y = logf(__ldg(rows.x + 2 * dr));
+    const float y = live ? logf(__ldg(rows.x + 2 * dr)) : 0.f;
     float u = (y - mu_y) / sigma_y;
     float logdet = -logf(sigma_y);
     float g = 0.f;
 #pragma unroll 1
     for (int k = 0; k < kTransforms; ++k) {
-        if (lane == 0) u_in[wib][k] = u;
-        rqs_warp<false>(u, logdet, B.Q + ((size_t)k * Rp + row) * kQRows, lane, g, scale);
+        if (sub == 0) u_in[wib][rw][k] = u;
+        rqs_quad<false>(u, logdet, B.Q + ((size_t)k * Rp + rowc) * kQRows, base, sub, live, g, scale);
     }
-    if (lane == 0) B.LP[row] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
+    if (sub == 0 && live) B.LP[row] = lp + (-0.5f * u * u - 0.9189385332046727f) + logdet - y;
     if (!backward) return;
     __syncwarp();
     g = -u;  // d/du of the standard-normal base log-density
 #pragma unroll 1
     for (int k = kTransforms - 1; k >= 0; --k) {
-        float uk = u_in[wib][k];
-        rqs_warp<true>(uk, logdet, B.Q + ((size_t)k * Rp + row) * kQRows, lane, g, scale);
+        float uk = u_in[wib][rw][k];
+        rqs_quad<true>(uk, logdet, B.Q + ((size_t)k * Rp + rowc) * kQRows, base, sub, live, g, scale);
     }
 }
 
@@ -745,7 +818,7 @@ DDM_API int mnle_train_nll_grad_f32(const float *params_dev, int n_choices, cons
                                         reinterpret_cast<const long long *>(row_index_dev), (long long)R, keep, B.LP, st);
         if (rc != DDM_OK) return rc;
     }
-    train_rows_kernel<<<(unsigned)((d.Rp + kRowWarps - 1) / kRowWarps), kRowWarps * 32, 0, st>>>(
+    train_rows_kernel<<<(unsigned)((d.Rp + kBlockRows - 1) / kBlockRows), kRowWarps * 32, 0, st>>>(
         params_dev, L, rows, d.Rp, -1.0f / (float)R, want_grad, B);
     DDM_CUDA_TRY(cudaGetLastError());
     int n_ss = 0;
@@ -940,7 +1013,7 @@ DDM_API int mnle_loglik_sum_grad_tc_f32(void *handle, const float *theta_dev, in
     int rc = tc_train_forward(H->params, L, B.pack, xr, cond, (long long)kCond, nullptr, R, keep, B.LP, st);
     if (rc != DDM_OK) return rc;
     // scale = +1: the "loss" is the sum of the rows' log-probabilities
-    train_rows_kernel<<<(unsigned)((d.Rp + kRowWarps - 1) / kRowWarps), kRowWarps * 32, 0, st>>>(H->params, L, rows, d.Rp, 1.0f, 1, B);
+    train_rows_kernel<<<(unsigned)((d.Rp + kBlockRows - 1) / kBlockRows), kRowWarps * 32, 0, st>>>(H->params, L, rows, d.Rp, 1.0f, 1, B);
     DDM_CUDA_TRY(cudaGetLastError());
     const TcTrainDump bwd{B.H, B.Q, B.LG, d.Rp, B.DH, nullptr};
     rc = tc_train_backward(L, B.pack, R, bwd, st);
