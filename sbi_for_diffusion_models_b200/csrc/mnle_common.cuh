@@ -111,6 +111,11 @@ struct TcTrainDump {
     const unsigned char *ctx;  // forward only: per 128-row tile the bf16 hi / lo context images (tc_prep_kernel)
     float *CX;     // forward only (may be null): [86][Rp] the gathered context rows [cond (85), choice], column-major --
                    // the X operand of the first layers' weight-gradient GEMMs
+    // backward pass of the POTENTIAL (d / d theta only; both null in the training step): DH may then be null (nothing
+    // but the theta columns of the first layers is wanted), W1T = [kNets][128][8] the five theta columns of every
+    // first layer (padded to eight), GP = [kNets][2][5][Rp] per row and column half: sum_j dh1[j] * W1[j][i]
+    float *GP;
+    const float *W1T;
 };
 size_t tc_train_pack_bytes(int n_choices, long long R);  // operand pack + context images of R rows
 int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, const float *x_dev, const float *cond_dev,

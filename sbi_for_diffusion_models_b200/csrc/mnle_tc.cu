@@ -400,9 +400,12 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
 // Backward-data epilogue: ncols accumulator columns (d loss / d activations) times the derivative of the
 // activation whose output h sits in global memory -> d loss / d pre-activations, written to global memory
 // and, when another stage follows, split into the bf16 hi / lo A operand of that stage.
+// d_row may be null (potential gradient: the derivatives are not kept); w1s (shared memory, [128][8], may be null): the
+// five theta columns of this net's first layer -- acc5[i] += sum_j d[j] * w1s[j][i] over this thread's columns.
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int ncols, const float *h_row, float *d_row, size_t ld,
-                                                 bool have, bool feeds_next, uint64_t *dfull, uint32_t parity)
+                                                 bool have, bool feeds_next, uint64_t *dfull, uint32_t parity,
+                                                 const float *w1s = nullptr, float *acc5 = nullptr)
 {
 #pragma unroll 1
     for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
@@ -428,9 +431,21 @@ __device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int nc
             tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
             tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
         }
-        if (have) {
+        if (have && d_row != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) d_row[(size_t)(c0 + j) * ld] = h[j];
+        }
+        if (w1s != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float4 wa = *reinterpret_cast<const float4 *>(w1s + (c0 + j) * 8);   // same address in every lane: broadcast
+                const float wb = w1s[(c0 + j) * 8 + 4];
+                acc5[0] = fmaf(h[j], wa.x, acc5[0]);
+                acc5[1] = fmaf(h[j], wa.y, acc5[1]);
+                acc5[2] = fmaf(h[j], wa.z, acc5[2]);
+                acc5[3] = fmaf(h[j], wa.w, acc5[3]);
+                acc5[4] = fmaf(h[j], wb, acc5[4]);
+            }
         }
     }
     tmem_wait_st();
@@ -622,6 +637,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int tile0 = bx >= n_pairs ? 2 * n_pairs + (bx - n_pairs) : bx * kTcTiles;
     const int n_active = bx >= n_pairs ? 1 : kTcTiles;
 
+    // potential gradient: the theta columns of this net's first layer, [128][8] floats, in the unused tail of tile 0's
+    // first A image (the backward pass fills K groups 0..9 of an image, this is groups 10 and 11)
+    float *w1s = reinterpret_cast<float *>(smem + kSmemATh + 10u * kKGroupBytes);
+    if (BWD && keep.GP != nullptr)
+        for (int i = tid; i < kHidden * 8; i += kTcThreads) w1s[i] = __ldg(keep.W1T + (size_t)net_id * kHidden * 8 + i);
     if (warp == kTcEpiWarps) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         for (int i = 0; i < kTcTiles; ++i) mbar_init(&turn[i], 1);
@@ -852,12 +872,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (BWD) {
                 const bool have = c_glob < keep.Rp;
                 const size_t at = ((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * kHidden * (size_t)keep.Rp + (size_t)(have ? c_glob : 0);
+                float *d_row = keep.DH != nullptr ? keep.DH + at : nullptr;
+                const bool last = !(s + 1 < n_st);
+                const float *wsel = (keep.GP != nullptr && last) ? w1s : nullptr;   // the last stage ends at the first layer
+                float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
                 if (st.epi == kEpiRelu)
-                    tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st,
-                                               &dfull[X], ph_d & 1u);
+                    tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, keep.H + at, d_row, (size_t)keep.Rp, have, !last,
+                                               &dfull[X], ph_d & 1u, wsel, acc5);
                 else
-                    tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, keep.H + at, keep.DH + at, (size_t)keep.Rp, have, s + 1 < n_st,
-                                                  &dfull[X], ph_d & 1u);
+                    tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, keep.H + at, d_row, (size_t)keep.Rp, have, !last,
+                                                  &dfull[X], ph_d & 1u, wsel, acc5);
+                if (wsel != nullptr && have) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i)   // [net][hf][i][row]: a warp writes 32 consecutive rows of one plane
+                        keep.GP[(((size_t)net_id * 2 + hf) * 5 + i) * (size_t)keep.Rp + (size_t)c_glob] = acc5[i];
+                }
                 ++ph_d;
                 tc_fence_before_sync();
                 mbar_arrive(&aready[X]);

@@ -908,33 +908,32 @@ __global__ void __launch_bounds__(256) potential_rows_kernel(const float *__rest
     }
 }
 
-constexpr int kGradTSplit = 8;  // trial ranges summed separately (fixed order afterwards: reproducible)
-
-// grid (chain blocks of 128, nets, trial splits): part[(net * kGradTSplit + ts) * C + c][5]
-__global__ void __launch_bounds__(128) potential_grad_partial_kernel(const float *__restrict__ params, Layout L,
-                                                                     const float *__restrict__ DH, long long Rp, int T, int C,
-                                                                     float *__restrict__ part)
+// the five theta columns of every first layer, [kNets][128][8] (three zeros of padding): what the backward kernel's
+// last epilogue contracts the first-layer derivatives with
+__global__ void __launch_bounds__(128) potential_w1_kernel(const float *__restrict__ params, Layout L, float *__restrict__ w1t)
 {
-    __shared__ float w_s[kHidden][5];
-    const int net = blockIdx.y, ts = blockIdx.z, c = blockIdx.x * 128 + threadIdx.x;
+    const int net = blockIdx.x, j = threadIdx.x;
     const int K = net == 0 ? kCond : kCtx;
     const float *W = params + (net == 0 ? L.cat_W0 : L.fl_W1[net - 1]);
-    for (int idx = threadIdx.x; idx < kHidden * 5; idx += 128) w_s[idx / 5][idx % 5] = __ldg(W + (size_t)(idx / 5) * K + idx % 5);
-    __syncthreads();
-    if (c >= C) return;
-    const float *dh = DH + ((size_t)net * 3 + 0) * kHidden * (size_t)Rp;
-    const int t0 = (int)((long long)T * ts / kGradTSplit), t1 = (int)((long long)T * (ts + 1) / kGradTSplit);
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int t = t0; t < t1; ++t) {
-        const float *col = dh + (size_t)t * C + c;
-#pragma unroll 8
-        for (int j = 0; j < kHidden; ++j) {
-            const float g = __ldcg(col + (size_t)j * Rp);
 #pragma unroll
-            for (int i = 0; i < 5; ++i) acc[i] = fmaf(g, w_s[j][i], acc[i]);
-        }
+    for (int i = 0; i < 8; ++i) w1t[((size_t)net * kHidden + j) * 8 + i] = i < 5 ? __ldg(W + (size_t)j * K + i) : 0.f;
+}
+
+constexpr int kGradPlanes = kNets * 2;   // (net, column half) partial gradients per row, written by the backward kernel
+
+// grid (chain blocks of 128, planes): part[(plane * C + c) * 5 + i] = sum_t GP[plane][i][t * C + c]  (fixed order)
+__global__ void __launch_bounds__(128) potential_grad_partial_kernel(const float *__restrict__ GP, long long Rp, int T, int C,
+                                                                     float *__restrict__ part)
+{
+    const int plane = blockIdx.y, c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= C) return;
+    const float *src = GP + (size_t)plane * 5 * (size_t)Rp + c;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) acc[i] += __ldcg(src + (size_t)i * Rp + (size_t)t * C);
     }
-    float *dst = part + ((size_t)(net * kGradTSplit + ts) * C + c) * 5;
+    float *dst = part + ((size_t)plane * C + c) * 5;
 #pragma unroll
     for (int i = 0; i < 5; ++i) dst[i] = acc[i];
 }
@@ -945,7 +944,7 @@ __global__ void __launch_bounds__(128) potential_grad_final_kernel(const float *
     const int c = blockIdx.x * 128 + threadIdx.x;
     if (c >= C) return;
     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < kNets * kGradTSplit; ++s)
+    for (int s = 0; s < kGradPlanes; ++s)
 #pragma unroll
         for (int i = 0; i < 5; ++i) acc[i] += part[((size_t)s * C + c) * 5 + i];
 #pragma unroll
@@ -962,7 +961,9 @@ static size_t potential_grad_floats(const Layout &L, long long T, long long C)
     auto up = [](size_t v) { return (v + 63) / 64 * 64; };
     size_t n = up(train_floats(L, d));
     n += up((size_t)R * kCond) + up(2 * (size_t)R);         // the expanded rows
-    n += (size_t)kNets * kGradTSplit * (size_t)C * 5;       // partial gradients
+    n += up((size_t)kNets * kHidden * 8);                   // theta columns of the first layers
+    n += up((size_t)kGradPlanes * 5 * (size_t)d.Rp);        // per-row partial gradients
+    n += (size_t)kGradPlanes * (size_t)C * 5;               // per-chain partial gradients
     return n;
 }
 
@@ -1004,7 +1005,11 @@ DDM_API int mnle_loglik_sum_grad_tc_f32(void *handle, const float *theta_dev, in
     auto up = [](size_t v) { return (v + 63) / 64 * 64; };
     float *cond = workspace_dev + up(train_floats(L, d));
     float *xr = cond + up((size_t)R * kCond);
-    float *part = xr + up(2 * (size_t)R);
+    float *w1t = xr + up(2 * (size_t)R);
+    float *gp = w1t + up((size_t)kNets * kHidden * 8);
+    float *part = gp + up((size_t)kGradPlanes * 5 * (size_t)d.Rp);
+    potential_w1_kernel<<<kNets, kHidden, 0, st>>>(H->params, L, w1t);
+    DDM_CUDA_TRY(cudaGetLastError());
     potential_rows_kernel<<<(unsigned)std::min<long long>((R * kCond + 255) / 256, 148 * 16), 256, 0, st>>>(
         theta_dev, ld_theta, x_dev, pulses_dev, ld_pulses, (int)T, (int)C, cond, xr);
     DDM_CUDA_TRY(cudaGetLastError());
@@ -1015,11 +1020,13 @@ DDM_API int mnle_loglik_sum_grad_tc_f32(void *handle, const float *theta_dev, in
     // scale = +1: the "loss" is the sum of the rows' log-probabilities
     train_rows_kernel<<<(unsigned)((d.Rp + kBlockRows - 1) / kBlockRows), kRowWarps * 32, 0, st>>>(H->params, L, rows, d.Rp, 1.0f, 1, B);
     DDM_CUDA_TRY(cudaGetLastError());
-    const TcTrainDump bwd{B.H, B.Q, B.LG, d.Rp, B.DH, nullptr};
+    // backward-data on tcgen05 without keeping the derivatives: the last epilogue of every net contracts d log p /
+    // d (first-layer pre-activations) with the five theta columns of that layer and leaves five numbers per row
+    const TcTrainDump bwd{B.H, B.Q, B.LG, d.Rp, nullptr, nullptr, nullptr, gp, w1t};
     rc = tc_train_backward(L, B.pack, R, bwd, st);
     if (rc != DDM_OK) return rc;
     const unsigned cb = (unsigned)((C + 127) / 128);
-    potential_grad_partial_kernel<<<dim3(cb, kNets, kGradTSplit), 128, 0, st>>>(H->params, L, B.DH, d.Rp, (int)T, (int)C, part);
+    potential_grad_partial_kernel<<<dim3(cb, kGradPlanes), 128, 0, st>>>(gp, d.Rp, (int)T, (int)C, part);
     DDM_CUDA_TRY(cudaGetLastError());
     potential_grad_final_kernel<<<cb, 128, 0, st>>>(part, B.LP, (int)T, (int)C, out_dev, grad_dev);
     DDM_CUDA_TRY(cudaGetLastError());
