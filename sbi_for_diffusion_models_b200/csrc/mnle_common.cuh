@@ -116,6 +116,10 @@ struct TcTrainDump {
     // first layer (padded to eight), GP = [kNets][2][5][Rp] per row and column half: sum_j dh1[j] * W1[j][i]
     float *GP;
     const float *W1T;
+    // potential mode, forward and backward: [kNets][3][4][Rp] sign masks of the ReLU layers' pre-activations (bit 31 - j
+    // of word c: column 32 c + j is negative) kept INSTEAD of the activations -- the backward-data pass needs nothing
+    // else from a ReLU layer, and 16 bytes per (row, layer) replace 512.  The sigmoid layers still go through H.
+    uint32_t *HM;
 };
 size_t tc_train_pack_bytes(int n_choices, long long R);  // operand pack + context images of R rows
 int tc_train_forward(const float *params_dev, const Layout &L, void *pack_dev, const float *x_dev, const float *cond_dev,

@@ -363,9 +363,13 @@ constexpr uint32_t kTmemD = 0, kTmemAHi = 128, kTmemALo = 192, kTmemTile = 256; 
 // `keep` (training forward): the activations of this row also go to global memory, COLUMN-major (element
 // (row, col) at keep[col * keep_ld], keep pointing at the row): a lane holds one row, so the 32 lanes of a
 // store instruction write 32 consecutive rows of one column = one 128-byte line.
+// `keep_m` (potential gradient, ReLU layers): instead of the activations only the SIGNS of the pre-activations are
+// kept, one 32-bit word per 32 columns (bit 31 - j: column c0 + j negative), words keep_ld apart.  (A pre-activation
+// of exactly +0 counts as active here and as inactive in torch's ReLU: it carries no gradient either way unless the
+// upstream gradient is non-zero at a measure-zero point.)
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int ncols, const float *bias,
-                                                float *keep = nullptr, size_t keep_ld = 0)
+                                                float *keep = nullptr, size_t keep_ld = 0, uint32_t *keep_m = nullptr)
 {
 #pragma unroll 1
     for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
@@ -373,6 +377,7 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
         tmem_ld32(trow + kTmemD + (uint32_t)c0, v);
         tmem_wait_ld();
         uint32_t hi[16], lo[16];
+        uint32_t neg = 0u;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const float4 b = *reinterpret_cast<const float4 *>(bias + c0 + 4 * g);
@@ -384,6 +389,10 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
 #pragma unroll
                 for (int j = 0; j < 4; ++j) f[j] = fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * f[j]));
             }
+            if (EPI == kEpiRelu && keep_m != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) neg = __funnelshift_l(__float_as_uint(f[j]), neg, 1);   // shift the sign bit in
+            }
             split_relu_bf16x2(f[0], f[1], hi[2 * g], lo[2 * g]);
             split_relu_bf16x2(f[2], f[3], hi[2 * g + 1], lo[2 * g + 1]);
             if (keep != nullptr) {  // (the ReLU is fused into the conversions above)
@@ -391,6 +400,7 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
                 for (int j = 0; j < 4; ++j) keep[(size_t)(c0 + 4 * g + j) * keep_ld] = EPI == kEpiRelu ? fmaxf(f[j], 0.f) : f[j];
             }
         }
+        if (EPI == kEpiRelu && keep_m != nullptr) keep_m[(size_t)((c0 - col0) >> 5) * keep_ld] = neg;
         tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
         tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
     }
@@ -402,16 +412,24 @@ __device__ __forceinline__ void tc_epilogue_act(uint32_t trow, int col0, int nco
 // and, when another stage follows, split into the bf16 hi / lo A operand of that stage.
 // d_row may be null (potential gradient: the derivatives are not kept); w1s (shared memory, [128][8], may be null): the
 // five theta columns of this net's first layer -- acc5[i] += sum_j d[j] * w1s[j][i] over this thread's columns.
-template <int EPI>
+// POT (the potential's gradient): ReLU layers read sign masks (m_row) instead of activations, nothing is written to
+// d_row, and the last stage contracts with w1s.  !POT (the training step): activations in, derivatives out.
+template <int EPI, bool POT>
 __device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int ncols, const float *h_row, float *d_row, size_t ld,
                                                  bool have, bool feeds_next, uint64_t *dfull, uint32_t parity,
-                                                 const float *w1s = nullptr, float *acc5 = nullptr)
+                                                 const float *w1s = nullptr, float *acc5 = nullptr, const uint32_t *m_row = nullptr)
 {
 #pragma unroll 1
     for (int c0 = col0; c0 < col0 + ncols; c0 += 32) {
         float h[32];  // column-major storage: every load / store below is one 128-byte line per warp
+        constexpr bool masks = POT && EPI == kEpiRelu;   // sign masks of the pre-activations instead of activations
+        uint32_t neg = 0xFFFFFFFFu;
+        if (masks) {
+            if (have) neg = m_row[(size_t)((c0 - col0) >> 5) * ld];
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = have ? h_row[(size_t)(c0 + j) * ld] : 0.f;
+            for (int j = 0; j < 32; ++j) h[j] = have ? h_row[(size_t)(c0 + j) * ld] : 0.f;
+        }
         if (c0 == col0) {  // the kept activations do not depend on the MMAs: their latency hides behind the wait
             mbar_wait(dfull, parity);
             tc_fence_after_sync();
@@ -422,7 +440,8 @@ __device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int nc
 #pragma unroll
         for (int j = 0; j < 32; ++j) {  // h <- d loss / d pre-activation, in place
             const float x = __uint_as_float(v[j]);
-            h[j] = EPI == kEpiRelu ? (h[j] > 0.f ? x : 0.f) : x * h[j] * (1.0f - h[j]);
+            if (masks) h[j] = (neg & (0x80000000u >> j)) ? 0.f : x;
+            else h[j] = EPI == kEpiRelu ? (h[j] > 0.f ? x : 0.f) : x * h[j] * (1.0f - h[j]);
         }
         if (feeds_next) {
             uint32_t hi[16], lo[16];
@@ -431,11 +450,11 @@ __device__ __forceinline__ void tc_epilogue_mask(uint32_t trow, int col0, int nc
             tmem_st16(trow + kTmemAHi + (uint32_t)(c0 >> 1), hi);
             tmem_st16(trow + kTmemALo + (uint32_t)(c0 >> 1), lo);
         }
-        if (have && d_row != nullptr) {
+        if (!POT && have) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) d_row[(size_t)(c0 + j) * ld] = h[j];
         }
-        if (w1s != nullptr) {
+        if (POT && w1s != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float4 wa = *reinterpret_cast<const float4 *>(w1s + (c0 + j) * 8);   // same address in every lane: broadcast
@@ -592,7 +611,7 @@ static void train_grid(long long n_tiles, int sms, int *n_pairs, long long *grid
 // BWD (rows layout, the training backward-data pass): the A image of a net's first stage holds the
 // gradient rows (d loss / d spline parameters or logits), the weight images are the transposed ones, and
 // every epilogue multiplies by the activation derivative (tc_epilogue_mask) and writes keep.DH.
-template <bool ROWS, bool KEEP = false, bool BWD = false>
+template <bool ROWS, bool KEEP = false, bool BWD = false, bool POT = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
     mnle_tc_kernel(const unsigned char *__restrict__ pack, const __grid_constant__ TcPlan plan,
                    const float *__restrict__ theta, long long ld_theta, const float *__restrict__ x,
@@ -604,6 +623,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 {
     static_assert(ROWS || !KEEP, "only the rows-mode kernel keeps activations");
     static_assert(!BWD || (ROWS && !KEEP), "the backward pass uses the rows-mode layout");
+    static_assert(!POT || BWD, "POT selects the potential-gradient flavour of the backward pass");
     extern __shared__ __align__(1024) unsigned char smem[];
     using SM = TcSmem<ROWS>;
     constexpr int kTcSlots = SM::kSlots;
@@ -640,7 +660,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // potential gradient: the theta columns of this net's first layer, [128][8] floats, in the unused tail of tile 0's
     // first A image (the backward pass fills K groups 0..9 of an image, this is groups 10 and 11)
     float *w1s = reinterpret_cast<float *>(smem + kSmemATh + 10u * kKGroupBytes);
-    if (BWD && keep.GP != nullptr)
+    if (BWD && POT)
         for (int i = tid; i < kHidden * 8; i += kTcThreads) w1s[i] = __ldg(keep.W1T + (size_t)net_id * kHidden * 8 + i);
     if (warp == kTcEpiWarps) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
@@ -872,17 +892,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (BWD) {
                 const bool have = c_glob < keep.Rp;
                 const size_t at = ((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * kHidden * (size_t)keep.Rp + (size_t)(have ? c_glob : 0);
-                float *d_row = keep.DH != nullptr ? keep.DH + at : nullptr;
+                float *d_row = POT ? nullptr : keep.DH + at;
                 const bool last = !(s + 1 < n_st);
-                const float *wsel = (keep.GP != nullptr && last) ? w1s : nullptr;   // the last stage ends at the first layer
+                const float *wsel = (POT && last) ? w1s : nullptr;   // the last stage ends at the first layer
                 float acc5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                const uint32_t *m_row = !POT ? nullptr
+                                        : keep.HM + (((size_t)st.net * 3 + ((st.pad & 0xFF) - 1)) * 4 + 2 * hf) * (size_t)keep.Rp +
+                                              (size_t)(have ? c_glob : 0);
                 if (st.epi == kEpiRelu)
-                    tc_epilogue_mask<kEpiRelu>(trow, 64 * hf, 64, keep.H + at, d_row, (size_t)keep.Rp, have, !last,
-                                               &dfull[X], ph_d & 1u, wsel, acc5);
+                    tc_epilogue_mask<kEpiRelu, POT>(trow, 64 * hf, 64, keep.H + at, d_row, (size_t)keep.Rp, have, !last,
+                                                    &dfull[X], ph_d & 1u, wsel, acc5, m_row);
                 else
-                    tc_epilogue_mask<kEpiSigmoid>(trow, 64 * hf, 64, keep.H + at, d_row, (size_t)keep.Rp, have, !last,
-                                                  &dfull[X], ph_d & 1u, wsel, acc5);
-                if (wsel != nullptr && have) {
+                    tc_epilogue_mask<kEpiSigmoid, POT>(trow, 64 * hf, 64, keep.H + at, d_row, (size_t)keep.Rp, have, !last,
+                                                       &dfull[X], ph_d & 1u, wsel, acc5);
+                if (POT && wsel != nullptr && have) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i)   // [net][hf][i][row]: a warp writes 32 consecutive rows of one plane
                         keep.GP[(((size_t)net_id * 2 + hf) * 5 + i) * (size_t)keep.Rp + (size_t)c_glob] = acc5[i];
@@ -920,10 +943,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 continue;
             }
             float *keep_h = nullptr;
-            if (KEEP && kept && st.pad != 0 && keep.H != nullptr)   // (H == null: only logits and spline parameters are kept)
-                keep_h = keep.H + ((size_t)st.net * 3 + (st.pad - 1)) * kHidden * (size_t)keep.Rp + (size_t)c_glob;
+            uint32_t *keep_m = nullptr;
+            if (KEEP && kept && st.pad != 0) {
+                if (keep.HM != nullptr && st.epi == kEpiRelu)   // potential gradient: sign masks instead of activations
+                    keep_m = keep.HM + (((size_t)st.net * 3 + (st.pad - 1)) * 4 + 2 * hf) * (size_t)keep.Rp + (size_t)c_glob;
+                else if (keep.H != nullptr)                      // (H == null: only logits and spline parameters are kept)
+                    keep_h = keep.H + ((size_t)st.net * 3 + (st.pad - 1)) * kHidden * (size_t)keep.Rp + (size_t)c_glob;
+            }
             if (st.epi == kEpiRelu) {
-                tc_epilogue_act<kEpiRelu>(trow, 64 * hf, 64, bias, keep_h, (size_t)keep.Rp);
+                tc_epilogue_act<kEpiRelu>(trow, 64 * hf, 64, bias, keep_h, (size_t)keep.Rp, keep_m);
             } else if (st.epi == kEpiSigmoid) {
                 tc_epilogue_act<kEpiSigmoid>(trow, 64 * hf, 64, bias, keep_h, (size_t)keep.Rp);
             } else if (st.epi == kEpiSpline) {
@@ -1226,11 +1254,20 @@ int tc_train_backward(const Layout &L, const void *pack_dev, long long R, const 
     DDM_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     train_grid((R + kTcM - 1) / kTcM, sms, &n_pairs, &grid);
     DDM_REQUIRE(grid <= 65535, "training minibatch too large for one launch (at most ~8e6 rows)");
-    DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)TcSmem<true>::kBytes));
-    mnle_tc_kernel<true, false, true><<<dim3(kNets, (unsigned)grid), kTcThreads, TcSmem<true>::kBytes, st>>>(
-        static_cast<const unsigned char *>(pack_dev), bplan, nullptr, 0, nullptr, nullptr, 1, 1, (int)R, n_pairs, 0.f, 1.f,
-        L.n_choices, nullptr, nullptr, nullptr, nullptr, nullptr, dump);
+    if (dump.GP != nullptr) {   // the potential's gradient: sign masks in, five numbers per row out
+        DDM_REQUIRE(dump.HM != nullptr && dump.W1T != nullptr, "tc_train_backward: potential mode needs HM and W1T");
+        DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)TcSmem<true>::kBytes));
+        mnle_tc_kernel<true, false, true, true><<<dim3(kNets, (unsigned)grid), kTcThreads, TcSmem<true>::kBytes, st>>>(
+            static_cast<const unsigned char *>(pack_dev), bplan, nullptr, 0, nullptr, nullptr, 1, 1, (int)R, n_pairs, 0.f, 1.f,
+            L.n_choices, nullptr, nullptr, nullptr, nullptr, nullptr, dump);
+    } else {
+        DDM_CUDA_TRY(cudaFuncSetAttribute(mnle_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)TcSmem<true>::kBytes));
+        mnle_tc_kernel<true, false, true><<<dim3(kNets, (unsigned)grid), kTcThreads, TcSmem<true>::kBytes, st>>>(
+            static_cast<const unsigned char *>(pack_dev), bplan, nullptr, 0, nullptr, nullptr, 1, 1, (int)R, n_pairs, 0.f, 1.f,
+            L.n_choices, nullptr, nullptr, nullptr, nullptr, nullptr, dump);
+    }
     DDM_CUDA_TRY(cudaGetLastError());
     return DDM_OK;
 }

@@ -963,7 +963,8 @@ static size_t potential_grad_floats(const Layout &L, long long T, long long C)
     n += up((size_t)R * kCond) + up(2 * (size_t)R);         // the expanded rows
     n += up((size_t)kNets * kHidden * 8);                   // theta columns of the first layers
     n += up((size_t)kGradPlanes * 5 * (size_t)d.Rp);        // per-row partial gradients
-    n += (size_t)kGradPlanes * (size_t)C * 5;               // per-chain partial gradients
+    n += up((size_t)kGradPlanes * (size_t)C * 5);           // per-chain partial gradients
+    n += (size_t)kNets * 3 * 4 * (size_t)d.Rp;              // sign masks of the ReLU layers
     return n;
 }
 
@@ -1008,13 +1009,14 @@ DDM_API int mnle_loglik_sum_grad_tc_f32(void *handle, const float *theta_dev, in
     float *w1t = xr + up(2 * (size_t)R);
     float *gp = w1t + up((size_t)kNets * kHidden * 8);
     float *part = gp + up((size_t)kGradPlanes * 5 * (size_t)d.Rp);
+    uint32_t *hm = reinterpret_cast<uint32_t *>(part + up((size_t)kGradPlanes * (size_t)C * 5));
     potential_w1_kernel<<<kNets, kHidden, 0, st>>>(H->params, L, w1t);
     DDM_CUDA_TRY(cudaGetLastError());
     potential_rows_kernel<<<(unsigned)std::min<long long>((R * kCond + 255) / 256, 148 * 16), 256, 0, st>>>(
         theta_dev, ld_theta, x_dev, pulses_dev, ld_pulses, (int)T, (int)C, cond, xr);
     DDM_CUDA_TRY(cudaGetLastError());
     TrainRows rows{xr, cond, nullptr, (long long)kCond, R};
-    const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp, nullptr, nullptr, nullptr};
+    const TcTrainDump keep{B.H, B.Q, B.LG, d.Rp, nullptr, nullptr, nullptr, nullptr, nullptr, hm};
     int rc = tc_train_forward(H->params, L, B.pack, xr, cond, (long long)kCond, nullptr, R, keep, B.LP, st);
     if (rc != DDM_OK) return rc;
     // scale = +1: the "loss" is the sum of the rows' log-probabilities
@@ -1022,7 +1024,7 @@ DDM_API int mnle_loglik_sum_grad_tc_f32(void *handle, const float *theta_dev, in
     DDM_CUDA_TRY(cudaGetLastError());
     // backward-data on tcgen05 without keeping the derivatives: the last epilogue of every net contracts d log p /
     // d (first-layer pre-activations) with the five theta columns of that layer and leaves five numbers per row
-    const TcTrainDump bwd{B.H, B.Q, B.LG, d.Rp, nullptr, nullptr, nullptr, gp, w1t};
+    const TcTrainDump bwd{B.H, B.Q, B.LG, d.Rp, nullptr, nullptr, nullptr, gp, w1t, hm};
     rc = tc_train_backward(L, B.pack, R, bwd, st);
     if (rc != DDM_OK) return rc;
     const unsigned cb = (unsigned)((C + 127) / 128);
