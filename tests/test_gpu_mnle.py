@@ -369,3 +369,27 @@ def test_other_numbers_of_choice_categories(K):
     assert float(((val.double() - want_sum[:9]).abs() / want_sum[:9].abs()).max()) < 1e-4
     err = (grad.double() - want_grad).abs() / (want_grad.abs() + 1e-2 * want_grad.abs().max())
     assert float(err.max()) < 2e-3, float(err.max())
+
+
+def test_potential_gradient_at_configs3_size_two_kernels_agree():
+    """configs[3] (T = 50 x C = 1024 = 400 row tiles: several waves of two-tile CTAs plus a wave of one-tile ones) on
+    the trained net: the reverse-mode tensor-core path -- sign masks instead of activations, the theta contraction
+    fused into the backward epilogue -- against the fp32 forward-mode kernel, which shares no code with it."""
+    p, packed = trained_net()
+    est = DeviceMNLE(packed)
+    T, C = 50, 1024
+    theta = orc.prior_sample(C, seed=33)
+    x, pulses = _session(T)
+    v_tc, g_tc = est.loglik_sum_and_grad(theta, x, pulses, kernel="tc")
+    v_fm, g_fm = est.loglik_sum_and_grad(theta, x, pulses, kernel="simt")
+    assert torch.isfinite(v_tc).all() and torch.isfinite(g_tc).all()
+    rel_v = ((v_tc - v_fm).abs() / v_fm.abs().clamp_min(1.0)).double()
+    assert float(rel_v.max()) < 5e-3 and float(rel_v.median()) < 1e-4, (float(rel_v.max()), float(rel_v.median()))
+    e = ((g_tc - g_fm).abs() / (g_fm.abs() + 1e-2 * g_fm.abs().max(dim=0, keepdim=True).values)).double()
+    # (single entries move when a ReLU unit or a spline knot sits within 1e-5 of its kink, see the test above)
+    assert float(e.median()) < 5e-3 and float(e.mean()) < 5e-2, (float(e.median()), float(e.mean()), float(e.max()))
+    v2, g2 = est.loglik_sum_and_grad(theta, x, pulses, kernel="tc")
+    assert torch.equal(v2, v_tc) and torch.equal(g2, g_tc)     # fixed-order reductions: reproducible bits
+    # the value of the gradient path is the forward kernel's value (same networks, same splines, other kernels)
+    v_fw = est.loglik_sum(theta, x, pulses, kernel="tc")
+    assert float(((v_tc - v_fw).abs() / v_fw.abs().clamp_min(1.0)).max()) < 5e-3
